@@ -1,0 +1,237 @@
+"""Attack classes with the reference's `.apply(audio, sr)` / `.name` interface
+(scripts/attacks.py there), executed by the batched CUDA kernels.
+
+Each class also has `.apply_batch(x, sr, rng)` taking a CUDA float32 tensor
+[n_clips, n_samples].  Randomness is explicit: start indices / band edges are drawn
+from the numpy Generator passed in (or given directly), never from global state
+(the reference draws from unseeded global RNGs, attacks.py:170,340,378).
+Filter design (scipy.signal.butter / firwin / lfilter_zi) stays on the host; only
+coefficients travel.  MP3Compression / TimeStretch / PitchShift shell out to
+ffmpeg / rubberband upstream and have no arithmetic to restate: not provided.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+_engine = None
+
+
+def set_engine(engine):
+    """Engine used by `.apply()`; `load()`-ed embedders expose theirs as `embedder.engine`."""
+    global _engine
+    _engine = engine
+
+
+def _eng(engine=None):
+    if engine is not None:
+        return engine
+    if _engine is None:
+        raise RuntimeError("aware_b200.attacks: call set_engine(embedder.engine) first")
+    return _engine
+
+
+def _warm_samples(a) -> int:
+    """Look-back length after which an IIR's memory is below float64 rounding."""
+    r = float(np.max(np.abs(np.roots(a)))) if len(a) > 1 else 0.0
+    if r <= 0.0:
+        return 64
+    if r >= 1.0:
+        raise ValueError("unstable filter")
+    return int(math.ceil(math.log(1e-18) / math.log(r))) + 64
+
+
+class Attack:
+    name = "attack"
+
+    def apply_batch(self, x: torch.Tensor, sr: int, rng=None, engine=None) -> torch.Tensor:
+        raise NotImplementedError
+
+    def apply(self, audio, sr):
+        """Single clip, numpy in -> numpy float32 out (reference calling convention)."""
+        eng = _eng()
+        x = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32)).reshape(1, -1).to(eng.device)
+        return self.apply_batch(x, sr, engine=eng)[0].cpu().numpy()
+
+
+class PCMBitDepthConversion(Attack):
+    def __init__(self, pcm=16):
+        self.pcm = pcm
+        self.name = f"pcm_{pcm}"
+
+    def apply_batch(self, x, sr, rng=None, engine=None):
+        return _eng(engine).attack_pcm(x, self.pcm)
+
+
+class DeleteSamples(Attack):
+    def __init__(self, percentage, start=None):
+        self.percentage, self.start = percentage, start
+        self.name = f"delete_{percentage}"
+
+    def apply_batch(self, x, sr, rng=None, engine=None):
+        n = x.shape[1]
+        n_del = int(self.percentage * n)
+        start = self.start
+        if start is None:
+            rng = rng or np.random.default_rng()
+            start = rng.integers(0, n - n_del, size=x.shape[0])
+        start = torch.as_tensor(np.broadcast_to(np.asarray(start), (x.shape[0],)).copy(), dtype=torch.int32)
+        return _eng(engine).attack_delete(x, start, n_del)
+
+
+class Cropout(Attack):
+    def __init__(self, percentage):
+        self.percentage = percentage
+        self.name = f"cropout_{percentage}"
+
+    def apply_batch(self, x, sr, rng=None, engine=None):
+        return _eng(engine).attack_cropout(x, int(self.percentage * sr))
+
+
+class SampleSupression(Attack):
+    def __init__(self, percentage, start=None):
+        self.percentage, self.start = percentage, start
+        self.name = f"sample_supression_{percentage}"
+
+    def apply_batch(self, x, sr, rng=None, engine=None):
+        n = x.shape[1]
+        n_zero = int(self.percentage * sr)
+        start = self.start
+        if start is None:
+            rng = rng or np.random.default_rng()
+            start = rng.integers(0, n - n_zero, size=x.shape[0])
+        start = torch.as_tensor(np.broadcast_to(np.asarray(start), (x.shape[0],)).copy(), dtype=torch.int32)
+        return _eng(engine).attack_suppress(x, start, n_zero)
+
+
+def polyphase_plan(n_in: int, up: int, down: int, window=("kaiser", 5.0)):
+    """Host half of scipy.signal.resample_poly(x, up, down) for float32 input: the FIR
+    (firwin, cast to float32, times `up`), its zero padding, the transposed+flipped tap
+    table scipy's upfirdn uses, and the output window.  Returns
+    (h_tf float32[up*taps_per_phase], taps_per_phase, first_out, n_out)."""
+    from scipy.signal import firwin
+    g = math.gcd(up, down)
+    up, down = up // g, down // g
+    n_out = n_in * up
+    n_out = n_out // down + bool(n_out % down)
+    max_rate = max(up, down)
+    half_len = 10 * max_rate
+    h = firwin(2 * half_len + 1, 1.0 / max_rate, window=window).astype(np.float32)
+    h *= up
+    n_pre_pad = down - half_len % down
+    n_post_pad = 0
+    n_pre_remove = (half_len + n_pre_pad) // down
+
+    def out_len(len_h):
+        return (((n_in - 1) * up + len_h) - 1) // down + 1
+
+    while out_len(len(h) + n_pre_pad + n_post_pad) < n_out + n_pre_remove:
+        n_post_pad += 1
+    h = np.concatenate((np.zeros(n_pre_pad, dtype=h.dtype), h, np.zeros(n_post_pad, dtype=h.dtype)))
+    pad = -len(h) % up
+    h_full = np.concatenate((h, np.zeros(pad, dtype=h.dtype)))
+    h_tf = np.ascontiguousarray(h_full.reshape(-1, up).T[:, ::-1]).ravel()
+    return h_tf, len(h_full) // up, n_pre_remove, n_out
+
+
+class Resample(Attack):
+    def __init__(self, target_sr=16000):
+        self.target_sr = target_sr
+        self.name = f"resample_{target_sr}"
+        self._plans = {}
+
+    def _plan(self, eng, n, up, down):
+        key = (n, up, down, eng.device.index)
+        if key not in self._plans:
+            h_tf, tpp, first, n_out = polyphase_plan(n, up, down)
+            self._plans[key] = (torch.from_numpy(h_tf).to(eng.device), tpp, first, n_out)
+        return self._plans[key]
+
+    def apply_batch(self, x, sr, rng=None, engine=None):
+        eng = _eng(engine)
+        f = sr // self.target_sr
+        if f > 1:                                     # decimate + np.interp back (attacks.py:276-287)
+            return eng.attack_decimate_interp(x, f)
+        up, down = 441, 160                           # polyphase there and back (attacks.py:289-294)
+        h1, t1, k1, n1 = self._plan(eng, x.shape[1], up, down)
+        mid = eng.attack_upfirdn(x, h1, t1, up, down, k1, n1)
+        h2, t2, k2, n2 = self._plan(eng, n1, down, up)
+        return eng.attack_upfirdn(mid, h2, t2, down, up, k2, n2)
+
+
+class _Butter(Attack):
+    def _design(self, sr):
+        raise NotImplementedError
+
+    def apply_batch(self, x, sr, rng=None, engine=None):
+        b, a = self._design(sr)
+        return _eng(engine).attack_lfilter(x, b, a, _warm_samples(a))
+
+
+class LowPassFilter(_Butter):
+    def __init__(self, cut_off=4000.0, order=6):
+        self.cut_off, self.order, self.name = cut_off, order, "low_pass"
+
+    def _design(self, sr):
+        from scipy.signal import butter
+        return butter(self.order, self.cut_off / (0.5 * sr), btype="low", analog=False)
+
+
+class HighPassFilter(_Butter):
+    def __init__(self, cut_off=500.0, order=4):
+        self.cut_off, self.order, self.name = cut_off, order, "high_pass"
+
+    def _design(self, sr):
+        from scipy.signal import butter
+        return butter(self.order, self.cut_off / (0.5 * sr), btype="highpass", analog=False)
+
+
+class RandomBandstop(Attack):
+    """One random 200 Hz stop band per call (as upstream: one draw per apply), zero-phase
+    Butterworth via filtfilt."""
+
+    def __init__(self, band_width=200.0, min_freq=300.0, max_freq=4000.0, order=4, f_low=None):
+        self.band_width, self.min_freq, self.max_freq = float(band_width), float(min_freq), float(max_freq)
+        self.order, self.f_low = int(order), f_low
+        self.name = f"bandstop_{int(band_width)}Hz"
+
+    def apply_batch(self, x, sr, rng=None, engine=None):
+        from scipy.signal import butter, lfilter_zi
+        f_low = self.f_low
+        if f_low is None:
+            rng = rng or np.random.default_rng()
+            f_low = float(rng.uniform(self.min_freq, self.max_freq - self.band_width))
+        nyq = sr / 2.0
+        b, a = butter(self.order, [f_low / nyq, (f_low + self.band_width) / nyq], btype="bandstop")
+        return _eng(engine).attack_filtfilt(x, b, a, lfilter_zi(b, a), _warm_samples(a))
+
+
+# ---- extensions named by the build brief that have no reference arithmetic ("parity unpinned")
+class AdditiveNoise(Attack):
+    """y = x + sigma * buf, buf a host-seeded standard-normal buffer."""
+
+    def __init__(self, sigma=0.01, seed=99):
+        self.sigma, self.seed, self.name = sigma, seed, f"noise_{sigma}"
+
+    def apply_batch(self, x, sr, rng=None, engine=None):
+        g = torch.Generator(device="cpu").manual_seed(self.seed)
+        buf = torch.randn(x.shape, generator=g, dtype=torch.float32).to(x.device)
+        return _eng(engine).attack_affine(x, 1.0, buf, self.sigma)
+
+
+class Gain(Attack):
+    def __init__(self, gain=0.5):
+        self.gain, self.name = gain, f"gain_{gain}"
+
+    def apply_batch(self, x, sr, rng=None, engine=None):
+        return _eng(engine).attack_affine(x, self.gain)
+
+
+def reference_suite():
+    """The in-scope part of scripts/test.py's attack_list (test.py:15-18)."""
+    return [PCMBitDepthConversion(8), PCMBitDepthConversion(12), PCMBitDepthConversion(16),
+            PCMBitDepthConversion(24), DeleteSamples(0.1), DeleteSamples(0.15), DeleteSamples(0.2),
+            Resample(), RandomBandstop(), SampleSupression(0.1), SampleSupression(0.25),
+            LowPassFilter(), HighPassFilter()]

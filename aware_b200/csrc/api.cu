@@ -1,0 +1,975 @@
+// aware_b200 C ABI (include/aware_b200.h): context, workspace and the batched
+// detect / embed / attack pipelines built from the kernels in this directory.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/aware_b200.h"
+#include "attacks.cuh"
+#include "common.cuh"
+#include "fft.cuh"
+#include "gemm.cuh"
+#include "net.cuh"
+
+namespace aw {
+thread_local char g_err[512] = "";
+int set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+}  // namespace aw
+
+using namespace aw;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static const int kC[5] = {128, 512, 1024, 1024, 40};     // channel widths (detector_net.py:58)
+static const int kCp[5] = {128, 512, 1024, 1024, 64};    // padded to GEMM tiles
+
+struct MelCfg {
+  int bin0, nbins, nnz;
+  int *rowptr, *col, *colptr, *row;
+  float *val, *valT;
+};
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct aw_ctx {
+  int device = 0, prec = AW_PREC_TF32;
+  int64_t launches = 0;
+  float* d_w[4] = {};    // forward weights  [kCp[l+1]][kCp[l]]
+  float* d_wt[4] = {};   // transposed       [kCp[l]][kCp[l+1]]
+  float* d_window = nullptr;
+  float2* d_twiddle = nullptr;
+  std::vector<float> h_mel;
+  float band_lo = 500.f, band_hi = 4000.f, tol_db = 6.f, threshold = 0.f;
+  std::vector<MelCfg> mels;
+  PFN_encodeTiled encode = nullptr;
+  CUtensorMap tm_w[4], tm_wt[4];
+  // workspace (grow-only)
+  Buf accum, peakx, mag, ph_u, ph_q, c0, c, m, v, cbest, dA, yoob, y, dpad, M, cs, sigma;
+  Buf act[5], ga, gb, dh4, dp0, part, stat[5], bstat, values, best, improved, pattern, itc, steps;
+  int ws_rows = 0;
+  CUtensorMap tm_act[4], tm_dh4, tm_ga1024, tm_ga512, tm_gb1024;
+  // state of the last embed wave (for aw_embed_state)
+  int last_n = 0, last_T = 0, last_nb = 0;
+};
+
+static int ensure(Buf& b, size_t bytes) {
+  if (bytes <= b.cap) return 0;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  AW_CUDA(cudaMalloc(&b.p, bytes));
+  b.cap = bytes;
+  return 0;
+}
+
+static int make_map(aw_ctx* ctx, CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t K,
+                    uint32_t box_rows) {
+  cuuint64_t gdim[2] = {K, rows};
+  cuuint64_t gstr[1] = {K * sizeof(float)};
+  cuuint32_t box[2] = {AW_GEMM_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed: %d", (int)r);
+  return 0;
+}
+
+static int bn_for(int n) { return n >= 256 ? 256 : (n >= 128 ? 128 : 64); }
+
+template <int BN, int EPI>
+static int launch_tc(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, int rows, int n,
+                     int k, const EpiArgs& ep, cudaStream_t st) {
+  dim3 grid(rows / 128, n / BN);
+  k_gemm_tc<BN, EPI><<<grid, 192, gemm_tc_smem<BN>(), st>>>(ma, mb, k, ep);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int EPI>
+static int launch_gemm_epi(aw_ctx* ctx, const CUtensorMap& ma, const float* a,
+                           const CUtensorMap& mb, const float* b, int rows, int n, int k,
+                           const EpiArgs& ep, int prec, cudaStream_t st) {
+  if (prec == AW_PREC_TF32) {
+    switch (bn_for(n)) {
+      case 256: return launch_tc<256, EPI>(ctx, ma, mb, rows, n, k, ep, st);
+      case 128: return launch_tc<128, EPI>(ctx, ma, mb, rows, n, k, ep, st);
+      default: return launch_tc<64, EPI>(ctx, ma, mb, rows, n, k, ep, st);
+    }
+  }
+  dim3 grid(rows / 64, (n + 63) / 64);
+  k_gemm_exact<<<grid, 256, 0, st>>>(a, b, k, n, ep.out, ep.ldo);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  if (EPI != EPI_PLAIN) {
+    dim3 g2(rows / 128, (n + 127) / 128);
+    k_epilogue_exact<EPI><<<g2, 128, 0, st>>>(ep, n);
+    ctx->launches++;
+    AW_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+static int launch_gemm(aw_ctx* ctx, int epi, const CUtensorMap& ma, const float* a,
+                       const CUtensorMap& mb, const float* b, int rows, int n, int k,
+                       const EpiArgs& ep, cudaStream_t st) {
+  switch (epi) {
+    case EPI_FWD: return launch_gemm_epi<EPI_FWD>(ctx, ma, a, mb, b, rows, n, k, ep, ctx->prec, st);
+    case EPI_BWD: return launch_gemm_epi<EPI_BWD>(ctx, ma, a, mb, b, rows, n, k, ep, ctx->prec, st);
+    default: return launch_gemm_epi<EPI_PLAIN>(ctx, ma, a, mb, b, rows, n, k, ep, ctx->prec, st);
+  }
+}
+
+template <int BN, int EPI>
+static int set_smem_attr() {
+  AW_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               gemm_tc_smem<BN>()));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" const char* aw_last_error(void) { return g_err; }
+extern "C" const char* aw_version(void) { return "aware_b200 0.1 (sm_100a)"; }
+
+extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
+  AW_REQUIRE(out && model, "aw_ctx_create: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_error("aw_ctx_create: no CUDA device (this library has no CPU fallback)");
+  AW_REQUIRE(device >= 0 && device < ndev, "aw_ctx_create: bad device %d", device);
+  AW_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  AW_CUDA(cudaGetDeviceProperties(&prop, device));
+  AW_REQUIRE(prop.major == 10, "aw_ctx_create: device is sm_%d%d, this build targets sm_100a",
+             prop.major, prop.minor);
+  aw_ctx* ctx = new aw_ctx();
+  ctx->device = device;
+  ctx->band_lo = model->band_lo_hz;
+  ctx->band_hi = model->band_hi_hz;
+  ctx->tol_db = model->tolerance_db;
+  ctx->threshold = model->threshold;
+  ctx->h_mel.assign(model->mel_basis, model->mel_basis + AW_NMEL * 513);
+
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  AW_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  AW_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+  ctx->encode = (PFN_encodeTiled)fn;
+
+  // weights: zero-padded forward copies and transposed copies for the input-gradient GEMMs
+  for (int l = 0; l < 4; ++l) {
+    const int co = kC[l + 1], ci = kC[l], cop = kCp[l + 1], cip = kCp[l];
+    std::vector<float> w((size_t)cop * cip, 0.f), wt((size_t)cip * cop, 0.f);
+    for (int o = 0; o < co; ++o)
+      for (int i = 0; i < ci; ++i) {
+        const float x = model->w[l][(size_t)o * ci + i];
+        w[(size_t)o * cip + i] = x;
+        wt[(size_t)i * cop + o] = x;
+      }
+    AW_CUDA(cudaMalloc(&ctx->d_w[l], w.size() * 4));
+    AW_CUDA(cudaMalloc(&ctx->d_wt[l], wt.size() * 4));
+    AW_CUDA(cudaMemcpy(ctx->d_w[l], w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    AW_CUDA(cudaMemcpy(ctx->d_wt[l], wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
+    if (make_map(ctx, &ctx->tm_w[l], ctx->d_w[l], cop, cip, bn_for(cop))) return 1;
+    if (make_map(ctx, &ctx->tm_wt[l], ctx->d_wt[l], cip, cop, bn_for(cip))) return 1;
+  }
+  AW_CUDA(cudaMalloc(&ctx->d_window, 1024 * 4));
+  AW_CUDA(cudaMemcpy(ctx->d_window, model->window, 1024 * 4, cudaMemcpyHostToDevice));
+  std::vector<float2> tw(1024);
+  for (int j = 0; j < 1024; ++j) {
+    const double a = 2.0 * M_PI * j / 1024.0;
+    tw[j] = make_float2((float)cos(a), (float)sin(a));
+  }
+  AW_CUDA(cudaMalloc(&ctx->d_twiddle, 1024 * sizeof(float2)));
+  AW_CUDA(cudaMemcpy(ctx->d_twiddle, tw.data(), 1024 * sizeof(float2), cudaMemcpyHostToDevice));
+
+  if (set_smem_attr<256, EPI_PLAIN>() || set_smem_attr<256, EPI_FWD>() || set_smem_attr<256, EPI_BWD>() ||
+      set_smem_attr<128, EPI_PLAIN>() || set_smem_attr<128, EPI_FWD>() || set_smem_attr<128, EPI_BWD>() ||
+      set_smem_attr<64, EPI_PLAIN>() || set_smem_attr<64, EPI_FWD>() || set_smem_attr<64, EPI_BWD>())
+    return 1;
+  AW_CUDA(cudaFuncSetAttribute(k_analysis<ANA_MAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_ANA_SMEM));
+  AW_CUDA(cudaFuncSetAttribute(k_analysis<ANA_INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_ANA_SMEM));
+  AW_CUDA(cudaFuncSetAttribute(k_analysis<ANA_LOOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_ANA_SMEM));
+  AW_CUDA(cudaFuncSetAttribute(k_analysis<ANA_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_ANA_SMEM));
+  AW_CUDA(cudaFuncSetAttribute(k_synthesis<SYN_OOB>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_SYN_SMEM));
+  AW_CUDA(cudaFuncSetAttribute(k_synthesis<SYN_WAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_SYN_SMEM));
+  AW_CUDA(cudaFuncSetAttribute(k_synthesis<SYN_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_SYN_SMEM));
+  *out = ctx;
+  return 0;
+}
+
+extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  for (int l = 0; l < 4; ++l) {
+    cudaFree(ctx->d_w[l]);
+    cudaFree(ctx->d_wt[l]);
+  }
+  cudaFree(ctx->d_window);
+  cudaFree(ctx->d_twiddle);
+  for (auto& mc : ctx->mels) {
+    cudaFree(mc.rowptr); cudaFree(mc.col); cudaFree(mc.val);
+    cudaFree(mc.colptr); cudaFree(mc.row); cudaFree(mc.valT);
+  }
+  Buf* bufs[] = {&ctx->accum, &ctx->peakx, &ctx->mag, &ctx->ph_u, &ctx->ph_q, &ctx->c0, &ctx->c,
+                 &ctx->m, &ctx->v, &ctx->cbest, &ctx->dA, &ctx->yoob, &ctx->y, &ctx->dpad, &ctx->M,
+                 &ctx->cs, &ctx->sigma, &ctx->act[0], &ctx->act[1], &ctx->act[2], &ctx->act[3],
+                 &ctx->act[4], &ctx->ga, &ctx->gb, &ctx->dh4, &ctx->dp0, &ctx->part, &ctx->stat[0],
+                 &ctx->stat[1], &ctx->stat[2], &ctx->stat[3], &ctx->stat[4], &ctx->bstat,
+                 &ctx->values, &ctx->best, &ctx->improved, &ctx->pattern, &ctx->itc, &ctx->steps};
+  for (Buf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  delete ctx;
+  return 0;
+}
+
+extern "C" int aw_ctx_set_precision(aw_ctx* ctx, int prec) {
+  AW_REQUIRE(ctx, "null ctx");
+  AW_REQUIRE(prec == AW_PREC_TF32 || prec == AW_PREC_FP32, "unknown precision %d", prec);
+  ctx->prec = prec;
+  return 0;
+}
+
+extern "C" int64_t aw_launch_count(aw_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// embedding/multibit_embedder.py:43-47: bins k with band_lo <= k*sr/1024 <= band_hi,
+// frequencies evaluated like np.fft.rfftfreq (k * (sr / 1024) in float64).
+extern "C" int aw_band_bins(aw_ctx* ctx, int sample_rate, int* bin0, int* nbins) {
+  AW_REQUIRE(ctx && bin0 && nbins, "null argument");
+  int lo = -1, hi = -1;
+  const double val = 1.0 / (1024.0 * (1.0 / sample_rate));
+  for (int k = 0; k <= 512; ++k) {
+    const double f = k * val;
+    if (f >= ctx->band_lo && f <= ctx->band_hi) {
+      if (lo < 0) lo = k;
+      hi = k;
+    }
+  }
+  AW_REQUIRE(lo >= 1 && hi <= 511 && hi - lo + 1 <= AW_MAX_BINS,
+             "embedding band [%g,%g] Hz at %d Hz maps to unsupported bins [%d,%d]", ctx->band_lo,
+             ctx->band_hi, sample_rate, lo, hi);
+  *bin0 = lo;
+  *nbins = hi - lo + 1;
+  return 0;
+}
+
+static int get_mel(aw_ctx* ctx, int bin0, int nbins, SparseMel* out) {
+  for (auto& mc : ctx->mels)
+    if (mc.bin0 == bin0 && mc.nbins == nbins) {
+      *out = SparseMel{mc.rowptr, mc.col, mc.val, mc.colptr, mc.row, mc.valT};
+      return 0;
+    }
+  std::vector<int> rowptr(AW_NMEL + 1, 0), col, colptr(nbins + 1, 0), row;
+  std::vector<float> val, valT;
+  for (int c = 0; c < AW_NMEL; ++c) {
+    for (int b = 0; b < nbins; ++b) {
+      const float w = ctx->h_mel[(size_t)c * 513 + bin0 + b];
+      if (w != 0.f) { col.push_back(b); val.push_back(w); }
+    }
+    rowptr[c + 1] = (int)col.size();
+  }
+  for (int b = 0; b < nbins; ++b) {
+    for (int c = 0; c < AW_NMEL; ++c) {
+      const float w = ctx->h_mel[(size_t)c * 513 + bin0 + b];
+      if (w != 0.f) { row.push_back(c); valT.push_back(w); }
+    }
+    colptr[b + 1] = (int)row.size();
+  }
+  MelCfg mc;
+  mc.bin0 = bin0; mc.nbins = nbins; mc.nnz = (int)col.size();
+  const size_t nz = col.size() ? col.size() : 1;
+  AW_CUDA(cudaMalloc(&mc.rowptr, rowptr.size() * 4));
+  AW_CUDA(cudaMalloc(&mc.col, nz * 4));
+  AW_CUDA(cudaMalloc(&mc.val, nz * 4));
+  AW_CUDA(cudaMalloc(&mc.colptr, colptr.size() * 4));
+  AW_CUDA(cudaMalloc(&mc.row, nz * 4));
+  AW_CUDA(cudaMalloc(&mc.valT, nz * 4));
+  AW_CUDA(cudaMemcpy(mc.rowptr, rowptr.data(), rowptr.size() * 4, cudaMemcpyHostToDevice));
+  AW_CUDA(cudaMemcpy(mc.colptr, colptr.data(), colptr.size() * 4, cudaMemcpyHostToDevice));
+  if (!col.empty()) {
+    AW_CUDA(cudaMemcpy(mc.col, col.data(), col.size() * 4, cudaMemcpyHostToDevice));
+    AW_CUDA(cudaMemcpy(mc.val, val.data(), val.size() * 4, cudaMemcpyHostToDevice));
+    AW_CUDA(cudaMemcpy(mc.row, row.data(), row.size() * 4, cudaMemcpyHostToDevice));
+    AW_CUDA(cudaMemcpy(mc.valT, valT.data(), valT.size() * 4, cudaMemcpyHostToDevice));
+  }
+  ctx->mels.push_back(mc);
+  *out = SparseMel{mc.rowptr, mc.col, mc.val, mc.colptr, mc.row, mc.valT};
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------
+struct Dims {
+  int n, N, T, L, Tp, Tp_pad, tiles, rows, bin0, nb;
+};
+
+static int make_dims(aw_ctx* ctx, int n, int N, int sr, Dims* d) {
+  AW_REQUIRE(n >= 1, "n_clips must be >= 1");
+  AW_REQUIRE(N > 1024, "clips must be longer than 1024 samples (got %d)", N);
+  d->n = n; d->N = N;
+  d->T = 1 + N / AW_HOP;
+  d->L = AW_HOP * (d->T - 1);
+  d->Tp = d->T / 2;
+  d->Tp_pad = (d->Tp + AW_ROW_TILE - 1) / AW_ROW_TILE * AW_ROW_TILE;
+  d->tiles = d->Tp_pad / AW_ROW_TILE;
+  d->rows = n * d->Tp_pad;
+  return aw_band_bins(ctx, sr, &d->bin0, &d->nb);
+}
+
+// accumulators cleared once per pass: [peak_y u64][s2 f64][chan_sum 256 f64][bsum 256 f64] per clip
+#define AW_ACC_PER_CLIP (2 + 256 + 256)
+struct Acc {
+  unsigned long long* peak_y; double* s2; double* chan_sum; double* bsum;
+};
+static Acc acc_view(aw_ctx* ctx, int n) {
+  Acc a;
+  double* base = (double*)ctx->accum.p;
+  a.peak_y = (unsigned long long*)base;
+  a.s2 = base + n;
+  a.chan_sum = base + 2 * (size_t)n;
+  a.bsum = base + 2 * (size_t)n + 256 * (size_t)n;
+  return a;
+}
+
+__global__ void k_iter_begin(double* accum, size_t count, int* it) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < count) accum[i] = 0.0;       // +0.0 == all-zero bits, valid for the u64 peak too
+  if (i == 0 && it) *it += 1;
+}
+
+static int ensure_net_ws(aw_ctx* ctx, const Dims& d, bool backward) {
+  const size_t n = d.n, R = d.rows;
+  if (ensure(ctx->accum, n * AW_ACC_PER_CLIP * 8)) return 1;
+  if (ensure(ctx->peakx, n * 8)) return 1;
+  if (ensure(ctx->mag, n * d.T * d.nb * 4)) return 1;
+  if (ensure(ctx->M, n * d.T * AW_NMEL * 4)) return 1;
+  if (ensure(ctx->cs, n * AW_NMEL * sizeof(ChanStats))) return 1;
+  if (ensure(ctx->sigma, n * 4)) return 1;
+  bool remap = false;
+  for (int l = 0; l < 5; ++l) {
+    void* before = ctx->act[l].p;
+    if (ensure(ctx->act[l], R * kCp[l] * 4)) return 1;
+    if (ensure(ctx->stat[l], n * kCp[l] * 2 * 4)) return 1;
+    remap |= before != ctx->act[l].p;
+  }
+  if (ensure(ctx->part, (R / 128) * 1024 * 2 * 4)) return 1;
+  if (ensure(ctx->values, n * AW_NBITS * 4)) return 1;
+  if (ensure(ctx->best, n * 4)) return 1;
+  if (ensure(ctx->improved, n * 4)) return 1;
+  if (ensure(ctx->itc, 4)) return 1;
+  if (backward) {
+    void *b0 = ctx->ga.p, *b1 = ctx->gb.p, *b2 = ctx->dh4.p;
+    if (ensure(ctx->ga, R * 1024 * 4)) return 1;
+    if (ensure(ctx->gb, R * 1024 * 4)) return 1;
+    if (ensure(ctx->dh4, R * 64 * 4)) return 1;
+    if (ensure(ctx->dp0, R * 128 * 4)) return 1;
+    if (ensure(ctx->bstat, n * 1024 * 2 * 4)) return 1;
+    remap |= b0 != ctx->ga.p || b1 != ctx->gb.p || b2 != ctx->dh4.p;
+  }
+  if (remap || ctx->ws_rows != d.rows) {
+    for (int l = 0; l < 4; ++l)
+      if (make_map(ctx, &ctx->tm_act[l], (float*)ctx->act[l].p, R, kCp[l], 128)) return 1;
+    if (ctx->ga.p) {
+      if (make_map(ctx, &ctx->tm_dh4, (float*)ctx->dh4.p, R, 64, 128)) return 1;
+      if (make_map(ctx, &ctx->tm_ga1024, (float*)ctx->ga.p, R, 1024, 128)) return 1;
+      if (make_map(ctx, &ctx->tm_ga512, (float*)ctx->ga.p, R, 512, 128)) return 1;
+      if (make_map(ctx, &ctx->tm_gb1024, (float*)ctx->gb.p, R, 1024, 128)) return 1;
+    }
+    ctx->ws_rows = d.rows;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// detector forward from band magnitudes (ctx->mag) to values (+ optional backward seed)
+// ---------------------------------------------------------------------------
+static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseMel& sm,
+                       cudaStream_t st) {
+  const int tf = ctx->prec == AW_PREC_TF32;
+  {
+    dim3 g((d.T + AW_MEL_FRAMES - 1) / AW_MEL_FRAMES, d.n);
+    k_mel<<<g, 128, AW_MEL_FRAMES * d.nb * 4, st>>>((float*)ctx->mag.p, d.T, d.nb, sm,
+                                                    (float*)ctx->M.p, acc.chan_sum);
+    ctx->launches++;
+    AW_LAUNCH_CHECK();
+    dim3 g2((d.Tp_pad + AW_P0_ROWS - 1) / AW_P0_ROWS, d.n);
+    k_p0<<<g2, 128, 0, st>>>((float*)ctx->M.p, d.T, d.Tp, d.Tp_pad, acc.chan_sum,
+                             (float*)ctx->act[0].p, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p, tf);
+    ctx->launches++;
+    AW_LAUNCH_CHECK();
+  }
+  for (int l = 0; l < 4; ++l) {
+    const int cin = kCp[l], cout = kCp[l + 1];
+    EpiArgs ep;
+    ep.out = (float*)ctx->act[l + 1].p; ep.ldo = cout; ep.n_valid = cout;
+    ep.part = (float*)ctx->part.p; ep.ldp = cout; ep.act = nullptr;
+    if (launch_gemm(ctx, EPI_FWD, ctx->tm_act[l], (float*)ctx->act[l].p, ctx->tm_w[l], ctx->d_w[l],
+                    d.rows, cout, cin, ep, st))
+      return 1;
+    dim3 g((cout + 127) / 128, d.n);
+    k_finalize_fwd<<<g, 128, 0, st>>>((float*)ctx->part.p, cout, d.tiles, cout, d.Tp,
+                                      (float*)ctx->stat[l + 1].p);
+    ctx->launches++;
+    AW_LAUNCH_CHECK();
+    k_norm_act<<<d.rows / 4, 256, 0, st>>>((float*)ctx->act[l + 1].p, cout, d.Tp, d.Tp_pad,
+                                           (float*)ctx->stat[l + 1].p, tf && l < 3);
+    ctx->launches++;
+    AW_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseMel& sm,
+                        cudaStream_t st) {
+  const int tf = ctx->prec == AW_PREC_TF32;
+  float* ga = (float*)ctx->ga.p;
+  float* gb = (float*)ctx->gb.p;
+  struct Step { const CUtensorMap* ma; const float* a; int l; float* out; };
+  // l = index of the weight matrix: dP_l = dH_{l+1} * W_l
+  const Step steps[3] = {{&ctx->tm_dh4, (float*)ctx->dh4.p, 3, ga},
+                         {&ctx->tm_ga1024, ga, 2, gb},
+                         {&ctx->tm_gb1024, gb, 1, ga}};
+  for (int s = 0; s < 3; ++s) {
+    const int l = steps[s].l, k = kCp[l + 1], n = kCp[l];
+    EpiArgs ep;
+    ep.out = steps[s].out; ep.ldo = n; ep.n_valid = n;
+    ep.part = (float*)ctx->part.p; ep.ldp = n; ep.act = (float*)ctx->act[l].p;
+    if (launch_gemm(ctx, EPI_BWD, *steps[s].ma, steps[s].a, ctx->tm_wt[l], ctx->d_wt[l], d.rows, n,
+                    k, ep, st))
+      return 1;
+    dim3 g((n + 127) / 128, d.n);
+    k_finalize_bwd<<<g, 128, 0, st>>>((float*)ctx->part.p, n, d.tiles, n, d.Tp,
+                                      (float*)ctx->bstat.p);
+    ctx->launches++;
+    AW_LAUNCH_CHECK();
+    k_in_bwd_apply<<<d.rows / 4, 256, 0, st>>>(steps[s].out, (float*)ctx->act[l].p, n, d.Tp,
+                                               d.Tp_pad, (float*)ctx->stat[l].p,
+                                               (float*)ctx->bstat.p, tf);
+    ctx->launches++;
+    AW_LAUNCH_CHECK();
+  }
+  {
+    EpiArgs ep;
+    ep.out = (float*)ctx->dp0.p; ep.ldo = 128; ep.n_valid = 128;
+    ep.part = nullptr; ep.ldp = 0; ep.act = nullptr;
+    if (launch_gemm(ctx, EPI_PLAIN, ctx->tm_ga512, ga, ctx->tm_wt[0], ctx->d_wt[0], d.rows, 128,
+                    512, ep, st))
+      return 1;
+  }
+  dim3 g1((2 * d.Tp + AW_P0B_FRAMES - 1) / AW_P0B_FRAMES, d.n);
+  k_p0_bwd_reduce<<<g1, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
+                                      (ChanStats*)ctx->cs.p, acc.bsum);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  dim3 g2((d.T + AW_P0A_FRAMES - 1) / AW_P0A_FRAMES, d.n);
+  k_p0_bwd_apply<<<g2, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
+                                     (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p, acc.bsum, sm,
+                                     d.nb, (float*)ctx->dA.p);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
+static int run_head(aw_ctx* ctx, const Dims& d, const float* pattern, float* values, float* losses,
+                    int n_total, bool backward, cudaStream_t st) {
+  HeadArgs h;
+  h.P4 = (float*)ctx->act[4].p; h.Tp = d.Tp; h.Tp_pad = d.Tp_pad;
+  h.stat4 = (float*)ctx->stat[4].p;
+  h.pattern = pattern; h.values = values; h.losses = losses;
+  h.best = (float*)ctx->best.p; h.improved = (int*)ctx->improved.p;
+  h.dH4 = backward ? (float*)ctx->dh4.p : nullptr;
+  h.it_ptr = (int*)ctx->itc.p; h.n_clips = n_total;
+  h.round_tf32 = ctx->prec == AW_PREC_TF32;
+  k_head<<<d.n, 256, 0, st>>>(h);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
+static AnaArgs ana_base(aw_ctx* ctx, const Dims& d) {
+  AnaArgs a;
+  memset(&a, 0, sizeof(a));
+  a.T = d.T; a.bin0 = d.bin0; a.nbins = d.nb;
+  a.window = ctx->d_window; a.twiddle = ctx->d_twiddle;
+  a.tol_ratio = (float)pow(10.0, -(double)ctx->tol_db / 20.0);
+  return a;
+}
+static SynArgs syn_base(aw_ctx* ctx, const Dims& d) {
+  SynArgs s;
+  memset(&s, 0, sizeof(s));
+  s.T = d.T; s.L = d.L; s.bin0 = d.bin0; s.nbins = d.nb;
+  s.window = ctx->d_window; s.twiddle = ctx->d_twiddle;
+  return s;
+}
+template <int MODE>
+static int launch_ana(aw_ctx* ctx, const Dims& d, const AnaArgs& a, cudaStream_t st) {
+  dim3 g((d.T + AW_ANA_FRAMES - 1) / AW_ANA_FRAMES, d.n);
+  k_analysis<MODE><<<g, 128, AW_ANA_SMEM, st>>>(a);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+template <int MODE>
+static int launch_syn(aw_ctx* ctx, const Dims& d, const SynArgs& s, cudaStream_t st) {
+  dim3 g((d.T + 3 + AW_SYN_HOPS - 1) / AW_SYN_HOPS, d.n);
+  k_synthesis<MODE><<<g, 128, AW_SYN_SMEM, st>>>(s);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+static int launch_peak(aw_ctx* ctx, const float* x, int64_t stride, int n, int n_clips,
+                       unsigned long long* peak, cudaStream_t st) {
+  AW_CUDA(cudaMemsetAsync(peak, 0, (size_t)n_clips * 8, st));
+  dim3 g(std::min((n + 2047) / 2048, 64), n_clips);
+  k_peak<<<g, 256, 0, st>>>(x, stride, n, peak);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+static int begin_pass(aw_ctx* ctx, int n, int* it, cudaStream_t st) {
+  const size_t cnt = (size_t)n * AW_ACC_PER_CLIP;
+  k_iter_begin<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>((double*)ctx->accum.p, cnt, it);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int aw_detect_batch(aw_ctx* ctx, const float* d_audio, int n_clips, int n_samples,
+                               int64_t stride, int sample_rate, float* d_values, void* stream) {
+  AW_REQUIRE(ctx && d_audio && d_values, "aw_detect_batch: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  AW_CUDA(cudaSetDevice(ctx->device));
+  Dims d;
+  if (make_dims(ctx, n_clips, n_samples, sample_rate, &d)) return 1;
+  if (ensure_net_ws(ctx, d, false)) return 1;
+  SparseMel sm;
+  if (get_mel(ctx, d.bin0, d.nb, &sm)) return 1;
+  const Acc acc = acc_view(ctx, d.n);
+  if (begin_pass(ctx, d.n, nullptr, st)) return 1;
+  if (launch_peak(ctx, d_audio, stride, n_samples, d.n, (unsigned long long*)ctx->peakx.p, st)) return 1;
+  AnaArgs a = ana_base(ctx, d);
+  a.sig = d_audio; a.sig_stride = stride; a.len = n_samples;
+  a.peak = (unsigned long long*)ctx->peakx.p;
+  a.mag = (float*)ctx->mag.p;
+  if (launch_ana<ANA_MAG>(ctx, d, a, st)) return 1;
+  if (net_forward(ctx, d, acc, sm, st)) return 1;
+  return run_head(ctx, d, nullptr, d_values, nullptr, d.n, false, st);
+}
+
+__global__ void k_pattern_to_float(const int32_t* p, float* o, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = (float)p[i];
+}
+__global__ void k_fill(float* p, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void k_set_int(int* p, int v) { *p = v; }
+
+// torch/optim/nadam.py scalars, Python-float arithmetic with the float32 mu_product
+static void nadam_table(int iters, std::vector<NadamStep>& out) {
+  out.resize(iters);
+  const double lr = 0.1, beta1 = 0.9, beta2 = 0.999, decay = 4e-3;
+  float mu_product = 1.0f;
+  for (int step = 1; step <= iters; ++step) {
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    const double mu = beta1 * (1.0 - 0.5 * pow(0.96, step * decay));
+    const double mu_next = beta1 * (1.0 - 0.5 * pow(0.96, (step + 1) * decay));
+    mu_product = mu_product * (float)mu;
+    const double mp = (double)mu_product;
+    NadamStep s;
+    s.a_g = (float)(-lr * (1.0 - mu) / (1.0 - mp));
+    s.a_m = (float)((-lr * mu_next) / (1.0 - mp * mu_next));
+    s.inv_bc2 = 1.0f / (float)bc2;
+    s.pad = 0.f;
+    out[step - 1] = s;
+  }
+}
+
+extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, int n_samples,
+                              int64_t stride, int sample_rate, const int32_t* d_pattern, int iters,
+                              const float* d_scale, float* d_out, int64_t out_stride,
+                              float* d_best_loss, float* d_losses, int wave_clips, void* stream) {
+  AW_REQUIRE(ctx && d_audio && d_pattern && d_out, "aw_embed_batch: null argument");
+  AW_REQUIRE(iters >= 0, "aw_embed_batch: iters < 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  AW_CUDA(cudaSetDevice(ctx->device));
+  if (wave_clips <= 0 || wave_clips > n_clips) wave_clips = n_clips;
+  Dims d;
+  if (make_dims(ctx, wave_clips, n_samples, sample_rate, &d)) return 1;
+  AW_REQUIRE(out_stride >= d.L, "aw_embed_batch: out_stride %lld < %d", (long long)out_stride, d.L);
+  if (ensure_net_ws(ctx, d, true)) return 1;
+  const size_t sp = (size_t)d.n * d.T * d.nb;
+  if (ensure(ctx->ph_u, sp * 8) || ensure(ctx->ph_q, sp * 8) || ensure(ctx->c0, sp * 4) ||
+      ensure(ctx->c, sp * 4) || ensure(ctx->m, sp * 4) || ensure(ctx->v, sp * 4) ||
+      ensure(ctx->cbest, sp * 4) || ensure(ctx->dA, sp * 4) ||
+      ensure(ctx->yoob, (size_t)d.n * d.L * 4) || ensure(ctx->y, (size_t)d.n * d.L * 4) ||
+      ensure(ctx->dpad, (size_t)d.n * (d.L + AW_NFFT) * 4) ||
+      ensure(ctx->pattern, (size_t)d.n * AW_NBITS * 4) ||
+      ensure(ctx->steps, (size_t)(iters > 0 ? iters : 1) * sizeof(NadamStep)))
+    return 1;
+  SparseMel sm;
+  if (get_mel(ctx, d.bin0, d.nb, &sm)) return 1;
+  std::vector<NadamStep> tab;
+  nadam_table(iters, tab);
+  if (iters > 0)
+    AW_CUDA(cudaMemcpyAsync(ctx->steps.p, tab.data(), tab.size() * sizeof(NadamStep),
+                            cudaMemcpyHostToDevice, st));
+  AW_CUDA(cudaStreamSynchronize(st));   // `tab` is pageable host memory
+
+  for (int w0 = 0; w0 < n_clips; w0 += wave_clips) {
+    Dims dw = d;
+    dw.n = std::min(wave_clips, n_clips - w0);
+    dw.rows = dw.n * dw.Tp_pad;
+    // tensor maps are encoded for d.rows; a smaller last wave only uses a prefix of rows
+    const Acc acc = acc_view(ctx, dw.n);
+    const float* x = d_audio + (size_t)w0 * stride;
+    int* itc = (int*)ctx->itc.p;
+
+    k_set_int<<<1, 1, 0, st>>>(itc, -1);
+    k_fill<<<(dw.n + 255) / 256, 256, 0, st>>>((float*)ctx->best.p, INFINITY, dw.n);
+    k_pattern_to_float<<<(dw.n * AW_NBITS + 255) / 256, 256, 0, st>>>(
+        d_pattern + (size_t)w0 * AW_NBITS, (float*)ctx->pattern.p, dw.n * AW_NBITS);
+    ctx->launches += 3;
+    AW_LAUNCH_CHECK();
+    if (launch_peak(ctx, x, stride, n_samples, dw.n, (unsigned long long*)ctx->peakx.p, st)) return 1;
+
+    // ---- pre-STFT, bounds, constant out-of-band waveform (multibit_embedder.py:143-160)
+    AnaArgs a0 = ana_base(ctx, dw);
+    a0.sig = x; a0.sig_stride = stride; a0.len = n_samples;
+    a0.peak = (unsigned long long*)ctx->peakx.p;
+    a0.mag = (float*)ctx->c0.p; a0.ph = (float2*)ctx->ph_u.p;
+    a0.c = (float*)ctx->c.p; a0.m = (float*)ctx->m.p; a0.v = (float*)ctx->v.p;
+    a0.cbest = (float*)ctx->cbest.p;
+    if (launch_ana<ANA_INIT>(ctx, dw, a0, st)) return 1;
+    SynArgs s0 = syn_base(ctx, dw);
+    s0.amp = (float*)ctx->c0.p; s0.ph = (float2*)ctx->ph_u.p; s0.scale = 1.0f / AW_NFFT;
+    s0.x = x; s0.x_stride = stride; s0.peak_x = (unsigned long long*)ctx->peakx.p;
+    s0.y_oob = (float*)ctx->yoob.p;
+    if (launch_syn<SYN_OOB>(ctx, dw, s0, st)) return 1;
+
+    // ---- optimisation loop (multibit_embedder.py:95-122)
+    for (int it = 0; it < iters; ++it) {
+      if (begin_pass(ctx, dw.n, itc, st)) return 1;
+      SynArgs s1 = syn_base(ctx, dw);
+      s1.amp = (float*)ctx->c.p; s1.ph = (float2*)ctx->ph_u.p; s1.scale = 1.0f / AW_NFFT;
+      s1.y_oob = (float*)ctx->yoob.p; s1.y = (float*)ctx->y.p; s1.peak_y = acc.peak_y;
+      if (launch_syn<SYN_WAVE>(ctx, dw, s1, st)) return 1;
+      AnaArgs a1 = ana_base(ctx, dw);
+      a1.sig = (float*)ctx->y.p; a1.sig_stride = dw.L; a1.len = dw.L; a1.peak = acc.peak_y;
+      a1.mag = (float*)ctx->mag.p; a1.ph = (float2*)ctx->ph_q.p;
+      if (launch_ana<ANA_LOOP>(ctx, dw, a1, st)) return 1;
+      if (net_forward(ctx, dw, acc, sm, st)) return 1;
+      if (run_head(ctx, dw, (float*)ctx->pattern.p, (float*)ctx->values.p,
+                   d_losses ? d_losses + w0 : nullptr, n_clips, true, st))
+        return 1;
+      if (net_backward(ctx, dw, acc, sm, st)) return 1;
+      SynArgs s2 = syn_base(ctx, dw);
+      s2.amp = (float*)ctx->dA.p; s2.ph = (float2*)ctx->ph_q.p; s2.scale = 0.5f;
+      s2.y = (float*)ctx->y.p; s2.peak_y = acc.peak_y;
+      s2.dpad = (float*)ctx->dpad.p; s2.s2 = acc.s2;
+      if (launch_syn<SYN_ADJ>(ctx, dw, s2, st)) return 1;
+      AnaArgs a2 = ana_base(ctx, dw);
+      a2.sig = (float*)ctx->dpad.p; a2.sig_stride = dw.L + AW_NFFT; a2.len = dw.L;
+      a2.peak = acc.peak_y;
+      a2.c = (float*)ctx->c.p; a2.m = (float*)ctx->m.p; a2.v = (float*)ctx->v.p;
+      a2.cbest = (float*)ctx->cbest.p; a2.c0 = (float*)ctx->c0.p; a2.u = (float2*)ctx->ph_u.p;
+      a2.y = (float*)ctx->y.p; a2.s2 = acc.s2; a2.improved = (int*)ctx->improved.p;
+      a2.steps = (NadamStep*)ctx->steps.p; a2.it_ptr = itc;
+      if (launch_ana<ANA_ADJ>(ctx, dw, a2, st)) return 1;
+    }
+
+    // ---- final synthesis from the best coefficients (multibit_embedder.py:173-192)
+    if (begin_pass(ctx, dw.n, nullptr, st)) return 1;
+    SynArgs sf = syn_base(ctx, dw);
+    sf.amp = (float*)ctx->cbest.p; sf.ph = (float2*)ctx->ph_u.p; sf.scale = 1.0f / AW_NFFT;
+    sf.y_oob = (float*)ctx->yoob.p; sf.y = (float*)ctx->y.p; sf.peak_y = acc.peak_y;
+    if (launch_syn<SYN_WAVE>(ctx, dw, sf, st)) return 1;
+    dim3 g(std::min((dw.L + 2047) / 2048, 64), dw.n);
+    k_final_normalize<<<g, 256, 0, st>>>((float*)ctx->y.p, dw.L, acc.peak_y,
+                                         d_scale ? d_scale + w0 : nullptr,
+                                         d_out + (size_t)w0 * out_stride, out_stride);
+    ctx->launches++;
+    AW_LAUNCH_CHECK();
+    if (d_best_loss)
+      AW_CUDA(cudaMemcpyAsync(d_best_loss + w0, ctx->best.p, (size_t)dw.n * 4,
+                              cudaMemcpyDeviceToDevice, st));
+    ctx->last_n = dw.n; ctx->last_T = dw.T; ctx->last_nb = dw.nb;
+  }
+  return 0;
+}
+
+extern "C" int aw_embed_state(aw_ctx* ctx, int which, float* d_dst, int64_t capacity, void* stream) {
+  AW_REQUIRE(ctx && d_dst, "null argument");
+  const size_t cnt = (size_t)ctx->last_n * ctx->last_T * ctx->last_nb;
+  AW_REQUIRE(cnt > 0 && (int64_t)cnt <= capacity, "aw_embed_state: capacity %lld < %zu",
+             (long long)capacity, cnt);
+  Buf* src[5] = {&ctx->c, &ctx->cbest, &ctx->c0, &ctx->m, &ctx->v};
+  AW_REQUIRE(which >= 0 && which < 5, "aw_embed_state: bad selector");
+  AW_CUDA(cudaMemcpyAsync(d_dst, src[which]->p, cnt * 4, cudaMemcpyDeviceToDevice,
+                          (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int aw_decide_and_count(aw_ctx* ctx, const float* d_values, const int32_t* d_ref_bits,
+                                   int n_clips, int32_t* d_bits_out, int32_t* d_err_per_clip,
+                                   uint64_t* d_counters, void* stream) {
+  AW_REQUIRE(ctx && d_values, "null argument");
+  k_decide_count<<<(n_clips + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+      d_values, d_ref_bits, ctx->threshold, n_clips, d_bits_out, d_err_per_clip,
+      (unsigned long long*)d_counters);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int aw_snr_batch(aw_ctx* ctx, const float* d_out, int64_t out_stride,
+                            const float* d_target, int64_t tgt_stride, int n_clips, int n,
+                            double* d_snr, double* d_snr_sum, void* stream) {
+  AW_REQUIRE(ctx && d_out && d_target && d_snr, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ensure(ctx->accum, (size_t)std::max(n_clips, 1) * AW_ACC_PER_CLIP * 8)) return 1;
+  AW_CUDA(cudaMemsetAsync(ctx->accum.p, 0, (size_t)n_clips * 16, st));
+  dim3 g(std::min((n + 2047) / 2048, 64), n_clips);
+  k_snr_partial<<<g, 256, 0, st>>>(d_out, out_stride, d_target, tgt_stride, n, (double*)ctx->accum.p);
+  k_snr_final<<<(n_clips + 127) / 128, 128, 0, st>>>((double*)ctx->accum.p, n_clips, d_snr, d_snr_sum);
+  ctx->launches += 2;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// stage-level entry points
+// ---------------------------------------------------------------------------
+extern "C" int aw_stft_band(aw_ctx* ctx, const float* d_audio, int n_clips, int n_samples,
+                            int64_t stride, int sample_rate, int normalize, float* d_mag,
+                            float* d_phasor, void* stream) {
+  AW_REQUIRE(ctx && d_audio && d_mag, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Dims d;
+  if (make_dims(ctx, n_clips, n_samples, sample_rate, &d)) return 1;
+  if (ensure(ctx->peakx, (size_t)n_clips * 8)) return 1;
+  if (normalize) {
+    if (launch_peak(ctx, d_audio, stride, n_samples, n_clips, (unsigned long long*)ctx->peakx.p, st)) return 1;
+  } else {
+    // peak = 1 - 1e-8 is not representable; use a packed peak of exactly 1.0 and accept the
+    // 1e-8 relative bias (documented: normalize=0 is only approximately un-normalised)
+    std::vector<unsigned long long> one(n_clips, ((unsigned long long)0x3f800000u << 32));
+    AW_CUDA(cudaMemcpyAsync(ctx->peakx.p, one.data(), (size_t)n_clips * 8, cudaMemcpyHostToDevice, st));
+    AW_CUDA(cudaStreamSynchronize(st));
+  }
+  AnaArgs a = ana_base(ctx, d);
+  a.sig = d_audio; a.sig_stride = stride; a.len = n_samples;
+  a.peak = (unsigned long long*)ctx->peakx.p;
+  a.mag = d_mag; a.ph = (float2*)d_phasor;
+  if (d_phasor) {
+    // ANA_LOOP writes mag + phasor but divides twice; use INIT semantics without state:
+    // route state writes to scratch buffers
+    const size_t sp = (size_t)n_clips * d.T * d.nb;
+    if (ensure(ctx->c, sp * 4) || ensure(ctx->m, sp * 4) || ensure(ctx->v, sp * 4) || ensure(ctx->cbest, sp * 4)) return 1;
+    a.c = (float*)ctx->c.p; a.m = (float*)ctx->m.p; a.v = (float*)ctx->v.p; a.cbest = (float*)ctx->cbest.p;
+    return launch_ana<ANA_INIT>(ctx, d, a, st);
+  }
+  return launch_ana<ANA_MAG>(ctx, d, a, st);
+}
+
+extern "C" int aw_istft_band(aw_ctx* ctx, const float* d_mag, const float* d_phasor, int n_clips,
+                             int n_frames, int sample_rate, float* d_wave, void* stream) {
+  AW_REQUIRE(ctx && d_mag && d_phasor && d_wave, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Dims d;
+  if (make_dims(ctx, n_clips, AW_HOP * (n_frames - 1) + 1, sample_rate, &d)) return 1;
+  AW_REQUIRE(d.T == n_frames, "internal: frame count");
+  if (ensure(ctx->accum, (size_t)n_clips * AW_ACC_PER_CLIP * 8)) return 1;
+  if (ensure(ctx->yoob, (size_t)n_clips * d.L * 4)) return 1;
+  AW_CUDA(cudaMemsetAsync(ctx->yoob.p, 0, (size_t)n_clips * d.L * 4, st));
+  const Acc acc = acc_view(ctx, n_clips);
+  if (begin_pass(ctx, n_clips, nullptr, st)) return 1;
+  SynArgs s = syn_base(ctx, d);
+  s.amp = d_mag; s.ph = (const float2*)d_phasor; s.scale = 1.0f / AW_NFFT;
+  s.y_oob = (float*)ctx->yoob.p; s.y = d_wave; s.peak_y = acc.peak_y;
+  return launch_syn<SYN_WAVE>(ctx, d, s, st);
+}
+
+extern "C" int aw_gemm(aw_ctx* ctx, const float* d_a, const float* d_b, float* d_d, int rows, int n,
+                       int k, int prec, void* stream) {
+  AW_REQUIRE(ctx && d_a && d_b && d_d, "null argument");
+  AW_REQUIRE(rows % 128 == 0 && k % 32 == 0 && n % 64 == 0, "aw_gemm: unsupported shape");
+  AW_REQUIRE(n % bn_for(n) == 0, "aw_gemm: n must be a multiple of its tile (%d)", bn_for(n));
+  CUtensorMap ma, mb;
+  if (make_map(ctx, &ma, d_a, rows, k, 128)) return 1;
+  if (make_map(ctx, &mb, d_b, n, k, bn_for(n))) return 1;
+  EpiArgs ep;
+  ep.out = d_d; ep.ldo = n; ep.n_valid = n; ep.part = nullptr; ep.ldp = 0; ep.act = nullptr;
+  return launch_gemm_epi<EPI_PLAIN>(ctx, ma, d_a, mb, d_b, rows, n, k, ep, prec, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------
+// attacks
+// ---------------------------------------------------------------------------
+static dim3 ew_grid(int n, int n_clips) { return dim3(std::min((n + 1023) / 1024, 256), n_clips); }
+
+extern "C" int aw_attack_pcm(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t in_stride,
+                             int bits, float* d_out, int64_t out_stride, void* stream) {
+  AW_REQUIRE(ctx && d_in && d_out, "null argument");
+  float S, lo, hi;
+  switch (bits) {
+    case 8: S = 127.f; lo = -128.f; hi = 127.f; break;
+    case 12: S = 4095.f; lo = -4096.f; hi = 4095.f; break;
+    case 16: S = 32767.f; lo = -32768.f; hi = 32767.f; break;
+    case 24: S = 8388607.f; lo = -8388608.f; hi = 8388607.f; break;
+    default: return set_error("Unsupported PCM bit depth: %d", bits);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ensure(ctx->peakx, (size_t)n_clips * 8)) return 1;
+  if (launch_peak(ctx, d_in, in_stride, n, n_clips, (unsigned long long*)ctx->peakx.p, st)) return 1;
+  k_attack_pcm<<<ew_grid(n, n_clips), 256, 0, st>>>(d_in, in_stride, n,
+                                                    (unsigned long long*)ctx->peakx.p, S, lo, hi,
+                                                    d_out, out_stride);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int aw_attack_decimate_interp(aw_ctx* ctx, const float* d_in, int n_clips, int n,
+                                         int64_t in_stride, int factor, float* d_out,
+                                         int64_t out_stride, void* stream) {
+  AW_REQUIRE(ctx && d_in && d_out && factor >= 2, "bad argument");
+  k_attack_decim_interp<<<ew_grid(n, n_clips), 256, 0, (cudaStream_t)stream>>>(
+      d_in, in_stride, n, factor, d_out, out_stride);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int aw_attack_upfirdn(aw_ctx* ctx, const float* d_in, int n_clips, int n_in,
+                                 int64_t in_stride, const float* d_h_tf, int taps_per_phase, int up,
+                                 int down, int first_out, int n_out, float* d_out,
+                                 int64_t out_stride, void* stream) {
+  AW_REQUIRE(ctx && d_in && d_out && d_h_tf, "null argument");
+  k_upfirdn<<<ew_grid(n_out, n_clips), 256, 0, (cudaStream_t)stream>>>(
+      d_in, in_stride, n_in, d_h_tf, taps_per_phase, up, down, first_out, n_out, d_out, out_stride);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
+static int fill_iir(IirArgs& a, const double* b, const double* av, const double* zi, int order) {
+  AW_REQUIRE(order >= 1 && order <= AW_IIR_MAXORD, "IIR order %d unsupported (max %d)", order,
+             AW_IIR_MAXORD);
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i <= order; ++i) { a.b[i] = b[i] / av[0]; a.a[i] = av[i] / av[0]; }
+  if (zi) for (int i = 0; i < order; ++i) a.zi[i] = zi[i];
+  a.order = order;
+  return 0;
+}
+
+#define AW_IIR_CHUNK 2048
+extern "C" int aw_attack_lfilter(aw_ctx* ctx, const float* d_in, int n_clips, int n,
+                                 int64_t in_stride, const double* b, const double* a, int order,
+                                 int warm, float* d_out, int64_t out_stride, void* stream) {
+  AW_REQUIRE(ctx && d_in && d_out && b && a, "null argument");
+  IirArgs ia;
+  if (fill_iir(ia, b, a, nullptr, order)) return 1;
+  ia.n = n; ia.chunk = AW_IIR_CHUNK; ia.warm = warm;
+  ia.x32 = d_in; ia.sx32 = in_stride; ia.n_x = n;
+  ia.o32 = d_out; ia.so32 = out_stride;
+  const int chunks = (n + ia.chunk - 1) / ia.chunk;
+  dim3 g((chunks + 127) / 128, n_clips);
+  k_iir<IIR_SRC_F32, IIR_DST_F32><<<g, 128, 0, (cudaStream_t)stream>>>(ia);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int aw_attack_filtfilt(aw_ctx* ctx, const float* d_in, int n_clips, int n,
+                                  int64_t in_stride, const double* b, const double* a,
+                                  const double* zi, int order, int warm, float* d_out,
+                                  int64_t out_stride, void* stream) {
+  AW_REQUIRE(ctx && d_in && d_out && b && a && zi, "null argument");
+  const int pad = 3 * (order + 1);
+  AW_REQUIRE(n > pad, "The length of the input vector x must be greater than padlen, which is %d.", pad);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int next = n + 2 * pad;
+  // two float64 scratch rows per clip, parked in the (otherwise idle) gradient buffers
+  if (ensure(ctx->ga, (size_t)n_clips * next * 8)) return 1;
+  ctx->ws_rows = 0;   // tensor maps over ga are stale now
+  IirArgs ia;
+  if (fill_iir(ia, b, a, zi, order)) return 1;
+  ia.n = next; ia.chunk = AW_IIR_CHUNK; ia.warm = warm; ia.padlen = pad; ia.use_zi = 1;
+  ia.x32 = d_in; ia.sx32 = in_stride; ia.n_x = n;
+  ia.o64 = (double*)ctx->ga.p; ia.so64 = next;
+  const int chunks = (next + ia.chunk - 1) / ia.chunk;
+  dim3 g((chunks + 127) / 128, n_clips);
+  k_iir<IIR_SRC_ODDEXT, IIR_DST_F64><<<g, 128, 0, st>>>(ia);
+  IirArgs ib = ia;
+  ib.x64 = (double*)ctx->ga.p; ib.sx64 = next;
+  ib.o32 = d_out; ib.so32 = out_stride;
+  k_iir<IIR_SRC_REV_F64, IIR_DST_REVTRIM_F32><<<g, 128, 0, st>>>(ib);
+  ctx->launches += 2;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int aw_attack_delete(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t in_stride,
+                                const int32_t* d_start, int n_delete, float* d_out,
+                                int64_t out_stride, void* stream) {
+  AW_REQUIRE(ctx && d_in && d_out && d_start && n_delete >= 0 && n_delete < n, "bad argument");
+  k_attack_delete<<<ew_grid(n - n_delete, n_clips), 256, 0, (cudaStream_t)stream>>>(
+      d_in, in_stride, n - n_delete, d_start, n_delete, d_out, out_stride);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int aw_attack_suppress(aw_ctx* ctx, const float* d_in, int n_clips, int n,
+                                  int64_t in_stride, const int32_t* d_start, int n_zero,
+                                  float* d_out, int64_t out_stride, void* stream) {
+  AW_REQUIRE(ctx && d_in && d_out && d_start, "bad argument");
+  k_attack_suppress<<<ew_grid(n, n_clips), 256, 0, (cudaStream_t)stream>>>(
+      d_in, in_stride, n, d_start, n_zero, d_out, out_stride);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int aw_attack_cropout(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t in_stride,
+                                 int n_drop, float* d_out, int64_t out_stride, void* stream) {
+  AW_REQUIRE(ctx && d_in && d_out && n_drop >= 0 && n_drop < n, "bad argument");
+  k_attack_affine<<<ew_grid(n - n_drop, n_clips), 256, 0, (cudaStream_t)stream>>>(
+      d_in + n_drop, in_stride, n - n_drop, 1.0f, nullptr, 0, 0.f, d_out, out_stride);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int aw_attack_affine(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t in_stride,
+                                float gain, const float* d_noise, int64_t noise_stride, float sigma,
+                                float* d_out, int64_t out_stride, void* stream) {
+  AW_REQUIRE(ctx && d_in && d_out, "null argument");
+  k_attack_affine<<<ew_grid(n, n_clips), 256, 0, (cudaStream_t)stream>>>(
+      d_in, in_stride, n, gain, d_noise, noise_stride, sigma, d_out, out_stride);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,181 @@
+// Attack simulations as streaming passes (reference
+// scripts/attacks.py).  All randomness (start indices, band-stop edge, noise
+// buffers) is drawn on the host and passed in, so runs are reproducible
+// (the reference draws it unseeded: attacks.py:170,340,378).
+#pragma once
+#include "common.cuh"
+
+namespace aw {
+
+// ---- A1 PCMBitDepthConversion (attacks.py:44-70) ------------------------------
+// a = x / max(|x| + 1e-8); q = trunc(clip(a * S, lo, hi)); out = float(q) / S
+__global__ void __launch_bounds__(256) k_attack_pcm(const float* __restrict__ x, long long sx,
+                                                    int n, const unsigned long long* peak,
+                                                    float S, float lo, float hi,
+                                                    float* __restrict__ out, long long so) {
+  const int clip = blockIdx.y;
+  const float d = peak_value(peak[clip]) + 1e-8f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float a = __fmul_rn(__fdiv_rn(x[(long long)clip * sx + i], d), S);
+    a = fminf(fmaxf(a, lo), hi);
+    out[(long long)clip * so + i] = __fdiv_rn(truncf(a), S);
+  }
+}
+
+// ---- A2 Resample, sr // 16000 > 1 (attacks.py:276-287) ---------------------------
+// decimate x[::f], then np.interp back (float64 arithmetic, last knot held)
+__global__ void __launch_bounds__(256) k_attack_decim_interp(const float* __restrict__ x,
+                                                             long long sx, int n, int f,
+                                                             float* __restrict__ out, long long so) {
+  const int clip = blockIdx.y;
+  const float* p = x + (long long)clip * sx;
+  const int last = ((n - 1) / f) * f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float r;
+    if (i >= last) {
+      r = p[last];
+    } else {
+      const int k0 = (i / f) * f;
+      const double y0 = p[k0], y1 = p[k0 + f];
+      const double slope = __ddiv_rn(__dsub_rn(y1, y0), (double)f);
+      r = (float)__dadd_rn(__dmul_rn(slope, (double)(i - k0)), y0);
+    }
+    out[(long long)clip * so + i] = r;
+  }
+}
+
+// ---- A2 Resample, polyphase branch (attacks.py:289-294): scipy upfirdn -----------
+// y[k] = sum over x_i in [xi-hpp+1, xi] of x[x_i] * h_tf[phase*hpp + (x_i - (xi-hpp+1))],
+// t = k*down, phase = t % up, xi = t / up, accumulated oldest sample first in float32
+// (scipy/signal/_upfirdn_apply.pyx _apply_impl).  h_tf is the transposed+flipped,
+// zero-padded filter prepared on the host; output k = k_off .. k_off + n_out - 1.
+__global__ void __launch_bounds__(256) k_upfirdn(const float* __restrict__ x, long long sx, int n_in,
+                                                 const float* __restrict__ h_tf, int hpp, int up,
+                                                 int down, int k_off, int n_out,
+                                                 float* __restrict__ out, long long so) {
+  const int clip = blockIdx.y;
+  const float* p = x + (long long)clip * sx;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_out; k += gridDim.x * blockDim.x) {
+    const long long t = (long long)(k + k_off) * down;
+    const int phase = (int)(t % up);
+    const int xi = (int)(t / up);
+    int x0 = xi - hpp + 1, hidx = phase * hpp;
+    if (x0 < 0) { hidx -= x0; x0 = 0; }
+    const int x1 = min(xi, n_in - 1);
+    float acc = 0.f;
+    for (int j = x0; j <= x1; ++j) acc = __fadd_rn(acc, __fmul_rn(p[j], h_tf[hidx++]));
+    out[(long long)clip * so + k] = acc;
+  }
+}
+
+// ---- A3/A4/A5 Butterworth IIR (attacks.py:342-349, 413-416, 451-453) ---------------
+// scipy lfilter = direct form II transposed in float64.  The recurrence is made
+// parallel by chunking: every thread owns one chunk and first runs `warm` samples
+// of look-back from zero state; the filter's memory of anything older has decayed
+// below double rounding (warm is chosen on the host from the largest pole radius),
+// so the state at the chunk start is the sequential one to ~1e-16 relative.  The
+// first chunk starts from the exact initial state.
+#define AW_IIR_MAXORD 8
+enum { IIR_SRC_F32 = 0, IIR_SRC_ODDEXT = 1, IIR_SRC_REV_F64 = 2 };
+enum { IIR_DST_F32 = 0, IIR_DST_F64 = 1, IIR_DST_REVTRIM_F32 = 2 };
+
+struct IirArgs {
+  double b[AW_IIR_MAXORD + 1], a[AW_IIR_MAXORD + 1], zi[AW_IIR_MAXORD];
+  int order;
+  int n;          // number of samples filtered (incl. extension)
+  int chunk, warm;
+  int padlen;     // ODDEXT / REVTRIM: edge extension length (27)
+  int use_zi;     // initial state = zi * first sample (filtfilt) else 0
+  const float* x32; long long sx32; int n_x;   // original signal
+  const double* x64; long long sx64;           // REV_F64 source (length n)
+  float* o32; long long so32;
+  double* o64; long long so64;
+};
+
+template <int SRC>
+__device__ __forceinline__ double iir_load(const IirArgs& a, int clip, int i) {
+  if (SRC == IIR_SRC_F32) return (double)a.x32[(long long)clip * a.sx32 + i];
+  if (SRC == IIR_SRC_REV_F64) return a.x64[(long long)clip * a.sx64 + (a.n - 1 - i)];
+  // odd extension: [2 x0 - x[pad..1], x, 2 x_last - x[n-2 .. n-pad-1]]
+  const float* p = a.x32 + (long long)clip * a.sx32;
+  const int j = i - a.padlen;
+  if (j < 0) return __dsub_rn(__dmul_rn(2.0, (double)p[0]), (double)p[-j]);
+  if (j >= a.n_x) return __dsub_rn(__dmul_rn(2.0, (double)p[a.n_x - 1]), (double)p[2 * (a.n_x - 1) - j]);
+  return (double)p[j];
+}
+
+template <int SRC, int DST>
+__global__ void __launch_bounds__(128) k_iir(IirArgs a) {
+  const int clip = blockIdx.y;
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int start = ch * a.chunk;
+  if (start >= a.n) return;
+  const int end = min(start + a.chunk, a.n);
+  double z[AW_IIR_MAXORD];
+#pragma unroll
+  for (int k = 0; k < AW_IIR_MAXORD; ++k) z[k] = 0.0;
+  int i = start - a.warm;
+  if (i <= 0) {
+    i = 0;
+    if (a.use_zi) {
+      const double x0 = iir_load<SRC>(a, clip, 0);
+#pragma unroll
+      for (int k = 0; k < AW_IIR_MAXORD; ++k) z[k] = k < a.order ? __dmul_rn(a.zi[k], x0) : 0.0;
+    }
+  }
+  for (; i < end; ++i) {
+    const double x = iir_load<SRC>(a, clip, i);
+    const double y = __dadd_rn(z[0], __dmul_rn(a.b[0], x));
+#pragma unroll
+    for (int k = 0; k < AW_IIR_MAXORD; ++k) {
+      if (k < a.order) {
+        const double zn = k + 1 < a.order ? z[k + 1 < AW_IIR_MAXORD ? k + 1 : 0] : 0.0;
+        z[k] = __dsub_rn(__dadd_rn(zn, __dmul_rn(x, a.b[k + 1])), __dmul_rn(y, a.a[k + 1]));
+      }
+    }
+    if (i >= start) {
+      if (DST == IIR_DST_F32) a.o32[(long long)clip * a.so32 + i] = (float)y;
+      if (DST == IIR_DST_F64) a.o64[(long long)clip * a.so64 + i] = y;
+      if (DST == IIR_DST_REVTRIM_F32) {
+        const int j = (a.n - 1 - i) - a.padlen;      // un-reverse, drop the extension
+        if (j >= 0 && j < a.n_x) a.o32[(long long)clip * a.so32 + j] = (float)y;
+      }
+    }
+  }
+}
+
+// ---- A6 DeleteSamples / A7 SampleSupression / A8 Cropout (attacks.py:162-205,370-385)
+__global__ void __launch_bounds__(256) k_attack_delete(const float* __restrict__ x, long long sx,
+                                                       int n_out, const int* __restrict__ start,
+                                                       int n_del, float* __restrict__ out,
+                                                       long long so) {
+  const int clip = blockIdx.y, s = start[clip];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += gridDim.x * blockDim.x)
+    out[(long long)clip * so + i] = x[(long long)clip * sx + (i < s ? i : i + n_del)];
+}
+
+__global__ void __launch_bounds__(256) k_attack_suppress(const float* __restrict__ x, long long sx,
+                                                         int n, const int* __restrict__ start,
+                                                         int n_zero, float* __restrict__ out,
+                                                         long long so) {
+  const int clip = blockIdx.y, s = start[clip];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[(long long)clip * so + i] = (i >= s && i < s + n_zero) ? 0.f : x[(long long)clip * sx + i];
+}
+
+// ---- extensions with no reference counterpart ("parity unpinned") ------
+// y = gain * x + sigma * noise   (noise: host-seeded buffer or null)
+__global__ void __launch_bounds__(256) k_attack_affine(const float* __restrict__ x, long long sx,
+                                                       int n, float gain,
+                                                       const float* __restrict__ noise,
+                                                       long long sn, float sigma,
+                                                       float* __restrict__ out, long long so) {
+  const int clip = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float v = __fmul_rn(gain, x[(long long)clip * sx + i]);
+    if (noise) v = __fadd_rn(v, __fmul_rn(sigma, noise[(long long)clip * sn + i]));
+    out[(long long)clip * so + i] = v;
+  }
+}
+
+}  // namespace aw

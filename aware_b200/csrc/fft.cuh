@@ -1,0 +1,516 @@
+// Shared-memory-staged radix FFT kernels for the band-limited STFT / iSTFT and
+// their adjoints (SURVEY K2,K3,K4,K13,K14; reference utils/audio/stft.py:28,48,55,62).
+//
+// One warp transforms TWO real frames at once as one 1024-point complex FFT
+// (z = a + i b), decomposed 32 x 32: a radix-32 pass held entirely in registers,
+// a twiddle multiply, a 32x32 transpose through a padded per-warp shared tile, and
+// a second in-register radix-32 pass.  No __syncthreads inside the transform.
+// Only the embedding band (bins bin0 .. bin0+nbins-1) is read or written: the
+// out-of-band bins never exist on the device (detection/multibit_detector.py:34-37,
+// embedding/multibit_embedder.py:104), and by linearity the out-of-band part of
+// the reference's iSTFT is a per-clip constant waveform (y_oob).
+#pragma once
+#include "common.cuh"
+
+namespace aw {
+
+// cos/sin(2 pi j / 32), j = 0..15
+__constant__ float c_cos32[16] = {
+    1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+    0.70710678118654757f, 0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f,
+    0.0f, -0.19509032201612819f, -0.38268343236508973f, -0.55557023301960196f,
+    -0.70710678118654746f, -0.83146961230254535f, -0.92387953251128674f, -0.98078528040323043f};
+__constant__ float c_sin32[16] = {
+    0.0f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
+    0.70710678118654746f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f,
+    1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254546f,
+    0.70710678118654757f, 0.55557023301960218f, 0.38268343236508989f, 0.19509032201612861f};
+
+// One radix-2 decimation-in-frequency stage over 32 register-resident points.
+// SIGN = -1: forward (e^{-i}), +1: inverse (e^{+i}).
+template <int SIGN, int HALF>
+__device__ __forceinline__ void fft32_stage(float (&re)[32], float (&im)[32]) {
+#pragma unroll
+  for (int g = 0; g < 32; g += 2 * HALF) {
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) {
+      const int i0 = g + j, i1 = g + j + HALF;
+      const float ar = re[i0], ai = im[i0], br = re[i1], bi = im[i1];
+      re[i0] = ar + br;
+      im[i0] = ai + bi;
+      const float dr = ar - br, di = ai - bi;
+      const int tw = j * (16 / HALF);
+      if (tw == 0) {
+        re[i1] = dr;
+        im[i1] = di;
+      } else if (tw == 8) {            // W = SIGN * i
+        re[i1] = -SIGN * di;
+        im[i1] = SIGN * dr;
+      } else {
+        const float c = c_cos32[tw], s = SIGN * c_sin32[tw];
+        re[i1] = dr * c - di * s;
+        im[i1] = dr * s + di * c;
+      }
+    }
+  }
+}
+
+__host__ __device__ constexpr int brev5(int p) {
+  return ((p & 1) << 4) | ((p & 2) << 2) | (p & 4) | ((p & 8) >> 2) | ((p & 16) >> 4);
+}
+
+// In-register 32-point DFT, natural order in and out.
+template <int SIGN>
+__device__ __forceinline__ void fft32(float (&re)[32], float (&im)[32]) {
+  fft32_stage<SIGN, 16>(re, im);
+  fft32_stage<SIGN, 8>(re, im);
+  fft32_stage<SIGN, 4>(re, im);
+  fft32_stage<SIGN, 2>(re, im);
+  fft32_stage<SIGN, 1>(re, im);
+#pragma unroll
+  for (int p = 0; p < 32; ++p) {
+    const int q = brev5(p);
+    if (p < q) {
+      float t = re[p]; re[p] = re[q]; re[q] = t;
+      t = im[p]; im[p] = im[q]; im[q] = t;
+    }
+  }
+}
+
+#define AW_TR_STRIDE 33
+#define AW_TR_FLOATS (2 * 32 * AW_TR_STRIDE)   // per-warp transpose tile (re + im)
+
+// 1024-point complex FFT across one warp.
+//   in : lane l, register j  holds x[32 j + l]
+//   out: lane k1, register k2 holds X[k1 + 32 k2]
+// s_tr: this warp's AW_TR_FLOATS floats; s_tw[j] = (cos, sin)(2 pi j / 1024).
+template <int SIGN>
+__device__ __forceinline__ void warp_fft1024(float (&re)[32], float (&im)[32], float* s_tr,
+                                             const float2* s_tw, int lane) {
+  fft32<SIGN>(re, im);
+  float* s_re = s_tr;
+  float* s_im = s_tr + 32 * AW_TR_STRIDE;
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) {
+    const float2 w = s_tw[lane * k1];
+    const float c = w.x, s = SIGN * w.y;
+    const float r = re[k1] * c - im[k1] * s;
+    const float i = re[k1] * s + im[k1] * c;
+    s_re[k1 * AW_TR_STRIDE + lane] = r;
+    s_im[k1 * AW_TR_STRIDE + lane] = i;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 32; ++n2) {
+    re[n2] = s_re[lane * AW_TR_STRIDE + n2];
+    im[n2] = s_im[lane * AW_TR_STRIDE + n2];
+  }
+  __syncwarp();
+  fft32<SIGN>(re, im);
+}
+
+// sum_t w^2[m - 256 t] over the frames that cover padded sample m (torch.istft's
+// window envelope), ascending t.
+__device__ __forceinline__ float ola_envelope(int m, int T, const float* s_win) {
+  int tlo = m >= AW_NFFT ? ((m - (AW_NFFT - 1) + (AW_HOP - 1)) >> 8) : 0;
+  int thi = m >> 8;
+  if (thi > T - 1) thi = T - 1;
+  float e = 0.f;
+  for (int t = tlo; t <= thi; ++t) {
+    const float w = s_win[m - (t << 8)];
+    e = __fmaf_rn(w, w, e);
+  }
+  return e;
+}
+
+// per-iteration NAdam scalars (torch/optim/nadam.py _single_tensor_nadam)
+struct NadamStep {
+  float a_g;      // -lr (1 - mu_t) / (1 - prod mu)
+  float a_m;      // -lr mu_{t+1} / (1 - prod mu * mu_{t+1})
+  float inv_bc2;  // 1 / (1 - beta2^t)   (ATen divides by a CPU scalar as x * (1/s))
+  float pad;
+};
+
+// ---------------------------------------------------------------------------
+// analysis: frames -> band spectrum
+// ---------------------------------------------------------------------------
+enum { ANA_MAG = 0, ANA_INIT = 1, ANA_LOOP = 2, ANA_ADJ = 3 };
+
+struct AnaArgs {
+  const float* sig;            // per clip signal (x, y or dpad)
+  long long sig_stride;
+  int len;                     // signal length (N for x, L for y / dy)
+  int T, bin0, nbins;
+  const unsigned long long* peak;   // [clip] packed peak of sig (MAG/INIT: of x; LOOP/ADJ: of y)
+  const float* window;         // [1024] device
+  const float2* twiddle;       // [1024] device
+  // outputs
+  float* mag;                  // [clip][T][nbins]  (MAG, INIT -> c0, LOOP -> A~)
+  float2* ph;                  // [clip][T][nbins]  (INIT -> u, LOOP -> q)
+  // embed state (INIT writes, ADJ updates)
+  float* c; float* m; float* v; float* cbest;
+  const float* c0;             // ADJ: bounds are recomputed from c0
+  const float2* u;             // ADJ
+  const float* y;              // ADJ: y (to read sign of the peak sample)
+  const double* s2;            // ADJ: [clip] sum dy2*y2
+  const int* improved;         // ADJ: [clip] loss < best this iteration
+  const NadamStep* steps;      // ADJ: [iters]
+  const int* it_ptr;           // ADJ: device iteration counter
+  float tol_ratio;             // 10^(-tolerance_db/20) as float32
+};
+
+#define AW_ANA_FRAMES 16
+#define AW_ANA_SIG (AW_ANA_FRAMES * AW_HOP + 768)
+#define AW_ANA_SMEM ((AW_ANA_SIG + 1024 + 2048 + 4 * AW_TR_FLOATS) * 4)
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_analysis(AnaArgs a) {
+  extern __shared__ float smem[];
+  float* s_sig = smem;
+  float* s_win = s_sig + AW_ANA_SIG;
+  float2* s_tw = reinterpret_cast<float2*>(s_win + 1024);
+  float* s_tr = reinterpret_cast<float*>(s_tw + 1024);
+
+  const int clip = blockIdx.y;
+  const int t0 = blockIdx.x * AW_ANA_FRAMES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = a.len, T = a.T;
+
+  for (int i = tid; i < 1024; i += 128) {
+    s_win[i] = a.window[i];
+    s_tw[i] = a.twiddle[i];
+  }
+  __syncthreads();   // s_win is needed by the ADJ loader (envelope)
+
+  // ---- stage the (scaled / padded) signal segment -------------------------
+  const float* sig = a.sig + (long long)clip * a.sig_stride;
+  const int m_end = AW_HOP * (T - 1) + AW_NFFT;   // padded length
+  if (MODE == ANA_ADJ) {
+    const unsigned long long pk = a.peak[clip];
+    const float p1 = peak_value(pk);
+    const int nstar = (int)peak_index(pk);
+    const float d1 = p1 + 1e-8f;
+    const float d2 = __fdiv_rn(p1, d1) + 1e-8f;
+    const float s2 = (float)a.s2[clip];
+    const float s1 = s2 * 1e-8f / d2;
+    const float ystar = a.y[(long long)clip * L + nstar];
+    const float corr = (ystar > 0.f ? 1.f : (ystar < 0.f ? -1.f : 0.f)) * (s2 / d2 + s1) / d1;
+    for (int j = tid; j < AW_ANA_SIG; j += 128) {
+      const int m = AW_HOP * t0 + j;
+      const int n = m - AW_HALF;
+      float val = 0.f;
+      if (n >= 0 && n < L && m < m_end) {
+        float dy2 = sig[m];
+        if (n >= 1 && n <= AW_HALF) dy2 += sig[AW_HALF - n];
+        if (n >= L - 513 && n <= L - 2) dy2 += sig[AW_HALF + 2 * (L - 1) - n];
+        float dy = __fdiv_rn(__fdiv_rn(dy2, d2), d1);
+        if (n == nstar) dy -= corr;
+        val = __fdiv_rn(dy, ola_envelope(m, T, s_win));
+      }
+      s_sig[j] = val;
+    }
+  } else {
+    const float p1 = peak_value(a.peak[clip]);
+    const float d1 = p1 + 1e-8f;
+    const float d2 = __fdiv_rn(p1, d1) + 1e-8f;
+    for (int j = tid; j < AW_ANA_SIG; j += 128) {
+      const int m = AW_HOP * t0 + j;
+      float val = 0.f;
+      if (m < m_end) {
+        const float x = sig[reflect_idx(m - AW_HALF, L)];
+        val = __fdiv_rn(x, d1);
+        if (MODE == ANA_LOOP) val = __fdiv_rn(val, d2);
+      }
+      s_sig[j] = val;
+    }
+  }
+  __syncthreads();
+
+  const int k2lo = a.bin0 >> 5, k2hi = (a.bin0 + a.nbins - 1) >> 5;
+  float* my_tr = s_tr + warp * AW_TR_FLOATS;
+
+  NadamStep st;
+  bool improved = false;
+  if (MODE == ANA_ADJ) {
+    st = a.steps[*a.it_ptr];
+    improved = a.improved[clip] != 0;
+  }
+
+  for (int p = warp; p < AW_ANA_FRAMES / 2; p += 4) {
+    const int ta = t0 + 2 * p, tb = ta + 1;
+    if (ta >= T) break;                     // warp-uniform
+    float re[32], im[32];
+    const int offa = AW_HOP * (2 * p);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int n = 32 * j + lane;
+      const float w = s_win[n];
+      re[j] = s_sig[offa + n] * w;
+      im[j] = s_sig[offa + AW_HOP + n] * w;  // frame tb (zeros past the end: staged as 0 * w)
+    }
+    warp_fft1024<-1>(re, im, my_tr, s_tw, lane);
+
+    const bool has_b = tb < T;
+    const int src = (32 - lane) & 31;
+#pragma unroll
+    for (int k2 = 0; k2 <= 16; ++k2) {
+      if (k2 < k2lo || k2 > k2hi) continue;   // warp-uniform
+      float mr = __shfl_sync(0xffffffffu, re[31 - k2 < 0 ? 0 : 31 - k2], src);
+      float mi = __shfl_sync(0xffffffffu, im[31 - k2 < 0 ? 0 : 31 - k2], src);
+      if (lane == 0 && k2 >= 1) {
+        mr = re[32 - k2];
+        mi = im[32 - k2];
+      }
+      const int k = lane + 32 * k2;
+      const int b = k - a.bin0;
+      if (b < 0 || b >= a.nbins) continue;
+      const float zr = re[k2], zi = im[k2];
+      // frame a: (Z[k] + conj Z[N-k]) / 2 ; frame b: (Z[k] - conj Z[N-k]) / (2i)
+      float fr[2] = {0.5f * (zr + mr), 0.5f * (zi + mi)};
+      float fi[2] = {0.5f * (zi - mi), 0.5f * (mr - zr)};
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        if (f == 1 && !has_b) break;
+        const long long o = ((long long)clip * T + (ta + f)) * a.nbins + b;
+        const float sr = fr[f], si = fi[f];
+        if (MODE == ANA_ADJ) {
+          // dX = (2/N) DFT(.) ; g = Re(dX conj(u))     (multibit_embedder.py:111)
+          const float2 uu = a.u[o];
+          const float g = (2.0f / AW_NFFT) * (sr * uu.x + si * uu.y);
+          // NAdam (torch/optim/nadam.py), clamp (:116-117), best (:120-122)
+          float mm = a.m[o], vv = a.v[o], cc = a.c[o];
+          mm = __fadd_rn(mm, __fmul_rn(0.1f, __fsub_rn(g, mm)));
+          vv = __fmul_rn(vv, 0.999f);
+          vv = __fadd_rn(vv, __fmul_rn(__fmul_rn(0.001f, g), g));
+          const float den = __fadd_rn(__fsqrt_rn(__fmul_rn(vv, st.inv_bc2)), 1e-8f);
+          cc = __fadd_rn(cc, __fdiv_rn(__fmul_rn(st.a_g, g), den));
+          cc = __fadd_rn(cc, __fdiv_rn(__fmul_rn(st.a_m, mm), den));
+          const float c0 = a.c0[o];
+          const float dl = __fmul_rn(c0, a.tol_ratio);
+          const float lo = fmaxf(0.f, __fsub_rn(c0, dl)), hi = __fadd_rn(c0, dl);
+          cc = fminf(fmaxf(cc, lo), hi);
+          a.m[o] = mm;
+          a.v[o] = vv;
+          a.c[o] = cc;
+          if (improved) a.cbest[o] = cc;
+        } else {
+          const float mag = sqrtf(sr * sr + si * si);
+          a.mag[o] = mag;
+          if (MODE == ANA_INIT || MODE == ANA_LOOP) {
+            const float inv = mag > 0.f ? 1.0f / mag : 0.f;
+            a.ph[o] = make_float2(sr * inv, si * inv);
+          }
+          if (MODE == ANA_INIT) {
+            a.c[o] = mag;
+            a.cbest[o] = mag;
+            a.m[o] = 0.f;
+            a.v[o] = 0.f;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// synthesis: band spectrum -> windowed overlap-add
+// ---------------------------------------------------------------------------
+enum { SYN_OOB = 0, SYN_WAVE = 1, SYN_ADJ = 2 };
+
+struct SynArgs {
+  const float* amp;            // [clip][T][nbins] real factor (c / cbest / dA~)
+  const float2* ph;            // [clip][T][nbins] unit phasor (u / q)
+  int T, L, bin0, nbins;
+  float scale;                 // 1/N (irfft) or 1/2 (STFT adjoint)
+  const float* window;
+  const float2* twiddle;
+  // SYN_OOB: y_oob = x/(peak_x+1e-8) - ola/env
+  const float* x; long long x_stride; const unsigned long long* peak_x;
+  float* y_oob;                // [clip][L]   (OOB: out; WAVE: in)
+  // SYN_WAVE: y = ola/env + y_oob, peak_y
+  float* y;                    // [clip][L]   (WAVE: out; ADJ: in)
+  unsigned long long* peak_y;  // [clip]      (WAVE: atomicMax out; ADJ: in)
+  // SYN_ADJ: dpad = ola (padded axis), s2 += dpad * y2[reflect]
+  float* dpad;                 // [clip][L + 1024]
+  double* s2;                  // [clip]
+};
+
+#define AW_SYN_FRAMES 32
+#define AW_SYN_HOPS 29
+#define AW_SYN_OLA (AW_SYN_FRAMES * AW_HOP + 768)
+#define AW_SYN_SMEM ((AW_SYN_OLA + 1024 + 2048 + 4 * AW_TR_FLOATS) * 4)
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_synthesis(SynArgs a) {
+  extern __shared__ float smem[];
+  float* s_ola = smem;
+  float* s_win = s_ola + AW_SYN_OLA;
+  float2* s_tw = reinterpret_cast<float2*>(s_win + 1024);
+  float* s_tr = reinterpret_cast<float*>(s_tw + 1024);
+  __shared__ unsigned long long s_pk[4];
+  __shared__ double s_red[32];
+
+  const int clip = blockIdx.y;
+  const int h0 = blockIdx.x * AW_SYN_HOPS;        // first output hop (padded axis)
+  const int f0 = h0 - 3;                           // first contributing frame
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = a.T, L = a.L;
+
+  for (int i = tid; i < 1024; i += 128) {
+    s_win[i] = a.window[i];
+    s_tw[i] = a.twiddle[i];
+  }
+  for (int i = tid; i < AW_SYN_OLA; i += 128) s_ola[i] = 0.f;
+  __syncthreads();
+
+  const int k2lo = a.bin0 >> 5, k2hi = (a.bin0 + a.nbins - 1) >> 5;
+  float* my_tr = s_tr + warp * AW_TR_FLOATS;
+  const float sc = a.scale;
+
+  // four phases; in phase r every warp owns frames f0+r+8w and f0+r+8w+4, all
+  // frames of one phase are >= 1024 samples apart, so '+=' needs no atomics and
+  // the accumulation order is fixed (deterministic).
+  for (int r = 0; r < 4; ++r) {
+    const int ta = f0 + r + 8 * warp, tb = ta + 4;
+    const bool va = ta >= 0 && ta < T, vb = tb >= 0 && tb < T;
+    if (va || vb) {                                  // warp-uniform
+      float re[32], im[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { re[j] = 0.f; im[j] = 0.f; }
+      const long long oa = ((long long)clip * T + ta) * a.nbins;
+      const long long ob = ((long long)clip * T + tb) * a.nbins;
+#pragma unroll
+      for (int k2 = 0; k2 <= 16; ++k2) {
+        if (k2 < k2lo || k2 > k2hi) continue;
+        // direct entry Z[k], k = lane + 32 k2
+        {
+          const int b = lane + 32 * k2 - a.bin0;
+          if (b >= 0 && b < a.nbins) {
+            float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
+            if (va) { const float s = a.amp[oa + b]; const float2 p = a.ph[oa + b]; ar = s * p.x; ai = s * p.y; }
+            if (vb) { const float s = a.amp[ob + b]; const float2 p = a.ph[ob + b]; br = s * p.x; bi = s * p.y; }
+            re[k2] = sc * (ar - bi);                  // Xa + i Xb
+            im[k2] = sc * (ai + br);
+          }
+        }
+        // mirrored entry Z[N-k'] = conj(Xa[k']) + i conj(Xb[k']), k' = ((32-lane)&31) + 32 k2,
+        // which lives in this lane at register 31-k2 (lane>0) or 32-k2 (lane 0).
+        {
+          const int kp = ((32 - lane) & 31) + 32 * k2;
+          const int b = kp - a.bin0;
+          if (b >= 0 && b < a.nbins && kp > 0) {
+            float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
+            if (va) { const float s = a.amp[oa + b]; const float2 p = a.ph[oa + b]; ar = s * p.x; ai = s * p.y; }
+            if (vb) { const float s = a.amp[ob + b]; const float2 p = a.ph[ob + b]; br = s * p.x; bi = s * p.y; }
+            const float zr = sc * (ar + bi), zi = sc * (br - ai);
+            if (lane == 0) {
+              if (k2 >= 1) { re[32 - k2] = zr; im[32 - k2] = zi; }
+            } else {
+              re[31 - k2 < 0 ? 0 : 31 - k2] = zr;
+              im[31 - k2 < 0 ? 0 : 31 - k2] = zi;
+            }
+          }
+        }
+      }
+      warp_fft1024<1>(re, im, my_tr, s_tw, lane);
+      const int offa = AW_HOP * (ta - f0), offb = AW_HOP * (tb - f0);
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) {
+        const int n = lane + 32 * k2;
+        const float w = s_win[n];
+        if (va) s_ola[offa + n] += w * re[k2];
+        if (vb) s_ola[offb + n] += w * im[k2];
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue over this tile's output samples ----------------------------
+  const int m_lo = AW_HOP * h0;
+  const int m_total = AW_HOP * (T - 1) + AW_NFFT;
+  int m_hi = m_lo + AW_HOP * AW_SYN_HOPS;
+  if (m_hi > m_total) m_hi = m_total;
+
+  if (MODE == SYN_ADJ) {
+    const float p1 = peak_value(a.peak_y[clip]);
+    const float d1 = p1 + 1e-8f;
+    const float d2 = __fdiv_rn(p1, d1) + 1e-8f;
+    const float* y = a.y + (long long)clip * L;
+    float* dpad = a.dpad + (long long)clip * (L + AW_NFFT);
+    double acc = 0.0;
+    for (int m = m_lo + tid; m < m_hi; m += 128) {
+      const float d = s_ola[m - AW_HOP * f0];
+      dpad[m] = d;
+      const float y2 = __fdiv_rn(__fdiv_rn(y[reflect_idx(m - AW_HALF, L)], d1), d2);
+      acc += (double)(d * y2);
+    }
+    acc = block_sum(acc, s_red);
+    if (tid == 0) atomicAdd(a.s2 + clip, acc);
+  } else {
+    unsigned long long pk = 0ull;
+    float dx = 1.f;
+    if (MODE == SYN_OOB) dx = peak_value(a.peak_x[clip]) + 1e-8f;
+    for (int m = m_lo + tid; m < m_hi; m += 128) {
+      const int n = m - AW_HALF;
+      if (n < 0 || n >= L) continue;
+      const float yb = __fdiv_rn(s_ola[m - AW_HOP * f0], ola_envelope(m, T, s_win));
+      const long long o = (long long)clip * L + n;
+      if (MODE == SYN_OOB) {
+        a.y_oob[o] = __fdiv_rn(a.x[(long long)clip * a.x_stride + n], dx) - yb;
+      } else {
+        const float yy = yb + a.y_oob[o];
+        a.y[o] = yy;
+        const unsigned long long q = pack_peak(fabsf(yy), (unsigned)n);
+        pk = q > pk ? q : pk;
+      }
+    }
+    if (MODE == SYN_WAVE) {
+      pk = warp_max_u64(pk);
+      if (lane == 0) s_pk[warp] = pk;
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 1; w < 4; ++w) pk = s_pk[w] > pk ? s_pk[w] : pk;
+        atomicMax(a.peak_y + clip, pk);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// per-clip peak |x| (utils/audio/waveform.py:19) and final normalise
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_peak(const float* x, long long stride, int n,
+                                              unsigned long long* peak) {
+  const int clip = blockIdx.y;
+  const float* p = x + (long long)clip * stride;
+  unsigned long long pk = 0ull;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long q = pack_peak(fabsf(p[i]), (unsigned)i);
+    pk = q > pk ? q : pk;
+  }
+  __shared__ unsigned long long s_pk[8];
+  pk = warp_max_u64(pk);
+  if ((threadIdx.x & 31) == 0) s_pk[threadIdx.x >> 5] = pk;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) pk = s_pk[w] > pk ? s_pk[w] : pk;
+    atomicMax(peak + clip, pk);
+  }
+}
+
+// out = y / (peak + 1e-8) [* scale[clip]]   (multibit_embedder.py:185-192, service/embed.py:73)
+__global__ void __launch_bounds__(256) k_final_normalize(const float* y, int L,
+                                                         const unsigned long long* peak,
+                                                         const float* scale, float* out,
+                                                         long long out_stride) {
+  const int clip = blockIdx.y;
+  const float d = peak_value(peak[clip]) + 1e-8f;
+  const float s = scale ? scale[clip] : 1.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+    float v = __fdiv_rn(y[(long long)clip * L + i], d);
+    if (scale) v = __fmul_rn(s, v);
+    out[(long long)clip * out_stride + i] = v;
+  }
+}
+
+}  // namespace aw

@@ -1,0 +1,410 @@
+// Detector front end / head and their adjoints (SURVEY K5-K8, K10-K12, K14, K16;
+// reference detection/multibit_detector_net.py:109-140, modules/mel.py:195,
+// globalStandardize.py:16-21, BRH.py:16-27, embedding/losses.py:38-42).
+// Layouts: spectra [clip][T][nbins]; mel [clip][T][128]; activations channels-last
+// [clip * Tp_pad + j][C] with Tp_pad = T' rounded up to 128 rows (pad rows are 0).
+#pragma once
+#include "common.cuh"
+
+namespace aw {
+
+struct SparseMel {
+  // CSR over mel channels (band-relative columns) and CSC over band bins
+  const int* rowptr;   // [129]
+  const int* col;      // [nnz]
+  const float* val;    // [nnz]
+  const int* colptr;   // [nbins + 1]
+  const int* row;      // [nnz]
+  const float* valT;   // [nnz]
+};
+
+struct ChanStats {      // per clip, per mel channel (forward, reused by backward)
+  float mu, rstd, varratio, pad;   // varratio = var / (var + eps)
+};
+
+// ---- mel projection + per-channel sums -------------------------------------
+#define AW_MEL_FRAMES 32
+__global__ void __launch_bounds__(128) k_mel(const float* __restrict__ mag, int T, int nb,
+                                             SparseMel sm, float* __restrict__ M,
+                                             double* __restrict__ chan_sum) {
+  extern __shared__ float s_a[];   // [AW_MEL_FRAMES][nb]
+  const int clip = blockIdx.y, t0 = blockIdx.x * AW_MEL_FRAMES, c = threadIdx.x;
+  const int nf = min(AW_MEL_FRAMES, T - t0);
+  const float* src = mag + ((long long)clip * T + t0) * nb;
+  for (int i = threadIdx.x; i < nf * nb; i += 128) s_a[i] = src[i];
+  __syncthreads();
+  const int e0 = sm.rowptr[c], e1 = sm.rowptr[c + 1];
+  double s1 = 0.0, s2 = 0.0;
+  for (int f = 0; f < nf; ++f) {
+    float acc = 0.f;
+    for (int e = e0; e < e1; ++e) acc = fmaf(sm.val[e], s_a[f * nb + sm.col[e]], acc);
+    M[((long long)clip * T + t0 + f) * AW_NMEL + c] = acc;
+    s1 += acc;
+    s2 += (double)acc * acc;
+  }
+  if (e1 > e0) {
+    atomicAdd(chan_sum + ((long long)clip * AW_NMEL + c) * 2, s1);
+    atomicAdd(chan_sum + ((long long)clip * AW_NMEL + c) * 2 + 1, s2);
+  }
+}
+
+// ---- InstanceNorm(128) -> GlobalStandardize -> AvgPool(2,2) -----------------
+// GlobalStandardize statistics are taken analytically from the channel
+// statistics: after InstanceNorm every channel has mean 0 and second moment
+// var/(var+eps), so mean_g = 0 and std_g^2 = T * sum_c var_c/(var_c+eps) / (128 T - 1).
+#define AW_P0_ROWS 32
+__global__ void __launch_bounds__(128) k_p0(const float* __restrict__ M, int T, int Tp, int Tp_pad,
+                                            const double* __restrict__ chan_sum,
+                                            float* __restrict__ P0, ChanStats* __restrict__ cs,
+                                            float* __restrict__ sigma_out, int round_tf32) {
+  __shared__ double s_red[32];
+  __shared__ float s_inv;
+  const int clip = blockIdx.y, c = threadIdx.x, j0 = blockIdx.x * AW_P0_ROWS;
+  const double s1 = chan_sum[((long long)clip * AW_NMEL + c) * 2];
+  const double s2 = chan_sum[((long long)clip * AW_NMEL + c) * 2 + 1];
+  const double mu = s1 / T;
+  double var = s2 / T - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + AW_IN_EPS);
+  const double vr = var / (var + AW_IN_EPS);
+  const double tot = block_sum(vr, s_red);
+  if (threadIdx.x == 0) {
+    const double n = 128.0 * T;
+    const double sigma = sqrt((double)T * tot / (n - 1.0));
+    s_inv = (float)(1.0 / (sigma + 1e-8));
+    if (blockIdx.x == 0) sigma_out[clip] = (float)sigma;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    ChanStats st;
+    st.mu = (float)mu; st.rstd = (float)rstd; st.varratio = (float)vr; st.pad = 0.f;
+    cs[(long long)clip * AW_NMEL + c] = st;
+  }
+  const float fmu = (float)mu, fr = (float)rstd, inv = s_inv;
+  const float* Mc = M + (long long)clip * T * AW_NMEL + c;
+  for (int j = j0; j < min(j0 + AW_P0_ROWS, Tp_pad); ++j) {
+    float p = 0.f;
+    if (j < Tp) {
+      const float g0 = (Mc[(long long)(2 * j) * AW_NMEL] - fmu) * fr * inv;
+      const float g1 = (Mc[(long long)(2 * j + 1) * AW_NMEL] - fmu) * fr * inv;
+      p = 0.5f * (g0 + g1);
+      if (round_tf32) p = to_tf32(p);
+    }
+    P0[((long long)clip * Tp_pad + j) * AW_NMEL + c] = p;
+  }
+}
+
+// ---- InstanceNorm statistics from per-tile partials --------------------------
+// part: [clip * tiles + tile][ldp][2] ; stat: [clip][C][2] = (mean, rstd)
+__global__ void __launch_bounds__(128) k_finalize_fwd(const float* __restrict__ part, int ldp,
+                                                      int tiles, int C, int Tp,
+                                                      float* __restrict__ stat) {
+  const int clip = blockIdx.y, c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int t = 0; t < tiles; ++t) {
+    const float* p = part + (((long long)clip * tiles + t) * ldp + c) * 2;
+    s1 += p[0];
+    s2 += p[1];
+  }
+  const double mu = s1 / Tp;
+  double var = s2 / Tp - mu * mu;
+  if (var < 0.0) var = 0.0;
+  stat[((long long)clip * C + c) * 2] = (float)mu;
+  stat[((long long)clip * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + AW_IN_EPS));
+}
+
+// bstat: [clip][C][2] = (mean_j dHhat, mean_j dHhat*Hhat)
+__global__ void __launch_bounds__(128) k_finalize_bwd(const float* __restrict__ part, int ldp,
+                                                      int tiles, int C, int Tp,
+                                                      float* __restrict__ bstat) {
+  const int clip = blockIdx.y, c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int t = 0; t < tiles; ++t) {
+    const float* p = part + (((long long)clip * tiles + t) * ldp + c) * 2;
+    s1 += p[0];
+    s2 += p[1];
+  }
+  bstat[((long long)clip * C + c) * 2] = (float)(s1 / Tp);
+  bstat[((long long)clip * C + c) * 2 + 1] = (float)(s2 / Tp);
+}
+
+// ---- P = LeakyReLU(InstanceNorm(H)), in place; pad rows forced to 0 -----------
+// grid = (rows / 4), block = 256; C % 4 == 0
+__global__ void __launch_bounds__(256) k_norm_act(float* __restrict__ H, int C, int Tp, int Tp_pad,
+                                                  const float* __restrict__ stat, int round_tf32) {
+  const int r0 = blockIdx.x * 4;
+  const int c4 = C >> 2;
+  for (int i = threadIdx.x; i < 4 * c4; i += 256) {
+    const int row = r0 + i / c4, c = (i % c4) * 4;
+    const int clip = row / Tp_pad, j = row - clip * Tp_pad;
+    float4* p = reinterpret_cast<float4*>(H + (long long)row * C + c);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < Tp) {
+      const float4 h = *p;
+      const float4 s01 = *reinterpret_cast<const float4*>(stat + ((long long)clip * C + c) * 2);
+      const float4 s23 = *reinterpret_cast<const float4*>(stat + ((long long)clip * C + c) * 2 + 4);
+      o.x = leaky((h.x - s01.x) * s01.y);
+      o.y = leaky((h.y - s01.z) * s01.w);
+      o.z = leaky((h.z - s23.x) * s23.y);
+      o.w = leaky((h.w - s23.z) * s23.w);
+      if (round_tf32) { o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w); }
+    }
+    *p = o;
+  }
+}
+
+// ---- dH = rstd * (dHhat - a1 - Hhat * a2), in place on dHhat ------------------
+__global__ void __launch_bounds__(256) k_in_bwd_apply(float* __restrict__ dH,
+                                                      const float* __restrict__ P, int C, int Tp,
+                                                      int Tp_pad, const float* __restrict__ stat,
+                                                      const float* __restrict__ bstat,
+                                                      int round_tf32) {
+  const int r0 = blockIdx.x * 4;
+  const int c4 = C >> 2;
+  for (int i = threadIdx.x; i < 4 * c4; i += 256) {
+    const int row = r0 + i / c4, c = (i % c4) * 4;
+    const int clip = row / Tp_pad, j = row - clip * Tp_pad;
+    float4* p = reinterpret_cast<float4*>(dH + (long long)row * C + c);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < Tp) {
+      const float4 d = *p;
+      const float4 a = *reinterpret_cast<const float4*>(P + (long long)row * C + c);
+      const float dd[4] = {d.x, d.y, d.z, d.w}, aa[4] = {a.x, a.y, a.z, a.w};
+      float oo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long sidx = ((long long)clip * C + c + k) * 2;
+        const float rstd = stat[sidx + 1];
+        const float a1 = bstat[sidx], a2 = bstat[sidx + 1];
+        const float hh = aa[k] > 0.f ? aa[k] : aa[k] * (1.0f / AW_LEAKY);
+        oo[k] = rstd * (dd[k] - a1 - hh * a2);
+        if (round_tf32) oo[k] = to_tf32(oo[k]);
+      }
+      o = make_float4(oo[0], oo[1], oo[2], oo[3]);
+    }
+    *p = o;
+  }
+}
+
+// ---- BRH head + loss + seed of the backward pass -------------------------------
+// one CTA (256 threads) per clip.  P4: [rows][64] (40 live channels).
+struct HeadArgs {
+  const float* P4; int Tp, Tp_pad;
+  const float* stat4;        // [clip][64][2]
+  const float* pattern;      // [clip][20] (+-1) or null (detect only)
+  float* values;             // [clip][20]
+  float* losses;             // [iters][n_clips] or null
+  float* best;               // [clip]
+  int* improved;             // [clip]
+  float* dH4;                // [rows][64] or null
+  const int* it_ptr; int n_clips;
+  int round_tf32;
+};
+
+__global__ void __launch_bounds__(256) k_head(HeadArgs a) {
+  __shared__ double s_acc[4][64];
+  __shared__ float s_z[64], s_dz[64], s_a1[64], s_a2[64];
+  const int clip = blockIdx.x, tid = threadIdx.x;
+  const int c = tid & 63, g = tid >> 6;
+  const float* P = a.P4 + (long long)clip * a.Tp_pad * 64;
+  double acc = 0.0;
+  for (int j = g; j < a.Tp; j += 4) acc += P[(long long)j * 64 + c];
+  s_acc[g][c] = acc;
+  __syncthreads();
+  if (tid < 64) s_z[tid] = (float)((s_acc[0][tid] + s_acc[1][tid] + s_acc[2][tid] + s_acc[3][tid]) / a.Tp);
+  __syncthreads();
+  if (tid < 32) {
+    float v = 0.f, p = 0.f;
+    if (tid < AW_NBITS) {
+      v = tanhf(s_z[2 * tid] - s_z[2 * tid + 1]);
+      a.values[(long long)clip * AW_NBITS + tid] = v;
+      if (a.pattern) p = a.pattern[(long long)clip * AW_NBITS + tid];
+    }
+    if (a.pattern) {
+      const float se = tid < AW_NBITS ? (v - p) * (v - p) : 0.f;
+      const float ab = tid < AW_NBITS ? fabsf(v) : 0.f;
+      const float mse = warp_sum(se) / AW_NBITS, pen = 0.1f * (warp_sum(ab) / AW_NBITS);
+      const float loss = mse - pen;
+      if (tid == 0) {
+        const int it = a.it_ptr ? *a.it_ptr : 0;
+        if (a.losses) a.losses[(long long)it * a.n_clips + clip] = loss;
+        const float b = a.best[clip];
+        const int imp = loss < b;
+        a.improved[clip] = imp;
+        if (imp) a.best[clip] = loss;
+      }
+      if (tid < AW_NBITS) {
+        const float sg = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
+        const float dv = 2.f * (v - p) / AW_NBITS - 0.1f * sg / AW_NBITS;
+        const float dd = dv * (1.f - v * v);
+        s_dz[2 * tid] = dd / a.Tp;
+        s_dz[2 * tid + 1] = -dd / a.Tp;
+      }
+    }
+  }
+  if (!a.pattern || !a.dH4) return;
+  if (tid >= 2 * AW_NBITS && tid < 64) s_dz[tid] = 0.f;
+  __syncthreads();
+  // a1 = mean_j dHhat, a2 = mean_j dHhat * Hhat
+  double q1 = 0.0, q2 = 0.0;
+  const float dz = s_dz[c];
+  for (int j = g; j < a.Tp; j += 4) {
+    const float p = P[(long long)j * 64 + c];
+    const bool pos = p > 0.f;
+    const float dh = pos ? dz : AW_LEAKY * dz;
+    q1 += dh;
+    q2 += (double)dh * (pos ? p : p * (1.0f / AW_LEAKY));
+  }
+  s_acc[g][c] = q1;
+  __syncthreads();
+  if (tid < 64) s_a1[tid] = (float)((s_acc[0][tid] + s_acc[1][tid] + s_acc[2][tid] + s_acc[3][tid]) / a.Tp);
+  __syncthreads();
+  s_acc[g][c] = q2;
+  __syncthreads();
+  if (tid < 64) s_a2[tid] = (float)((s_acc[0][tid] + s_acc[1][tid] + s_acc[2][tid] + s_acc[3][tid]) / a.Tp);
+  __syncthreads();
+  const float rstd = a.stat4[((long long)clip * 64 + c) * 2 + 1];
+  const float a1 = s_a1[c], a2 = s_a2[c];
+  float* D = a.dH4 + (long long)clip * a.Tp_pad * 64;
+  for (int j = g; j < a.Tp_pad; j += 4) {
+    float o = 0.f;
+    if (j < a.Tp && c < 2 * AW_NBITS) {
+      const float p = P[(long long)j * 64 + c];
+      const bool pos = p > 0.f;
+      const float dh = pos ? dz : AW_LEAKY * dz;
+      o = rstd * (dh - a1 - (pos ? p : p * (1.0f / AW_LEAKY)) * a2);
+      if (a.round_tf32) o = to_tf32(o);
+    }
+    D[(long long)j * 64 + c] = o;
+  }
+}
+
+// ---- adjoint of pool / GlobalStandardize / InstanceNorm(128) / mel -------------
+// pass 1: S1_c = sum_t dG, S2_c = sum_t dG * Mhat   (dG[t] = dP0[t/2]/2, 0 for the odd tail)
+#define AW_P0B_FRAMES 64
+__global__ void __launch_bounds__(128) k_p0_bwd_reduce(const float* __restrict__ dP0,
+                                                       const float* __restrict__ M, int T, int Tp,
+                                                       int Tp_pad, const ChanStats* __restrict__ cs,
+                                                       double* __restrict__ bsum) {
+  const int clip = blockIdx.y, c = threadIdx.x, t0 = blockIdx.x * AW_P0B_FRAMES;
+  const ChanStats st = cs[(long long)clip * AW_NMEL + c];
+  double s1 = 0.0, s2 = 0.0;
+  const int t1 = min(t0 + AW_P0B_FRAMES, 2 * Tp);
+  for (int t = t0; t < t1; ++t) {
+    const float dg = 0.5f * dP0[((long long)clip * Tp_pad + (t >> 1)) * AW_NMEL + c];
+    const float mh = (M[((long long)clip * T + t) * AW_NMEL + c] - st.mu) * st.rstd;
+    s1 += dg;
+    s2 += (double)dg * mh;
+  }
+  atomicAdd(bsum + ((long long)clip * AW_NMEL + c) * 2, s1);
+  atomicAdd(bsum + ((long long)clip * AW_NMEL + c) * 2 + 1, s2);
+}
+
+// pass 2: dM, then dA~[t][b] = sum_c mel[c][b] dM[t][c]
+#define AW_P0A_FRAMES 16
+__global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ dP0,
+                                                      const float* __restrict__ M, int T, int Tp,
+                                                      int Tp_pad, const ChanStats* __restrict__ cs,
+                                                      const float* __restrict__ sigma_in,
+                                                      const double* __restrict__ bsum, SparseMel sm,
+                                                      int nb, float* __restrict__ dA) {
+  __shared__ double s_red[32];
+  __shared__ float s_dm[AW_P0A_FRAMES][AW_NMEL];
+  __shared__ float s_ab[3];
+  const int clip = blockIdx.y, c = threadIdx.x, t0 = blockIdx.x * AW_P0A_FRAMES;
+  const double S1 = bsum[((long long)clip * AW_NMEL + c) * 2];
+  const double S2 = bsum[((long long)clip * AW_NMEL + c) * 2 + 1];
+  const double tS1 = block_sum(S1, s_red);
+  __syncthreads();
+  const double tS2 = block_sum(S2, s_red);
+  if (threadIdx.x == 0) {
+    const double n = 128.0 * T, sg = sigma_in[clip];
+    s_ab[0] = (float)(1.0 / (sg + 1e-8));                                      // alpha
+    s_ab[1] = (float)(tS2 / ((n - 1.0) * sg * (sg + 1e-8) * (sg + 1e-8)));      // beta
+    s_ab[2] = (float)(tS1 / n);                                                 // mean dG
+  }
+  __syncthreads();
+  const float alpha = s_ab[0], beta = s_ab[1], meanG = s_ab[2];
+  const ChanStats st = cs[(long long)clip * AW_NMEL + c];
+  const float A1 = alpha * ((float)(S1 / T) - meanG);
+  const float A2 = alpha * (float)(S2 / T) - beta * st.varratio;
+  const int nf = min(AW_P0A_FRAMES, T - t0);
+  for (int f = 0; f < nf; ++f) {
+    const int t = t0 + f;
+    const float dg = t < 2 * Tp ? 0.5f * dP0[((long long)clip * Tp_pad + (t >> 1)) * AW_NMEL + c] : 0.f;
+    const float mh = (M[((long long)clip * T + t) * AW_NMEL + c] - st.mu) * st.rstd;
+    const float dmh = alpha * (dg - meanG) - beta * mh;
+    s_dm[f][c] = st.rstd * (dmh - A1 - mh * A2);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nf * nb; i += 128) {
+    const int f = i / nb, b = i - f * nb;
+    float acc = 0.f;
+    for (int e = sm.colptr[b]; e < sm.colptr[b + 1]; ++e) acc = fmaf(sm.valT[e], s_dm[f][sm.row[e]], acc);
+    dA[((long long)clip * T + t0 + f) * nb + b] = acc;
+  }
+}
+
+// ---- bit decision + BER counters (utils/watermark/decoder.py:51,63; metrics/audio.py:15)
+// counters: [0] bit errors, [1] bits compared, [2] clips
+__global__ void __launch_bounds__(128) k_decide_count(const float* __restrict__ values,
+                                                      const int* __restrict__ ref_bits,
+                                                      float thr, int n_clips,
+                                                      int* __restrict__ bits_out,
+                                                      int* __restrict__ err_per_clip,
+                                                      unsigned long long* __restrict__ counters) {
+  const int clip = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (clip >= n_clips) return;
+  int bit = 0, err = 0;
+  if (lane < AW_NBITS) {
+    bit = values[(long long)clip * AW_NBITS + lane] > thr ? 1 : 0;
+    if (bits_out) bits_out[(long long)clip * AW_NBITS + lane] = bit;
+    if (ref_bits) err = bit != ref_bits[(long long)clip * AW_NBITS + lane];
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, err);
+  if (lane == 0 && ref_bits) {
+    const int e = __popc(m);
+    if (err_per_clip) err_per_clip[clip] = e;
+    if (counters) {
+      atomicAdd(counters + 0, (unsigned long long)e);
+      atomicAdd(counters + 1, (unsigned long long)AW_NBITS);
+      atomicAdd(counters + 2, 1ull);
+    }
+  }
+}
+
+// ---- SNR (metrics/audio.py:68-89): per clip 10 log10(sum o^2 / sum (o-t)^2) -------
+__global__ void __launch_bounds__(256) k_snr_partial(const float* __restrict__ out, long long so,
+                                                     const float* __restrict__ tgt, long long st_,
+                                                     int n, double* __restrict__ acc) {
+  __shared__ double s_red[32];
+  const int clip = blockIdx.y;
+  double p = 0.0, e = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float o = out[(long long)clip * so + i], t = tgt[(long long)clip * st_ + i];
+    const float d = o - t;
+    p += (double)o * o;
+    e += (double)d * d;
+  }
+  p = block_sum(p, s_red);
+  __syncthreads();
+  e = block_sum(e, s_red);
+  if (threadIdx.x == 0) {
+    atomicAdd(acc + 2 * clip, p);
+    atomicAdd(acc + 2 * clip + 1, e);
+  }
+}
+
+__global__ void k_snr_final(const double* __restrict__ acc, int n_clips, double* __restrict__ snr,
+                            double* __restrict__ snr_sum) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_clips) return;
+  const double p = acc[2 * i], e = acc[2 * i + 1];
+  const double s = e == 0.0 ? INFINITY : 10.0 * log10(p / e);
+  snr[i] = s;
+  if (snr_sum && e != 0.0) atomicAdd(snr_sum, s);
+}
+
+}  // namespace aw

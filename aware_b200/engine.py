@@ -1,0 +1,236 @@
+"""Batched device engine: torch tensors for memory / streams, the C ABI for compute.
+
+One Engine per process and device.  Every method takes and returns CUDA tensors
+(audio: float32 [n_clips, n_samples]); the reference-shaped numpy API in
+aware_b200.service / .embedding / .detection is a thin layer over it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+N_BITS = 20
+HOP = 256
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    def __init__(self, weights, mel_basis, window, bands=(500.0, 4000.0), tolerance_db=6.0,
+                 threshold=0.0, precision="tf32", device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("aware_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.lib()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        ws = [np.ascontiguousarray(w, dtype=np.float32) for w in weights]
+        mel = np.ascontiguousarray(mel_basis, dtype=np.float32)
+        win = np.ascontiguousarray(window, dtype=np.float32)
+        assert [w.shape for w in ws] == [(512, 128), (1024, 512), (1024, 1024), (40, 1024)]
+        assert mel.shape == (128, 513) and win.shape == (1024,)
+        m = _lib.AwModel()
+        for i, w in enumerate(ws):
+            m.w[i] = w.ctypes.data_as(C.POINTER(C.c_float))
+        m.mel_basis = mel.ctypes.data_as(C.POINTER(C.c_float))
+        m.window = win.ctypes.data_as(C.POINTER(C.c_float))
+        m.band_lo_hz, m.band_hi_hz = float(bands[0]), float(bands[1])
+        m.tolerance_db, m.threshold = float(tolerance_db), float(threshold)
+        self._ctx = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aw_ctx_create(C.byref(self._ctx), self.device.index, C.byref(m)))
+        self.threshold = float(threshold)
+        self.set_precision(precision)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ctx", None):
+                self.lib.aw_ctx_destroy(self._ctx)
+                self._ctx = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ misc
+    def set_precision(self, precision: str):
+        code = {"tf32": _lib.PREC_TF32, "fp32": _lib.PREC_FP32}[precision]
+        _lib.check(self.lib.aw_ctx_set_precision(self._ctx, code))
+        self.precision = precision
+
+    def launch_count(self) -> int:
+        return int(self.lib.aw_launch_count(self._ctx))
+
+    def band_bins(self, sample_rate: int):
+        b0, nb = C.c_int(), C.c_int()
+        _lib.check(self.lib.aw_band_bins(self._ctx, int(sample_rate), C.byref(b0), C.byref(nb)))
+        return b0.value, nb.value
+
+    def _audio(self, x):
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
+                and x.stride(1) == 1):
+            raise ValueError("expected a CUDA float32 tensor [n_clips, n_samples] with unit inner stride")
+        return x
+
+    # ------------------------------------------------------------- hot path
+    def detect(self, audio: torch.Tensor, sample_rate: int) -> torch.Tensor:
+        """[n, N] -> [n, 20] tanh outputs (AWAREDetector.detect for a batch)."""
+        x = self._audio(audio)
+        n, N = x.shape
+        out = torch.empty((n, N_BITS), dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.aw_detect_batch(self._ctx, _ptr(x), n, N, x.stride(0), int(sample_rate),
+                                            _ptr(out), _stream()))
+        return out
+
+    def embed(self, audio: torch.Tensor, sample_rate: int, pattern: torch.Tensor, iters: int = 400,
+              scale: torch.Tensor | None = None, wave_clips: int = 0, return_losses: bool = False):
+        """[n, N] + [n, 20] int32 (+-1) -> [n, 256*(N//256)] watermarked, peak-normalised
+        (AWAREEmbedder.embed for a batch); optionally multiplied per clip by `scale`."""
+        x = self._audio(audio)
+        n, N = x.shape
+        L = HOP * (N // HOP)
+        pat = pattern.to(device=x.device, dtype=torch.int32).contiguous()
+        if pat.shape != (n, N_BITS):
+            raise ValueError("Invalid watermark length.")
+        out = torch.empty((n, L), dtype=torch.float32, device=x.device)
+        best = torch.empty((n,), dtype=torch.float32, device=x.device)
+        losses = torch.zeros((max(iters, 1), n), dtype=torch.float32, device=x.device) if return_losses else None
+        sc = scale.to(device=x.device, dtype=torch.float32).contiguous() if scale is not None else None
+        _lib.check(self.lib.aw_embed_batch(self._ctx, _ptr(x), n, N, x.stride(0), int(sample_rate),
+                                           _ptr(pat), int(iters), _ptr(sc), _ptr(out), out.stride(0),
+                                           _ptr(best), _ptr(losses), int(wave_clips), _stream()))
+        if return_losses:
+            return out, best, losses
+        return out
+
+    def embed_state(self, which: str, n: int, n_frames: int, sample_rate: int) -> torch.Tensor:
+        """Optimisation state of the last embed wave, [n, T, nbins] (parity hooks)."""
+        sel = {"c": 0, "best": 1, "c0": 2, "m": 3, "v": 4}[which]
+        _, nb = self.band_bins(sample_rate)
+        dst = torch.empty((n, n_frames, nb), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.aw_embed_state(self._ctx, sel, _ptr(dst), dst.numel(), _stream()))
+        return dst
+
+    def decide(self, values: torch.Tensor, ref_bits: torch.Tensor | None = None,
+               counters: torch.Tensor | None = None):
+        """values [n,20] -> bits int32 [n,20] (strict '>' threshold); with ref_bits also
+        per-clip error counts, and `counters` (int64[3]: errors, bits, clips) is incremented."""
+        n = values.shape[0]
+        bits = torch.empty((n, N_BITS), dtype=torch.int32, device=values.device)
+        errs = torch.zeros((n,), dtype=torch.int32, device=values.device) if ref_bits is not None else None
+        ref = ref_bits.to(device=values.device, dtype=torch.int32).contiguous() if ref_bits is not None else None
+        _lib.check(self.lib.aw_decide_and_count(self._ctx, _ptr(values.contiguous()), _ptr(ref), n,
+                                                _ptr(bits), _ptr(errs), _ptr(counters), _stream()))
+        return (bits, errs) if ref_bits is not None else bits
+
+    def snr(self, out: torch.Tensor, target: torch.Tensor, snr_sum: torch.Tensor | None = None):
+        n = out.shape[0]
+        m = min(out.shape[1], target.shape[1])
+        res = torch.empty((n,), dtype=torch.float64, device=out.device)
+        _lib.check(self.lib.aw_snr_batch(self._ctx, _ptr(out), out.stride(0), _ptr(target), target.stride(0),
+                                         n, m, _ptr(res), _ptr(snr_sum), _stream()))
+        return res
+
+    # ---------------------------------------------------------- stage hooks
+    def stft_band(self, audio, sample_rate, normalize=True, phasor=False):
+        x = self._audio(audio)
+        n, N = x.shape
+        T = 1 + N // HOP
+        _, nb = self.band_bins(sample_rate)
+        mag = torch.empty((n, T, nb), dtype=torch.float32, device=x.device)
+        ph = torch.empty((n, T, nb, 2), dtype=torch.float32, device=x.device) if phasor else None
+        _lib.check(self.lib.aw_stft_band(self._ctx, _ptr(x), n, N, x.stride(0), int(sample_rate),
+                                         int(bool(normalize)), _ptr(mag), _ptr(ph), _stream()))
+        return (mag, ph) if phasor else mag
+
+    def istft_band(self, mag, phasor, sample_rate):
+        n, T, nb = mag.shape
+        wave = torch.empty((n, HOP * (T - 1)), dtype=torch.float32, device=mag.device)
+        _lib.check(self.lib.aw_istft_band(self._ctx, _ptr(mag.contiguous()), _ptr(phasor.contiguous()), n, T,
+                                          int(sample_rate), _ptr(wave), _stream()))
+        return wave
+
+    def gemm(self, a, b, precision=None):
+        rows, k = a.shape
+        n = b.shape[0]
+        out = torch.empty((rows, n), dtype=torch.float32, device=a.device)
+        prec = {"tf32": _lib.PREC_TF32, "fp32": _lib.PREC_FP32}[precision or self.precision]
+        _lib.check(self.lib.aw_gemm(self._ctx, _ptr(a.contiguous()), _ptr(b.contiguous()), _ptr(out),
+                                    rows, n, k, prec, _stream()))
+        return out
+
+    # -------------------------------------------------------------- attacks
+    def _out_like(self, x, n_out=None):
+        return torch.empty((x.shape[0], x.shape[1] if n_out is None else n_out), dtype=torch.float32,
+                           device=x.device)
+
+    def attack_pcm(self, x, bits):
+        x = self._audio(x); out = self._out_like(x)
+        _lib.check(self.lib.aw_attack_pcm(self._ctx, _ptr(x), x.shape[0], x.shape[1], x.stride(0), int(bits),
+                                          _ptr(out), out.stride(0), _stream()))
+        return out
+
+    def attack_decimate_interp(self, x, factor):
+        x = self._audio(x); out = self._out_like(x)
+        _lib.check(self.lib.aw_attack_decimate_interp(self._ctx, _ptr(x), x.shape[0], x.shape[1], x.stride(0),
+                                                      int(factor), _ptr(out), out.stride(0), _stream()))
+        return out
+
+    def attack_upfirdn(self, x, h_tf, taps_per_phase, up, down, first_out, n_out):
+        x = self._audio(x); out = self._out_like(x, n_out)
+        _lib.check(self.lib.aw_attack_upfirdn(self._ctx, _ptr(x), x.shape[0], x.shape[1], x.stride(0),
+                                              _ptr(h_tf), int(taps_per_phase), int(up), int(down),
+                                              int(first_out), int(n_out), _ptr(out), out.stride(0), _stream()))
+        return out
+
+    @staticmethod
+    def _dbl(v):
+        a = np.ascontiguousarray(v, dtype=np.float64)
+        return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+    def attack_lfilter(self, x, b, a, warm):
+        x = self._audio(x); out = self._out_like(x)
+        bb, bp = self._dbl(b); aa, ap = self._dbl(a)
+        _lib.check(self.lib.aw_attack_lfilter(self._ctx, _ptr(x), x.shape[0], x.shape[1], x.stride(0), bp, ap,
+                                              len(bb) - 1, int(warm), _ptr(out), out.stride(0), _stream()))
+        return out
+
+    def attack_filtfilt(self, x, b, a, zi, warm):
+        x = self._audio(x); out = self._out_like(x)
+        bb, bp = self._dbl(b); aa, ap = self._dbl(a); zz, zp = self._dbl(zi)
+        _lib.check(self.lib.aw_attack_filtfilt(self._ctx, _ptr(x), x.shape[0], x.shape[1], x.stride(0), bp, ap,
+                                               zp, len(bb) - 1, int(warm), _ptr(out), out.stride(0), _stream()))
+        return out
+
+    def attack_delete(self, x, start, n_delete):
+        x = self._audio(x); out = self._out_like(x, x.shape[1] - n_delete)
+        st = start.to(device=x.device, dtype=torch.int32).contiguous()
+        _lib.check(self.lib.aw_attack_delete(self._ctx, _ptr(x), x.shape[0], x.shape[1], x.stride(0), _ptr(st),
+                                             int(n_delete), _ptr(out), out.stride(0), _stream()))
+        return out
+
+    def attack_suppress(self, x, start, n_zero):
+        x = self._audio(x); out = self._out_like(x)
+        st = start.to(device=x.device, dtype=torch.int32).contiguous()
+        _lib.check(self.lib.aw_attack_suppress(self._ctx, _ptr(x), x.shape[0], x.shape[1], x.stride(0), _ptr(st),
+                                               int(n_zero), _ptr(out), out.stride(0), _stream()))
+        return out
+
+    def attack_cropout(self, x, n_drop):
+        x = self._audio(x); out = self._out_like(x, x.shape[1] - n_drop)
+        _lib.check(self.lib.aw_attack_cropout(self._ctx, _ptr(x), x.shape[0], x.shape[1], x.stride(0),
+                                              int(n_drop), _ptr(out), out.stride(0), _stream()))
+        return out
+
+    def attack_affine(self, x, gain=1.0, noise=None, sigma=0.0):
+        x = self._audio(x); out = self._out_like(x)
+        ns = noise.stride(0) if noise is not None else 0
+        _lib.check(self.lib.aw_attack_affine(self._ctx, _ptr(x), x.shape[0], x.shape[1], x.stride(0), float(gain),
+                                             _ptr(noise), ns, float(sigma), _ptr(out), out.stride(0), _stream()))
+        return out

@@ -1,0 +1,144 @@
+/* aware_b200 -- C ABI of the B200-native AWARE hot path.
+ *
+ * The reference (deepmarkpy/aware) is pure Python; it has no FFI of its own.  Each
+ * entry point below replaces the body of one reference function (cited as
+ * file:line relative to the reference tree) for a whole BATCH of clips.  The
+ * Python mirror of the reference API (aware_b200/service, aware_b200/utils/models,
+ * aware_b200/metrics, aware_b200/attacks) binds these with ctypes; see
+ * INTEGRATION.md for the stub a maintainer would add to the reference itself.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure;
+ *     aw_last_error() returns a message for the calling thread.
+ *   - all `d_` pointers are DEVICE pointers owned by the caller; audio is float32,
+ *     one clip per row, `stride` elements between consecutive clips.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing
+ *     synchronises unless stated.  A context is bound to one device and must be
+ *     used by one host thread at a time.
+ *   - there is no CPU fallback: without a CUDA device aw_ctx_create fails.
+ */
+#ifndef AWARE_B200_H
+#define AWARE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct aw_ctx aw_ctx;
+
+/* GEMM arithmetic for the detector's 1x1-conv stack. */
+enum {
+  AW_PREC_TF32 = 0, /* tcgen05 tensor cores, TF32 operands, fp32 accumulate (default) */
+  AW_PREC_FP32 = 1  /* CUDA-core fp32 (validation / sub-TF32 margins)                */
+};
+
+/* Model description handed over once (reference: utils/models/load_model.py:6-76,
+ * cards/config.yaml, detection/multibit_detector_net.py:58-80).  Host pointers. */
+typedef struct aw_model {
+  const float* w[4];      /* conv weights, (C_out, C_in) row-major: 512x128, 1024x512,
+                             1024x1024, 40x1024 (multibit_detector_net.py:58-70)      */
+  const float* mel_basis; /* 128 x 513 (detection/modules/mel.py:105-149)             */
+  const float* window;    /* 1024, torch.hann_window (utils/audio/stft.py:17)         */
+  float band_lo_hz, band_hi_hz; /* config.yaml:13 embedding_bands                     */
+  float tolerance_db;     /* config.yaml:14                                           */
+  float threshold;        /* config.yaml:46                                           */
+} aw_model;
+
+const char* aw_last_error(void);
+const char* aw_version(void);
+
+int aw_ctx_create(aw_ctx** out, int device, const aw_model* model);
+int aw_ctx_destroy(aw_ctx* ctx);
+int aw_ctx_set_precision(aw_ctx* ctx, int prec);
+/* band bins for a sample rate (embedding/multibit_embedder.py:43-47) */
+int aw_band_bins(aw_ctx* ctx, int sample_rate, int* bin0, int* nbins);
+/* number of CUDA kernels launched by this context since creation */
+int64_t aw_launch_count(aw_ctx* ctx);
+
+/* ---- detection: AWAREDetector.detect (detection/multibit_detector.py:28-42) for a batch.
+ * d_values: [n_clips][20] float32 tanh outputs. */
+int aw_detect_batch(aw_ctx* ctx, const float* d_audio, int n_clips, int n_samples,
+                    int64_t stride, int sample_rate, float* d_values, void* stream);
+
+/* ---- embedding: AWAREEmbedder.embed (embedding/multibit_embedder.py:141-197) for a batch.
+ * d_pattern : [n_clips][20] int32 in {-1,+1} (utils/watermark/encoder.py:35-45)
+ * d_scale   : optional [n_clips] float32; output is multiplied by it
+ *             (service/embed.py:69,73 rescale by the signed max) -- may be NULL
+ * d_out     : [n_clips][out_stride], each clip gets 256*(n_samples/256) samples
+ * d_best_loss: optional [n_clips]; d_losses: optional [iters][n_clips]
+ * wave_clips: clips processed together per optimisation wave (0 = all). */
+int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, int n_samples, int64_t stride,
+                   int sample_rate, const int32_t* d_pattern, int iters, const float* d_scale,
+                   float* d_out, int64_t out_stride, float* d_best_loss, float* d_losses,
+                   int wave_clips, void* stream);
+/* debug/parity hooks: after aw_embed_batch, copy the optimisation state of the LAST wave.
+ * which: 0 coeffs c, 1 best coeffs, 2 initial coeffs c0, 3 last gradient-free state m, 4 v
+ * layout [clip][T][nbins] float32. */
+int aw_embed_state(aw_ctx* ctx, int which, float* d_dst, int64_t capacity, void* stream);
+
+/* ---- bit decision + BER counters (utils/watermark/decoder.py:51,63; metrics/audio.py:15)
+ * d_ref_bits may be NULL (no counting). d_counters: uint64[3] += {errors, bits, clips}. */
+int aw_decide_and_count(aw_ctx* ctx, const float* d_values, const int32_t* d_ref_bits,
+                        int n_clips, int32_t* d_bits_out, int32_t* d_err_per_clip,
+                        uint64_t* d_counters, void* stream);
+
+/* ---- SNR (metrics/audio.py:68-89): d_snr [n_clips] float64 dB, d_snr_sum float64[1] += */
+int aw_snr_batch(aw_ctx* ctx, const float* d_out, int64_t out_stride, const float* d_target,
+                 int64_t tgt_stride, int n_clips, int n, double* d_snr, double* d_snr_sum,
+                 void* stream);
+
+/* ---- stage-level entry points (used by the parity tests and by callers that
+ * want the STFT/iSTFT alone; reference utils/audio/stft.py:28,48,55,62) */
+int aw_stft_band(aw_ctx* ctx, const float* d_audio, int n_clips, int n_samples, int64_t stride,
+                 int sample_rate, int normalize, float* d_mag, float* d_phasor, void* stream);
+int aw_istft_band(aw_ctx* ctx, const float* d_mag, const float* d_phasor, int n_clips,
+                  int n_frames, int sample_rate, float* d_wave, void* stream);
+/* D[rows][N] = A[rows][K] * B[N][K]^T ; rows % 128 == 0, K % 32 == 0, N in {64,128,256,512,1024} */
+int aw_gemm(aw_ctx* ctx, const float* d_a, const float* d_b, float* d_d, int rows, int n, int k,
+            int prec, void* stream);
+
+/* ---- attacks (scripts/attacks.py); every one is batch-wise, out-of-place ---------- */
+/* A1 PCMBitDepthConversion.apply (attacks.py:44-70); bits in {8,12,16,24} */
+int aw_attack_pcm(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t in_stride, int bits,
+                  float* d_out, int64_t out_stride, void* stream);
+/* A2 Resample.apply, sr // target > 1 branch (attacks.py:276-287) */
+int aw_attack_decimate_interp(aw_ctx* ctx, const float* d_in, int n_clips, int n,
+                              int64_t in_stride, int factor, float* d_out, int64_t out_stride,
+                              void* stream);
+/* A2 Resample.apply, polyphase branch: one scipy.signal.upfirdn pass (attacks.py:289-294).
+ * d_h_tf: transposed+flipped zero-padded taps [up][taps_per_phase] (host prepares). */
+int aw_attack_upfirdn(aw_ctx* ctx, const float* d_in, int n_clips, int n_in, int64_t in_stride,
+                      const float* d_h_tf, int taps_per_phase, int up, int down, int first_out,
+                      int n_out, float* d_out, int64_t out_stride, void* stream);
+/* A3/A4 LowPassFilter / HighPassFilter .apply: scipy.signal.lfilter(b, a, x) in float64
+ * (attacks.py:413-416, 451-453).  order <= 8; warm = look-back samples for the chunked scan. */
+int aw_attack_lfilter(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t in_stride,
+                      const double* b, const double* a, int order, int warm, float* d_out,
+                      int64_t out_stride, void* stream);
+/* A5 RandomBandstop.apply: scipy.signal.filtfilt(b, a, x) (attacks.py:348-349), odd padding
+ * 3*max(len(a),len(b)), zi = lfilter_zi(b, a) supplied by the host. */
+int aw_attack_filtfilt(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t in_stride,
+                       const double* b, const double* a, const double* zi, int order, int warm,
+                       float* d_out, int64_t out_stride, void* stream);
+/* A6 DeleteSamples.apply (attacks.py:162-178): d_start [n_clips] int32, host-drawn */
+int aw_attack_delete(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t in_stride,
+                     const int32_t* d_start, int n_delete, float* d_out, int64_t out_stride,
+                     void* stream);
+/* A7 SampleSupression.apply (attacks.py:370-385) */
+int aw_attack_suppress(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t in_stride,
+                       const int32_t* d_start, int n_zero, float* d_out, int64_t out_stride,
+                       void* stream);
+/* A8 Cropout.apply (attacks.py:192-205): drop the first n_drop samples */
+int aw_attack_cropout(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t in_stride,
+                      int n_drop, float* d_out, int64_t out_stride, void* stream);
+/* extensions without a reference counterpart (parity unpinned): out = gain*x + sigma*noise */
+int aw_attack_affine(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t in_stride,
+                     float gain, const float* d_noise, int64_t noise_stride, float sigma,
+                     float* d_out, int64_t out_stride, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AWARE_B200_H */

@@ -1,0 +1,144 @@
+"""Host-side logic of aware_b200 that needs no GPU: the reference-shaped API
+objects, codec/metrics, attack planning, and that the C-ABI library loads and
+exports every declared symbol."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import aware_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from aware_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "aware_b200.h")).read()
+    declared = set(re.findall(r"\b(aw_[a-z0-9_]+)\s*\(", header))
+    declared -= {"aw_ctx", "aw_model"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    handle = _lib.lib()                      # raises AttributeError on a missing export
+    for name in declared:
+        assert getattr(handle, name) is not None
+    assert b"sm_100a" in handle.aw_version()
+
+
+def test_context_creation_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from aware_b200.engine import Engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine(O.make_weights(), O.mel_basis(), O.hann().numpy())
+    # and at the C level
+    from aware_b200 import _lib
+    ctx = ctypes.c_void_p()
+    m = _lib.AwModel()
+    assert _lib.lib().aw_ctx_create(ctypes.byref(ctx), 0, ctypes.byref(m)) != 0
+    assert b"no CUDA device" in _lib.lib().aw_last_error()
+
+
+def test_load_builds_reference_shaped_objects():
+    from aware_b200.utils.models import load
+    state = torch.random.get_rng_state()
+    emb, det = load()
+    torch.random.set_rng_state(state)
+    assert det.detection_net is emb.detection_net            # shared net (load_model.py:56 upstream)
+    assert emb.pattern_mode == det.pattern_mode == "bits2bipolar"
+    assert emb.detection_net.output_length == 20 and det.threshold == 0.0
+    assert (emb.tolerance_db, emb.num_iterations, emb.embedding_bands) == (6.0, 400, (500, 4000))
+    assert emb.optimizer_name == "nadam" and emb.scheduler_name == "reduce_lr_on_plateau"
+    assert emb.detection_net.get_model_info()["total_parameters"] == 1681960
+    for w, wo in zip(emb.detection_net.weights, O.make_weights()):
+        np.testing.assert_array_equal(w, wo.numpy())
+    np.testing.assert_array_equal(emb.detection_net.mel_filter_bank, O.mel_basis())
+
+
+def test_service_validation_matches_reference():
+    from aware_b200.service import detect_watermark, embed_watermark
+    from aware_b200.utils.models import load
+    emb, det = load()
+    x = np.zeros(16000, dtype=np.float32)
+    bits = np.zeros(20, dtype=np.int32)
+    with pytest.raises(ValueError, match="Invalid sample rate"):
+        embed_watermark(x, 44100, bits, emb)
+    with pytest.raises(ValueError, match="Invalid sample rate"):
+        detect_watermark(x, 22050, det)
+    with pytest.raises(ValueError, match="Invalid watermark length"):
+        embed_watermark(x, 16000, np.zeros(19, dtype=np.int32), emb)
+    with pytest.raises(ValueError, match="Invalid audio shape"):
+        embed_watermark(np.zeros((10, 3), dtype=np.float32), 16000, bits, emb)
+    with pytest.raises(ValueError, match="Invalid audio shape"):
+        detect_watermark(np.zeros((10, 1), dtype=np.float32), 16000, det)   # Q22: (N,1) rejected
+
+
+def test_codec_matches_oracle():
+    from aware_b200.utils.watermark import PatternDecoder, PatternEncoder
+    bits = O.synth_bits(3)[1]
+    np.testing.assert_array_equal(PatternEncoder("bits2bipolar")(bits), O.encode_bits(bits))
+    v = np.array([0.0, 1e-9, -0.3, 0.7, -1e-9], dtype=np.float32)
+    np.testing.assert_array_equal(PatternDecoder(0.0, "bits2bipolar")(v), O.decode_values(v))
+    assert PatternEncoder("bytes2bits")(b"\xa5").tolist() == [1, 0, 1, 0, 0, 1, 0, 1]
+    assert PatternDecoder(0.5, "bytes2bits")(np.array([0.9, 0.1, 0.6])) == bytes([1, 0, 1])
+
+
+def test_metrics_match_oracle():
+    from aware_b200.metrics.audio import BER, SNR
+    rng = np.random.default_rng(0)
+    a, b = rng.integers(0, 2, 20), rng.integers(0, 2, 20)
+    assert BER()(a, b) == O.ber_percent(a, b)
+    x = rng.standard_normal(1000).astype(np.float32)
+    y = x + 0.01 * rng.standard_normal(1000).astype(np.float32)
+    assert SNR()(y, x[:900]) == pytest.approx(O.snr_db(y, x[:900]), rel=1e-12)
+    assert SNR()(x, x) == float("inf")
+
+
+def test_synth_matches_oracle_generator():
+    from aware_b200 import synth
+    np.testing.assert_array_equal(synth.synth_clip(4, 0.3, 44100), O.synth_clip(4, 0.3, 44100))
+    np.testing.assert_array_equal(synth.synth_bits(5), O.synth_bits(5))
+    b = synth.synth_batch(40, 0.1, 16000, unique=16)
+    assert b.shape == (40, 1600) and len({bytes(r) for r in b}) == 40
+
+
+def _upfirdn_model(x, h_tf, hpp, up, down, k_off, n_out):
+    """numpy transcription of csrc/attacks.cuh:k_upfirdn (float32, oldest sample first)."""
+    out = np.zeros(n_out, dtype=np.float32)
+    n_in = len(x)
+    for k in range(n_out):
+        t = (k + k_off) * down
+        phase, xi = t % up, t // up
+        x0, hidx = xi - hpp + 1, phase * hpp
+        if x0 < 0:
+            hidx -= x0
+            x0 = 0
+        acc = np.float32(0)
+        for j in range(x0, min(xi, n_in - 1) + 1):
+            acc = np.float32(acc + np.float32(x[j] * h_tf[hidx]))
+            hidx += 1
+        out[k] = acc
+    return out
+
+
+def test_polyphase_plan_reproduces_scipy_resample_poly():
+    from scipy.signal import resample_poly
+    from aware_b200.attacks import polyphase_plan
+    x = O.synth_clip(9, 0.02, 16000)                 # 320 samples
+    for up, down in ((441, 160), (160, 441)):
+        h_tf, hpp, k_off, n_out = polyphase_plan(len(x), up, down)
+        got = _upfirdn_model(x, h_tf, hpp, up, down, k_off, n_out)
+        want = resample_poly(x, up, down)
+        assert got.shape == want.shape and want.dtype == np.float32
+        np.testing.assert_array_equal(got, want)
+
+
+def test_warm_up_length_bounds_filter_memory():
+    from aware_b200.attacks import _warm_samples
+    for kind, sr, kw in (("lowpass", 44100, {}), ("highpass", 44100, {}), ("bandstop", 44100, {"f_low": 3800.0}),
+                         ("bandstop", 16000, {"f_low": 300.0})):
+        b, a = O.butter_coeffs(kind, sr, **kw)
+        w = _warm_samples(a)
+        r = np.max(np.abs(np.roots(a)))
+        assert r ** w < 1e-17 and w < 20000

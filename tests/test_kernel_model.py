@@ -1,0 +1,59 @@
+"""The kernel decomposition (tests/kernel_model.py) against torch autograd on the
+oracle's forward, in float64 -- proves the hand-derived adjoints the CUDA
+kernels implement are the reference's gradient."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import aware_oracle as O
+from kernel_model import Model
+
+
+def _autograd_reference(x, sr, pattern):
+    """Oracle loop body (multibit_embedder.py:95-111) in float64."""
+    dt = torch.float64
+    w = torch.hann_window(1024, dtype=dt)
+    xn = torch.from_numpy(x).to(dt)
+    xn = xn / torch.max(torch.abs(xn) + 1e-8)
+    spec = torch.stft(xn, 1024, 256, window=w, center=True, return_complex=True)
+    mag, phase = spec.abs(), torch.angle(spec)
+    fi, nfi = O.band_indices(sr)
+    c = mag[fi].clone().requires_grad_(True)
+    wm = mag.clone()
+    wm[fi] = c
+    y = torch.istft(wm * torch.exp(1j * phase), 1024, 256, window=w, center=True)
+    y = y / torch.max(torch.abs(y) + 1e-8)
+    y = y / torch.max(torch.abs(y) + 1e-8)
+    m2 = torch.stft(y, 1024, 256, window=w, center=True, return_complex=True).abs()
+    m2[nfi] = 0.0
+    mel = torch.from_numpy(O.mel_basis()).to(dt)
+    m = (mel @ m2).unsqueeze(0)
+    mh = F.instance_norm(m, eps=1e-5)
+    g = (mh - mh.mean()) / (mh.std() + 1e-8)
+    p = F.avg_pool1d(g, 2, 2)
+    for wl in O.make_weights():
+        p = F.leaky_relu(F.instance_norm(F.conv1d(p, wl.to(dt).unsqueeze(-1)), eps=1e-5), 0.2)
+    z = p.mean(2)
+    v = torch.tanh(z[:, 0::2] - z[:, 1::2]).reshape(-1)
+    t = torch.from_numpy(pattern).to(dt)
+    loss = F.mse_loss(v, t) - 0.1 * torch.mean(torch.abs(v))
+    loss.backward()
+    return loss.item(), v.detach().numpy(), c.grad.numpy(), mag[fi].numpy()
+
+
+@pytest.mark.parametrize("sr,secs", [(16000, 0.6), (44100, 0.35)])
+def test_decomposition_matches_autograd(sr, secs):
+    x = O.synth_clip(2, secs, sr)
+    pattern = O.encode_bits(O.synth_bits(4)[2]).astype(np.float64)
+    loss_ref, v_ref, g_ref, c0_ref = _autograd_reference(x, sr, pattern)
+    fi, _ = O.band_indices(sr)
+    mdl = Model(O.make_weights(), O.mel_basis(), fi)
+    c0 = mdl.init(x)
+    np.testing.assert_allclose(c0, c0_ref.T, rtol=1e-9, atol=1e-11)
+    loss, v = mdl.forward(c0, pattern)
+    np.testing.assert_allclose(v, v_ref, rtol=0, atol=1e-9)
+    assert abs(loss - loss_ref) < 1e-10
+    g = mdl.backward(pattern)
+    scale = np.abs(g_ref).max()
+    assert np.abs(g - g_ref.T).max() <= 1e-7 * scale
