@@ -35,6 +35,9 @@ SIGNATURES = {
     "aw_ctx_set_precision": (_i, [_vp, _i]),
     "aw_band_bins": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i)]),
     "aw_launch_count": (_i64, [_vp]),
+    "aw_profile_enable": (_i, [_vp, _i]),
+    "aw_profile_read": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i),
+                             C.POINTER(_i64), _dp]),
     "aw_detect_batch": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp]),
     "aw_embed_batch": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _i, _vp, _vp, _i64, _vp, _vp, _i, _vp]),
     "aw_embed_state": (_i, [_vp, _i, _vp, _i64, _vp]),

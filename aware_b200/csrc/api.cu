@@ -67,7 +67,23 @@ struct aw_ctx {
   CUtensorMap tm_act[4], tm_dh4, tm_ga1024, tm_ga512, tm_gb1024;
   // state of the last embed wave (for aw_embed_state)
   int last_n = 0, last_T = 0, last_nb = 0;
+  // optional CUDA-event timing of the GEMM launches (aw_profile_*)
+  struct ProfRec { int n, k, epi; cudaEvent_t a, b; };
+  bool prof_on = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
 };
+
+static cudaEvent_t prof_event(aw_ctx* ctx) {
+  cudaEvent_t e;
+  if (!ctx->ev_pool.empty()) {
+    e = ctx->ev_pool.back();
+    ctx->ev_pool.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
 
 static int ensure(Buf& b, size_t bytes) {
   if (bytes <= b.cap) return 0;
@@ -98,7 +114,17 @@ template <int BN, int EPI>
 static int launch_tc(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, int rows, int n,
                      int k, const EpiArgs& ep, cudaStream_t st) {
   dim3 grid(rows / 128, n / BN);
+  aw_ctx::ProfRec pr;
+  if (ctx->prof_on) {
+    pr.n = n; pr.k = k; pr.epi = EPI;
+    pr.a = prof_event(ctx); pr.b = prof_event(ctx);
+    cudaEventRecord(pr.a, st);
+  }
   k_gemm_tc<BN, EPI><<<grid, 192, gemm_tc_smem<BN>(), st>>>(ma, mb, k, ep);
+  if (ctx->prof_on) {
+    cudaEventRecord(pr.b, st);
+    ctx->prof.push_back(pr);
+  }
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
@@ -250,6 +276,39 @@ extern "C" int aw_ctx_set_precision(aw_ctx* ctx, int prec) {
 
 extern "C" int64_t aw_launch_count(aw_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int aw_profile_enable(aw_ctx* ctx, int on) {
+  AW_REQUIRE(ctx, "null ctx");
+  ctx->prof_on = on != 0;
+  return 0;
+}
+
+// Sum the recorded tensor-core GEMM launches by (n, k, epilogue); waits for their events.
+extern "C" int aw_profile_read(aw_ctx* ctx, int max_classes, int* n_classes, int* cls_n, int* cls_k,
+                               int* cls_epi, int64_t* cls_count, double* cls_ms) {
+  AW_REQUIRE(ctx && n_classes, "null argument");
+  int nc = 0;
+  for (auto& r : ctx->prof) {
+    AW_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    AW_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    int c = 0;
+    for (; c < nc; ++c)
+      if (cls_n[c] == r.n && cls_k[c] == r.k && cls_epi[c] == r.epi) break;
+    if (c == nc) {
+      if (nc >= max_classes) continue;
+      cls_n[c] = r.n; cls_k[c] = r.k; cls_epi[c] = r.epi; cls_count[c] = 0; cls_ms[c] = 0.0;
+      ++nc;
+    }
+    cls_count[c] += 1;
+    cls_ms[c] += ms;
+    ctx->ev_pool.push_back(r.a);
+    ctx->ev_pool.push_back(r.b);
+  }
+  ctx->prof.clear();
+  *n_classes = nc;
+  return 0;
+}
+
 // embedding/multibit_embedder.py:43-47: bins k with band_lo <= k*sr/1024 <= band_hi,
 // frequencies evaluated like np.fft.rfftfreq (k * (sr / 1024) in float64).
 extern "C" int aw_band_bins(aw_ctx* ctx, int sample_rate, int* bin0, int* nbins) {
@@ -335,30 +394,40 @@ static int make_dims(aw_ctx* ctx, int n, int N, int sr, Dims* d) {
   return aw_band_bins(ctx, sr, &d->bin0, &d->nb);
 }
 
-// accumulators cleared once per pass: [peak_y u64][s2 f64][chan_sum 256 f64][bsum 256 f64] per clip
-#define AW_ACC_PER_CLIP (2 + 256 + 256)
+// per-clip peak of the synthesised waveform (u64 atomicMax, order independent) is the only
+// accumulator cleared per pass; every sum is a per-block partial reduced in fixed order.
 struct Acc {
-  unsigned long long* peak_y; double* s2; double* chan_sum; double* bsum;
+  unsigned long long* peak_y; double* s2_part; double* chan_part; double* bpart;
+  int mel_blocks, syn_tiles, p0b_blocks;
 };
-static Acc acc_view(aw_ctx* ctx, int n) {
-  Acc a;
-  double* base = (double*)ctx->accum.p;
-  a.peak_y = (unsigned long long*)base;
-  a.s2 = base + n;
-  a.chan_sum = base + 2 * (size_t)n;
-  a.bsum = base + 2 * (size_t)n + 256 * (size_t)n;
-  return a;
+static Acc acc_view(aw_ctx* ctx, const struct Dims& d);
+
+__global__ void k_iter_begin(unsigned long long* peak, int n, int* it) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) peak[i] = 0ull;
+  if (i == 0 && it) *it += 1;
 }
 
-__global__ void k_iter_begin(double* accum, size_t count, int* it) {
-  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i < count) accum[i] = 0.0;       // +0.0 == all-zero bits, valid for the u64 peak too
-  if (i == 0 && it) *it += 1;
+static int mel_blocks(const Dims& d) { return (d.T + AW_MEL_FRAMES - 1) / AW_MEL_FRAMES; }
+static int syn_tiles(const Dims& d) { return (d.T + 3 + AW_SYN_HOPS - 1) / AW_SYN_HOPS; }
+static int p0b_blocks(const Dims& d) { return (2 * d.Tp + AW_P0B_FRAMES - 1) / AW_P0B_FRAMES; }
+static size_t acc_doubles(const Dims& d) {
+  return (size_t)d.n * (1 + syn_tiles(d) + 256 * (size_t)mel_blocks(d) + 256 * (size_t)p0b_blocks(d));
+}
+static Acc acc_view(aw_ctx* ctx, const Dims& d) {
+  Acc a;
+  a.mel_blocks = mel_blocks(d); a.syn_tiles = syn_tiles(d); a.p0b_blocks = p0b_blocks(d);
+  double* base = (double*)ctx->accum.p;
+  a.peak_y = (unsigned long long*)base;
+  a.s2_part = base + d.n;
+  a.chan_part = a.s2_part + (size_t)d.n * a.syn_tiles;
+  a.bpart = a.chan_part + (size_t)d.n * 256 * a.mel_blocks;
+  return a;
 }
 
 static int ensure_net_ws(aw_ctx* ctx, const Dims& d, bool backward) {
   const size_t n = d.n, R = d.rows;
-  if (ensure(ctx->accum, n * AW_ACC_PER_CLIP * 8)) return 1;
+  if (ensure(ctx->accum, acc_doubles(d) * 8)) return 1;
   if (ensure(ctx->peakx, n * 8)) return 1;
   if (ensure(ctx->mag, n * d.T * d.nb * 4)) return 1;
   if (ensure(ctx->M, n * d.T * AW_NMEL * 4)) return 1;
@@ -408,11 +477,11 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
   {
     dim3 g((d.T + AW_MEL_FRAMES - 1) / AW_MEL_FRAMES, d.n);
     k_mel<<<g, 128, AW_MEL_FRAMES * d.nb * 4, st>>>((float*)ctx->mag.p, d.T, d.nb, sm,
-                                                    (float*)ctx->M.p, acc.chan_sum);
+                                                    (float*)ctx->M.p, acc.chan_part);
     ctx->launches++;
     AW_LAUNCH_CHECK();
     dim3 g2((d.Tp_pad + AW_P0_ROWS - 1) / AW_P0_ROWS, d.n);
-    k_p0<<<g2, 128, 0, st>>>((float*)ctx->M.p, d.T, d.Tp, d.Tp_pad, acc.chan_sum,
+    k_p0<<<g2, 128, 0, st>>>((float*)ctx->M.p, d.T, d.Tp, d.Tp_pad, acc.chan_part, acc.mel_blocks,
                              (float*)ctx->act[0].p, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p, tf);
     ctx->launches++;
     AW_LAUNCH_CHECK();
@@ -477,12 +546,13 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
   }
   dim3 g1((2 * d.Tp + AW_P0B_FRAMES - 1) / AW_P0B_FRAMES, d.n);
   k_p0_bwd_reduce<<<g1, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
-                                      (ChanStats*)ctx->cs.p, acc.bsum);
+                                      (ChanStats*)ctx->cs.p, acc.bpart);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   dim3 g2((d.T + AW_P0A_FRAMES - 1) / AW_P0A_FRAMES, d.n);
   k_p0_bwd_apply<<<g2, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
-                                     (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p, acc.bsum, sm,
+                                     (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p, acc.bpart,
+                                     acc.p0b_blocks, sm,
                                      d.nb, (float*)ctx->dA.p);
   ctx->launches++;
   AW_LAUNCH_CHECK();
@@ -546,8 +616,7 @@ static int launch_peak(aw_ctx* ctx, const float* x, int64_t stride, int n, int n
   return 0;
 }
 static int begin_pass(aw_ctx* ctx, int n, int* it, cudaStream_t st) {
-  const size_t cnt = (size_t)n * AW_ACC_PER_CLIP;
-  k_iter_begin<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>((double*)ctx->accum.p, cnt, it);
+  k_iter_begin<<<(n + 255) / 256, 256, 0, st>>>((unsigned long long*)ctx->accum.p, n, it);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
@@ -564,7 +633,7 @@ extern "C" int aw_detect_batch(aw_ctx* ctx, const float* d_audio, int n_clips, i
   if (ensure_net_ws(ctx, d, false)) return 1;
   SparseMel sm;
   if (get_mel(ctx, d.bin0, d.nb, &sm)) return 1;
-  const Acc acc = acc_view(ctx, d.n);
+  const Acc acc = acc_view(ctx, d);
   if (begin_pass(ctx, d.n, nullptr, st)) return 1;
   if (launch_peak(ctx, d_audio, stride, n_samples, d.n, (unsigned long long*)ctx->peakx.p, st)) return 1;
   AnaArgs a = ana_base(ctx, d);
@@ -642,7 +711,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
     dw.n = std::min(wave_clips, n_clips - w0);
     dw.rows = dw.n * dw.Tp_pad;
     // tensor maps are encoded for d.rows; a smaller last wave only uses a prefix of rows
-    const Acc acc = acc_view(ctx, dw.n);
+    const Acc acc = acc_view(ctx, dw);
     const float* x = d_audio + (size_t)w0 * stride;
     int* itc = (int*)ctx->itc.p;
 
@@ -687,14 +756,14 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       SynArgs s2 = syn_base(ctx, dw);
       s2.amp = (float*)ctx->dA.p; s2.ph = (float2*)ctx->ph_q.p; s2.scale = 0.5f;
       s2.y = (float*)ctx->y.p; s2.peak_y = acc.peak_y;
-      s2.dpad = (float*)ctx->dpad.p; s2.s2 = acc.s2;
+      s2.dpad = (float*)ctx->dpad.p; s2.s2_part = acc.s2_part;
       if (launch_syn<SYN_ADJ>(ctx, dw, s2, st)) return 1;
       AnaArgs a2 = ana_base(ctx, dw);
       a2.sig = (float*)ctx->dpad.p; a2.sig_stride = dw.L + AW_NFFT; a2.len = dw.L;
       a2.peak = acc.peak_y;
       a2.c = (float*)ctx->c.p; a2.m = (float*)ctx->m.p; a2.v = (float*)ctx->v.p;
       a2.cbest = (float*)ctx->cbest.p; a2.c0 = (float*)ctx->c0.p; a2.u = (float2*)ctx->ph_u.p;
-      a2.y = (float*)ctx->y.p; a2.s2 = acc.s2; a2.improved = (int*)ctx->improved.p;
+      a2.y = (float*)ctx->y.p; a2.s2_part = acc.s2_part; a2.s2_tiles = acc.syn_tiles; a2.improved = (int*)ctx->improved.p;
       a2.steps = (NadamStep*)ctx->steps.p; a2.it_ptr = itc;
       if (launch_ana<ANA_ADJ>(ctx, dw, a2, st)) return 1;
     }
@@ -748,11 +817,11 @@ extern "C" int aw_snr_batch(aw_ctx* ctx, const float* d_out, int64_t out_stride,
                             double* d_snr, double* d_snr_sum, void* stream) {
   AW_REQUIRE(ctx && d_out && d_target && d_snr, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (ensure(ctx->accum, (size_t)std::max(n_clips, 1) * AW_ACC_PER_CLIP * 8)) return 1;
-  AW_CUDA(cudaMemsetAsync(ctx->accum.p, 0, (size_t)n_clips * 16, st));
+  if (ensure(ctx->bstat, (size_t)std::max(n_clips, 1) * 16)) return 1;
+  AW_CUDA(cudaMemsetAsync(ctx->bstat.p, 0, (size_t)n_clips * 16, st));
   dim3 g(std::min((n + 2047) / 2048, 64), n_clips);
-  k_snr_partial<<<g, 256, 0, st>>>(d_out, out_stride, d_target, tgt_stride, n, (double*)ctx->accum.p);
-  k_snr_final<<<(n_clips + 127) / 128, 128, 0, st>>>((double*)ctx->accum.p, n_clips, d_snr, d_snr_sum);
+  k_snr_partial<<<g, 256, 0, st>>>(d_out, out_stride, d_target, tgt_stride, n, (double*)ctx->bstat.p);
+  k_snr_final<<<(n_clips + 127) / 128, 128, 0, st>>>((double*)ctx->bstat.p, n_clips, d_snr, d_snr_sum);
   ctx->launches += 2;
   AW_LAUNCH_CHECK();
   return 0;
@@ -800,10 +869,10 @@ extern "C" int aw_istft_band(aw_ctx* ctx, const float* d_mag, const float* d_pha
   Dims d;
   if (make_dims(ctx, n_clips, AW_HOP * (n_frames - 1) + 1, sample_rate, &d)) return 1;
   AW_REQUIRE(d.T == n_frames, "internal: frame count");
-  if (ensure(ctx->accum, (size_t)n_clips * AW_ACC_PER_CLIP * 8)) return 1;
+  if (ensure(ctx->accum, acc_doubles(d) * 8)) return 1;
   if (ensure(ctx->yoob, (size_t)n_clips * d.L * 4)) return 1;
   AW_CUDA(cudaMemsetAsync(ctx->yoob.p, 0, (size_t)n_clips * d.L * 4, st));
-  const Acc acc = acc_view(ctx, n_clips);
+  const Acc acc = acc_view(ctx, d);
   if (begin_pass(ctx, n_clips, nullptr, st)) return 1;
   SynArgs s = syn_base(ctx, d);
   s.amp = d_mag; s.ph = (const float2*)d_phasor; s.scale = 1.0f / AW_NFFT;

@@ -152,7 +152,8 @@ struct AnaArgs {
   const float* c0;             // ADJ: bounds are recomputed from c0
   const float2* u;             // ADJ
   const float* y;              // ADJ: y (to read sign of the peak sample)
-  const double* s2;            // ADJ: [clip] sum dy2*y2
+  const double* s2_part;       // ADJ: [clip][s2_tiles] per-tile partial sums of dy2*y2
+  int s2_tiles;
   const int* improved;         // ADJ: [clip] loss < best this iteration
   const NadamStep* steps;      // ADJ: [iters]
   const int* it_ptr;           // ADJ: device iteration counter
@@ -191,7 +192,9 @@ __global__ void __launch_bounds__(128) k_analysis(AnaArgs a) {
     const int nstar = (int)peak_index(pk);
     const float d1 = p1 + 1e-8f;
     const float d2 = __fdiv_rn(p1, d1) + 1e-8f;
-    const float s2 = (float)a.s2[clip];
+    double s2d = 0.0;                       // fixed-order sum of the synthesis tiles' partials
+    for (int i = 0; i < a.s2_tiles; ++i) s2d += a.s2_part[(long long)clip * a.s2_tiles + i];
+    const float s2 = (float)s2d;
     const float s1 = s2 * 1e-8f / d2;
     const float ystar = a.y[(long long)clip * L + nstar];
     const float corr = (ystar > 0.f ? 1.f : (ystar < 0.f ? -1.f : 0.f)) * (s2 / d2 + s1) / d1;
@@ -332,7 +335,7 @@ struct SynArgs {
   unsigned long long* peak_y;  // [clip]      (WAVE: atomicMax out; ADJ: in)
   // SYN_ADJ: dpad = ola (padded axis), s2 += dpad * y2[reflect]
   float* dpad;                 // [clip][L + 1024]
-  double* s2;                  // [clip]
+  double* s2_part;             // [clip][gridDim.x]
 };
 
 #define AW_SYN_FRAMES 32
@@ -445,7 +448,7 @@ __global__ void __launch_bounds__(128) k_synthesis(SynArgs a) {
       acc += (double)(d * y2);
     }
     acc = block_sum(acc, s_red);
-    if (tid == 0) atomicAdd(a.s2 + clip, acc);
+    if (tid == 0) a.s2_part[(long long)clip * gridDim.x + blockIdx.x] = acc;
   } else {
     unsigned long long pk = 0ull;
     float dx = 1.f;

@@ -26,7 +26,7 @@ struct ChanStats {      // per clip, per mel channel (forward, reused by backwar
 #define AW_MEL_FRAMES 32
 __global__ void __launch_bounds__(128) k_mel(const float* __restrict__ mag, int T, int nb,
                                              SparseMel sm, float* __restrict__ M,
-                                             double* __restrict__ chan_sum) {
+                                             double* __restrict__ chan_part) {
   extern __shared__ float s_a[];   // [AW_MEL_FRAMES][nb]
   const int clip = blockIdx.y, t0 = blockIdx.x * AW_MEL_FRAMES, c = threadIdx.x;
   const int nf = min(AW_MEL_FRAMES, T - t0);
@@ -42,9 +42,21 @@ __global__ void __launch_bounds__(128) k_mel(const float* __restrict__ mag, int 
     s1 += acc;
     s2 += (double)acc * acc;
   }
-  if (e1 > e0) {
-    atomicAdd(chan_sum + ((long long)clip * AW_NMEL + c) * 2, s1);
-    atomicAdd(chan_sum + ((long long)clip * AW_NMEL + c) * 2 + 1, s2);
+  // per-block partial sums, reduced in fixed order by the consumers (deterministic)
+  double* p = chan_part + (((long long)clip * gridDim.x + blockIdx.x) * AW_NMEL + c) * 2;
+  p[0] = s1;
+  p[1] = s2;
+}
+
+// sum of `nblk` per-block partials [clip][nblk][128][2] for channel c, in block order
+__device__ __forceinline__ void sum_partials(const double* __restrict__ part, int clip, int nblk, int c,
+                                             double& s1, double& s2) {
+  s1 = 0.0;
+  s2 = 0.0;
+  const double* p = part + ((long long)clip * nblk * AW_NMEL + c) * 2;
+  for (int b = 0; b < nblk; ++b) {
+    s1 += p[(long long)b * AW_NMEL * 2];
+    s2 += p[(long long)b * AW_NMEL * 2 + 1];
   }
 }
 
@@ -54,14 +66,14 @@ __global__ void __launch_bounds__(128) k_mel(const float* __restrict__ mag, int 
 // var/(var+eps), so mean_g = 0 and std_g^2 = T * sum_c var_c/(var_c+eps) / (128 T - 1).
 #define AW_P0_ROWS 32
 __global__ void __launch_bounds__(128) k_p0(const float* __restrict__ M, int T, int Tp, int Tp_pad,
-                                            const double* __restrict__ chan_sum,
+                                            const double* __restrict__ chan_part, int nblk,
                                             float* __restrict__ P0, ChanStats* __restrict__ cs,
                                             float* __restrict__ sigma_out, int round_tf32) {
   __shared__ double s_red[32];
   __shared__ float s_inv;
   const int clip = blockIdx.y, c = threadIdx.x, j0 = blockIdx.x * AW_P0_ROWS;
-  const double s1 = chan_sum[((long long)clip * AW_NMEL + c) * 2];
-  const double s2 = chan_sum[((long long)clip * AW_NMEL + c) * 2 + 1];
+  double s1, s2;
+  sum_partials(chan_part, clip, nblk, c, s1, s2);
   const double mu = s1 / T;
   double var = s2 / T - mu * mu;
   if (var < 0.0) var = 0.0;
@@ -287,7 +299,7 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
 __global__ void __launch_bounds__(128) k_p0_bwd_reduce(const float* __restrict__ dP0,
                                                        const float* __restrict__ M, int T, int Tp,
                                                        int Tp_pad, const ChanStats* __restrict__ cs,
-                                                       double* __restrict__ bsum) {
+                                                       double* __restrict__ bpart) {
   const int clip = blockIdx.y, c = threadIdx.x, t0 = blockIdx.x * AW_P0B_FRAMES;
   const ChanStats st = cs[(long long)clip * AW_NMEL + c];
   double s1 = 0.0, s2 = 0.0;
@@ -298,8 +310,9 @@ __global__ void __launch_bounds__(128) k_p0_bwd_reduce(const float* __restrict__
     s1 += dg;
     s2 += (double)dg * mh;
   }
-  atomicAdd(bsum + ((long long)clip * AW_NMEL + c) * 2, s1);
-  atomicAdd(bsum + ((long long)clip * AW_NMEL + c) * 2 + 1, s2);
+  double* p = bpart + (((long long)clip * gridDim.x + blockIdx.x) * AW_NMEL + c) * 2;
+  p[0] = s1;
+  p[1] = s2;
 }
 
 // pass 2: dM, then dA~[t][b] = sum_c mel[c][b] dM[t][c]
@@ -308,14 +321,15 @@ __global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ 
                                                       const float* __restrict__ M, int T, int Tp,
                                                       int Tp_pad, const ChanStats* __restrict__ cs,
                                                       const float* __restrict__ sigma_in,
-                                                      const double* __restrict__ bsum, SparseMel sm,
+                                                      const double* __restrict__ bpart, int nblk,
+                                                      SparseMel sm,
                                                       int nb, float* __restrict__ dA) {
   __shared__ double s_red[32];
   __shared__ float s_dm[AW_P0A_FRAMES][AW_NMEL];
   __shared__ float s_ab[3];
   const int clip = blockIdx.y, c = threadIdx.x, t0 = blockIdx.x * AW_P0A_FRAMES;
-  const double S1 = bsum[((long long)clip * AW_NMEL + c) * 2];
-  const double S2 = bsum[((long long)clip * AW_NMEL + c) * 2 + 1];
+  double S1, S2;
+  sum_partials(bpart, clip, nblk, c, S1, S2);
   const double tS1 = block_sum(S1, s_red);
   __syncthreads();
   const double tS2 = block_sum(S2, s_red);

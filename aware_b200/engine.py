@@ -67,6 +67,18 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.aw_launch_count(self._ctx))
 
+    def profile(self, on: bool):
+        _lib.check(self.lib.aw_profile_enable(self._ctx, int(on)))
+
+    def profile_read(self):
+        """[(n, k, epilogue, launches, total_ms)] of the tensor-core GEMMs since the last read."""
+        mx = 32
+        nc = C.c_int()
+        n, k, e = (C.c_int * mx)(), (C.c_int * mx)(), (C.c_int * mx)()
+        cnt, ms = (C.c_int64 * mx)(), (C.c_double * mx)()
+        _lib.check(self.lib.aw_profile_read(self._ctx, mx, C.byref(nc), n, k, e, cnt, ms))
+        return [(n[i], k[i], e[i], int(cnt[i]), float(ms[i])) for i in range(nc.value)]
+
     def band_bins(self, sample_rate: int):
         b0, nb = C.c_int(), C.c_int()
         _lib.check(self.lib.aw_band_bins(self._ctx, int(sample_rate), C.byref(b0), C.byref(nb)))

@@ -56,6 +56,12 @@ int aw_ctx_set_precision(aw_ctx* ctx, int prec);
 int aw_band_bins(aw_ctx* ctx, int sample_rate, int* bin0, int* nbins);
 /* number of CUDA kernels launched by this context since creation */
 int64_t aw_launch_count(aw_ctx* ctx);
+/* CUDA-event timing of the tensor-core GEMM launches, on the launching stream (bench.py's
+ * roofline).  aw_profile_read sums the launches recorded since the last read by
+ * (n, k, epilogue kind) and clears the record. */
+int aw_profile_enable(aw_ctx* ctx, int on);
+int aw_profile_read(aw_ctx* ctx, int max_classes, int* n_classes, int* cls_n, int* cls_k,
+                    int* cls_epi, int64_t* cls_count, double* cls_ms);
 
 /* ---- detection: AWAREDetector.detect (detection/multibit_detector.py:28-42) for a batch.
  * d_values: [n_clips][20] float32 tanh outputs. */
