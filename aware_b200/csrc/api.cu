@@ -954,17 +954,32 @@ static int fill_iir(IirArgs& a, const double* b, const double* av, const double*
 }
 
 #define AW_IIR_CHUNK 2048
+// warm > 0: chunk-parallel scan with `warm` look-back samples; warm <= 0: sequential
+// (one thread per clip), bit-identical to scipy's recurrence.
+static void iir_plan(IirArgs& ia, int n, int n_clips, int warm, dim3* grid) {
+  ia.n = n; ia.n_clips = n_clips;
+  if (warm > 0) {
+    ia.chunk = std::max(AW_IIR_CHUNK, (warm / 2 + 255) / 256 * 256);
+    ia.warm = warm;
+  } else {
+    ia.chunk = n;
+    ia.warm = 0;
+  }
+  ia.n_chunks = (n + ia.chunk - 1) / ia.chunk;
+  const long long items = (long long)n_clips * ia.n_chunks;
+  *grid = dim3((unsigned)((items + 127) / 128));
+}
+
 extern "C" int aw_attack_lfilter(aw_ctx* ctx, const float* d_in, int n_clips, int n,
                                  int64_t in_stride, const double* b, const double* a, int order,
                                  int warm, float* d_out, int64_t out_stride, void* stream) {
   AW_REQUIRE(ctx && d_in && d_out && b && a, "null argument");
   IirArgs ia;
   if (fill_iir(ia, b, a, nullptr, order)) return 1;
-  ia.n = n; ia.chunk = AW_IIR_CHUNK; ia.warm = warm;
+  dim3 g;
+  iir_plan(ia, n, n_clips, warm, &g);
   ia.x32 = d_in; ia.sx32 = in_stride; ia.n_x = n;
   ia.o32 = d_out; ia.so32 = out_stride;
-  const int chunks = (n + ia.chunk - 1) / ia.chunk;
-  dim3 g((chunks + 127) / 128, n_clips);
   k_iir<IIR_SRC_F32, IIR_DST_F32><<<g, 128, 0, (cudaStream_t)stream>>>(ia);
   ctx->launches++;
   AW_LAUNCH_CHECK();
@@ -985,11 +1000,11 @@ extern "C" int aw_attack_filtfilt(aw_ctx* ctx, const float* d_in, int n_clips, i
   ctx->ws_rows = 0;   // tensor maps over ga are stale now
   IirArgs ia;
   if (fill_iir(ia, b, a, zi, order)) return 1;
-  ia.n = next; ia.chunk = AW_IIR_CHUNK; ia.warm = warm; ia.padlen = pad; ia.use_zi = 1;
+  dim3 g;
+  iir_plan(ia, next, n_clips, warm, &g);
+  ia.padlen = pad; ia.use_zi = 1;
   ia.x32 = d_in; ia.sx32 = in_stride; ia.n_x = n;
   ia.o64 = (double*)ctx->ga.p; ia.so64 = next;
-  const int chunks = (next + ia.chunk - 1) / ia.chunk;
-  dim3 g((chunks + 127) / 128, n_clips);
   k_iir<IIR_SRC_ODDEXT, IIR_DST_F64><<<g, 128, 0, st>>>(ia);
   IirArgs ib = ia;
   ib.x64 = (double*)ctx->ga.p; ib.sx64 = next;

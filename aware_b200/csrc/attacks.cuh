@@ -83,6 +83,7 @@ struct IirArgs {
   double b[AW_IIR_MAXORD + 1], a[AW_IIR_MAXORD + 1], zi[AW_IIR_MAXORD];
   int order;
   int n;          // number of samples filtered (incl. extension)
+  int n_clips, n_chunks;
   int chunk, warm;
   int padlen;     // ODDEXT / REVTRIM: edge extension length (27)
   int use_zi;     // initial state = zi * first sample (filtfilt) else 0
@@ -104,10 +105,16 @@ __device__ __forceinline__ double iir_load(const IirArgs& a, int clip, int i) {
   return (double)p[j];
 }
 
+// One thread per (clip, chunk).  n_chunks == 1 is the sequential mode: one thread walks a whole
+// clip from the exact initial state and reproduces scipy's recurrence bit for bit (needed for
+// the direct-form band-stop, whose own round-off noise reaches 1e-6..1e-3: any re-start of the
+// recurrence lands on a different noise realisation).
 template <int SRC, int DST>
 __global__ void __launch_bounds__(128) k_iir(IirArgs a) {
-  const int clip = blockIdx.y;
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= (long long)a.n_clips * a.n_chunks) return;
+  const int clip = (int)(item / a.n_chunks);
+  const int ch = (int)(item - (long long)clip * a.n_chunks);
   const int start = ch * a.chunk;
   if (start >= a.n) return;
   const int end = min(start + a.chunk, a.n);

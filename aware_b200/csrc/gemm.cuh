@@ -307,14 +307,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------
 // exact fp32 GEMM (CUDA cores) + standalone epilogue with the same semantics
 // ---------------------------------------------------------------------------
-// D[rows][ldo] = A[rows][K] * B[N][K]^T ; 64x64 tile, 256 threads, 4x4 per thread
+// D[rows][ldo] = A[rows][K] * B[N][K]^T ; 64x64 tile, 256 threads, 4x4 per thread.
+// Products and sums are carried in float64 so the result is the correctly rounded fp32 of
+// the exact dot product (better than any fp32 summation order): this path is the
+// validation yardstick, not the fast path.
 __global__ void __launch_bounds__(256) k_gemm_exact(const float* __restrict__ A,
                                                     const float* __restrict__ B, int K, int N,
                                                     float* __restrict__ D, int ldo) {
   __shared__ float sa[16][64 + 1], sb[16][64 + 1];
   const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][4] = {};
+  double acc[4][4] = {};
   for (int k0 = 0; k0 < K; k0 += 16) {
     for (int i = threadIdx.x; i < 64 * 16; i += 256) {
       const int r = i >> 4, k = i & 15;
@@ -324,13 +327,13 @@ __global__ void __launch_bounds__(256) k_gemm_exact(const float* __restrict__ A,
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      float a[4], b[4];
+      double a[4], b[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { a[i] = sa[k][ty * 4 + i]; b[i] = sb[k][tx * 4 + i]; }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(256) k_gemm_exact(const float* __restrict__ A,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = c0 + tx * 4 + j;
-      if (c < N) D[(long long)(r0 + ty * 4 + i) * ldo + c] = acc[i][j];
+      if (c < N) D[(long long)(r0 + ty * 4 + i) * ldo + c] = (float)acc[i][j];
     }
 }
 

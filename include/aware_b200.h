@@ -119,7 +119,9 @@ int aw_attack_upfirdn(aw_ctx* ctx, const float* d_in, int n_clips, int n_in, int
                       const float* d_h_tf, int taps_per_phase, int up, int down, int first_out,
                       int n_out, float* d_out, int64_t out_stride, void* stream);
 /* A3/A4 LowPassFilter / HighPassFilter .apply: scipy.signal.lfilter(b, a, x) in float64
- * (attacks.py:413-416, 451-453).  order <= 8; warm = look-back samples for the chunked scan. */
+ * (attacks.py:413-416, 451-453).  order <= 8.  warm <= 0: sequential scan, one thread per clip,
+ * bit-identical to scipy; warm > 0: chunk-parallel scan with `warm` look-back samples (faster,
+ * agrees to the filter's own round-off noise). */
 int aw_attack_lfilter(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t in_stride,
                       const double* b, const double* a, int order, int warm, float* d_out,
                       int64_t out_stride, void* stream);
