@@ -1,6 +1,7 @@
 // aware_b200 C ABI (include/aware_b200.h): context, workspace and the batched
 // detect / embed / attack pipelines built from the kernels in this directory.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -53,18 +54,23 @@ struct aw_ctx {
   int64_t launches = 0;
   float* d_w[4] = {};    // forward weights  [kCp[l+1]][kCp[l]]
   float* d_wt[4] = {};   // transposed       [kCp[l]][kCp[l+1]]
+  __nv_bfloat16* d_w16[4] = {};    // bf16 copies (embed loop in bf16)
+  __nv_bfloat16* d_wt16[4] = {};
+  int num_sms = 148;
   float* d_window = nullptr;
   float2* d_twiddle = nullptr;
   std::vector<float> h_mel;
   float band_lo = 500.f, band_hi = 4000.f, tol_db = 6.f, threshold = 0.f;
   std::vector<MelCfg> mels;
   PFN_encodeTiled encode = nullptr;
-  CUtensorMap tm_w[4], tm_wt[4];
+  CUtensorMap tm_w[4], tm_wt[4], tm_w16[4], tm_wt16[4];
   // workspace (grow-only)
   Buf accum, peakx, mag, ph_u, ph_q, c0, c, m, v, cbest, dA, yoob, y, dpad, M, cs, sigma;
   Buf act[5], ga, gb, dh4, dp0, part, stat[5], bstat, values, best, improved, pattern, itc, steps;
   int ws_rows = 0;
-  CUtensorMap tm_act[4], tm_dh4, tm_ga1024, tm_ga512, tm_gb1024;
+  // activation tensor maps, [0] = float32 view, [1] = bf16 view of the same buffers
+  CUtensorMap tm_act[2][4], tm_dh4[2], tm_ga1024[2], tm_ga512[2], tm_gb1024[2];
+  Buf cvt_a, cvt_b;    // aw_gemm bf16 test hook
   // state of the last embed wave (for aw_embed_state)
   int last_n = 0, last_T = 0, last_nb = 0;
   // optional CUDA-event timing of the GEMM launches (aw_profile_*)
@@ -95,32 +101,44 @@ static int ensure(Buf& b, size_t bytes) {
   return 0;
 }
 
-static int make_map(aw_ctx* ctx, CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t K,
-                    uint32_t box_rows) {
+// 2-D K-major tensor map with 128-byte swizzle; one box row = 128 bytes of K.
+static int make_map(aw_ctx* ctx, CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t K,
+                    uint32_t box_rows, bool bf16) {
+  const uint64_t esz = bf16 ? 2 : 4;
   cuuint64_t gdim[2] = {K, rows};
-  cuuint64_t gstr[1] = {K * sizeof(float)};
-  cuuint32_t box[2] = {AW_GEMM_BK, box_rows};
+  cuuint64_t gstr[1] = {K * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = ctx->encode(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                           2, (void*)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed: %d", (int)r);
   return 0;
 }
 
 static int bn_for(int n) { return n >= 256 ? 256 : (n >= 128 ? 128 : 64); }
 
-template <int BN, int EPI>
+template <typename T, typename OT, int BN, int EPI>
 static int launch_tc(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, int rows, int n,
-                     int k, const EpiArgs& ep, cudaStream_t st) {
-  dim3 grid(rows / 128, n / BN);
+                     int k, const EpiArgsT<OT>& ep, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AW_CUDA(cudaFuncSetAttribute(k_gemm_tc<T, OT, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 gemm_tc_smem<BN>()));
+    attr_set = true;
+  }
+  const int n_row_tiles = rows / 128, n_col_tiles = n / BN;
+  const int tiles = n_row_tiles * n_col_tiles;
+  const int grid = std::min(tiles, ctx->num_sms);
   aw_ctx::ProfRec pr;
   if (ctx->prof_on) {
     pr.n = n; pr.k = k; pr.epi = EPI;
     pr.a = prof_event(ctx); pr.b = prof_event(ctx);
     cudaEventRecord(pr.a, st);
   }
-  k_gemm_tc<BN, EPI><<<grid, 192, gemm_tc_smem<BN>(), st>>>(ma, mb, k, ep);
+  k_gemm_tc<T, OT, BN, EPI><<<grid, AW_GEMM_THREADS, gemm_tc_smem<BN>(), st>>>(ma, mb, k, n_row_tiles,
+                                                                              n_col_tiles, ep);
   if (ctx->prof_on) {
     cudaEventRecord(pr.b, st);
     ctx->prof.push_back(pr);
@@ -130,17 +148,23 @@ static int launch_tc(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, 
   return 0;
 }
 
-template <int EPI>
-static int launch_gemm_epi(aw_ctx* ctx, const CUtensorMap& ma, const float* a,
-                           const CUtensorMap& mb, const float* b, int rows, int n, int k,
-                           const EpiArgs& ep, int prec, cudaStream_t st) {
-  if (prec == AW_PREC_TF32) {
-    switch (bn_for(n)) {
-      case 256: return launch_tc<256, EPI>(ctx, ma, mb, rows, n, k, ep, st);
-      case 128: return launch_tc<128, EPI>(ctx, ma, mb, rows, n, k, ep, st);
-      default: return launch_tc<64, EPI>(ctx, ma, mb, rows, n, k, ep, st);
-    }
+// tensor-core GEMM, operands of type T, output/activation type OT
+template <typename T, typename OT, int EPI>
+static int launch_tc_bn(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, int rows, int n,
+                        int k, const EpiArgsT<OT>& ep, cudaStream_t st) {
+  switch (bn_for(n)) {
+    case 256: return launch_tc<T, OT, 256, EPI>(ctx, ma, mb, rows, n, k, ep, st);
+    case 128: return launch_tc<T, OT, 128, EPI>(ctx, ma, mb, rows, n, k, ep, st);
+    default: return launch_tc<T, OT, 64, EPI>(ctx, ma, mb, rows, n, k, ep, st);
   }
+}
+
+// exact fp32 path: CUDA-core GEMM + stand-alone epilogue kernel
+template <int EPI>
+static int launch_exact(aw_ctx* ctx, const float* a, const float* b, int rows, int n, int k,
+                        const EpiArgsT<float>& ept, cudaStream_t st) {
+  EpiArgs ep;
+  ep.out = ept.out; ep.ldo = ept.ldo; ep.n_valid = n; ep.part = ept.part; ep.ldp = ept.ldp; ep.act = ept.act;
   dim3 grid(rows / 64, (n + 63) / 64);
   k_gemm_exact<<<grid, 256, 0, st>>>(a, b, k, n, ep.out, ep.ldo);
   ctx->launches++;
@@ -151,23 +175,6 @@ static int launch_gemm_epi(aw_ctx* ctx, const CUtensorMap& ma, const float* a,
     ctx->launches++;
     AW_LAUNCH_CHECK();
   }
-  return 0;
-}
-
-static int launch_gemm(aw_ctx* ctx, int epi, const CUtensorMap& ma, const float* a,
-                       const CUtensorMap& mb, const float* b, int rows, int n, int k,
-                       const EpiArgs& ep, cudaStream_t st) {
-  switch (epi) {
-    case EPI_FWD: return launch_gemm_epi<EPI_FWD>(ctx, ma, a, mb, b, rows, n, k, ep, ctx->prec, st);
-    case EPI_BWD: return launch_gemm_epi<EPI_BWD>(ctx, ma, a, mb, b, rows, n, k, ep, ctx->prec, st);
-    default: return launch_gemm_epi<EPI_PLAIN>(ctx, ma, a, mb, b, rows, n, k, ep, ctx->prec, st);
-  }
-}
-
-template <int BN, int EPI>
-static int set_smem_attr() {
-  AW_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               gemm_tc_smem<BN>()));
   return 0;
 }
 
@@ -214,9 +221,19 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
     AW_CUDA(cudaMalloc(&ctx->d_wt[l], wt.size() * 4));
     AW_CUDA(cudaMemcpy(ctx->d_w[l], w.data(), w.size() * 4, cudaMemcpyHostToDevice));
     AW_CUDA(cudaMemcpy(ctx->d_wt[l], wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
-    if (make_map(ctx, &ctx->tm_w[l], ctx->d_w[l], cop, cip, bn_for(cop))) return 1;
-    if (make_map(ctx, &ctx->tm_wt[l], ctx->d_wt[l], cip, cop, bn_for(cip))) return 1;
+    if (make_map(ctx, &ctx->tm_w[l], ctx->d_w[l], cop, cip, bn_for(cop), false)) return 1;
+    if (make_map(ctx, &ctx->tm_wt[l], ctx->d_wt[l], cip, cop, bn_for(cip), false)) return 1;
+    std::vector<__nv_bfloat16> w16(w.size()), wt16(wt.size());
+    for (size_t i = 0; i < w.size(); ++i) w16[i] = __float2bfloat16_rn(w[i]);
+    for (size_t i = 0; i < wt.size(); ++i) wt16[i] = __float2bfloat16_rn(wt[i]);
+    AW_CUDA(cudaMalloc(&ctx->d_w16[l], w16.size() * 2));
+    AW_CUDA(cudaMalloc(&ctx->d_wt16[l], wt16.size() * 2));
+    AW_CUDA(cudaMemcpy(ctx->d_w16[l], w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
+    AW_CUDA(cudaMemcpy(ctx->d_wt16[l], wt16.data(), wt16.size() * 2, cudaMemcpyHostToDevice));
+    if (make_map(ctx, &ctx->tm_w16[l], ctx->d_w16[l], cop, cip, bn_for(cop), true)) return 1;
+    if (make_map(ctx, &ctx->tm_wt16[l], ctx->d_wt16[l], cip, cop, bn_for(cip), true)) return 1;
   }
+  ctx->num_sms = prop.multiProcessorCount;
   AW_CUDA(cudaMalloc(&ctx->d_window, 1024 * 4));
   AW_CUDA(cudaMemcpy(ctx->d_window, model->window, 1024 * 4, cudaMemcpyHostToDevice));
   std::vector<float2> tw(1024);
@@ -227,10 +244,6 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
   AW_CUDA(cudaMalloc(&ctx->d_twiddle, 1024 * sizeof(float2)));
   AW_CUDA(cudaMemcpy(ctx->d_twiddle, tw.data(), 1024 * sizeof(float2), cudaMemcpyHostToDevice));
 
-  if (set_smem_attr<256, EPI_PLAIN>() || set_smem_attr<256, EPI_FWD>() || set_smem_attr<256, EPI_BWD>() ||
-      set_smem_attr<128, EPI_PLAIN>() || set_smem_attr<128, EPI_FWD>() || set_smem_attr<128, EPI_BWD>() ||
-      set_smem_attr<64, EPI_PLAIN>() || set_smem_attr<64, EPI_FWD>() || set_smem_attr<64, EPI_BWD>())
-    return 1;
   AW_CUDA(cudaFuncSetAttribute(k_analysis<ANA_MAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_ANA_SMEM));
   AW_CUDA(cudaFuncSetAttribute(k_analysis<ANA_INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_ANA_SMEM));
   AW_CUDA(cudaFuncSetAttribute(k_analysis<ANA_LOOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_ANA_SMEM));
@@ -248,6 +261,8 @@ extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
   for (int l = 0; l < 4; ++l) {
     cudaFree(ctx->d_w[l]);
     cudaFree(ctx->d_wt[l]);
+    cudaFree(ctx->d_w16[l]);
+    cudaFree(ctx->d_wt16[l]);
   }
   cudaFree(ctx->d_window);
   cudaFree(ctx->d_twiddle);
@@ -269,7 +284,8 @@ extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
 
 extern "C" int aw_ctx_set_precision(aw_ctx* ctx, int prec) {
   AW_REQUIRE(ctx, "null ctx");
-  AW_REQUIRE(prec == AW_PREC_TF32 || prec == AW_PREC_FP32, "unknown precision %d", prec);
+  AW_REQUIRE(prec == AW_PREC_TF32 || prec == AW_PREC_FP32 || prec == AW_PREC_BF16,
+             "unknown precision %d", prec);
   ctx->prec = prec;
   return 0;
 }
@@ -455,13 +471,15 @@ static int ensure_net_ws(aw_ctx* ctx, const Dims& d, bool backward) {
     remap |= b0 != ctx->ga.p || b1 != ctx->gb.p || b2 != ctx->dh4.p;
   }
   if (remap || ctx->ws_rows != d.rows) {
-    for (int l = 0; l < 4; ++l)
-      if (make_map(ctx, &ctx->tm_act[l], (float*)ctx->act[l].p, R, kCp[l], 128)) return 1;
-    if (ctx->ga.p) {
-      if (make_map(ctx, &ctx->tm_dh4, (float*)ctx->dh4.p, R, 64, 128)) return 1;
-      if (make_map(ctx, &ctx->tm_ga1024, (float*)ctx->ga.p, R, 1024, 128)) return 1;
-      if (make_map(ctx, &ctx->tm_ga512, (float*)ctx->ga.p, R, 512, 128)) return 1;
-      if (make_map(ctx, &ctx->tm_gb1024, (float*)ctx->gb.p, R, 1024, 128)) return 1;
+    for (int b = 0; b < 2; ++b) {
+      for (int l = 0; l < 4; ++l)
+        if (make_map(ctx, &ctx->tm_act[b][l], ctx->act[l].p, R, kCp[l], 128, b)) return 1;
+      if (ctx->ga.p) {
+        if (make_map(ctx, &ctx->tm_dh4[b], ctx->dh4.p, R, 64, 128, b)) return 1;
+        if (make_map(ctx, &ctx->tm_ga1024[b], ctx->ga.p, R, 1024, 128, b)) return 1;
+        if (make_map(ctx, &ctx->tm_ga512[b], ctx->ga.p, R, 512, 128, b)) return 1;
+        if (make_map(ctx, &ctx->tm_gb1024[b], ctx->gb.p, R, 1024, 128, b)) return 1;
+      }
     }
     ctx->ws_rows = d.rows;
   }
@@ -471,8 +489,44 @@ static int ensure_net_ws(aw_ctx* ctx, const Dims& d, bool backward) {
 // ---------------------------------------------------------------------------
 // detector forward from band magnitudes (ctx->mag) to values (+ optional backward seed)
 // ---------------------------------------------------------------------------
+// AT = activation storage type: float (fp32 / TF32 modes) or bf16 (bf16 mode)
+template <typename AT, int EPI>
+static int gemm_layer(aw_ctx* ctx, const CUtensorMap& ma, const void* a, const CUtensorMap& mb,
+                      const void* b, int rows, int n, int k, const EpiArgsT<AT>& ep, cudaStream_t st);
+
+template <>
+int gemm_layer<float, EPI_FWD>(aw_ctx* ctx, const CUtensorMap& ma, const void* a, const CUtensorMap& mb,
+                               const void* b, int rows, int n, int k, const EpiArgsT<float>& ep, cudaStream_t st) {
+  if (ctx->prec == AW_PREC_FP32) return launch_exact<EPI_FWD>(ctx, (const float*)a, (const float*)b, rows, n, k, ep, st);
+  return launch_tc_bn<float, float, EPI_FWD>(ctx, ma, mb, rows, n, k, ep, st);
+}
+template <>
+int gemm_layer<float, EPI_BWD>(aw_ctx* ctx, const CUtensorMap& ma, const void* a, const CUtensorMap& mb,
+                               const void* b, int rows, int n, int k, const EpiArgsT<float>& ep, cudaStream_t st) {
+  if (ctx->prec == AW_PREC_FP32) return launch_exact<EPI_BWD>(ctx, (const float*)a, (const float*)b, rows, n, k, ep, st);
+  return launch_tc_bn<float, float, EPI_BWD>(ctx, ma, mb, rows, n, k, ep, st);
+}
+template <>
+int gemm_layer<__nv_bfloat16, EPI_FWD>(aw_ctx* ctx, const CUtensorMap& ma, const void*, const CUtensorMap& mb,
+                                       const void*, int rows, int n, int k, const EpiArgsT<__nv_bfloat16>& ep,
+                                       cudaStream_t st) {
+  if (n >= 256) return launch_tc<__nv_bfloat16, __nv_bfloat16, 256, EPI_FWD>(ctx, ma, mb, rows, n, k, ep, st);
+  return launch_tc<__nv_bfloat16, __nv_bfloat16, 64, EPI_FWD>(ctx, ma, mb, rows, n, k, ep, st);
+}
+template <>
+int gemm_layer<__nv_bfloat16, EPI_BWD>(aw_ctx* ctx, const CUtensorMap& ma, const void*, const CUtensorMap& mb,
+                                       const void*, int rows, int n, int k, const EpiArgsT<__nv_bfloat16>& ep,
+                                       cudaStream_t st) {
+  return launch_tc<__nv_bfloat16, __nv_bfloat16, 256, EPI_BWD>(ctx, ma, mb, rows, n, k, ep, st);
+}
+
+template <typename AT> struct ModeOf { static constexpr int B = 0; };
+template <> struct ModeOf<__nv_bfloat16> { static constexpr int B = 1; };
+
+template <typename AT>
 static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseMel& sm,
                        cudaStream_t st) {
+  constexpr int B = ModeOf<AT>::B;
   const int tf = ctx->prec == AW_PREC_TF32;
   {
     dim3 g((d.T + AW_MEL_FRAMES - 1) / AW_MEL_FRAMES, d.n);
@@ -481,68 +535,78 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
     ctx->launches++;
     AW_LAUNCH_CHECK();
     dim3 g2((d.Tp_pad + AW_P0_ROWS - 1) / AW_P0_ROWS, d.n);
-    k_p0<<<g2, 128, 0, st>>>((float*)ctx->M.p, d.T, d.Tp, d.Tp_pad, acc.chan_part, acc.mel_blocks,
-                             (float*)ctx->act[0].p, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p, tf);
+    k_p0<AT><<<g2, 128, 0, st>>>((float*)ctx->M.p, d.T, d.Tp, d.Tp_pad, acc.chan_part, acc.mel_blocks,
+                                 (AT*)ctx->act[0].p, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p, tf);
     ctx->launches++;
     AW_LAUNCH_CHECK();
   }
   for (int l = 0; l < 4; ++l) {
     const int cin = kCp[l], cout = kCp[l + 1];
-    EpiArgs ep;
-    ep.out = (float*)ctx->act[l + 1].p; ep.ldo = cout; ep.n_valid = cout;
+    EpiArgsT<AT> ep;
+    ep.out = (AT*)ctx->act[l + 1].p; ep.ldo = cout;
     ep.part = (float*)ctx->part.p; ep.ldp = cout; ep.act = nullptr;
-    if (launch_gemm(ctx, EPI_FWD, ctx->tm_act[l], (float*)ctx->act[l].p, ctx->tm_w[l], ctx->d_w[l],
-                    d.rows, cout, cin, ep, st))
+    const CUtensorMap& mw = B ? ctx->tm_w16[l] : ctx->tm_w[l];
+    const void* w = B ? (const void*)ctx->d_w16[l] : (const void*)ctx->d_w[l];
+    if (gemm_layer<AT, EPI_FWD>(ctx, ctx->tm_act[B][l], ctx->act[l].p, mw, w, d.rows, cout, cin, ep, st))
       return 1;
     dim3 g((cout + 127) / 128, d.n);
     k_finalize_fwd<<<g, 128, 0, st>>>((float*)ctx->part.p, cout, d.tiles, cout, d.Tp,
                                       (float*)ctx->stat[l + 1].p);
     ctx->launches++;
     AW_LAUNCH_CHECK();
-    k_norm_act<<<d.rows / 4, 256, 0, st>>>((float*)ctx->act[l + 1].p, cout, d.Tp, d.Tp_pad,
-                                           (float*)ctx->stat[l + 1].p, tf && l < 3);
+    k_norm_act<AT><<<d.rows / 4, 256, 0, st>>>((AT*)ctx->act[l + 1].p, cout, d.Tp, d.Tp_pad,
+                                               (float*)ctx->stat[l + 1].p, tf && l < 3);
     ctx->launches++;
     AW_LAUNCH_CHECK();
   }
   return 0;
 }
 
+template <typename AT>
 static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseMel& sm,
                         cudaStream_t st) {
+  constexpr int B = ModeOf<AT>::B;
   const int tf = ctx->prec == AW_PREC_TF32;
-  float* ga = (float*)ctx->ga.p;
-  float* gb = (float*)ctx->gb.p;
-  struct Step { const CUtensorMap* ma; const float* a; int l; float* out; };
+  AT* ga = (AT*)ctx->ga.p;
+  AT* gb = (AT*)ctx->gb.p;
+  struct Step { const CUtensorMap* ma; const AT* a; int l; AT* out; };
   // l = index of the weight matrix: dP_l = dH_{l+1} * W_l
-  const Step steps[3] = {{&ctx->tm_dh4, (float*)ctx->dh4.p, 3, ga},
-                         {&ctx->tm_ga1024, ga, 2, gb},
-                         {&ctx->tm_gb1024, gb, 1, ga}};
+  const Step steps[3] = {{&ctx->tm_dh4[B], (AT*)ctx->dh4.p, 3, ga},
+                         {&ctx->tm_ga1024[B], ga, 2, gb},
+                         {&ctx->tm_gb1024[B], gb, 1, ga}};
   for (int s = 0; s < 3; ++s) {
     const int l = steps[s].l, k = kCp[l + 1], n = kCp[l];
-    EpiArgs ep;
-    ep.out = steps[s].out; ep.ldo = n; ep.n_valid = n;
-    ep.part = (float*)ctx->part.p; ep.ldp = n; ep.act = (float*)ctx->act[l].p;
-    if (launch_gemm(ctx, EPI_BWD, *steps[s].ma, steps[s].a, ctx->tm_wt[l], ctx->d_wt[l], d.rows, n,
-                    k, ep, st))
-      return 1;
+    EpiArgsT<AT> ep;
+    ep.out = steps[s].out; ep.ldo = n;
+    ep.part = (float*)ctx->part.p; ep.ldp = n; ep.act = (AT*)ctx->act[l].p;
+    const CUtensorMap& mw = B ? ctx->tm_wt16[l] : ctx->tm_wt[l];
+    const void* w = B ? (const void*)ctx->d_wt16[l] : (const void*)ctx->d_wt[l];
+    if (gemm_layer<AT, EPI_BWD>(ctx, *steps[s].ma, steps[s].a, mw, w, d.rows, n, k, ep, st)) return 1;
     dim3 g((n + 127) / 128, d.n);
     k_finalize_bwd<<<g, 128, 0, st>>>((float*)ctx->part.p, n, d.tiles, n, d.Tp,
                                       (float*)ctx->bstat.p);
     ctx->launches++;
     AW_LAUNCH_CHECK();
-    k_in_bwd_apply<<<d.rows / 4, 256, 0, st>>>(steps[s].out, (float*)ctx->act[l].p, n, d.Tp,
-                                               d.Tp_pad, (float*)ctx->stat[l].p,
-                                               (float*)ctx->bstat.p, tf);
+    k_in_bwd_apply<AT><<<d.rows / 4, 256, 0, st>>>(steps[s].out, (AT*)ctx->act[l].p, n, d.Tp,
+                                                   d.Tp_pad, (float*)ctx->stat[l].p,
+                                                   (float*)ctx->bstat.p, tf);
     ctx->launches++;
     AW_LAUNCH_CHECK();
   }
   {
-    EpiArgs ep;
-    ep.out = (float*)ctx->dp0.p; ep.ldo = 128; ep.n_valid = 128;
+    // dP0 = dH1 * W0 stays float32 (128 columns; feeds the fp32 front-end adjoints)
+    EpiArgsT<float> ep;
+    ep.out = (float*)ctx->dp0.p; ep.ldo = 128;
     ep.part = nullptr; ep.ldp = 0; ep.act = nullptr;
-    if (launch_gemm(ctx, EPI_PLAIN, ctx->tm_ga512, ga, ctx->tm_wt[0], ctx->d_wt[0], d.rows, 128,
-                    512, ep, st))
-      return 1;
+    if (B) {
+      if (launch_tc<__nv_bfloat16, float, 128, EPI_PLAIN>(ctx, ctx->tm_ga512[1], ctx->tm_wt16[0], d.rows, 128, 512, ep, st))
+        return 1;
+    } else if (ctx->prec == AW_PREC_FP32) {
+      if (launch_exact<EPI_PLAIN>(ctx, (const float*)ga, ctx->d_wt[0], d.rows, 128, 512, ep, st)) return 1;
+    } else {
+      if (launch_tc<float, float, 128, EPI_PLAIN>(ctx, ctx->tm_ga512[0], ctx->tm_wt[0], d.rows, 128, 512, ep, st))
+        return 1;
+    }
   }
   dim3 g1((2 * d.Tp + AW_P0B_FRAMES - 1) / AW_P0B_FRAMES, d.n);
   k_p0_bwd_reduce<<<g1, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
@@ -552,24 +616,24 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
   dim3 g2((d.T + AW_P0A_FRAMES - 1) / AW_P0A_FRAMES, d.n);
   k_p0_bwd_apply<<<g2, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
                                      (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p, acc.bpart,
-                                     acc.p0b_blocks, sm,
-                                     d.nb, (float*)ctx->dA.p);
+                                     acc.p0b_blocks, sm, d.nb, (float*)ctx->dA.p);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
 }
 
+template <typename AT>
 static int run_head(aw_ctx* ctx, const Dims& d, const float* pattern, float* values, float* losses,
                     int n_total, bool backward, cudaStream_t st) {
-  HeadArgs h;
-  h.P4 = (float*)ctx->act[4].p; h.Tp = d.Tp; h.Tp_pad = d.Tp_pad;
+  HeadArgs<AT> h;
+  h.P4 = (AT*)ctx->act[4].p; h.Tp = d.Tp; h.Tp_pad = d.Tp_pad;
   h.stat4 = (float*)ctx->stat[4].p;
   h.pattern = pattern; h.values = values; h.losses = losses;
   h.best = (float*)ctx->best.p; h.improved = (int*)ctx->improved.p;
-  h.dH4 = backward ? (float*)ctx->dh4.p : nullptr;
+  h.dH4 = backward ? (AT*)ctx->dh4.p : nullptr;
   h.it_ptr = (int*)ctx->itc.p; h.n_clips = n_total;
   h.round_tf32 = ctx->prec == AW_PREC_TF32;
-  k_head<<<d.n, 256, 0, st>>>(h);
+  k_head<AT><<<d.n, 256, 0, st>>>(h);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
@@ -641,10 +705,18 @@ extern "C" int aw_detect_batch(aw_ctx* ctx, const float* d_audio, int n_clips, i
   a.peak = (unsigned long long*)ctx->peakx.p;
   a.mag = (float*)ctx->mag.p;
   if (launch_ana<ANA_MAG>(ctx, d, a, st)) return 1;
-  if (net_forward(ctx, d, acc, sm, st)) return 1;
-  return run_head(ctx, d, nullptr, d_values, nullptr, d.n, false, st);
+  if (ctx->prec == AW_PREC_BF16) {
+    if (net_forward<__nv_bfloat16>(ctx, d, acc, sm, st)) return 1;
+    return run_head<__nv_bfloat16>(ctx, d, nullptr, d_values, nullptr, d.n, false, st);
+  }
+  if (net_forward<float>(ctx, d, acc, sm, st)) return 1;
+  return run_head<float>(ctx, d, nullptr, d_values, nullptr, d.n, false, st);
 }
 
+__global__ void k_to_bf16(const float* in, __nv_bfloat16* out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
 __global__ void k_pattern_to_float(const int32_t* p, float* o, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) o[i] = (float)p[i];
@@ -748,11 +820,18 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       a1.sig = (float*)ctx->y.p; a1.sig_stride = dw.L; a1.len = dw.L; a1.peak = acc.peak_y;
       a1.mag = (float*)ctx->mag.p; a1.ph = (float2*)ctx->ph_q.p;
       if (launch_ana<ANA_LOOP>(ctx, dw, a1, st)) return 1;
-      if (net_forward(ctx, dw, acc, sm, st)) return 1;
-      if (run_head(ctx, dw, (float*)ctx->pattern.p, (float*)ctx->values.p,
-                   d_losses ? d_losses + w0 : nullptr, n_clips, true, st))
-        return 1;
-      if (net_backward(ctx, dw, acc, sm, st)) return 1;
+      float* lp = d_losses ? d_losses + w0 : nullptr;
+      if (ctx->prec == AW_PREC_BF16) {
+        if (net_forward<__nv_bfloat16>(ctx, dw, acc, sm, st)) return 1;
+        if (run_head<__nv_bfloat16>(ctx, dw, (float*)ctx->pattern.p, (float*)ctx->values.p, lp, n_clips, true, st))
+          return 1;
+        if (net_backward<__nv_bfloat16>(ctx, dw, acc, sm, st)) return 1;
+      } else {
+        if (net_forward<float>(ctx, dw, acc, sm, st)) return 1;
+        if (run_head<float>(ctx, dw, (float*)ctx->pattern.p, (float*)ctx->values.p, lp, n_clips, true, st))
+          return 1;
+        if (net_backward<float>(ctx, dw, acc, sm, st)) return 1;
+      }
       SynArgs s2 = syn_base(ctx, dw);
       s2.amp = (float*)ctx->dA.p; s2.ph = (float2*)ctx->ph_q.p; s2.scale = 0.5f;
       s2.y = (float*)ctx->y.p; s2.peak_y = acc.peak_y;
@@ -885,12 +964,24 @@ extern "C" int aw_gemm(aw_ctx* ctx, const float* d_a, const float* d_b, float* d
   AW_REQUIRE(ctx && d_a && d_b && d_d, "null argument");
   AW_REQUIRE(rows % 128 == 0 && k % 32 == 0 && n % 64 == 0, "aw_gemm: unsupported shape");
   AW_REQUIRE(n % bn_for(n) == 0, "aw_gemm: n must be a multiple of its tile (%d)", bn_for(n));
+  cudaStream_t st = (cudaStream_t)stream;
+  EpiArgsT<float> ep;
+  ep.out = d_d; ep.ldo = n; ep.part = nullptr; ep.ldp = 0; ep.act = nullptr;
+  if (prec == AW_PREC_FP32) return launch_exact<EPI_PLAIN>(ctx, d_a, d_b, rows, n, k, ep, st);
   CUtensorMap ma, mb;
-  if (make_map(ctx, &ma, d_a, rows, k, 128)) return 1;
-  if (make_map(ctx, &mb, d_b, n, k, bn_for(n))) return 1;
-  EpiArgs ep;
-  ep.out = d_d; ep.ldo = n; ep.n_valid = n; ep.part = nullptr; ep.ldp = 0; ep.act = nullptr;
-  return launch_gemm_epi<EPI_PLAIN>(ctx, ma, d_a, mb, d_b, rows, n, k, ep, prec, (cudaStream_t)stream);
+  if (prec == AW_PREC_BF16) {
+    AW_REQUIRE(k % 64 == 0, "aw_gemm: bf16 needs k %% 64 == 0");
+    if (ensure(ctx->cvt_a, (size_t)rows * k * 2) || ensure(ctx->cvt_b, (size_t)n * k * 2)) return 1;
+    k_to_bf16<<<256, 256, 0, st>>>(d_a, (__nv_bfloat16*)ctx->cvt_a.p, (size_t)rows * k);
+    k_to_bf16<<<256, 256, 0, st>>>(d_b, (__nv_bfloat16*)ctx->cvt_b.p, (size_t)n * k);
+    ctx->launches += 2;
+    if (make_map(ctx, &ma, ctx->cvt_a.p, rows, k, 128, true)) return 1;
+    if (make_map(ctx, &mb, ctx->cvt_b.p, n, k, bn_for(n), true)) return 1;
+    return launch_tc_bn<__nv_bfloat16, float, EPI_PLAIN>(ctx, ma, mb, rows, n, k, ep, st);
+  }
+  if (make_map(ctx, &ma, d_a, rows, k, 128, false)) return 1;
+  if (make_map(ctx, &mb, d_b, n, k, bn_for(n), false)) return 1;
+  return launch_tc_bn<float, float, EPI_PLAIN>(ctx, ma, mb, rows, n, k, ep, st);
 }
 
 // ---------------------------------------------------------------------------

@@ -16,6 +16,7 @@
 //   parity tests, and for detection at margins below TF32 resolution).
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace aw {
@@ -143,35 +144,115 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-#define AW_GEMM_BK 32                     // 32 fp32 = one 128-byte swizzle row
 #define AW_GEMM_STAGES 4
+#define AW_GEMM_THREADS 320               // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+
+// Operand element: float -> kind::tf32 (32 elements per 128-byte swizzle row, K=8 per MMA),
+// __nv_bfloat16 -> kind::f16 (64 elements per row, K=16 per MMA).  Either way one k-block is
+// 128 bytes wide and one MMA consumes 32 bytes of it.
+template <typename T> struct GemmElem;
+template <> struct GemmElem<float> {
+  static constexpr int BK = 32;
+  static constexpr uint32_t FMT = 2;       // TF32
+  static __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc,
+                                             uint32_t acc) {
+    tc_mma_tf32(d, a, b, idesc, acc);
+  }
+};
+template <> struct GemmElem<__nv_bfloat16> {
+  static constexpr int BK = 64;
+  static constexpr uint32_t FMT = 1;       // BF16
+  static __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc,
+                                             uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d),
+        "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+};
+
+// 32 consecutive output / activation elements of one row <-> registers
+__device__ __forceinline__ void load_row32(const float* p, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p + i);
+    v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void load_row32(const __nv_bfloat16* p, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p + i);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[i + 2 * j] = __uint_as_float(w[j] << 16);
+      v[i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    }
+  }
+}
+__device__ __forceinline__ void store_row32(float* p, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4)
+    *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
+__device__ __forceinline__ void store_row32(__nv_bfloat16* p, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+      w[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p + i) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+template <typename OT>
+struct EpiArgsT {
+  OT* out;               // [rows][ldo]
+  int ldo;
+  float* part;           // [row_tiles][ldp][2] per-tile column partial sums (FWD/BWD)
+  int ldp;
+  const OT* act;         // BWD: P_{l-1} [rows][ldo] (post-LeakyReLU activations)
+};
 
 template <int BN>
 constexpr int gemm_tc_smem() {
   return AW_GEMM_STAGES * (128 * 128 + BN * 128) + 1024 /*align*/ + 256 /*barriers*/ +
-         2 * 4 * BN * 4 /*column partials*/;
+         2 * 2 * 4 * BN * 4 /*double-buffered column partials*/;
 }
 
-// grid = (row_tiles, N / BN), block = 192 threads:
-//   warp 0: TMA producer, warp 1: MMA issuer (+TMEM alloc), warps 2..5: epilogue.
-template <int BN, int EPI>
-__global__ void __launch_bounds__(192, 1)
+// Persistent tcgen05 GEMM.  grid = min(#tiles, #SMs); every CTA walks tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ... (column tile fastest, so the CTAs that run
+// concurrently share A row tiles in L2).  The fp32 accumulator is double-buffered in TMEM
+// (2 x BN columns): while the 8 epilogue warps drain tile i, the MMA warp already
+// accumulates tile i+1 and the TMA warp prefetches tile i+2's operands.
+template <typename T, typename OT, int BN, int EPI>
+__global__ void __launch_bounds__(AW_GEMM_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-          int K, EpiArgs ep) {
+          int K, int n_row_tiles, int n_col_tiles, EpiArgsT<OT> ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
+  constexpr int BK = GemmElem<T>::BK;
   constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE = A_BYTES + B_BYTES;
   uint8_t* tiles = smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + AW_GEMM_STAGES * STAGE);
   uint64_t* empty = full + AW_GEMM_STAGES;
-  uint64_t* acc_full = empty + AW_GEMM_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-  float* s_part = reinterpret_cast<float*>(smem + AW_GEMM_STAGES * STAGE + 256);  // [2][4][BN]
+  uint64_t* tfull = empty + AW_GEMM_STAGES;     // [2] accumulator ready
+  uint64_t* tempty = tfull + 2;                 // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_part = reinterpret_cast<float*>(smem + AW_GEMM_STAGES * STAGE + 256);  // [2][2][4][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row_tile = blockIdx.x, n0 = blockIdx.y * BN;
-  const int nkb = K / AW_GEMM_BK;
+  const int nkb = K / BK;
+  const int n_tiles = n_row_tiles * n_col_tiles;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -180,13 +261,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       mbar_init(full + s, 1);
       mbar_init(empty + s, 1);
     }
-    mbar_init(acc_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull + b, 1);
+      mbar_init(tempty + b, 8);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_slot)),
-                 "n"(BN)
+                 "n"(2 * BN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -196,110 +280,126 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % AW_GEMM_STAGES;
-        const uint32_t ph = (kb / AW_GEMM_STAGES) & 1;
-        mbar_wait(empty + s, ph ^ 1);
-        mbar_expect_tx(full + s, STAGE);
-        tma_load_2d(tiles + s * STAGE, &map_a, full + s, kb * AW_GEMM_BK, row_tile * 128);
-        tma_load_2d(tiles + s * STAGE + A_BYTES, &map_b, full + s, kb * AW_GEMM_BK, n0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = (tile / n_col_tiles) * 128, n0 = (tile % n_col_tiles) * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty + s, ph ^ 1);
+          mbar_expect_tx(full + s, STAGE);
+          tma_load_2d(tiles + s * STAGE, &map_a, full + s, kb * BK, row0);
+          tma_load_2d(tiles + s * STAGE + A_BYTES, &map_b, full + s, kb * BK, n0);
+          if (++s == AW_GEMM_STAGES) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
+    // ------------------------------- MMA issuer -------------------------------
     if (lane == 0) {
-      // instruction descriptor: D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
-      // K-major A/B, N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                             ((uint32_t)(128 >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % AW_GEMM_STAGES;
-        const uint32_t ph = (kb / AW_GEMM_STAGES) & 1;
-        mbar_wait(full + s, ph);
+      // instruction descriptor: D=F32 [4,6)=1, A/B format [7,10),[10,13), K-major A/B,
+      // N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (GemmElem<T>::FMT << 7) | (GemmElem<T>::FMT << 10) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int ab = it & 1;
+        mbar_wait(tempty + ab, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint64_t ad = make_sw128_desc(smem_u32(tiles + s * STAGE));
-        const uint64_t bd = make_sw128_desc(smem_u32(tiles + s * STAGE + A_BYTES));
+        const uint32_t d = tmem_base + (uint32_t)(ab * BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint64_t ad = make_sw128_desc(smem_u32(tiles + s * STAGE));
+          const uint64_t bd = make_sw128_desc(smem_u32(tiles + s * STAGE + A_BYTES));
 #pragma unroll
-        for (int k = 0; k < AW_GEMM_BK / 8; ++k) {
-          // advance 8 tf32 = 32 bytes inside the swizzle row: +2 in the (>>4) address field
-          tc_mma_tf32(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
-                      (kb | k) != 0);
+          for (int k = 0; k < 4; ++k)   // 4 x 32 bytes per 128-byte swizzle row
+            GemmElem<T>::mma(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          tc_commit(empty + s);
+          if (++s == AW_GEMM_STAGES) { s = 0; ph ^= 1; }
         }
-        tc_commit(empty + s);
+        tc_commit(tfull + ab);
       }
-      tc_commit(acc_full);
     }
   } else {
-    // ------------------------------ epilogue --------------------------------
+    // -------------------------------- epilogue --------------------------------
+    const int e = warp - 2;
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
-    const int row = row_tile * 128 + q * 32 + lane;
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    float* orow = ep.out + (long long)row * ep.ldo;
-    const float* arow = EPI == EPI_BWD ? ep.act + (long long)row * ep.ldo : nullptr;
+    const int half = e >> 2;                        // which half of the BN columns
+    constexpr int CHUNKS = BN / 64;                 // 32-column chunks per warp
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1;
+      const int row_tile = tile / n_col_tiles, n0 = (tile % n_col_tiles) * BN;
+      const int row = row_tile * 128 + q * 32 + lane;
+      OT* orow = ep.out + (long long)row * ep.ldo + n0 + half * (BN / 2);
+      const OT* arow = EPI == EPI_BWD ? ep.act + (long long)row * ep.ldo + n0 + half * (BN / 2) : nullptr;
+      float* sp = s_part + ab * (2 * 4 * BN);
+      float pa[32];
+      if (EPI == EPI_BWD) load_row32(arow, pa);     // overlaps the wait for the accumulator
+      mbar_wait(tfull + ab, (it >> 1) & 1);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      const int col = n0 + c0;
-      if (EPI == EPI_BWD) {
-        // d(IN out) = dP * LeakyReLU'(P);  IN out recovered from P
-        float hh[32];
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int c0 = half * (BN / 2) + c * 32;    // column inside the tile
+        float v[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0), v);
+        if (c == CHUNKS - 1) {                      // accumulator fully read: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tempty + ab)) : "memory");
+        }
+        if (EPI == EPI_BWD) {
+          // d(IN out) = dP * LeakyReLU'(P);  IN out recovered from P
+          float hh[32];
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 p = *reinterpret_cast<const float4*>(arow + col + i);
-          const float pp[4] = {p.x, p.y, p.z, p.w};
+          for (int i = 0; i < 32; ++i) {
+            const bool pos = pa[i] > 0.f;
+            v[i] = pos ? v[i] : AW_LEAKY * v[i];
+            hh[i] = (pos ? pa[i] : pa[i] * (1.0f / AW_LEAKY)) * v[i];
+          }
+          if (c + 1 < CHUNKS) load_row32(arow + (c + 1) * 32, pa);   // prefetch next chunk
+          store_row32(orow + c * 32, v);
+          const float s1 = warp_colsum32(v, lane);
+          const float s2 = warp_colsum32(hh, lane);
+          sp[(0 * 4 + q) * BN + c0 + lane] = s1;
+          sp[(1 * 4 + q) * BN + c0 + lane] = s2;
+        } else {
+          store_row32(orow + c * 32, v);
+          if (EPI == EPI_FWD) {
+            float sq[32];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const bool pos = pp[j] > 0.f;
-            v[i + j] = pos ? v[i + j] : AW_LEAKY * v[i + j];
-            hh[i + j] = (pos ? pp[j] : pp[j] * (1.0f / AW_LEAKY)) * v[i + j];
+            for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+            const float s1 = warp_colsum32(v, lane);
+            const float s2 = warp_colsum32(sq, lane);
+            sp[(0 * 4 + q) * BN + c0 + lane] = s1;
+            sp[(1 * 4 + q) * BN + c0 + lane] = s2;
           }
         }
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          if (col + i < ep.n_valid)
-            *reinterpret_cast<float4*>(orow + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        const float s1 = warp_colsum32(v, lane);
-        const float s2 = warp_colsum32(hh, lane);
-        s_part[(0 * 4 + q) * BN + c0 + lane] = s1;
-        s_part[(1 * 4 + q) * BN + c0 + lane] = s2;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          if (col + i < ep.n_valid)
-            *reinterpret_cast<float4*>(orow + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        if (EPI == EPI_FWD) {
-          float sq[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
-          const float s1 = warp_colsum32(v, lane);
-          const float s2 = warp_colsum32(sq, lane);
-          s_part[(0 * 4 + q) * BN + c0 + lane] = s1;
-          s_part[(1 * 4 + q) * BN + c0 + lane] = s2;
-        }
       }
-    }
-    if (EPI != EPI_PLAIN) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
-      const int t = threadIdx.x - 64;                  // 0..127
-      for (int c = t; c < BN; c += 128) {
-        float s1 = 0.f, s2 = 0.f;
+      if (EPI != EPI_PLAIN) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps
+        const int t = threadIdx.x - 64;                  // 0..255
+        for (int cc = t; cc < BN; cc += 256) {
+          float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          s1 += s_part[(0 * 4 + w) * BN + c];
-          s2 += s_part[(1 * 4 + w) * BN + c];
+          for (int w = 0; w < 4; ++w) {
+            s1 += sp[(0 * 4 + w) * BN + cc];
+            s2 += sp[(1 * 4 + w) * BN + cc];
+          }
+          float* p = ep.part + ((long long)row_tile * ep.ldp + n0 + cc) * 2;
+          p[0] = s1;
+          p[1] = s2;
         }
-        float* p = ep.part + ((long long)row_tile * ep.ldp + n0 + c) * 2;
-        p[0] = s1;
-        p[1] = s2;
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN)
                  : "memory");
   }
 }

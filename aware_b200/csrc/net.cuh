@@ -4,9 +4,33 @@
 // Layouts: spectra [clip][T][nbins]; mel [clip][T][128]; activations channels-last
 // [clip * Tp_pad + j][C] with Tp_pad = T' rounded up to 128 rows (pad rows are 0).
 #pragma once
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace aw {
+
+// activation element access (float for the fp32 / TF32 paths, bf16 for the bf16 embed path)
+__device__ __forceinline__ float act_ld(const float* p) { return *p; }
+__device__ __forceinline__ float act_ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void act_st(float* p, float v) { *p = v; }
+__device__ __forceinline__ void act_st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void act_ld4(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void act_ld4(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+  v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+__device__ __forceinline__ void act_st4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void act_st4(__nv_bfloat16* p, const float (&v)[4]) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a),
+                                            *reinterpret_cast<const uint32_t*>(&b));
+}
 
 struct SparseMel {
   // CSR over mel channels (band-relative columns) and CSC over band bins
@@ -65,9 +89,10 @@ __device__ __forceinline__ void sum_partials(const double* __restrict__ part, in
 // statistics: after InstanceNorm every channel has mean 0 and second moment
 // var/(var+eps), so mean_g = 0 and std_g^2 = T * sum_c var_c/(var_c+eps) / (128 T - 1).
 #define AW_P0_ROWS 32
+template <typename AT>
 __global__ void __launch_bounds__(128) k_p0(const float* __restrict__ M, int T, int Tp, int Tp_pad,
                                             const double* __restrict__ chan_part, int nblk,
-                                            float* __restrict__ P0, ChanStats* __restrict__ cs,
+                                            AT* __restrict__ P0, ChanStats* __restrict__ cs,
                                             float* __restrict__ sigma_out, int round_tf32) {
   __shared__ double s_red[32];
   __shared__ float s_inv;
@@ -102,7 +127,7 @@ __global__ void __launch_bounds__(128) k_p0(const float* __restrict__ M, int T, 
       p = 0.5f * (g0 + g1);
       if (round_tf32) p = to_tf32(p);
     }
-    P0[((long long)clip * Tp_pad + j) * AW_NMEL + c] = p;
+    act_st(P0 + ((long long)clip * Tp_pad + j) * AW_NMEL + c, p);
   }
 }
 
@@ -144,32 +169,35 @@ __global__ void __launch_bounds__(128) k_finalize_bwd(const float* __restrict__ 
 
 // ---- P = LeakyReLU(InstanceNorm(H)), in place; pad rows forced to 0 -----------
 // grid = (rows / 4), block = 256; C % 4 == 0
-__global__ void __launch_bounds__(256) k_norm_act(float* __restrict__ H, int C, int Tp, int Tp_pad,
+template <typename AT>
+__global__ void __launch_bounds__(256) k_norm_act(AT* __restrict__ H, int C, int Tp, int Tp_pad,
                                                   const float* __restrict__ stat, int round_tf32) {
   const int r0 = blockIdx.x * 4;
   const int c4 = C >> 2;
   for (int i = threadIdx.x; i < 4 * c4; i += 256) {
     const int row = r0 + i / c4, c = (i % c4) * 4;
     const int clip = row / Tp_pad, j = row - clip * Tp_pad;
-    float4* p = reinterpret_cast<float4*>(H + (long long)row * C + c);
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    AT* p = H + (long long)row * C + c;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
     if (j < Tp) {
-      const float4 h = *p;
+      float h[4];
+      act_ld4(p, h);
       const float4 s01 = *reinterpret_cast<const float4*>(stat + ((long long)clip * C + c) * 2);
       const float4 s23 = *reinterpret_cast<const float4*>(stat + ((long long)clip * C + c) * 2 + 4);
-      o.x = leaky((h.x - s01.x) * s01.y);
-      o.y = leaky((h.y - s01.z) * s01.w);
-      o.z = leaky((h.z - s23.x) * s23.y);
-      o.w = leaky((h.w - s23.z) * s23.w);
-      if (round_tf32) { o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w); }
+      o[0] = leaky((h[0] - s01.x) * s01.y);
+      o[1] = leaky((h[1] - s01.z) * s01.w);
+      o[2] = leaky((h[2] - s23.x) * s23.y);
+      o[3] = leaky((h[3] - s23.z) * s23.w);
+      if (round_tf32) { o[0] = to_tf32(o[0]); o[1] = to_tf32(o[1]); o[2] = to_tf32(o[2]); o[3] = to_tf32(o[3]); }
     }
-    *p = o;
+    act_st4(p, o);
   }
 }
 
 // ---- dH = rstd * (dHhat - a1 - Hhat * a2), in place on dHhat ------------------
-__global__ void __launch_bounds__(256) k_in_bwd_apply(float* __restrict__ dH,
-                                                      const float* __restrict__ P, int C, int Tp,
+template <typename AT>
+__global__ void __launch_bounds__(256) k_in_bwd_apply(AT* __restrict__ dH,
+                                                      const AT* __restrict__ P, int C, int Tp,
                                                       int Tp_pad, const float* __restrict__ stat,
                                                       const float* __restrict__ bstat,
                                                       int round_tf32) {
@@ -178,13 +206,12 @@ __global__ void __launch_bounds__(256) k_in_bwd_apply(float* __restrict__ dH,
   for (int i = threadIdx.x; i < 4 * c4; i += 256) {
     const int row = r0 + i / c4, c = (i % c4) * 4;
     const int clip = row / Tp_pad, j = row - clip * Tp_pad;
-    float4* p = reinterpret_cast<float4*>(dH + (long long)row * C + c);
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    AT* p = dH + (long long)row * C + c;
+    float oo[4] = {0.f, 0.f, 0.f, 0.f};
     if (j < Tp) {
-      const float4 d = *p;
-      const float4 a = *reinterpret_cast<const float4*>(P + (long long)row * C + c);
-      const float dd[4] = {d.x, d.y, d.z, d.w}, aa[4] = {a.x, a.y, a.z, a.w};
-      float oo[4];
+      float dd[4], aa[4];
+      act_ld4(p, dd);
+      act_ld4(P + (long long)row * C + c, aa);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const long long sidx = ((long long)clip * C + c + k) * 2;
@@ -194,35 +221,36 @@ __global__ void __launch_bounds__(256) k_in_bwd_apply(float* __restrict__ dH,
         oo[k] = rstd * (dd[k] - a1 - hh * a2);
         if (round_tf32) oo[k] = to_tf32(oo[k]);
       }
-      o = make_float4(oo[0], oo[1], oo[2], oo[3]);
     }
-    *p = o;
+    act_st4(p, oo);
   }
 }
 
 // ---- BRH head + loss + seed of the backward pass -------------------------------
 // one CTA (256 threads) per clip.  P4: [rows][64] (40 live channels).
+template <typename AT>
 struct HeadArgs {
-  const float* P4; int Tp, Tp_pad;
+  const AT* P4; int Tp, Tp_pad;
   const float* stat4;        // [clip][64][2]
   const float* pattern;      // [clip][20] (+-1) or null (detect only)
   float* values;             // [clip][20]
   float* losses;             // [iters][n_clips] or null
   float* best;               // [clip]
   int* improved;             // [clip]
-  float* dH4;                // [rows][64] or null
+  AT* dH4;                   // [rows][64] or null
   const int* it_ptr; int n_clips;
   int round_tf32;
 };
 
-__global__ void __launch_bounds__(256) k_head(HeadArgs a) {
+template <typename AT>
+__global__ void __launch_bounds__(256) k_head(HeadArgs<AT> a) {
   __shared__ double s_acc[4][64];
   __shared__ float s_z[64], s_dz[64], s_a1[64], s_a2[64];
   const int clip = blockIdx.x, tid = threadIdx.x;
   const int c = tid & 63, g = tid >> 6;
-  const float* P = a.P4 + (long long)clip * a.Tp_pad * 64;
+  const AT* P = a.P4 + (long long)clip * a.Tp_pad * 64;
   double acc = 0.0;
-  for (int j = g; j < a.Tp; j += 4) acc += P[(long long)j * 64 + c];
+  for (int j = g; j < a.Tp; j += 4) acc += act_ld(P + (long long)j * 64 + c);
   s_acc[g][c] = acc;
   __syncthreads();
   if (tid < 64) s_z[tid] = (float)((s_acc[0][tid] + s_acc[1][tid] + s_acc[2][tid] + s_acc[3][tid]) / a.Tp);
@@ -263,7 +291,7 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
   double q1 = 0.0, q2 = 0.0;
   const float dz = s_dz[c];
   for (int j = g; j < a.Tp; j += 4) {
-    const float p = P[(long long)j * 64 + c];
+    const float p = act_ld(P + (long long)j * 64 + c);
     const bool pos = p > 0.f;
     const float dh = pos ? dz : AW_LEAKY * dz;
     q1 += dh;
@@ -279,17 +307,17 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
   __syncthreads();
   const float rstd = a.stat4[((long long)clip * 64 + c) * 2 + 1];
   const float a1 = s_a1[c], a2 = s_a2[c];
-  float* D = a.dH4 + (long long)clip * a.Tp_pad * 64;
+  AT* D = a.dH4 + (long long)clip * a.Tp_pad * 64;
   for (int j = g; j < a.Tp_pad; j += 4) {
     float o = 0.f;
     if (j < a.Tp && c < 2 * AW_NBITS) {
-      const float p = P[(long long)j * 64 + c];
+      const float p = act_ld(P + (long long)j * 64 + c);
       const bool pos = p > 0.f;
       const float dh = pos ? dz : AW_LEAKY * dz;
       o = rstd * (dh - a1 - (pos ? p : p * (1.0f / AW_LEAKY)) * a2);
       if (a.round_tf32) o = to_tf32(o);
     }
-    D[(long long)j * 64 + c] = o;
+    act_st(D + (long long)j * 64 + c, o);
   }
 }
 

@@ -48,6 +48,7 @@ class Engine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.aw_ctx_create(C.byref(self._ctx), self.device.index, C.byref(m)))
         self.threshold = float(threshold)
+        self.embed_precision = None      # None: same as `precision`; "bf16" speeds up the embed loop
         self.set_precision(precision)
 
     def __del__(self):
@@ -59,10 +60,25 @@ class Engine:
             pass
 
     # ------------------------------------------------------------------ misc
+    _PREC = {"tf32": _lib.PREC_TF32, "fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+
     def set_precision(self, precision: str):
-        code = {"tf32": _lib.PREC_TF32, "fp32": _lib.PREC_FP32}[precision]
-        _lib.check(self.lib.aw_ctx_set_precision(self._ctx, code))
+        """GEMM arithmetic of the detector stack: "tf32" (tcgen05, TF32 operands), "fp32" (CUDA
+        cores, validation) or "bf16" (tcgen05, bf16 operands and bf16 activation storage)."""
+        _lib.check(self.lib.aw_ctx_set_precision(self._ctx, self._PREC[precision]))
         self.precision = precision
+
+    def _with_precision(self, precision):
+        class _Ctx:
+            def __enter__(c):
+                c.prev = self.precision
+                if precision and precision != c.prev:
+                    self.set_precision(precision)
+
+            def __exit__(c, *a):
+                if self.precision != c.prev:
+                    self.set_precision(c.prev)
+        return _Ctx()
 
     def launch_count(self) -> int:
         return int(self.lib.aw_launch_count(self._ctx))
@@ -101,7 +117,8 @@ class Engine:
         return out
 
     def embed(self, audio: torch.Tensor, sample_rate: int, pattern: torch.Tensor, iters: int = 400,
-              scale: torch.Tensor | None = None, wave_clips: int = 0, return_losses: bool = False):
+              scale: torch.Tensor | None = None, wave_clips: int = 0, return_losses: bool = False,
+              precision: str | None = None):
         """[n, N] + [n, 20] int32 (+-1) -> [n, 256*(N//256)] watermarked, peak-normalised
         (AWAREEmbedder.embed for a batch); optionally multiplied per clip by `scale`."""
         x = self._audio(audio)
@@ -114,9 +131,10 @@ class Engine:
         best = torch.empty((n,), dtype=torch.float32, device=x.device)
         losses = torch.zeros((max(iters, 1), n), dtype=torch.float32, device=x.device) if return_losses else None
         sc = scale.to(device=x.device, dtype=torch.float32).contiguous() if scale is not None else None
-        _lib.check(self.lib.aw_embed_batch(self._ctx, _ptr(x), n, N, x.stride(0), int(sample_rate),
-                                           _ptr(pat), int(iters), _ptr(sc), _ptr(out), out.stride(0),
-                                           _ptr(best), _ptr(losses), int(wave_clips), _stream()))
+        with self._with_precision(precision or self.embed_precision):
+            _lib.check(self.lib.aw_embed_batch(self._ctx, _ptr(x), n, N, x.stride(0), int(sample_rate),
+                                               _ptr(pat), int(iters), _ptr(sc), _ptr(out), out.stride(0),
+                                               _ptr(best), _ptr(losses), int(wave_clips), _stream()))
         if return_losses:
             return out, best, losses
         return out
@@ -172,7 +190,7 @@ class Engine:
         rows, k = a.shape
         n = b.shape[0]
         out = torch.empty((rows, n), dtype=torch.float32, device=a.device)
-        prec = {"tf32": _lib.PREC_TF32, "fp32": _lib.PREC_FP32}[precision or self.precision]
+        prec = self._PREC[precision or self.precision]
         _lib.check(self.lib.aw_gemm(self._ctx, _ptr(a.contiguous()), _ptr(b.contiguous()), _ptr(out),
                                     rows, n, k, prec, _stream()))
         return out

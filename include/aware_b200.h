@@ -31,7 +31,8 @@ typedef struct aw_ctx aw_ctx;
 /* GEMM arithmetic for the detector's 1x1-conv stack. */
 enum {
   AW_PREC_TF32 = 0, /* tcgen05 tensor cores, TF32 operands, fp32 accumulate (default) */
-  AW_PREC_FP32 = 1  /* CUDA-core fp32 (validation / sub-TF32 margins)                */
+  AW_PREC_FP32 = 1, /* CUDA-core GEMMs with float64 accumulation (validation yardstick)       */
+  AW_PREC_BF16 = 2  /* tcgen05, bf16 operands AND bf16 activation storage (embed loop speed) */
 };
 
 /* Model description handed over once (reference: utils/models/load_model.py:6-76,

@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 OUT = os.path.join(ROOT, "gpurun_out")
 
-STAGES = ["stft", "istft", "attacks", "detect_fp32", "gemm_tc", "detect_tf32", "embed1_fp32",
+STAGES = ["gradmap", "stft", "istft", "attacks", "detect_fp32", "gemm_tc", "detect_tf32", "embed1_fp32",
           "embed1_tf32", "embed3", "embed_full", "timing"]
 
 
@@ -150,16 +150,21 @@ def stage_gemm_tc(res):
     eng = _engine("tf32")
     torch.manual_seed(0)
     for rows, n, k in ((128, 64, 32), (128, 64, 64), (256, 128, 128), (256, 256, 512), (384, 512, 128),
-                       (256, 1024, 1024), (1280, 1024, 512), (256, 64, 1024), (256, 128, 512), (256, 1024, 64)):
+                       (256, 1024, 1024), (1280, 1024, 512), (256, 64, 1024), (256, 128, 512), (256, 1024, 64),
+                       (128 * 300, 1024, 1024), (128 * 149, 512, 128)):
         a = torch.randn(rows, k, device="cuda")
         b = torch.randn(n, k, device="cuda") / k ** 0.5
         want = (a.double() @ b.double().T)
         got_tc = eng.gemm(a, b, "tf32").double()
         got_ex = eng.gemm(a, b, "fp32").double()
+        r = dict(tf32_rel=float((got_tc - want).abs().max().item() / (want.abs().max().item())),
+                 fp32_rel=float((got_ex - want).abs().max().item() / (want.abs().max().item())))
+        if k % 64 == 0:
+            got_bf = eng.gemm(a, b, "bf16").double()
+            want_bf = a.bfloat16().double() @ b.bfloat16().double().T
+            r["bf16_rel_vs_bf16_inputs"] = float((got_bf - want_bf).abs().max().item() / want_bf.abs().max().item())
         torch.cuda.synchronize()
-        scale = want.abs().max().item()
-        res["%dx%dx%d" % (rows, n, k)] = dict(tf32_rel=float((got_tc - want).abs().max().item() / scale),
-                                              fp32_rel=float((got_ex - want).abs().max().item() / scale))
+        res["%dx%dx%d" % (rows, n, k)] = r
 
 
 def _embed_iters(res, precision, iters, sr=16000, secs=1.0, idx=(0, 1)):
@@ -201,6 +206,43 @@ def stage_embed1_tf32(res):
     _embed_iters(res, "tf32", 1)
 
 
+def stage_gradmap(res):
+    """Structure of the 1-iteration gradient error vs the float64 kernel model."""
+    import numpy as np
+    import torch
+    import aware_oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from kernel_model import Model
+    eng = _engine("fp32")
+    for sr, secs in ((44100, 0.8), (16000, 1.0), (44100, 1.37)):
+        x = _clips([0], secs, sr)
+        pat = np.stack([O.encode_bits(O.synth_bits(8)[0])])
+        eng.embed(torch.from_numpy(x).cuda(), sr, torch.from_numpy(pat), iters=1)
+        T = 1 + x.shape[1] // 256
+        g = eng.embed_state("m", 1, T, sr).cpu().numpy()[0] / 0.1
+        keep = {}
+        O.embed(x[0], sr, pat[0], num_iters=1, keep=keep)
+        fi, _ = O.band_indices(sr)
+        B = len(fi)
+        g_ref = keep["grads"][0].numpy().reshape(B, T).T
+        mdl = Model(O.make_weights(), O.mel_basis(), fi)
+        mdl.forward(mdl.init(x[0]), pat[0].astype(np.float64))
+        g64 = mdl.backward(pat[0].astype(np.float64))
+        e = np.abs(g - g64)
+        er = np.abs(g_ref - g64)
+        med = float(np.median(np.abs(g64)))
+        by_t = e.max(1)
+        by_b = e.max(0)
+        top_t = np.argsort(-by_t)[:8]
+        top_b = np.argsort(-by_b)[:8]
+        res["sr%d_s%g" % (sr, secs)] = dict(
+            T=T, B=B, median_abs_g=med, rms_err_gpu=float(np.sqrt((e ** 2).mean())),
+            rms_err_torch=float(np.sqrt((er ** 2).mean())), max_err_gpu=float(e.max()), max_err_torch=float(er.max()),
+            top_frames=[(int(t), float(by_t[t])) for t in top_t], top_bins=[(int(b), float(by_b[b])) for b in top_b],
+            median_err_gpu=float(np.median(e)), median_err_torch=float(np.median(er)),
+            nstar_frame=int(mdl.s["nstar"] // 256))
+
+
 def stage_embed3(res):
     _embed_iters(res.setdefault("fp32", {}), "fp32", 3)
     _embed_iters(res.setdefault("tf32", {}), "tf32", 3)
@@ -210,8 +252,9 @@ def stage_embed_full(res):
     import numpy as np
     import torch
     import aware_oracle as O
-    for precision in ("tf32", "fp32"):
-        eng = _engine(precision)
+    for precision in ("tf32", "bf16", "fp32"):
+        eng = _engine("tf32" if precision == "bf16" else precision)
+        eng.embed_precision = precision
         sr = 16000
         x = _clips([1, 2, 3], 2.0, sr)
         bits = O.synth_bits(8)[1:4]
@@ -238,9 +281,10 @@ def stage_timing(res):
     import torch
     from aware_b200.synth import synth_batch, synth_bits
     from aware_b200.utils.watermark import PatternEncoder
-    eng = _engine("tf32")
     sr = 44100
-    for n, iters in ((32, 20), (128, 10)):
+    for n, iters, prec in ((32, 20, "tf32"), (128, 10, "tf32"), (128, 10, "bf16")):
+        eng = _engine("tf32")
+        eng.embed_precision = prec
         x = torch.from_numpy(synth_batch(n, 10.0, sr)).cuda()
         pat = torch.from_numpy(np.stack([PatternEncoder()(b) for b in synth_bits(n)]))
         eng.embed(x, sr, pat, iters=2)
@@ -253,7 +297,7 @@ def stage_timing(res):
         v = eng.detect(out, sr)
         torch.cuda.synchronize()
         dd = time.time() - t1
-        res["n%d" % n] = dict(ms_per_iter=1e3 * dt / iters, est_400it_audio_s_per_s=n * 10.0 / (dt / iters * 400),
+        res["n%d_%s" % (n, prec)] = dict(ms_per_iter=1e3 * dt / iters, est_400it_audio_s_per_s=n * 10.0 / (dt / iters * 400),
                               detect_ms=1e3 * dd, detect_audio_s_per_s=n * 10.0 / dd)
 
 
