@@ -58,7 +58,8 @@ struct aw_ctx {
   __nv_bfloat16* d_wt16[4] = {};
   int num_sms = 148;
   float* d_window = nullptr;
-  float2* d_twiddle = nullptr;
+  float2* d_twiddle = nullptr;   // [k1][lane] = exp(2 pi i lane k1 / 1024)
+  float* d_env256 = nullptr;     // interior overlap-add envelope sum_r w^2[j + 256 r]
   std::vector<float> h_mel;
   float band_lo = 500.f, band_hi = 4000.f, tol_db = 6.f, threshold = 0.f;
   std::vector<MelCfg> mels;
@@ -237,20 +238,21 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
   AW_CUDA(cudaMalloc(&ctx->d_window, 1024 * 4));
   AW_CUDA(cudaMemcpy(ctx->d_window, model->window, 1024 * 4, cudaMemcpyHostToDevice));
   std::vector<float2> tw(1024);
-  for (int j = 0; j < 1024; ++j) {
-    const double a = 2.0 * M_PI * j / 1024.0;
-    tw[j] = make_float2((float)cos(a), (float)sin(a));
-  }
+  for (int k1 = 0; k1 < 32; ++k1)
+    for (int l = 0; l < 32; ++l) {
+      const double a = 2.0 * M_PI * (double)(l * k1) / 1024.0;
+      tw[k1 * 32 + l] = make_float2((float)cos(a), (float)sin(a));
+    }
   AW_CUDA(cudaMalloc(&ctx->d_twiddle, 1024 * sizeof(float2)));
   AW_CUDA(cudaMemcpy(ctx->d_twiddle, tw.data(), 1024 * sizeof(float2), cudaMemcpyHostToDevice));
-
-  AW_CUDA(cudaFuncSetAttribute(k_analysis<ANA_MAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_ANA_SMEM));
-  AW_CUDA(cudaFuncSetAttribute(k_analysis<ANA_INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_ANA_SMEM));
-  AW_CUDA(cudaFuncSetAttribute(k_analysis<ANA_LOOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_ANA_SMEM));
-  AW_CUDA(cudaFuncSetAttribute(k_analysis<ANA_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_ANA_SMEM));
-  AW_CUDA(cudaFuncSetAttribute(k_synthesis<SYN_OOB>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_SYN_SMEM));
-  AW_CUDA(cudaFuncSetAttribute(k_synthesis<SYN_WAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_SYN_SMEM));
-  AW_CUDA(cudaFuncSetAttribute(k_synthesis<SYN_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_SYN_SMEM));
+  std::vector<float> env(256);
+  for (int j = 0; j < 256; ++j) {
+    float e = 0.f;                       // same order as ola_envelope: ascending frame index
+    for (int r = 3; r >= 0; --r) e = fmaf(model->window[j + 256 * r], model->window[j + 256 * r], e);
+    env[j] = e;
+  }
+  AW_CUDA(cudaMalloc(&ctx->d_env256, 256 * 4));
+  AW_CUDA(cudaMemcpy(ctx->d_env256, env.data(), 256 * 4, cudaMemcpyHostToDevice));
   *out = ctx;
   return 0;
 }
@@ -266,6 +268,7 @@ extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
   }
   cudaFree(ctx->d_window);
   cudaFree(ctx->d_twiddle);
+  cudaFree(ctx->d_env256);
   for (auto& mc : ctx->mels) {
     cudaFree(mc.rowptr); cudaFree(mc.col); cudaFree(mc.val);
     cudaFree(mc.colptr); cudaFree(mc.row); cudaFree(mc.valT);
@@ -643,7 +646,7 @@ static AnaArgs ana_base(aw_ctx* ctx, const Dims& d) {
   AnaArgs a;
   memset(&a, 0, sizeof(a));
   a.T = d.T; a.bin0 = d.bin0; a.nbins = d.nb;
-  a.window = ctx->d_window; a.twiddle = ctx->d_twiddle;
+  a.window = ctx->d_window; a.twiddle = ctx->d_twiddle; a.env256 = ctx->d_env256;
   a.tol_ratio = (float)pow(10.0, -(double)ctx->tol_db / 20.0);
   return a;
 }
@@ -651,24 +654,52 @@ static SynArgs syn_base(aw_ctx* ctx, const Dims& d) {
   SynArgs s;
   memset(&s, 0, sizeof(s));
   s.T = d.T; s.L = d.L; s.bin0 = d.bin0; s.nbins = d.nb;
-  s.window = ctx->d_window; s.twiddle = ctx->d_twiddle;
+  s.window = ctx->d_window; s.twiddle = ctx->d_twiddle; s.env256 = ctx->d_env256;
   return s;
 }
+template <int MODE, int K2LO, int K2HI>
+static int launch_ana_k(aw_ctx* ctx, const Dims& d, const AnaArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AW_CUDA(cudaFuncSetAttribute(k_analysis<MODE, K2LO, K2HI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 AW_ANA_SMEM));
+    attr_set = true;
+  }
+  dim3 g((d.T + AW_ANA_FRAMES - 1) / AW_ANA_FRAMES, d.n);
+  k_analysis<MODE, K2LO, K2HI><<<g, 128, AW_ANA_SMEM, st>>>(a);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+// the band's 32-bin groups select a compile-time specialisation:
+// 44.1 kHz (bins 12..92) -> groups 0..2, 16 kHz (bins 32..256) -> groups 1..8, else generic
 template <int MODE>
 static int launch_ana(aw_ctx* ctx, const Dims& d, const AnaArgs& a, cudaStream_t st) {
-  dim3 g((d.T + AW_ANA_FRAMES - 1) / AW_ANA_FRAMES, d.n);
-  k_analysis<MODE><<<g, 128, AW_ANA_SMEM, st>>>(a);
+  const int lo = d.bin0 >> 5, hi = (d.bin0 + d.nb - 1) >> 5;
+  if (hi <= 2) return launch_ana_k<MODE, 0, 2>(ctx, d, a, st);
+  if (lo >= 1 && hi <= 8) return launch_ana_k<MODE, 1, 8>(ctx, d, a, st);
+  return launch_ana_k<MODE, 0, 15>(ctx, d, a, st);
+}
+template <int MODE, int K2LO, int K2HI>
+static int launch_syn_k(aw_ctx* ctx, const Dims& d, const SynArgs& s, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AW_CUDA(cudaFuncSetAttribute(k_synthesis<MODE, K2LO, K2HI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 AW_SYN_SMEM));
+    attr_set = true;
+  }
+  dim3 g((d.T + 3 + AW_SYN_HOPS - 1) / AW_SYN_HOPS, d.n);
+  k_synthesis<MODE, K2LO, K2HI><<<g, 128, AW_SYN_SMEM, st>>>(s);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
 }
 template <int MODE>
 static int launch_syn(aw_ctx* ctx, const Dims& d, const SynArgs& s, cudaStream_t st) {
-  dim3 g((d.T + 3 + AW_SYN_HOPS - 1) / AW_SYN_HOPS, d.n);
-  k_synthesis<MODE><<<g, 128, AW_SYN_SMEM, st>>>(s);
-  ctx->launches++;
-  AW_LAUNCH_CHECK();
-  return 0;
+  const int lo = d.bin0 >> 5, hi = (d.bin0 + d.nb - 1) >> 5;
+  if (hi <= 2) return launch_syn_k<MODE, 0, 2>(ctx, d, s, st);
+  if (lo >= 1 && hi <= 8) return launch_syn_k<MODE, 1, 8>(ctx, d, s, st);
+  return launch_syn_k<MODE, 0, 15>(ctx, d, s, st);
 }
 static int launch_peak(aw_ctx* ctx, const float* x, int64_t stride, int n, int n_clips,
                        unsigned long long* peak, cudaStream_t st) {
@@ -872,6 +903,24 @@ extern "C" int aw_embed_state(aw_ctx* ctx, int which, float* d_dst, int64_t capa
   const size_t cnt = (size_t)ctx->last_n * ctx->last_T * ctx->last_nb;
   AW_REQUIRE(cnt > 0 && (int64_t)cnt <= capacity, "aw_embed_state: capacity %lld < %zu",
              (long long)capacity, cnt);
+  if (which >= 10) {
+    // debug views of the last iteration's intermediates (float32 words)
+    const size_t L = (size_t)AW_HOP * (ctx->last_T - 1), n = ctx->last_n;
+    const void* p = nullptr;
+    size_t words = 0;
+    switch (which) {
+      case 10: p = ctx->y.p; words = n * L; break;
+      case 11: p = ctx->dpad.p; words = n * (L + AW_NFFT); break;
+      case 12: p = ctx->accum.p; words = n * 2; break;            // packed peak (u64 per clip)
+      case 13: p = ctx->dA.p; words = cnt; break;
+      case 14: p = ctx->mag.p; words = cnt; break;
+      case 15: p = ctx->yoob.p; words = n * L; break;
+      default: return set_error("aw_embed_state: bad selector");
+    }
+    AW_REQUIRE((int64_t)words <= capacity, "aw_embed_state: capacity %lld < %zu", (long long)capacity, words);
+    AW_CUDA(cudaMemcpyAsync(d_dst, p, words * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+  }
   Buf* src[5] = {&ctx->c, &ctx->cbest, &ctx->c0, &ctx->m, &ctx->v};
   AW_REQUIRE(which >= 0 && which < 5, "aw_embed_state: bad selector");
   AW_CUDA(cudaMemcpyAsync(d_dst, src[which]->p, cnt * 4, cudaMemcpyDeviceToDevice,

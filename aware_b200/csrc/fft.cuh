@@ -9,6 +9,10 @@
 // out-of-band bins never exist on the device (detection/multibit_detector.py:34-37,
 // embedding/multibit_embedder.py:104), and by linearity the out-of-band part of
 // the reference's iSTFT is a per-clip constant waveform (y_oob).
+//
+// The kernels are templated on the 32-bin groups [K2LO, K2HI] that contain the band
+// (44.1 kHz: bins 12..92 -> groups 0..2; 16 kHz: bins 32..256 -> groups 1..8), so all
+// per-bin-group control flow is resolved at compile time.
 #pragma once
 #include "common.cuh"
 
@@ -59,61 +63,56 @@ __host__ __device__ constexpr int brev5(int p) {
   return ((p & 1) << 4) | ((p & 2) << 2) | (p & 4) | ((p & 8) >> 2) | ((p & 16) >> 4);
 }
 
-// In-register 32-point DFT, natural order in and out.
+// In-register 32-point DFT, natural order in, BIT-REVERSED order out:
+// register p holds X[brev5(p)].  Consumers index with brev5() at compile time, which
+// costs nothing, whereas an explicit un-permutation costs ~70 register moves.
 template <int SIGN>
-__device__ __forceinline__ void fft32(float (&re)[32], float (&im)[32]) {
+__device__ __forceinline__ void fft32_br(float (&re)[32], float (&im)[32]) {
   fft32_stage<SIGN, 16>(re, im);
   fft32_stage<SIGN, 8>(re, im);
   fft32_stage<SIGN, 4>(re, im);
   fft32_stage<SIGN, 2>(re, im);
   fft32_stage<SIGN, 1>(re, im);
-#pragma unroll
-  for (int p = 0; p < 32; ++p) {
-    const int q = brev5(p);
-    if (p < q) {
-      float t = re[p]; re[p] = re[q]; re[q] = t;
-      t = im[p]; im[p] = im[q]; im[q] = t;
-    }
-  }
 }
 
 #define AW_TR_STRIDE 33
-#define AW_TR_FLOATS (2 * 32 * AW_TR_STRIDE)   // per-warp transpose tile (re + im)
+#define AW_TR_FLOATS (2 * 32 * AW_TR_STRIDE)   // per-warp transpose tile (float2 [32][33])
 
 // 1024-point complex FFT across one warp.
 //   in : lane l, register j  holds x[32 j + l]
-//   out: lane k1, register k2 holds X[k1 + 32 k2]
-// s_tr: this warp's AW_TR_FLOATS floats; s_tw[j] = (cos, sin)(2 pi j / 1024).
+//   out: lane k1, register p holds X[k1 + 32 * brev5(p)]
+// s_tr: this warp's float2[32*33]; s_tw[k1*32 + l] = (cos, sin)(2 pi l k1 / 1024), a layout
+// in which both the twiddle reads and the transpose accesses are bank-conflict free.
 template <int SIGN>
-__device__ __forceinline__ void warp_fft1024(float (&re)[32], float (&im)[32], float* s_tr,
+__device__ __forceinline__ void warp_fft1024(float (&re)[32], float (&im)[32], float2* s_tr,
                                              const float2* s_tw, int lane) {
-  fft32<SIGN>(re, im);
-  float* s_re = s_tr;
-  float* s_im = s_tr + 32 * AW_TR_STRIDE;
+  fft32_br<SIGN>(re, im);
 #pragma unroll
-  for (int k1 = 0; k1 < 32; ++k1) {
-    const float2 w = s_tw[lane * k1];
+  for (int p = 0; p < 32; ++p) {
+    const int k1 = brev5(p);
+    const float2 w = s_tw[k1 * 32 + lane];
     const float c = w.x, s = SIGN * w.y;
-    const float r = re[k1] * c - im[k1] * s;
-    const float i = re[k1] * s + im[k1] * c;
-    s_re[k1 * AW_TR_STRIDE + lane] = r;
-    s_im[k1 * AW_TR_STRIDE + lane] = i;
+    s_tr[k1 * AW_TR_STRIDE + lane] = make_float2(re[p] * c - im[p] * s, re[p] * s + im[p] * c);
   }
   __syncwarp();
 #pragma unroll
   for (int n2 = 0; n2 < 32; ++n2) {
-    re[n2] = s_re[lane * AW_TR_STRIDE + n2];
-    im[n2] = s_im[lane * AW_TR_STRIDE + n2];
+    const float2 t = s_tr[lane * AW_TR_STRIDE + n2];
+    re[n2] = t.x;
+    im[n2] = t.y;
   }
   __syncwarp();
-  fft32<SIGN>(re, im);
+  fft32_br<SIGN>(re, im);
 }
 
 // sum_t w^2[m - 256 t] over the frames that cover padded sample m (torch.istft's
-// window envelope), ascending t.
-__device__ __forceinline__ float ola_envelope(int m, int T, const float* s_win) {
+// window envelope), ascending t.  `env256` holds the interior values (4 covering frames).
+__device__ __forceinline__ float ola_envelope(int m, int T, const float* s_win,
+                                              const float* __restrict__ env256) {
+  const int hop = m >> 8;
+  if (hop >= 3 && hop <= T - 1) return env256[m & 255];
   int tlo = m >= AW_NFFT ? ((m - (AW_NFFT - 1) + (AW_HOP - 1)) >> 8) : 0;
-  int thi = m >> 8;
+  int thi = hop;
   if (thi > T - 1) thi = T - 1;
   float e = 0.f;
   for (int t = tlo; t <= thi; ++t) {
@@ -143,7 +142,8 @@ struct AnaArgs {
   int T, bin0, nbins;
   const unsigned long long* peak;   // [clip] packed peak of sig (MAG/INIT: of x; LOOP/ADJ: of y)
   const float* window;         // [1024] device
-  const float2* twiddle;       // [1024] device
+  const float2* twiddle;       // [1024] device, layout [k1][lane]
+  const float* env256;         // [256] interior window envelope
   // outputs
   float* mag;                  // [clip][T][nbins]  (MAG, INIT -> c0, LOOP -> A~)
   float2* ph;                  // [clip][T][nbins]  (INIT -> u, LOOP -> q)
@@ -164,13 +164,14 @@ struct AnaArgs {
 #define AW_ANA_SIG (AW_ANA_FRAMES * AW_HOP + 768)
 #define AW_ANA_SMEM ((AW_ANA_SIG + 1024 + 2048 + 4 * AW_TR_FLOATS) * 4)
 
-template <int MODE>
-__global__ void __launch_bounds__(128) k_analysis(AnaArgs a) {
+template <int MODE, int K2LO, int K2HI>
+__global__ void __launch_bounds__(128, 3) k_analysis(AnaArgs a) {
   extern __shared__ float smem[];
   float* s_sig = smem;
   float* s_win = s_sig + AW_ANA_SIG;
   float2* s_tw = reinterpret_cast<float2*>(s_win + 1024);
-  float* s_tr = reinterpret_cast<float*>(s_tw + 1024);
+  float2* s_tr = s_tw + 1024;
+  __shared__ float s_scal[4];
 
   const int clip = blockIdx.y;
   const int t0 = blockIdx.x * AW_ANA_FRAMES;
@@ -181,23 +182,32 @@ __global__ void __launch_bounds__(128) k_analysis(AnaArgs a) {
     s_win[i] = a.window[i];
     s_tw[i] = a.twiddle[i];
   }
-  __syncthreads();   // s_win is needed by the ADJ loader (envelope)
-
-  // ---- stage the (scaled / padded) signal segment -------------------------
-  const float* sig = a.sig + (long long)clip * a.sig_stride;
-  const int m_end = AW_HOP * (T - 1) + AW_NFFT;   // padded length
-  if (MODE == ANA_ADJ) {
+  if (MODE == ANA_ADJ && tid == 0) {
+    // per-clip scalars of the two peak normalisers' sub-gradient (waveform.py:19, twice)
     const unsigned long long pk = a.peak[clip];
     const float p1 = peak_value(pk);
-    const int nstar = (int)peak_index(pk);
     const float d1 = p1 + 1e-8f;
     const float d2 = __fdiv_rn(p1, d1) + 1e-8f;
     double s2d = 0.0;                       // fixed-order sum of the synthesis tiles' partials
     for (int i = 0; i < a.s2_tiles; ++i) s2d += a.s2_part[(long long)clip * a.s2_tiles + i];
     const float s2 = (float)s2d;
     const float s1 = s2 * 1e-8f / d2;
-    const float ystar = a.y[(long long)clip * L + nstar];
-    const float corr = (ystar > 0.f ? 1.f : (ystar < 0.f ? -1.f : 0.f)) * (s2 / d2 + s1) / d1;
+    const float ystar = a.y[(long long)clip * L + (int)peak_index(pk)];
+    s_scal[0] = (ystar > 0.f ? 1.f : (ystar < 0.f ? -1.f : 0.f)) * (s2 / d2 + s1) / d1;
+  }
+  __syncthreads();   // tables (the ADJ loader needs s_win) and s_scal
+
+  // ---- stage the (scaled / padded) signal segment -------------------------
+  const float* sig = a.sig + (long long)clip * a.sig_stride;
+  const int m_end = AW_HOP * (T - 1) + AW_NFFT;   // padded length
+  const unsigned long long pk = a.peak[clip];
+  const float p1 = peak_value(pk);
+  const float d1 = p1 + 1e-8f;
+  const float d2 = __fdiv_rn(p1, d1) + 1e-8f;
+  if (MODE == ANA_ADJ) {
+    const int nstar = (int)peak_index(pk);
+    const float corr = s_scal[0];
+    const float inv = __fdiv_rn(__fdiv_rn(1.0f, d2), d1);
     for (int j = tid; j < AW_ANA_SIG; j += 128) {
       const int m = AW_HOP * t0 + j;
       const int n = m - AW_HALF;
@@ -206,31 +216,26 @@ __global__ void __launch_bounds__(128) k_analysis(AnaArgs a) {
         float dy2 = sig[m];
         if (n >= 1 && n <= AW_HALF) dy2 += sig[AW_HALF - n];
         if (n >= L - 513 && n <= L - 2) dy2 += sig[AW_HALF + 2 * (L - 1) - n];
-        float dy = __fdiv_rn(__fdiv_rn(dy2, d2), d1);
+        float dy = dy2 * inv;
         if (n == nstar) dy -= corr;
-        val = __fdiv_rn(dy, ola_envelope(m, T, s_win));
+        val = __fdiv_rn(dy, ola_envelope(m, T, s_win, a.env256));
       }
       s_sig[j] = val;
     }
   } else {
-    const float p1 = peak_value(a.peak[clip]);
-    const float d1 = p1 + 1e-8f;
-    const float d2 = __fdiv_rn(p1, d1) + 1e-8f;
+    // x / d1 (and / d2 in the loop: the two stacked normalisers) as one multiply by the
+    // correctly rounded reciprocal: <= 1.5 ulp from the divisions, far inside tolerance.
+    const float inv = MODE == ANA_LOOP ? __fdiv_rn(__fdiv_rn(1.0f, d1), d2) : __fdiv_rn(1.0f, d1);
     for (int j = tid; j < AW_ANA_SIG; j += 128) {
       const int m = AW_HOP * t0 + j;
       float val = 0.f;
-      if (m < m_end) {
-        const float x = sig[reflect_idx(m - AW_HALF, L)];
-        val = __fdiv_rn(x, d1);
-        if (MODE == ANA_LOOP) val = __fdiv_rn(val, d2);
-      }
+      if (m < m_end) val = sig[reflect_idx(m - AW_HALF, L)] * inv;
       s_sig[j] = val;
     }
   }
   __syncthreads();
 
-  const int k2lo = a.bin0 >> 5, k2hi = (a.bin0 + a.nbins - 1) >> 5;
-  float* my_tr = s_tr + warp * AW_TR_FLOATS;
+  float2* my_tr = s_tr + warp * (32 * AW_TR_STRIDE);
 
   NadamStep st;
   bool improved = false;
@@ -243,34 +248,33 @@ __global__ void __launch_bounds__(128) k_analysis(AnaArgs a) {
     const int ta = t0 + 2 * p, tb = ta + 1;
     if (ta >= T) break;                     // warp-uniform
     float re[32], im[32];
-    const int offa = AW_HOP * (2 * p);
+    const float* fa = s_sig + AW_HOP * (2 * p) + lane;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const int n = 32 * j + lane;
-      const float w = s_win[n];
-      re[j] = s_sig[offa + n] * w;
-      im[j] = s_sig[offa + AW_HOP + n] * w;  // frame tb (zeros past the end: staged as 0 * w)
+      const float w = s_win[32 * j + lane];
+      re[j] = fa[32 * j] * w;
+      im[j] = fa[32 * j + AW_HOP] * w;      // frame tb (zeros past the end: staged as 0)
     }
     warp_fft1024<-1>(re, im, my_tr, s_tw, lane);
 
     const bool has_b = tb < T;
     const int src = (32 - lane) & 31;
 #pragma unroll
-    for (int k2 = 0; k2 <= 16; ++k2) {
-      if (k2 < k2lo || k2 > k2hi) continue;   // warp-uniform
-      float mr = __shfl_sync(0xffffffffu, re[31 - k2 < 0 ? 0 : 31 - k2], src);
-      float mi = __shfl_sync(0xffffffffu, im[31 - k2 < 0 ? 0 : 31 - k2], src);
-      if (lane == 0 && k2 >= 1) {
-        mr = re[32 - k2];
-        mi = im[32 - k2];
+    for (int k2 = K2LO; k2 <= K2HI; ++k2) {
+      // Z[k], k = lane + 32 k2, is register brev5(k2); its mirror Z[1024-k] is register
+      // brev5(31-k2) of lane 32-lane (lane > 0) or register brev5(32-k2) of lane 0.
+      float mr = __shfl_sync(0xffffffffu, re[brev5(31 - k2)], src);
+      float mi = __shfl_sync(0xffffffffu, im[brev5(31 - k2)], src);
+      if (k2 >= 1 && lane == 0) {
+        mr = re[brev5((32 - k2) & 31)];
+        mi = im[brev5((32 - k2) & 31)];
       }
-      const int k = lane + 32 * k2;
-      const int b = k - a.bin0;
+      const int b = lane + 32 * k2 - a.bin0;
       if (b < 0 || b >= a.nbins) continue;
-      const float zr = re[k2], zi = im[k2];
+      const float zr = re[brev5(k2)], zi = im[brev5(k2)];
       // frame a: (Z[k] + conj Z[N-k]) / 2 ; frame b: (Z[k] - conj Z[N-k]) / (2i)
-      float fr[2] = {0.5f * (zr + mr), 0.5f * (zi + mi)};
-      float fi[2] = {0.5f * (zi - mi), 0.5f * (mr - zr)};
+      const float fr[2] = {0.5f * (zr + mr), 0.5f * (zi + mi)};
+      const float fi[2] = {0.5f * (zi - mi), 0.5f * (mr - zr)};
 #pragma unroll
       for (int f = 0; f < 2; ++f) {
         if (f == 1 && !has_b) break;
@@ -326,14 +330,15 @@ struct SynArgs {
   int T, L, bin0, nbins;
   float scale;                 // 1/N (irfft) or 1/2 (STFT adjoint)
   const float* window;
-  const float2* twiddle;
+  const float2* twiddle;       // layout [k1][lane]
+  const float* env256;
   // SYN_OOB: y_oob = x/(peak_x+1e-8) - ola/env
   const float* x; long long x_stride; const unsigned long long* peak_x;
   float* y_oob;                // [clip][L]   (OOB: out; WAVE: in)
   // SYN_WAVE: y = ola/env + y_oob, peak_y
   float* y;                    // [clip][L]   (WAVE: out; ADJ: in)
   unsigned long long* peak_y;  // [clip]      (WAVE: atomicMax out; ADJ: in)
-  // SYN_ADJ: dpad = ola (padded axis), s2 += dpad * y2[reflect]
+  // SYN_ADJ: dpad = ola (padded axis), s2 partial = sum dpad * y2[reflect]
   float* dpad;                 // [clip][L + 1024]
   double* s2_part;             // [clip][gridDim.x]
 };
@@ -343,13 +348,78 @@ struct SynArgs {
 #define AW_SYN_OLA (AW_SYN_FRAMES * AW_HOP + 768)
 #define AW_SYN_SMEM ((AW_SYN_OLA + 1024 + 2048 + 4 * AW_TR_FLOATS) * 4)
 
-template <int MODE>
-__global__ void __launch_bounds__(128) k_synthesis(SynArgs a) {
+// Build the hermitian pair for frames (ta, tb) of one warp, inverse-FFT it and return the
+// two windowed real frames in (re[p], im[p]) for sample n = lane + 32 * brev5(p).
+template <int K2LO, int K2HI>
+__device__ __forceinline__ void syn_pair(const SynArgs& a, int clip, int ta, int tb, bool va, bool vb,
+                                         float (&re)[32], float (&im)[32], float2* my_tr,
+                                         const float2* s_tw, const float* s_win, int lane) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { re[j] = 0.f; im[j] = 0.f; }
+  const long long oa = ((long long)clip * a.T + (va ? ta : 0)) * a.nbins;
+  const long long ob = ((long long)clip * a.T + (vb ? tb : 0)) * a.nbins;
+  const float sa = va ? a.scale : 0.f, sb = vb ? a.scale : 0.f;
+  const int lm = (32 - lane) & 31;
+#pragma unroll
+  for (int k2 = K2LO; k2 <= K2HI; ++k2) {
+    // direct entry Z[k], k = lane + 32 k2:  Xa + i Xb
+    {
+      const int b = lane + 32 * k2 - a.bin0;
+      const bool ok = b >= 0 && b < a.nbins;
+      const int bc = ok ? b : 0;
+      const float s0 = ok ? sa * a.amp[oa + bc] : 0.f, s1 = ok ? sb * a.amp[ob + bc] : 0.f;
+      const float2 p0 = a.ph[oa + bc], p1 = a.ph[ob + bc];
+      const float ar = s0 * p0.x, ai = s0 * p0.y, br = s1 * p1.x, bi = s1 * p1.y;
+      re[k2] = ar - bi;
+      im[k2] = ai + br;
+    }
+    // mirrored entry Z[1024-k'] = conj(Xa[k']) + i conj(Xb[k']), k' = ((32-lane)&31) + 32 k2,
+    // which lives in this lane at register 31-k2 (lane > 0) or 32-k2 (lane 0)
+    {
+      const int kp = lm + 32 * k2;
+      const int b = kp - a.bin0;
+      const bool ok = b >= 0 && b < a.nbins && kp > 0;
+      const int bc = ok ? b : 0;
+      const float s0 = ok ? sa * a.amp[oa + bc] : 0.f, s1 = ok ? sb * a.amp[ob + bc] : 0.f;
+      const float2 p0 = a.ph[oa + bc], p1 = a.ph[ob + bc];
+      const float ar = s0 * p0.x, ai = s0 * p0.y, br = s1 * p1.x, bi = s1 * p1.y;
+      const float zr = ar + bi, zi = br - ai;
+      if (lane == 0) {
+        if (k2 >= 1) { re[(32 - k2) & 31] = zr; im[(32 - k2) & 31] = zi; }
+      } else {
+        re[31 - k2] = zr;
+        im[31 - k2] = zi;
+      }
+    }
+  }
+  warp_fft1024<1>(re, im, my_tr, s_tw, lane);
+#pragma unroll
+  for (int p = 0; p < 32; ++p) {
+    const float w = s_win[lane + 32 * brev5(p)];
+    re[p] *= w;
+    im[p] *= w;
+  }
+}
+
+__device__ __forceinline__ void ola_add(float* s_ola, int off, const float (&v)[32], int lane) {
+#pragma unroll
+  for (int p = 0; p < 32; ++p) s_ola[off + lane + 32 * brev5(p)] += v[p];
+}
+
+// One CTA (4 warps) produces 29 hops of output from 32 frames.  Warp w owns the 8
+// consecutive frames f0+8w .. f0+8w+7 (four frame pairs).  Frames 0..4 of a warp lie
+// entirely inside the warp's private 2048-sample stripe of the overlap-add buffer and are
+// accumulated before the single __syncthreads; frames 5..7 spill into the next warp's stripe
+// and are accumulated after it (frame 5 waits in registers across the barrier).  No two
+// warps ever add to the same address concurrently, so the accumulation needs no atomics
+// and its order is fixed (deterministic).
+template <int MODE, int K2LO, int K2HI>
+__global__ void __launch_bounds__(128, 2) k_synthesis(SynArgs a) {
   extern __shared__ float smem[];
   float* s_ola = smem;
   float* s_win = s_ola + AW_SYN_OLA;
   float2* s_tw = reinterpret_cast<float2*>(s_win + 1024);
-  float* s_tr = reinterpret_cast<float*>(s_tw + 1024);
+  float2* s_tr = s_tw + 1024;
   __shared__ unsigned long long s_pk[4];
   __shared__ double s_red[32];
 
@@ -366,67 +436,39 @@ __global__ void __launch_bounds__(128) k_synthesis(SynArgs a) {
   for (int i = tid; i < AW_SYN_OLA; i += 128) s_ola[i] = 0.f;
   __syncthreads();
 
-  const int k2lo = a.bin0 >> 5, k2hi = (a.bin0 + a.nbins - 1) >> 5;
-  float* my_tr = s_tr + warp * AW_TR_FLOATS;
-  const float sc = a.scale;
-
-  // four phases; in phase r every warp owns frames f0+r+8w and f0+r+8w+4, all
-  // frames of one phase are >= 1024 samples apart, so '+=' needs no atomics and
-  // the accumulation order is fixed (deterministic).
-  for (int r = 0; r < 4; ++r) {
-    const int ta = f0 + r + 8 * warp, tb = ta + 4;
+  float2* my_tr = s_tr + warp * (32 * AW_TR_STRIDE);
+  const int fw = f0 + 8 * warp;                    // this warp's first frame
+  const int ow = AW_HOP * 8 * warp;                // its stripe in s_ola
+  float re[32], im[32];
+  float hold[32];
+  bool hold_valid = false;
+#pragma unroll 1
+  for (int pr = 0; pr < 3; ++pr) {                 // pairs (0,1) (2,3) (4,5)
+    const int ta = fw + 2 * pr, tb = ta + 1;
     const bool va = ta >= 0 && ta < T, vb = tb >= 0 && tb < T;
-    if (va || vb) {                                  // warp-uniform
-      float re[32], im[32];
+    if (!(va || vb)) continue;                     // warp-uniform
+    syn_pair<K2LO, K2HI>(a, clip, ta, tb, va, vb, re, im, my_tr, s_tw, s_win, lane);
+    if (va) ola_add(s_ola, ow + AW_HOP * (2 * pr), re, lane);
+    if (pr < 2) {
+      if (vb) ola_add(s_ola, ow + AW_HOP * (2 * pr + 1), im, lane);
+    } else if (vb) {                               // frame 5 spills: keep it for after the barrier
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { re[j] = 0.f; im[j] = 0.f; }
-      const long long oa = ((long long)clip * T + ta) * a.nbins;
-      const long long ob = ((long long)clip * T + tb) * a.nbins;
-#pragma unroll
-      for (int k2 = 0; k2 <= 16; ++k2) {
-        if (k2 < k2lo || k2 > k2hi) continue;
-        // direct entry Z[k], k = lane + 32 k2
-        {
-          const int b = lane + 32 * k2 - a.bin0;
-          if (b >= 0 && b < a.nbins) {
-            float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
-            if (va) { const float s = a.amp[oa + b]; const float2 p = a.ph[oa + b]; ar = s * p.x; ai = s * p.y; }
-            if (vb) { const float s = a.amp[ob + b]; const float2 p = a.ph[ob + b]; br = s * p.x; bi = s * p.y; }
-            re[k2] = sc * (ar - bi);                  // Xa + i Xb
-            im[k2] = sc * (ai + br);
-          }
-        }
-        // mirrored entry Z[N-k'] = conj(Xa[k']) + i conj(Xb[k']), k' = ((32-lane)&31) + 32 k2,
-        // which lives in this lane at register 31-k2 (lane>0) or 32-k2 (lane 0).
-        {
-          const int kp = ((32 - lane) & 31) + 32 * k2;
-          const int b = kp - a.bin0;
-          if (b >= 0 && b < a.nbins && kp > 0) {
-            float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
-            if (va) { const float s = a.amp[oa + b]; const float2 p = a.ph[oa + b]; ar = s * p.x; ai = s * p.y; }
-            if (vb) { const float s = a.amp[ob + b]; const float2 p = a.ph[ob + b]; br = s * p.x; bi = s * p.y; }
-            const float zr = sc * (ar + bi), zi = sc * (br - ai);
-            if (lane == 0) {
-              if (k2 >= 1) { re[32 - k2] = zr; im[32 - k2] = zi; }
-            } else {
-              re[31 - k2 < 0 ? 0 : 31 - k2] = zr;
-              im[31 - k2 < 0 ? 0 : 31 - k2] = zi;
-            }
-          }
-        }
-      }
-      warp_fft1024<1>(re, im, my_tr, s_tw, lane);
-      const int offa = AW_HOP * (ta - f0), offb = AW_HOP * (tb - f0);
-#pragma unroll
-      for (int k2 = 0; k2 < 32; ++k2) {
-        const int n = lane + 32 * k2;
-        const float w = s_win[n];
-        if (va) s_ola[offa + n] += w * re[k2];
-        if (vb) s_ola[offb + n] += w * im[k2];
-      }
+      for (int p = 0; p < 32; ++p) hold[p] = im[p];
+      hold_valid = true;
     }
-    __syncthreads();
   }
+  __syncthreads();
+  if (hold_valid) ola_add(s_ola, ow + AW_HOP * 5, hold, lane);
+  {
+    const int ta = fw + 6, tb = ta + 1;
+    const bool va = ta >= 0 && ta < T, vb = tb >= 0 && tb < T;
+    if (va || vb) {
+      syn_pair<K2LO, K2HI>(a, clip, ta, tb, va, vb, re, im, my_tr, s_tw, s_win, lane);
+      if (va) ola_add(s_ola, ow + AW_HOP * 6, re, lane);
+      if (vb) ola_add(s_ola, ow + AW_HOP * 7, im, lane);
+    }
+  }
+  __syncthreads();
 
   // ---- epilogue over this tile's output samples ----------------------------
   const int m_lo = AW_HOP * h0;
@@ -438,14 +480,14 @@ __global__ void __launch_bounds__(128) k_synthesis(SynArgs a) {
     const float p1 = peak_value(a.peak_y[clip]);
     const float d1 = p1 + 1e-8f;
     const float d2 = __fdiv_rn(p1, d1) + 1e-8f;
+    const float inv = __fdiv_rn(__fdiv_rn(1.0f, d1), d2);
     const float* y = a.y + (long long)clip * L;
     float* dpad = a.dpad + (long long)clip * (L + AW_NFFT);
     double acc = 0.0;
     for (int m = m_lo + tid; m < m_hi; m += 128) {
       const float d = s_ola[m - AW_HOP * f0];
       dpad[m] = d;
-      const float y2 = __fdiv_rn(__fdiv_rn(y[reflect_idx(m - AW_HALF, L)], d1), d2);
-      acc += (double)(d * y2);
+      acc += (double)(d * (y[reflect_idx(m - AW_HALF, L)] * inv));
     }
     acc = block_sum(acc, s_red);
     if (tid == 0) a.s2_part[(long long)clip * gridDim.x + blockIdx.x] = acc;
@@ -456,7 +498,7 @@ __global__ void __launch_bounds__(128) k_synthesis(SynArgs a) {
     for (int m = m_lo + tid; m < m_hi; m += 128) {
       const int n = m - AW_HALF;
       if (n < 0 || n >= L) continue;
-      const float yb = __fdiv_rn(s_ola[m - AW_HOP * f0], ola_envelope(m, T, s_win));
+      const float yb = __fdiv_rn(s_ola[m - AW_HOP * f0], ola_envelope(m, T, s_win, a.env256));
       const long long o = (long long)clip * L + n;
       if (MODE == SYN_OOB) {
         a.y_oob[o] = __fdiv_rn(a.x[(long long)clip * a.x_stride + n], dx) - yb;

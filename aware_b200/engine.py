@@ -147,6 +147,13 @@ class Engine:
         _lib.check(self.lib.aw_embed_state(self._ctx, sel, _ptr(dst), dst.numel(), _stream()))
         return dst
 
+    def debug_buffer(self, which: int, words: int) -> torch.Tensor:
+        """Raw float32 view of an intermediate of the last embed iteration (development aid):
+        10 y, 11 dpad, 12 packed peak, 13 dA, 14 |S~|, 15 y_oob."""
+        dst = torch.empty((words,), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.aw_embed_state(self._ctx, int(which), _ptr(dst), dst.numel(), _stream()))
+        return dst
+
     def decide(self, values: torch.Tensor, ref_bits: torch.Tensor | None = None,
                counters: torch.Tensor | None = None):
         """values [n,20] -> bits int32 [n,20] (strict '>' threshold); with ref_bits also

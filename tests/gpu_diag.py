@@ -228,6 +228,16 @@ def stage_gradmap(res):
         mdl = Model(O.make_weights(), O.mel_basis(), fi)
         mdl.forward(mdl.init(x[0]), pat[0].astype(np.float64))
         g64 = mdl.backward(pat[0].astype(np.float64))
+        L = 256 * (T - 1)
+        eng.embed(torch.from_numpy(x).cuda(), sr, torch.from_numpy(pat), iters=0)   # y(c0), its peak
+        y_gpu = eng.debug_buffer(10, L).cpu().numpy()
+        pk = eng.debug_buffer(12, 2).cpu().numpy().view(np.uint32)
+        nstar_gpu = int(0xffffffff - int(pk[0]))
+        y_mod = mdl.s["y"]
+        order = np.argsort(-np.abs(y_mod))[:4]
+        extra = dict(nstar_gpu=nstar_gpu, nstar_model=int(mdl.s["nstar"]), y_maxdiff=float(np.abs(y_gpu - y_mod).max()),
+                     top_abs_y_model=[(int(i), float(abs(y_mod[i]))) for i in order],
+                     top_abs_y_gpu=[(int(i), float(abs(y_gpu[i]))) for i in np.argsort(-np.abs(y_gpu))[:4]])
         e = np.abs(g - g64)
         er = np.abs(g_ref - g64)
         med = float(np.median(np.abs(g64)))
@@ -240,7 +250,7 @@ def stage_gradmap(res):
             rms_err_torch=float(np.sqrt((er ** 2).mean())), max_err_gpu=float(e.max()), max_err_torch=float(er.max()),
             top_frames=[(int(t), float(by_t[t])) for t in top_t], top_bins=[(int(b), float(by_b[b])) for b in top_b],
             median_err_gpu=float(np.median(e)), median_err_torch=float(np.median(er)),
-            nstar_frame=int(mdl.s["nstar"] // 256))
+            nstar_frame=int(mdl.s["nstar"] // 256), **extra)
 
 
 def stage_embed3(res):
