@@ -245,14 +245,15 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
     }
   AW_CUDA(cudaMalloc(&ctx->d_twiddle, 1024 * sizeof(float2)));
   AW_CUDA(cudaMemcpy(ctx->d_twiddle, tw.data(), 1024 * sizeof(float2), cudaMemcpyHostToDevice));
-  std::vector<float> env(256);
+  std::vector<float> env(512);           // [0,256): envelope, [256,512): its reciprocal
   for (int j = 0; j < 256; ++j) {
     float e = 0.f;                       // same order as ola_envelope: ascending frame index
     for (int r = 3; r >= 0; --r) e = fmaf(model->window[j + 256 * r], model->window[j + 256 * r], e);
     env[j] = e;
+    env[256 + j] = 1.0f / e;
   }
-  AW_CUDA(cudaMalloc(&ctx->d_env256, 256 * 4));
-  AW_CUDA(cudaMemcpy(ctx->d_env256, env.data(), 256 * 4, cudaMemcpyHostToDevice));
+  AW_CUDA(cudaMalloc(&ctx->d_env256, 512 * 4));
+  AW_CUDA(cudaMemcpy(ctx->d_env256, env.data(), 512 * 4, cudaMemcpyHostToDevice));
   *out = ctx;
   return 0;
 }
@@ -901,8 +902,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
 extern "C" int aw_embed_state(aw_ctx* ctx, int which, float* d_dst, int64_t capacity, void* stream) {
   AW_REQUIRE(ctx && d_dst, "null argument");
   const size_t cnt = (size_t)ctx->last_n * ctx->last_T * ctx->last_nb;
-  AW_REQUIRE(cnt > 0 && (int64_t)cnt <= capacity, "aw_embed_state: capacity %lld < %zu",
-             (long long)capacity, cnt);
+  AW_REQUIRE(cnt > 0, "aw_embed_state: no embed has run");
   if (which >= 10) {
     // debug views of the last iteration's intermediates (float32 words)
     const size_t L = (size_t)AW_HOP * (ctx->last_T - 1), n = ctx->last_n;
@@ -921,6 +921,7 @@ extern "C" int aw_embed_state(aw_ctx* ctx, int which, float* d_dst, int64_t capa
     AW_CUDA(cudaMemcpyAsync(d_dst, p, words * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
   }
+  AW_REQUIRE((int64_t)cnt <= capacity, "aw_embed_state: capacity %lld < %zu", (long long)capacity, cnt);
   Buf* src[5] = {&ctx->c, &ctx->cbest, &ctx->c0, &ctx->m, &ctx->v};
   AW_REQUIRE(which >= 0 && which < 5, "aw_embed_state: bad selector");
   AW_CUDA(cudaMemcpyAsync(d_dst, src[which]->p, cnt * 4, cudaMemcpyDeviceToDevice,

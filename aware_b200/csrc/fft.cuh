@@ -105,12 +105,14 @@ __device__ __forceinline__ void warp_fft1024(float (&re)[32], float (&im)[32], f
   fft32_br<SIGN>(re, im);
 }
 
-// sum_t w^2[m - 256 t] over the frames that cover padded sample m (torch.istft's
-// window envelope), ascending t.  `env256` holds the interior values (4 covering frames).
-__device__ __forceinline__ float ola_envelope(int m, int T, const float* s_win,
-                                              const float* __restrict__ env256) {
+// 1 / sum_t w^2[m - 256 t] over the frames that cover padded sample m (torch.istft's window
+// envelope, accumulated in ascending t).  `env256[256 + j]` holds the reciprocal of the
+// interior value (4 covering frames); edges are evaluated directly.  Multiplying by the
+// correctly rounded reciprocal differs from torch's division by <= 1 ulp.
+__device__ __forceinline__ float ola_inv_envelope(int m, int T, const float* s_win,
+                                                  const float* __restrict__ env256) {
   const int hop = m >> 8;
-  if (hop >= 3 && hop <= T - 1) return env256[m & 255];
+  if (hop >= 3 && hop <= T - 1) return env256[256 + (m & 255)];
   int tlo = m >= AW_NFFT ? ((m - (AW_NFFT - 1) + (AW_HOP - 1)) >> 8) : 0;
   int thi = hop;
   if (thi > T - 1) thi = T - 1;
@@ -119,7 +121,7 @@ __device__ __forceinline__ float ola_envelope(int m, int T, const float* s_win,
     const float w = s_win[m - (t << 8)];
     e = __fmaf_rn(w, w, e);
   }
-  return e;
+  return __fdiv_rn(1.0f, e);
 }
 
 // per-iteration NAdam scalars (torch/optim/nadam.py _single_tensor_nadam)
@@ -208,19 +210,32 @@ __global__ void __launch_bounds__(128, 3) k_analysis(AnaArgs a) {
     const int nstar = (int)peak_index(pk);
     const float corr = s_scal[0];
     const float inv = __fdiv_rn(__fdiv_rn(1.0f, d2), d1);
-    for (int j = tid; j < AW_ANA_SIG; j += 128) {
-      const int m = AW_HOP * t0 + j;
-      const int n = m - AW_HALF;
-      float val = 0.f;
-      if (n >= 0 && n < L && m < m_end) {
-        float dy2 = sig[m];
-        if (n >= 1 && n <= AW_HALF) dy2 += sig[AW_HALF - n];
-        if (n >= L - 513 && n <= L - 2) dy2 += sig[AW_HALF + 2 * (L - 1) - n];
-        float dy = dy2 * inv;
-        if (n == nstar) dy -= corr;
-        val = __fdiv_rn(dy, ola_envelope(m, T, s_win, a.env256));
+    const int m0 = AW_HOP * t0;
+    // interior tiles: no reflect-fold terms, interior envelope, everything in range
+    const bool interior = (m0 - AW_HALF > AW_HALF) && (m0 + AW_ANA_SIG - AW_HALF < L - 513) &&
+                          (t0 >= 3) && (t0 + AW_ANA_FRAMES + 3 <= T - 1);
+    if (interior) {
+      for (int j = tid; j < AW_ANA_SIG; j += 128) {
+        const int m = m0 + j;
+        float dy = sig[m] * inv;
+        if (m - AW_HALF == nstar) dy -= corr;
+        s_sig[j] = dy * a.env256[256 + (m & 255)];
       }
-      s_sig[j] = val;
+    } else {
+      for (int j = tid; j < AW_ANA_SIG; j += 128) {
+        const int m = m0 + j;
+        const int n = m - AW_HALF;
+        float val = 0.f;
+        if (n >= 0 && n < L && m < m_end) {
+          float dy2 = sig[m];
+          if (n >= 1 && n <= AW_HALF) dy2 += sig[AW_HALF - n];
+          if (n >= L - 513 && n <= L - 2) dy2 += sig[AW_HALF + 2 * (L - 1) - n];
+          float dy = dy2 * inv;
+          if (n == nstar) dy -= corr;
+          val = dy * ola_inv_envelope(m, T, s_win, a.env256);
+        }
+        s_sig[j] = val;
+      }
     }
   } else {
     // x / d1 (and / d2 in the loop: the two stacked normalisers) as one multiply by the
@@ -290,8 +305,9 @@ __global__ void __launch_bounds__(128, 3) k_analysis(AnaArgs a) {
           vv = __fmul_rn(vv, 0.999f);
           vv = __fadd_rn(vv, __fmul_rn(__fmul_rn(0.001f, g), g));
           const float den = __fadd_rn(__fsqrt_rn(__fmul_rn(vv, st.inv_bc2)), 1e-8f);
-          cc = __fadd_rn(cc, __fdiv_rn(__fmul_rn(st.a_g, g), den));
-          cc = __fadd_rn(cc, __fdiv_rn(__fmul_rn(st.a_m, mm), den));
+          const float rden = __frcp_rn(den);     // one reciprocal for both addcdiv terms (<= 1 ulp)
+          cc = __fadd_rn(cc, __fmul_rn(__fmul_rn(st.a_g, g), rden));
+          cc = __fadd_rn(cc, __fmul_rn(__fmul_rn(st.a_m, mm), rden));
           const float c0 = a.c0[o];
           const float dl = __fmul_rn(c0, a.tol_ratio);
           const float lo = fmaxf(0.f, __fsub_rn(c0, dl)), hi = __fadd_rn(c0, dl);
@@ -492,24 +508,51 @@ __global__ void __launch_bounds__(128, 2) k_synthesis(SynArgs a) {
     acc = block_sum(acc, s_red);
     if (tid == 0) a.s2_part[(long long)clip * gridDim.x + blockIdx.x] = acc;
   } else {
-    unsigned long long pk = 0ull;
-    float dx = 1.f;
-    if (MODE == SYN_OOB) dx = peak_value(a.peak_x[clip]) + 1e-8f;
-    for (int m = m_lo + tid; m < m_hi; m += 128) {
-      const int n = m - AW_HALF;
-      if (n < 0 || n >= L) continue;
-      const float yb = __fdiv_rn(s_ola[m - AW_HOP * f0], ola_envelope(m, T, s_win, a.env256));
-      const long long o = (long long)clip * L + n;
-      if (MODE == SYN_OOB) {
-        a.y_oob[o] = __fdiv_rn(a.x[(long long)clip * a.x_stride + n], dx) - yb;
-      } else {
-        const float yy = yb + a.y_oob[o];
-        a.y[o] = yy;
-        const unsigned long long q = pack_peak(fabsf(yy), (unsigned)n);
-        pk = q > pk ? q : pk;
+    float best = -1.f;
+    int best_n = 0;
+    float rdx = 1.f;
+    if (MODE == SYN_OOB) rdx = __fdiv_rn(1.0f, peak_value(a.peak_x[clip]) + 1e-8f);
+    const bool interior = h0 >= 3 && h0 + AW_SYN_HOPS <= T - 1 && m_lo >= AW_HALF && m_hi - AW_HALF <= L;
+    if (interior) {
+      // 4 consecutive samples per thread: float4 traffic, table envelope, no range checks
+      const float* so = s_ola + (m_lo - AW_HOP * f0);
+      const long long ob = (long long)clip * L + (m_lo - AW_HALF);
+      for (int i = tid * 4; i < AW_HOP * AW_SYN_HOPS; i += 512) {
+        const float4 o4 = *reinterpret_cast<const float4*>(so + i);
+        const float4 e4 = *reinterpret_cast<const float4*>(a.env256 + 256 + (i & 255));
+        float yb[4] = {o4.x * e4.x, o4.y * e4.y, o4.z * e4.z, o4.w * e4.w};
+        if (MODE == SYN_OOB) {
+          const float* xp = a.x + (long long)clip * a.x_stride + (m_lo - AW_HALF) + i;
+          *reinterpret_cast<float4*>(a.y_oob + ob + i) =
+              make_float4(xp[0] * rdx - yb[0], xp[1] * rdx - yb[1], xp[2] * rdx - yb[2], xp[3] * rdx - yb[3]);
+        } else {
+          const float4 q4 = *reinterpret_cast<const float4*>(a.y_oob + ob + i);
+          const float yy[4] = {yb[0] + q4.x, yb[1] + q4.y, yb[2] + q4.z, yb[3] + q4.w};
+          *reinterpret_cast<float4*>(a.y + ob + i) = make_float4(yy[0], yy[1], yy[2], yy[3]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (fabsf(yy[k]) > best) { best = fabsf(yy[k]); best_n = m_lo - AW_HALF + i + k; }
+        }
+      }
+    } else {
+      for (int m = m_lo + tid; m < m_hi; m += 128) {
+        const int n = m - AW_HALF;
+        if (n < 0 || n >= L) continue;
+        const float yb = s_ola[m - AW_HOP * f0] * ola_inv_envelope(m, T, s_win, a.env256);
+        const long long o = (long long)clip * L + n;
+        if (MODE == SYN_OOB) {
+          a.y_oob[o] = a.x[(long long)clip * a.x_stride + n] * rdx - yb;
+        } else {
+          const float yy = yb + a.y_oob[o];
+          a.y[o] = yy;
+          if (fabsf(yy) > best) { best = fabsf(yy); best_n = n; }
+        }
       }
     }
     if (MODE == SYN_WAVE) {
+      // strict '>' in ascending sample order keeps the lowest index per thread; the packed
+      // u64 max then keeps the lowest index across threads, warps and tiles
+      unsigned long long pk = best >= 0.f ? pack_peak(best, (unsigned)best_n) : 0ull;
       pk = warp_max_u64(pk);
       if (lane == 0) s_pk[warp] = pk;
       __syncthreads();
