@@ -915,6 +915,9 @@ extern "C" int aw_embed_state(aw_ctx* ctx, int which, float* d_dst, int64_t capa
       case 13: p = ctx->dA.p; words = cnt; break;
       case 14: p = ctx->mag.p; words = cnt; break;
       case 15: p = ctx->yoob.p; words = n * L; break;
+      case 16: p = ctx->ph_q.p; words = cnt * 2; break;
+      case 17: p = ctx->M.p; words = n * ctx->last_T * AW_NMEL; break;
+      case 18: p = ctx->dp0.p; words = (size_t)ctx->ws_rows * 128; break;
       default: return set_error("aw_embed_state: bad selector");
     }
     AW_REQUIRE((int64_t)words <= capacity, "aw_embed_state: capacity %lld < %zu", (long long)capacity, words);

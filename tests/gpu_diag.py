@@ -238,6 +238,22 @@ def stage_gradmap(res):
         extra = dict(nstar_gpu=nstar_gpu, nstar_model=int(mdl.s["nstar"]), y_maxdiff=float(np.abs(y_gpu - y_mod).max()),
                      top_abs_y_model=[(int(i), float(abs(y_mod[i]))) for i in order],
                      top_abs_y_gpu=[(int(i), float(abs(y_gpu[i]))) for i in np.argsort(-np.abs(y_gpu))[:4]])
+        # forward re-STFT and back-propagated dA of iteration 0, against the float64 model
+        eng.embed(torch.from_numpy(x).cuda(), sr, torch.from_numpy(pat), iters=1)
+        mag_gpu = eng.debug_buffer(14, T * B).cpu().numpy().reshape(T, B)
+        q_gpu = eng.debug_buffer(16, T * B * 2).cpu().numpy().reshape(T, B, 2)
+        dA_gpu = eng.debug_buffer(13, T * B).cpu().numpy().reshape(T, B)
+        from kernel_model import analysis as _ana
+        S64 = _ana(mdl.s["y2"], T, np.asarray(fi), "reflect")
+        S_gpu = mag_gpu * (q_gpu[..., 0] + 1j * q_gpu[..., 1])
+        relS = np.abs(S_gpu - S64) / np.abs(S64)
+        iS = np.argsort(-relS.ravel())[:6]
+        St = O.stft(torch.from_numpy(mdl.s["y2"].astype(np.float32))).numpy()[fi].T
+        relT = np.abs(St - S64) / np.abs(S64)
+        extra.update(relS_gpu_top=[(int(i // B), int(i % B), float(relS.ravel()[i]), float(np.abs(S64).ravel()[i])) for i in iS],
+                     relS_gpu_median=float(np.median(relS)), relS_torch_median=float(np.median(relT)),
+                     relS_torch_max=float(relT.max()), absS_err_gpu_max=float(np.abs(S_gpu - S64).max()),
+                     absS_err_torch_max=float(np.abs(St - S64).max()))
         e = np.abs(g - g64)
         er = np.abs(g_ref - g64)
         med = float(np.median(np.abs(g64)))

@@ -285,9 +285,22 @@ def test_embed_one_iteration_matches_oracle(eng, sr, secs):
     mdl.forward(mdl.init(x[0]), pat[0].astype(np.float64))
     g64 = mdl.backward(pat[0].astype(np.float64))
     rms = lambda a: float(np.sqrt(np.mean(a ** 2)))        # noqa: E731
-    err_gpu, err_ref = rms(g_gpu - g64), rms(g_ref - g64)
+    # LeakyReLU is not differentiable at 0: a pre-activation within fp32 rounding of the kink
+    # (|IN output| ~ 1e-6) takes slope 1 in one fp32 evaluation order and 0.2 in another, and
+    # that one pooled row's gradient then differs by O(1 %) in either implementation.  Rows
+    # whose float64 pre-activation is that close to 0 reach frames 2j-3 .. 2j+4 through the
+    # STFT/iSTFT adjoints (7-frame support): those frames are compared separately.
+    kink = np.zeros(T, dtype=bool)
+    for P in mdl.s["P"][1:]:
+        hh = np.abs(np.where(P > 0, P, P / 0.2))
+        for j in np.nonzero((hh < 2e-5).any(axis=1))[0]:
+            kink[max(0, 2 * j - 4):2 * j + 6] = True
+    assert kink.mean() < 0.5
+    ok = ~kink
+    err_gpu, err_ref = rms((g_gpu - g64)[ok]), rms((g_ref - g64)[ok])
     assert err_gpu <= 5 * err_ref + 1e-12, (err_gpu, err_ref)   # as close to the truth as torch-fp32 is
-    assert rms(g_gpu - g_ref) <= 1e-3 * rms(g_ref)
+    assert rms((g_gpu - g_ref)[ok]) <= 1e-3 * rms(g_ref[ok])
+    assert rms(g_gpu - g_ref) <= 5e-2 * rms(g_ref)              # kink frames: bounded, not equal
     d = np.abs(st["c"][0] - c_ref)
     assert (d <= 1e-4 * np.maximum(1.0, np.abs(c_ref))).mean() >= 0.995
     assert _snr(out[0], y) >= 75 and np.abs(out[0] - y).max() <= 1e-3
