@@ -16,6 +16,7 @@
 #include "fft.cuh"
 #include "gemm.cuh"
 #include "net.cuh"
+#include "spec.cuh"
 
 namespace aw {
 thread_local char g_err[512] = "";
@@ -66,6 +67,8 @@ struct aw_ctx {
   PFN_encodeTiled encode = nullptr;
   CUtensorMap tm_w[4], tm_wt[4], tm_w16[4], tm_wt16[4];
   // workspace (grow-only)
+  bool legacy_spec = false;   // AW_B200_LEGACY_SPEC=1: separate synthesis / analysis kernels
+  Buf scal;
   Buf accum, peakx, mag, ph_u, ph_q, c0, c, m, v, cbest, dA, yoob, y, dpad, M, cs, sigma;
   Buf act[5], ga, gb, dh4, dp0, part, stat[5], bstat, values, best, improved, pattern, itc, steps;
   int ws_rows = 0;
@@ -201,6 +204,10 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
   ctx->tol_db = model->tolerance_db;
   ctx->threshold = model->threshold;
   ctx->h_mel.assign(model->mel_basis, model->mel_basis + AW_NMEL * 513);
+  {
+    const char* e = getenv("AW_B200_LEGACY_SPEC");
+    ctx->legacy_spec = e && e[0] == '1';
+  }
 
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -279,7 +286,8 @@ extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
                  &ctx->cs, &ctx->sigma, &ctx->act[0], &ctx->act[1], &ctx->act[2], &ctx->act[3],
                  &ctx->act[4], &ctx->ga, &ctx->gb, &ctx->dh4, &ctx->dp0, &ctx->part, &ctx->stat[0],
                  &ctx->stat[1], &ctx->stat[2], &ctx->stat[3], &ctx->stat[4], &ctx->bstat,
-                 &ctx->values, &ctx->best, &ctx->improved, &ctx->pattern, &ctx->itc, &ctx->steps};
+                 &ctx->values, &ctx->best, &ctx->improved, &ctx->pattern, &ctx->itc, &ctx->steps,
+                 &ctx->scal};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   delete ctx;
@@ -431,8 +439,10 @@ __global__ void k_iter_begin(unsigned long long* peak, int n, int* it) {
 static int mel_blocks(const Dims& d) { return (d.T + AW_MEL_FRAMES - 1) / AW_MEL_FRAMES; }
 static int syn_tiles(const Dims& d) { return (d.T + 3 + AW_SYN_HOPS - 1) / AW_SYN_HOPS; }
 static int p0b_blocks(const Dims& d) { return (2 * d.Tp + AW_P0B_FRAMES - 1) / AW_P0B_FRAMES; }
+static int p0a_blocks(const Dims& d) { return (d.T + AW_P0A_FRAMES - 1) / AW_P0A_FRAMES; }
+static int s2_slots(const Dims& d) { return std::max(syn_tiles(d), p0a_blocks(d)); }
 static size_t acc_doubles(const Dims& d) {
-  return (size_t)d.n * (1 + syn_tiles(d) + 256 * (size_t)mel_blocks(d) + 256 * (size_t)p0b_blocks(d));
+  return (size_t)d.n * (1 + s2_slots(d) + 256 * (size_t)mel_blocks(d) + 256 * (size_t)p0b_blocks(d));
 }
 static Acc acc_view(aw_ctx* ctx, const Dims& d) {
   Acc a;
@@ -440,7 +450,7 @@ static Acc acc_view(aw_ctx* ctx, const Dims& d) {
   double* base = (double*)ctx->accum.p;
   a.peak_y = (unsigned long long*)base;
   a.s2_part = base + d.n;
-  a.chan_part = a.s2_part + (size_t)d.n * a.syn_tiles;
+  a.chan_part = a.s2_part + (size_t)d.n * s2_slots(d);
   a.bpart = a.chan_part + (size_t)d.n * 256 * a.mel_blocks;
   return a;
 }
@@ -529,13 +539,13 @@ template <> struct ModeOf<__nv_bfloat16> { static constexpr int B = 1; };
 
 template <typename AT>
 static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseMel& sm,
-                       cudaStream_t st) {
+                       cudaStream_t st, const unsigned long long* peak_scale = nullptr) {
   constexpr int B = ModeOf<AT>::B;
   const int tf = ctx->prec == AW_PREC_TF32;
   {
     dim3 g((d.T + AW_MEL_FRAMES - 1) / AW_MEL_FRAMES, d.n);
     k_mel<<<g, 128, AW_MEL_FRAMES * d.nb * 4, st>>>((float*)ctx->mag.p, d.T, d.nb, sm,
-                                                    (float*)ctx->M.p, acc.chan_part);
+                                                    (float*)ctx->M.p, acc.chan_part, peak_scale);
     ctx->launches++;
     AW_LAUNCH_CHECK();
     dim3 g2((d.Tp_pad + AW_P0_ROWS - 1) / AW_P0_ROWS, d.n);
@@ -568,7 +578,7 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
 
 template <typename AT>
 static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseMel& sm,
-                        cudaStream_t st) {
+                        cudaStream_t st, bool euler_s2 = false) {
   constexpr int B = ModeOf<AT>::B;
   const int tf = ctx->prec == AW_PREC_TF32;
   AT* ga = (AT*)ctx->ga.p;
@@ -620,7 +630,8 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
   dim3 g2((d.T + AW_P0A_FRAMES - 1) / AW_P0A_FRAMES, d.n);
   k_p0_bwd_apply<<<g2, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
                                      (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p, acc.bpart,
-                                     acc.p0b_blocks, sm, d.nb, (float*)ctx->dA.p);
+                                     acc.p0b_blocks, sm, d.nb, (float*)ctx->dA.p,
+                                     euler_s2 ? (const float*)ctx->mag.p : nullptr, acc.s2_part);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
@@ -701,6 +712,31 @@ static int launch_syn(aw_ctx* ctx, const Dims& d, const SynArgs& s, cudaStream_t
   if (hi <= 2) return launch_syn_k<MODE, 0, 2>(ctx, d, s, st);
   if (lo >= 1 && hi <= 8) return launch_syn_k<MODE, 1, 8>(ctx, d, s, st);
   return launch_syn_k<MODE, 0, 15>(ctx, d, s, st);
+}
+template <int MODE, int K2LO, int K2HI>
+static int launch_spec_k(aw_ctx* ctx, const Dims& d, SpecArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AW_CUDA(cudaFuncSetAttribute(k_spec<MODE, K2LO, K2HI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 AW_SP_SMEM));
+    attr_set = true;
+  }
+  a.n_clips = d.n; a.T = d.T; a.L = d.L; a.bin0 = d.bin0; a.nbins = d.nb;
+  a.tiles = (d.T + AW_SP_FA - 1) / AW_SP_FA;
+  a.window = ctx->d_window; a.twiddle = ctx->d_twiddle; a.env256 = ctx->d_env256;
+  const int items = a.n_clips * a.tiles;
+  const int grid = std::min(items, 2 * ctx->num_sms);
+  k_spec<MODE, K2LO, K2HI><<<grid, 32 * AW_SP_WARPS, AW_SP_SMEM, st>>>(a);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+template <int MODE>
+static int launch_spec(aw_ctx* ctx, const Dims& d, SpecArgs& a, cudaStream_t st) {
+  const int lo = d.bin0 >> 5, hi = (d.bin0 + d.nb - 1) >> 5;
+  if (hi <= 2) return launch_spec_k<MODE, 0, 2>(ctx, d, a, st);
+  if (lo >= 1 && hi <= 8) return launch_spec_k<MODE, 1, 8>(ctx, d, a, st);
+  return launch_spec_k<MODE, 0, 15>(ctx, d, a, st);
 }
 static int launch_peak(aw_ctx* ctx, const float* x, int64_t stride, int n, int n_clips,
                        unsigned long long* peak, cudaStream_t st) {
@@ -798,7 +834,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       ensure(ctx->cbest, sp * 4) || ensure(ctx->dA, sp * 4) ||
       ensure(ctx->yoob, (size_t)d.n * d.L * 4) || ensure(ctx->y, (size_t)d.n * d.L * 4) ||
       ensure(ctx->dpad, (size_t)d.n * (d.L + AW_NFFT) * 4) ||
-      ensure(ctx->pattern, (size_t)d.n * AW_NBITS * 4) ||
+      ensure(ctx->pattern, (size_t)d.n * AW_NBITS * 4) || ensure(ctx->scal, (size_t)d.n * sizeof(ClipScal)) ||
       ensure(ctx->steps, (size_t)(iters > 0 ? iters : 1) * sizeof(NadamStep)))
     return 1;
   SparseMel sm;
@@ -842,7 +878,42 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
     if (launch_syn<SYN_OOB>(ctx, dw, s0, st)) return 1;
 
     // ---- optimisation loop (multibit_embedder.py:95-122)
-    for (int it = 0; it < iters; ++it) {
+    for (int it = 0; it < iters && !ctx->legacy_spec; ++it) {
+      // fused spectral passes (spec.cuh): y and dpad never leave shared memory
+      if (begin_pass(ctx, dw.n, itc, st)) return 1;
+      SpecArgs f;
+      memset(&f, 0, sizeof(f));
+      f.amp = (float*)ctx->c.p; f.ph = (float2*)ctx->ph_u.p;
+      f.y_oob = (float*)ctx->yoob.p; f.peak_y = acc.peak_y;
+      f.mag = (float*)ctx->mag.p; f.q = (float2*)ctx->ph_q.p;
+      if (launch_spec<SPEC_FWD>(ctx, dw, f, st)) return 1;
+      float* lp = d_losses ? d_losses + w0 : nullptr;
+      if (ctx->prec == AW_PREC_BF16) {
+        if (net_forward<__nv_bfloat16>(ctx, dw, acc, sm, st, acc.peak_y)) return 1;
+        if (run_head<__nv_bfloat16>(ctx, dw, (float*)ctx->pattern.p, (float*)ctx->values.p, lp, n_clips, true, st))
+          return 1;
+        if (net_backward<__nv_bfloat16>(ctx, dw, acc, sm, st, true)) return 1;
+      } else {
+        if (net_forward<float>(ctx, dw, acc, sm, st, acc.peak_y)) return 1;
+        if (run_head<float>(ctx, dw, (float*)ctx->pattern.p, (float*)ctx->values.p, lp, n_clips, true, st))
+          return 1;
+        if (net_backward<float>(ctx, dw, acc, sm, st, true)) return 1;
+      }
+      k_clip_scalars<<<(dw.n + 127) / 128, 128, 0, st>>>(acc.peak_y, acc.s2_part, p0a_blocks(dw), dw.n,
+                                                         (ClipScal*)ctx->scal.p);
+      ctx->launches++;
+      AW_LAUNCH_CHECK();
+      SpecArgs b;
+      memset(&b, 0, sizeof(b));
+      b.amp = (float*)ctx->dA.p; b.ph = (float2*)ctx->ph_q.p;
+      b.scal = (ClipScal*)ctx->scal.p; b.u = (float2*)ctx->ph_u.p;
+      b.c = (float*)ctx->c.p; b.m = (float*)ctx->m.p; b.v = (float*)ctx->v.p;
+      b.cbest = (float*)ctx->cbest.p; b.c0 = (float*)ctx->c0.p;
+      b.improved = (int*)ctx->improved.p; b.steps = (NadamStep*)ctx->steps.p; b.it_ptr = itc;
+      b.tol_ratio = (float)pow(10.0, -(double)ctx->tol_db / 20.0);
+      if (launch_spec<SPEC_BWD>(ctx, dw, b, st)) return 1;
+    }
+    for (int it = 0; it < iters && ctx->legacy_spec; ++it) {
       if (begin_pass(ctx, dw.n, itc, st)) return 1;
       SynArgs s1 = syn_base(ctx, dw);
       s1.amp = (float*)ctx->c.p; s1.ph = (float2*)ctx->ph_u.p; s1.scale = 1.0f / AW_NFFT;

@@ -48,14 +48,24 @@ struct ChanStats {      // per clip, per mel channel (forward, reused by backwar
 
 // ---- mel projection + per-channel sums -------------------------------------
 #define AW_MEL_FRAMES 32
+// peak_y != null: `mag` is the spectrum of the UN-normalised waveform (spec.cuh) and the two
+// stacked peak normalisers (waveform.py:19) are applied here as one factor 1/(d1 d2).
 __global__ void __launch_bounds__(128) k_mel(const float* __restrict__ mag, int T, int nb,
                                              SparseMel sm, float* __restrict__ M,
-                                             double* __restrict__ chan_part) {
+                                             double* __restrict__ chan_part,
+                                             const unsigned long long* __restrict__ peak_y) {
   extern __shared__ float s_a[];   // [AW_MEL_FRAMES][nb]
   const int clip = blockIdx.y, t0 = blockIdx.x * AW_MEL_FRAMES, c = threadIdx.x;
   const int nf = min(AW_MEL_FRAMES, T - t0);
   const float* src = mag + ((long long)clip * T + t0) * nb;
-  for (int i = threadIdx.x; i < nf * nb; i += 128) s_a[i] = src[i];
+  float inv = 1.f;
+  if (peak_y) {
+    const float p1 = peak_value(peak_y[clip]);
+    const float d1 = p1 + 1e-8f;
+    const float d2 = __fdiv_rn(p1, d1) + 1e-8f;
+    inv = __fdiv_rn(__fdiv_rn(1.0f, d1), d2);
+  }
+  for (int i = threadIdx.x; i < nf * nb; i += 128) s_a[i] = src[i] * inv;
   __syncthreads();
   const int e0 = sm.rowptr[c], e1 = sm.rowptr[c + 1];
   double s1 = 0.0, s2 = 0.0;
@@ -351,7 +361,9 @@ __global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ 
                                                       const float* __restrict__ sigma_in,
                                                       const double* __restrict__ bpart, int nblk,
                                                       SparseMel sm,
-                                                      int nb, float* __restrict__ dA) {
+                                                      int nb, float* __restrict__ dA,
+                                                      const float* __restrict__ mag_un,
+                                                      double* __restrict__ s2_part) {
   __shared__ double s_red[32];
   __shared__ float s_dm[AW_P0A_FRAMES][AW_NMEL];
   __shared__ float s_ab[3];
@@ -381,11 +393,21 @@ __global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ 
     s_dm[f][c] = st.rstd * (dmh - A1 - mh * A2);
   }
   __syncthreads();
+  double s2 = 0.0;
   for (int i = threadIdx.x; i < nf * nb; i += 128) {
     const int f = i / nb, b = i - f * nb;
     float acc = 0.f;
     for (int e = sm.colptr[b]; e < sm.colptr[b + 1]; ++e) acc = fmaf(sm.valT[e], s_dm[f][sm.row[e]], acc);
-    dA[((long long)clip * T + t0 + f) * nb + b] = acc;
+    const long long o = ((long long)clip * T + t0 + f) * nb + b;
+    dA[o] = acc;
+    if (mag_un) s2 += (double)(acc * mag_un[o]);
+  }
+  if (mag_un) {
+    // Euler: sum_n dy2[n] y2[n] = sum_{t,b} dA~ A~ (|STFT| is 1-homogeneous); the factor
+    // 1/(d1 d2) that turns the un-normalised magnitudes into A~ is applied by k_clip_scalars
+    __syncthreads();
+    s2 = block_sum(s2, s_red);
+    if (threadIdx.x == 0) s2_part[(long long)clip * gridDim.x + blockIdx.x] = s2;
   }
 }
 
