@@ -38,6 +38,7 @@ SIGNATURES = {
     "aw_profile_enable": (_i, [_vp, _i]),
     "aw_profile_read": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i),
                              C.POINTER(_i64), _dp]),
+    "aw_profile_read_named": (_i, [_vp, _i, C.POINTER(_i), C.c_char_p, C.POINTER(_i64), _dp]),
     "aw_detect_batch": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp]),
     "aw_embed_batch": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _i, _vp, _vp, _i64, _vp, _vp, _i, _vp]),
     "aw_embed_state": (_i, [_vp, _i, _vp, _i64, _vp]),

@@ -67,6 +67,8 @@ struct aw_ctx {
   PFN_encodeTiled encode = nullptr;
   CUtensorMap tm_w[4], tm_wt[4], tm_w16[4], tm_wt16[4];
   // workspace (grow-only)
+  bool no_fuse_norm = true;   // AW_B200_FUSE_NORM=1 opts into the in-GEMM InstanceNorm application
+  Buf ready;                  // [6 fused launches][clips][4] finished-row-tile counters (gemm.cuh FUSE)
   bool legacy_spec = false;   // AW_B200_LEGACY_SPEC=1: separate synthesis / analysis kernels
   Buf scal;
   Buf accum, peakx, mag, ph_u, ph_q, c0, c, m, v, cbest, dA, yoob, y, dpad, M, cs, sigma;
@@ -81,6 +83,9 @@ struct aw_ctx {
   struct ProfRec { int n, k, epi; cudaEvent_t a, b; };
   bool prof_on = false;
   std::vector<ProfRec> prof;
+  // every-launch timeline: an event before each launch; a kernel's time = next mark - its mark
+  struct Mark { const char* label; cudaEvent_t e; };
+  std::vector<Mark> marks;
   std::vector<cudaEvent_t> ev_pool;
 };
 
@@ -93,6 +98,27 @@ static cudaEvent_t prof_event(aw_ctx* ctx) {
     cudaEventCreate(&e);
   }
   return e;
+}
+
+// Timeline mark in front of a launch (label = nullptr closes the previous interval).
+static void prof_mark(aw_ctx* ctx, cudaStream_t st, const char* label) {
+  if (!ctx->prof_on) return;
+  cudaEvent_t e = prof_event(ctx);
+  cudaEventRecord(e, st);
+  ctx->marks.push_back({label, e});
+}
+
+// interned "gemm_<epi>_n<N>_k<K>" labels (pointers stay valid for the process lifetime)
+static const char* gemm_label(int epi, int n, int k) {
+  static char table[32][32];
+  static int used = 0;
+  char buf[32];
+  snprintf(buf, sizeof(buf), "gemm_%s_n%d_k%d", epi == 1 ? "fwd" : (epi == 2 ? "bwd" : "plain"), n, k);
+  for (int i = 0; i < used; ++i)
+    if (strcmp(table[i], buf) == 0) return table[i];
+  if (used == 32) return "gemm_other";
+  strcpy(table[used], buf);
+  return table[used++];
 }
 
 static int ensure(Buf& b, size_t bytes) {
@@ -123,12 +149,12 @@ static int make_map(aw_ctx* ctx, CUtensorMap* map, const void* ptr, uint64_t row
 
 static int bn_for(int n) { return n >= 256 ? 256 : (n >= 128 ? 128 : 64); }
 
-template <typename T, typename OT, int BN, int EPI>
+template <typename T, typename OT, int BN, int EPI, bool FUSE = false>
 static int launch_tc(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, int rows, int n,
                      int k, const EpiArgsT<OT>& ep, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    AW_CUDA(cudaFuncSetAttribute(k_gemm_tc<T, OT, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AW_CUDA(cudaFuncSetAttribute(k_gemm_tc<T, OT, BN, EPI, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  gemm_tc_smem<BN>()));
     attr_set = true;
   }
@@ -141,8 +167,9 @@ static int launch_tc(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, 
     pr.a = prof_event(ctx); pr.b = prof_event(ctx);
     cudaEventRecord(pr.a, st);
   }
-  k_gemm_tc<T, OT, BN, EPI><<<grid, AW_GEMM_THREADS, gemm_tc_smem<BN>(), st>>>(ma, mb, k, n_row_tiles,
-                                                                              n_col_tiles, ep);
+  prof_mark(ctx, st, gemm_label(EPI, n, k));
+  k_gemm_tc<T, OT, BN, EPI, FUSE><<<grid, FUSE ? AW_GEMM_THREADS_FUSED : AW_GEMM_THREADS,
+                                    gemm_tc_smem<BN>(), st>>>(ma, mb, k, n_row_tiles, n_col_tiles, ep);
   if (ctx->prof_on) {
     cudaEventRecord(pr.b, st);
     ctx->prof.push_back(pr);
@@ -170,11 +197,13 @@ static int launch_exact(aw_ctx* ctx, const float* a, const float* b, int rows, i
   EpiArgs ep;
   ep.out = ept.out; ep.ldo = ept.ldo; ep.n_valid = n; ep.part = ept.part; ep.ldp = ept.ldp; ep.act = ept.act;
   dim3 grid(rows / 64, (n + 63) / 64);
+  prof_mark(ctx, st, "gemm_exact");
   k_gemm_exact<<<grid, 256, 0, st>>>(a, b, k, n, ep.out, ep.ldo);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   if (EPI != EPI_PLAIN) {
     dim3 g2(rows / 128, (n + 127) / 128);
+    prof_mark(ctx, st, "epilogue_exact");
     k_epilogue_exact<EPI><<<g2, 128, 0, st>>>(ep, n);
     ctx->launches++;
     AW_LAUNCH_CHECK();
@@ -207,6 +236,12 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
   {
     const char* e = getenv("AW_B200_LEGACY_SPEC");
     ctx->legacy_spec = e && e[0] == '1';
+    // measured on B200 (128 x 10 s clips, TF32): 5.44 ms/iteration fused vs 5.50 ms unfused, detect
+    // 2.33 vs 2.10 ms -- the 4 normaliser warps per SM are latency-bound, so the L2-hot
+    // re-read buys nothing.  Kept as an opt-in experiment (single stream only: the kernel's
+    // CTAs wait on one another).
+    e = getenv("AW_B200_FUSE_NORM");
+    ctx->no_fuse_norm = !(e && e[0] == '1');
   }
 
   void* fn = nullptr;
@@ -287,7 +322,7 @@ extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
                  &ctx->act[4], &ctx->ga, &ctx->gb, &ctx->dh4, &ctx->dp0, &ctx->part, &ctx->stat[0],
                  &ctx->stat[1], &ctx->stat[2], &ctx->stat[3], &ctx->stat[4], &ctx->bstat,
                  &ctx->values, &ctx->best, &ctx->improved, &ctx->pattern, &ctx->itc, &ctx->steps,
-                 &ctx->scal};
+                 &ctx->scal, &ctx->ready};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   delete ctx;
@@ -333,6 +368,37 @@ extern "C" int aw_profile_read(aw_ctx* ctx, int max_classes, int* n_classes, int
     ctx->ev_pool.push_back(r.b);
   }
   ctx->prof.clear();
+  *n_classes = nc;
+  return 0;
+}
+
+// Per-kernel-class device time of everything launched since the last read (every launch is
+// bracketed by events on the launching stream).  names: [max_classes][32] chars.
+extern "C" int aw_profile_read_named(aw_ctx* ctx, int max_classes, int* n_classes, char* names,
+                                     int64_t* cls_count, double* cls_ms) {
+  AW_REQUIRE(ctx && n_classes && names && cls_count && cls_ms, "null argument");
+  int nc = 0;
+  for (size_t i = 0; i + 1 < ctx->marks.size(); ++i) {
+    const aw_ctx::Mark& a = ctx->marks[i];
+    if (!a.label) continue;
+    AW_CUDA(cudaEventSynchronize(ctx->marks[i + 1].e));
+    float ms = 0.f;
+    AW_CUDA(cudaEventElapsedTime(&ms, a.e, ctx->marks[i + 1].e));
+    int c = 0;
+    for (; c < nc; ++c)
+      if (strncmp(names + 32 * c, a.label, 31) == 0) break;
+    if (c == nc) {
+      if (nc >= max_classes) continue;
+      strncpy(names + 32 * c, a.label, 31);
+      names[32 * c + 31] = 0;
+      cls_count[c] = 0; cls_ms[c] = 0.0;
+      ++nc;
+    }
+    cls_count[c] += 1;
+    cls_ms[c] += ms;
+  }
+  for (auto& m : ctx->marks) ctx->ev_pool.push_back(m.e);
+  ctx->marks.clear();
   *n_classes = nc;
   return 0;
 }
@@ -430,10 +496,11 @@ struct Acc {
 };
 static Acc acc_view(aw_ctx* ctx, const struct Dims& d);
 
-__global__ void k_iter_begin(unsigned long long* peak, int n, int* it) {
+__global__ void k_iter_begin(unsigned long long* peak, int n, int* it, int* ready, int n_ready) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) peak[i] = 0ull;
   if (i == 0 && it) *it += 1;
+  for (int j = i; j < n_ready; j += gridDim.x * blockDim.x) ready[j] = 0;
 }
 
 static int mel_blocks(const Dims& d) { return (d.T + AW_MEL_FRAMES - 1) / AW_MEL_FRAMES; }
@@ -475,6 +542,7 @@ static int ensure_net_ws(aw_ctx* ctx, const Dims& d, bool backward) {
   if (ensure(ctx->best, n * 4)) return 1;
   if (ensure(ctx->improved, n * 4)) return 1;
   if (ensure(ctx->itc, 4)) return 1;
+  if (ensure(ctx->ready, n * 6 * 4 * sizeof(int))) return 1;
   if (backward) {
     void *b0 = ctx->ga.p, *b1 = ctx->gb.p, *b2 = ctx->dh4.p;
     if (ensure(ctx->ga, R * 1024 * 4)) return 1;
@@ -512,12 +580,14 @@ template <>
 int gemm_layer<float, EPI_FWD>(aw_ctx* ctx, const CUtensorMap& ma, const void* a, const CUtensorMap& mb,
                                const void* b, int rows, int n, int k, const EpiArgsT<float>& ep, cudaStream_t st) {
   if (ctx->prec == AW_PREC_FP32) return launch_exact<EPI_FWD>(ctx, (const float*)a, (const float*)b, rows, n, k, ep, st);
+  if (ep.ready) return launch_tc<float, float, 256, EPI_FWD, true>(ctx, ma, mb, rows, n, k, ep, st);
   return launch_tc_bn<float, float, EPI_FWD>(ctx, ma, mb, rows, n, k, ep, st);
 }
 template <>
 int gemm_layer<float, EPI_BWD>(aw_ctx* ctx, const CUtensorMap& ma, const void* a, const CUtensorMap& mb,
                                const void* b, int rows, int n, int k, const EpiArgsT<float>& ep, cudaStream_t st) {
   if (ctx->prec == AW_PREC_FP32) return launch_exact<EPI_BWD>(ctx, (const float*)a, (const float*)b, rows, n, k, ep, st);
+  if (ep.ready) return launch_tc<float, float, 256, EPI_BWD, true>(ctx, ma, mb, rows, n, k, ep, st);
   return launch_tc_bn<float, float, EPI_BWD>(ctx, ma, mb, rows, n, k, ep, st);
 }
 template <>
@@ -544,11 +614,13 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
   const int tf = ctx->prec == AW_PREC_TF32;
   {
     dim3 g((d.T + AW_MEL_FRAMES - 1) / AW_MEL_FRAMES, d.n);
+    prof_mark(ctx, st, "mel");
     k_mel<<<g, 128, AW_MEL_FRAMES * d.nb * 4, st>>>((float*)ctx->mag.p, d.T, d.nb, sm,
                                                     (float*)ctx->M.p, acc.chan_part, peak_scale);
     ctx->launches++;
     AW_LAUNCH_CHECK();
     dim3 g2((d.Tp_pad + AW_P0_ROWS - 1) / AW_P0_ROWS, d.n);
+    prof_mark(ctx, st, "p0");
     k_p0<AT><<<g2, 128, 0, st>>>((float*)ctx->M.p, d.T, d.Tp, d.Tp_pad, acc.chan_part, acc.mel_blocks,
                                  (AT*)ctx->act[0].p, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p, tf);
     ctx->launches++;
@@ -559,17 +631,27 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
     EpiArgsT<AT> ep;
     ep.out = (AT*)ctx->act[l + 1].p; ep.ldo = cout;
     ep.part = (float*)ctx->part.p; ep.ldp = cout; ep.act = nullptr;
+    const bool fuse = !B && ctx->prec == AW_PREC_TF32 && cout >= 256 && !ctx->no_fuse_norm;
+    ep.ready = fuse ? (int*)ctx->ready.p + (size_t)l * d.n * 4 : nullptr;
+    ep.tiles_per_clip = d.tiles; ep.Tp = d.Tp;
+    ep.stat = (float*)ctx->stat[l + 1].p; ep.round_tf32 = tf && l < 3;
     const CUtensorMap& mw = B ? ctx->tm_w16[l] : ctx->tm_w[l];
     const void* w = B ? (const void*)ctx->d_w16[l] : (const void*)ctx->d_w[l];
     if (gemm_layer<AT, EPI_FWD>(ctx, ctx->tm_act[B][l], ctx->act[l].p, mw, w, d.rows, cout, cin, ep, st))
       return 1;
+    if (fuse) continue;   // statistics + normalise + LeakyReLU already applied inside the GEMM kernel
     dim3 g((cout + 127) / 128, d.n);
+    prof_mark(ctx, st, "finalize_fwd");
     k_finalize_fwd<<<g, 128, 0, st>>>((float*)ctx->part.p, cout, d.tiles, cout, d.Tp,
                                       (float*)ctx->stat[l + 1].p);
     ctx->launches++;
     AW_LAUNCH_CHECK();
-    k_norm_act<AT><<<d.rows / 4, 256, 0, st>>>((AT*)ctx->act[l + 1].p, cout, d.Tp, d.Tp_pad,
-                                               (float*)ctx->stat[l + 1].p, tf && l < 3);
+    prof_mark(ctx, st, "norm_act");
+    {
+      dim3 gn(d.Tp_pad / AW_NORM_ROWS, (cout / 4 + 127) / 128, d.n);
+      k_norm_rows<AT, NORM_FWD><<<gn, 128, 0, st>>>((AT*)ctx->act[l + 1].p, nullptr, cout, d.Tp, d.Tp_pad,
+                                                    (float*)ctx->stat[l + 1].p, nullptr, tf && l < 3);
+    }
     ctx->launches++;
     AW_LAUNCH_CHECK();
   }
@@ -593,23 +675,33 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
     EpiArgsT<AT> ep;
     ep.out = steps[s].out; ep.ldo = n;
     ep.part = (float*)ctx->part.p; ep.ldp = n; ep.act = (AT*)ctx->act[l].p;
+    const bool fuse = !B && ctx->prec == AW_PREC_TF32 && n >= 256 && !ctx->no_fuse_norm;
+    ep.ready = fuse ? (int*)ctx->ready.p + (size_t)(3 + s) * d.n * 4 : nullptr;
+    ep.tiles_per_clip = d.tiles; ep.Tp = d.Tp;
+    ep.stat = (float*)ctx->stat[l].p; ep.round_tf32 = tf;
     const CUtensorMap& mw = B ? ctx->tm_wt16[l] : ctx->tm_wt[l];
     const void* w = B ? (const void*)ctx->d_wt16[l] : (const void*)ctx->d_wt[l];
     if (gemm_layer<AT, EPI_BWD>(ctx, *steps[s].ma, steps[s].a, mw, w, d.rows, n, k, ep, st)) return 1;
+    if (fuse) continue;   // InstanceNorm adjoint already applied inside the GEMM kernel
     dim3 g((n + 127) / 128, d.n);
+    prof_mark(ctx, st, "finalize_bwd");
     k_finalize_bwd<<<g, 128, 0, st>>>((float*)ctx->part.p, n, d.tiles, n, d.Tp,
                                       (float*)ctx->bstat.p);
     ctx->launches++;
     AW_LAUNCH_CHECK();
-    k_in_bwd_apply<AT><<<d.rows / 4, 256, 0, st>>>(steps[s].out, (AT*)ctx->act[l].p, n, d.Tp,
-                                                   d.Tp_pad, (float*)ctx->stat[l].p,
-                                                   (float*)ctx->bstat.p, tf);
+    prof_mark(ctx, st, "in_bwd_apply");
+    {
+      dim3 gn(d.Tp_pad / AW_NORM_ROWS, (n / 4 + 127) / 128, d.n);
+      k_norm_rows<AT, NORM_BWD><<<gn, 128, 0, st>>>(steps[s].out, (AT*)ctx->act[l].p, n, d.Tp, d.Tp_pad,
+                                                    (float*)ctx->stat[l].p, (float*)ctx->bstat.p, tf);
+    }
     ctx->launches++;
     AW_LAUNCH_CHECK();
   }
   {
     // dP0 = dH1 * W0 stays float32 (128 columns; feeds the fp32 front-end adjoints)
     EpiArgsT<float> ep;
+    memset(&ep, 0, sizeof(ep));
     ep.out = (float*)ctx->dp0.p; ep.ldo = 128;
     ep.part = nullptr; ep.ldp = 0; ep.act = nullptr;
     if (B) {
@@ -623,11 +715,13 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
     }
   }
   dim3 g1((2 * d.Tp + AW_P0B_FRAMES - 1) / AW_P0B_FRAMES, d.n);
+  prof_mark(ctx, st, "p0_bwd_reduce");
   k_p0_bwd_reduce<<<g1, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
                                       (ChanStats*)ctx->cs.p, acc.bpart);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   dim3 g2((d.T + AW_P0A_FRAMES - 1) / AW_P0A_FRAMES, d.n);
+  prof_mark(ctx, st, "p0_bwd_apply");
   k_p0_bwd_apply<<<g2, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
                                      (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p, acc.bpart,
                                      acc.p0b_blocks, sm, d.nb, (float*)ctx->dA.p,
@@ -648,6 +742,7 @@ static int run_head(aw_ctx* ctx, const Dims& d, const float* pattern, float* val
   h.dH4 = backward ? (AT*)ctx->dh4.p : nullptr;
   h.it_ptr = (int*)ctx->itc.p; h.n_clips = n_total;
   h.round_tf32 = ctx->prec == AW_PREC_TF32;
+  prof_mark(ctx, st, "head");
   k_head<AT><<<d.n, 256, 0, st>>>(h);
   ctx->launches++;
   AW_LAUNCH_CHECK();
@@ -678,6 +773,7 @@ static int launch_ana_k(aw_ctx* ctx, const Dims& d, const AnaArgs& a, cudaStream
     attr_set = true;
   }
   dim3 g((d.T + AW_ANA_FRAMES - 1) / AW_ANA_FRAMES, d.n);
+  prof_mark(ctx, st, MODE == ANA_MAG ? "analysis_mag" : (MODE == ANA_INIT ? "analysis_init" : "analysis_legacy"));
   k_analysis<MODE, K2LO, K2HI><<<g, 128, AW_ANA_SMEM, st>>>(a);
   ctx->launches++;
   AW_LAUNCH_CHECK();
@@ -701,6 +797,7 @@ static int launch_syn_k(aw_ctx* ctx, const Dims& d, const SynArgs& s, cudaStream
     attr_set = true;
   }
   dim3 g((d.T + 3 + AW_SYN_HOPS - 1) / AW_SYN_HOPS, d.n);
+  prof_mark(ctx, st, MODE == SYN_OOB ? "synthesis_oob" : (MODE == SYN_WAVE ? "synthesis_wave" : "synthesis_legacy"));
   k_synthesis<MODE, K2LO, K2HI><<<g, 128, AW_SYN_SMEM, st>>>(s);
   ctx->launches++;
   AW_LAUNCH_CHECK();
@@ -726,6 +823,7 @@ static int launch_spec_k(aw_ctx* ctx, const Dims& d, SpecArgs& a, cudaStream_t s
   a.window = ctx->d_window; a.twiddle = ctx->d_twiddle; a.env256 = ctx->d_env256;
   const int items = a.n_clips * a.tiles;
   const int grid = std::min(items, 2 * ctx->num_sms);
+  prof_mark(ctx, st, MODE == SPEC_FWD ? "spec_fwd" : "spec_bwd");
   k_spec<MODE, K2LO, K2HI><<<grid, 32 * AW_SP_WARPS, AW_SP_SMEM, st>>>(a);
   ctx->launches++;
   AW_LAUNCH_CHECK();
@@ -742,13 +840,17 @@ static int launch_peak(aw_ctx* ctx, const float* x, int64_t stride, int n, int n
                        unsigned long long* peak, cudaStream_t st) {
   AW_CUDA(cudaMemsetAsync(peak, 0, (size_t)n_clips * 8, st));
   dim3 g(std::min((n + 2047) / 2048, 64), n_clips);
+  prof_mark(ctx, st, "peak");
   k_peak<<<g, 256, 0, st>>>(x, stride, n, peak);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
 }
 static int begin_pass(aw_ctx* ctx, int n, int* it, cudaStream_t st) {
-  k_iter_begin<<<(n + 255) / 256, 256, 0, st>>>((unsigned long long*)ctx->accum.p, n, it);
+  prof_mark(ctx, st, "iter_begin");
+  k_iter_begin<<<(n + 255) / 256, 256, 0, st>>>((unsigned long long*)ctx->accum.p, n, it,
+                                                (int*)ctx->ready.p,
+                                                (int)std::min<size_t>((size_t)6 * n * 4, ctx->ready.cap / 4));
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
@@ -775,10 +877,14 @@ extern "C" int aw_detect_batch(aw_ctx* ctx, const float* d_audio, int n_clips, i
   if (launch_ana<ANA_MAG>(ctx, d, a, st)) return 1;
   if (ctx->prec == AW_PREC_BF16) {
     if (net_forward<__nv_bfloat16>(ctx, d, acc, sm, st)) return 1;
-    return run_head<__nv_bfloat16>(ctx, d, nullptr, d_values, nullptr, d.n, false, st);
+    if (run_head<__nv_bfloat16>(ctx, d, nullptr, d_values, nullptr, d.n, false, st)) return 1;
+    prof_mark(ctx, st, nullptr);
+    return 0;
   }
   if (net_forward<float>(ctx, d, acc, sm, st)) return 1;
-  return run_head<float>(ctx, d, nullptr, d_values, nullptr, d.n, false, st);
+  if (run_head<float>(ctx, d, nullptr, d_values, nullptr, d.n, false, st)) return 1;
+  prof_mark(ctx, st, nullptr);
+  return 0;
 }
 
 __global__ void k_to_bf16(const float* in, __nv_bfloat16* out, size_t n) {
@@ -899,6 +1005,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
           return 1;
         if (net_backward<float>(ctx, dw, acc, sm, st, true)) return 1;
       }
+      prof_mark(ctx, st, "clip_scalars");
       k_clip_scalars<<<(dw.n + 127) / 128, 128, 0, st>>>(acc.peak_y, acc.s2_part, p0a_blocks(dw), dw.n,
                                                          (ClipScal*)ctx->scal.p);
       ctx->launches++;
@@ -957,6 +1064,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
     sf.y_oob = (float*)ctx->yoob.p; sf.y = (float*)ctx->y.p; sf.peak_y = acc.peak_y;
     if (launch_syn<SYN_WAVE>(ctx, dw, sf, st)) return 1;
     dim3 g(std::min((dw.L + 2047) / 2048, 64), dw.n);
+    prof_mark(ctx, st, "final_normalize");
     k_final_normalize<<<g, 256, 0, st>>>((float*)ctx->y.p, dw.L, acc.peak_y,
                                          d_scale ? d_scale + w0 : nullptr,
                                          d_out + (size_t)w0 * out_stride, out_stride);
@@ -967,6 +1075,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
                               cudaMemcpyDeviceToDevice, st));
     ctx->last_n = dw.n; ctx->last_T = dw.T; ctx->last_nb = dw.nb;
   }
+  prof_mark(ctx, st, nullptr);
   return 0;
 }
 
@@ -1090,6 +1199,7 @@ extern "C" int aw_gemm(aw_ctx* ctx, const float* d_a, const float* d_b, float* d
   AW_REQUIRE(n % bn_for(n) == 0, "aw_gemm: n must be a multiple of its tile (%d)", bn_for(n));
   cudaStream_t st = (cudaStream_t)stream;
   EpiArgsT<float> ep;
+  memset(&ep, 0, sizeof(ep));
   ep.out = d_d; ep.ldo = n; ep.part = nullptr; ep.ldp = 0; ep.act = nullptr;
   if (prec == AW_PREC_FP32) return launch_exact<EPI_PLAIN>(ctx, d_a, d_b, rows, n, k, ep, st);
   CUtensorMap ma, mb;

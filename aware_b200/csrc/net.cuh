@@ -177,62 +177,63 @@ __global__ void __launch_bounds__(128) k_finalize_bwd(const float* __restrict__ 
   bstat[((long long)clip * C + c) * 2 + 1] = (float)(s2 / Tp);
 }
 
-// ---- P = LeakyReLU(InstanceNorm(H)), in place; pad rows forced to 0 -----------
-// grid = (rows / 4), block = 256; C % 4 == 0
-template <typename AT>
-__global__ void __launch_bounds__(256) k_norm_act(AT* __restrict__ H, int C, int Tp, int Tp_pad,
-                                                  const float* __restrict__ stat, int round_tf32) {
-  const int r0 = blockIdx.x * 4;
-  const int c4 = C >> 2;
-  for (int i = threadIdx.x; i < 4 * c4; i += 256) {
-    const int row = r0 + i / c4, c = (i % c4) * 4;
-    const int clip = row / Tp_pad, j = row - clip * Tp_pad;
-    AT* p = H + (long long)row * C + c;
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
-    if (j < Tp) {
-      float h[4];
-      act_ld4(p, h);
-      const float4 s01 = *reinterpret_cast<const float4*>(stat + ((long long)clip * C + c) * 2);
-      const float4 s23 = *reinterpret_cast<const float4*>(stat + ((long long)clip * C + c) * 2 + 4);
-      o[0] = leaky((h[0] - s01.x) * s01.y);
-      o[1] = leaky((h[1] - s01.z) * s01.w);
-      o[2] = leaky((h[2] - s23.x) * s23.y);
-      o[3] = leaky((h[3] - s23.z) * s23.w);
-      if (round_tf32) { o[0] = to_tf32(o[0]); o[1] = to_tf32(o[1]); o[2] = to_tf32(o[2]); o[3] = to_tf32(o[3]); }
+// ---- row-wise InstanceNorm application, in place --------------------------------
+// NORM_FWD: P  = LeakyReLU((H - mean) * rstd)                      (conv1d.py:40-41)
+// NORM_BWD: dH = rstd * (dHhat - a1 - Hhat * a2), Hhat recovered from P
+// pad rows (j >= Tp) are forced to 0.  One thread owns 4 adjacent channels of one clip for
+// AW_NORM_ROWS rows: the per-channel statistics are loaded once into registers and the
+// row loop is pure 16-byte streaming with 8 independent loads in flight.
+// grid = (Tp_pad / AW_NORM_ROWS, C / (4 * 128) rounded up, n_clips), block = 128.
+enum { NORM_FWD = 0, NORM_BWD = 1 };
+#define AW_NORM_ROWS 32
+template <typename AT, int MODE>
+__global__ void __launch_bounds__(128) k_norm_rows(AT* __restrict__ X, const AT* __restrict__ P, int C,
+                                                   int Tp, int Tp_pad, const float* __restrict__ stat,
+                                                   const float* __restrict__ bstat, int round_tf32) {
+  const int clip = blockIdx.z;
+  const int c = (blockIdx.y * 128 + threadIdx.x) * 4;
+  if (c >= C) return;
+  const int j0 = blockIdx.x * AW_NORM_ROWS;
+  float mu[4], rs[4], a1[4], a2[4];
+  {
+    const float4 s01 = *reinterpret_cast<const float4*>(stat + ((long long)clip * C + c) * 2);
+    const float4 s23 = *reinterpret_cast<const float4*>(stat + ((long long)clip * C + c) * 2 + 4);
+    mu[0] = s01.x; rs[0] = s01.y; mu[1] = s01.z; rs[1] = s01.w;
+    mu[2] = s23.x; rs[2] = s23.y; mu[3] = s23.z; rs[3] = s23.w;
+    if (MODE == NORM_BWD) {
+      const float4 b01 = *reinterpret_cast<const float4*>(bstat + ((long long)clip * C + c) * 2);
+      const float4 b23 = *reinterpret_cast<const float4*>(bstat + ((long long)clip * C + c) * 2 + 4);
+      a1[0] = b01.x; a2[0] = b01.y; a1[1] = b01.z; a2[1] = b01.w;
+      a1[2] = b23.x; a2[2] = b23.y; a1[3] = b23.z; a2[3] = b23.w;
     }
-    act_st4(p, o);
   }
-}
-
-// ---- dH = rstd * (dHhat - a1 - Hhat * a2), in place on dHhat ------------------
-template <typename AT>
-__global__ void __launch_bounds__(256) k_in_bwd_apply(AT* __restrict__ dH,
-                                                      const AT* __restrict__ P, int C, int Tp,
-                                                      int Tp_pad, const float* __restrict__ stat,
-                                                      const float* __restrict__ bstat,
-                                                      int round_tf32) {
-  const int r0 = blockIdx.x * 4;
-  const int c4 = C >> 2;
-  for (int i = threadIdx.x; i < 4 * c4; i += 256) {
-    const int row = r0 + i / c4, c = (i % c4) * 4;
-    const int clip = row / Tp_pad, j = row - clip * Tp_pad;
-    AT* p = dH + (long long)row * C + c;
-    float oo[4] = {0.f, 0.f, 0.f, 0.f};
-    if (j < Tp) {
-      float dd[4], aa[4];
-      act_ld4(p, dd);
-      act_ld4(P + (long long)row * C + c, aa);
+  AT* x = X + ((long long)clip * Tp_pad + j0) * C + c;
+  const AT* p = MODE == NORM_BWD ? P + ((long long)clip * Tp_pad + j0) * C + c : nullptr;
+  constexpr int NB = 8;
+#pragma unroll 1
+  for (int r0 = 0; r0 < AW_NORM_ROWS; r0 += NB) {
+    float h[NB][4], a[NB][4];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      act_ld4(x + (long long)(r0 + i) * C, h[i]);
+      if (MODE == NORM_BWD) act_ld4(p + (long long)(r0 + i) * C, a[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      float o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const long long sidx = ((long long)clip * C + c + k) * 2;
-        const float rstd = stat[sidx + 1];
-        const float a1 = bstat[sidx], a2 = bstat[sidx + 1];
-        const float hh = aa[k] > 0.f ? aa[k] : aa[k] * (1.0f / AW_LEAKY);
-        oo[k] = rstd * (dd[k] - a1 - hh * a2);
-        if (round_tf32) oo[k] = to_tf32(oo[k]);
+        if (MODE == NORM_FWD) {
+          o[k] = leaky((h[i][k] - mu[k]) * rs[k]);
+        } else {
+          const float hh = a[i][k] > 0.f ? a[i][k] : a[i][k] * (1.0f / AW_LEAKY);
+          o[k] = rs[k] * (h[i][k] - a1[k] - hh * a2[k]);
+        }
+        if (round_tf32) o[k] = to_tf32(o[k]);
+        if (j0 + r0 + i >= Tp) o[k] = 0.f;
       }
+      act_st4(x + (long long)(r0 + i) * C, o);
     }
-    act_st4(p, oo);
   }
 }
 

@@ -95,6 +95,17 @@ class Engine:
         _lib.check(self.lib.aw_profile_read(self._ctx, mx, C.byref(nc), n, k, e, cnt, ms))
         return [(n[i], k[i], e[i], int(cnt[i]), float(ms[i])) for i in range(nc.value)]
 
+    def profile_read_named(self):
+        """{kernel class: (launches, total_ms)} of EVERY kernel launched since the last read."""
+        mx = 64
+        nc = C.c_int()
+        names = C.create_string_buffer(32 * mx)
+        cnt, ms = (C.c_int64 * mx)(), (C.c_double * mx)()
+        _lib.check(self.lib.aw_profile_read_named(self._ctx, mx, C.byref(nc), names, cnt, ms))
+        raw = names.raw
+        return {raw[32 * i:32 * i + 32].split(b"\0", 1)[0].decode(): (int(cnt[i]), float(ms[i]))
+                for i in range(nc.value)}
+
     def band_bins(self, sample_rate: int):
         b0, nb = C.c_int(), C.c_int()
         _lib.check(self.lib.aw_band_bins(self._ctx, int(sample_rate), C.byref(b0), C.byref(nb)))

@@ -63,6 +63,10 @@ int64_t aw_launch_count(aw_ctx* ctx);
 int aw_profile_enable(aw_ctx* ctx, int on);
 int aw_profile_read(aw_ctx* ctx, int max_classes, int* n_classes, int* cls_n, int* cls_k,
                     int* cls_epi, int64_t* cls_count, double* cls_ms);
+/* Device time of every kernel launched since the last read, summed per kernel class
+ * (events on the launching stream around each launch).  names: max_classes x 32 chars. */
+int aw_profile_read_named(aw_ctx* ctx, int max_classes, int* n_classes, char* names,
+                          int64_t* cls_count, double* cls_ms);
 
 /* ---- detection: AWAREDetector.detect (detection/multibit_detector.py:28-42) for a batch.
  * d_values: [n_clips][20] float32 tanh outputs. */

@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 OUT = os.path.join(ROOT, "gpurun_out")
 
 STAGES = ["gradmap", "stft", "istft", "attacks", "detect_fp32", "gemm_tc", "detect_tf32", "embed1_fp32",
-          "embed1_tf32", "embed3", "embed_full", "timing"]
+          "embed1_tf32", "embed3", "embed_full", "timing", "dual", "timeline"]
 
 
 def _engine(precision="fp32"):
@@ -325,6 +325,67 @@ def stage_timing(res):
         dd = time.time() - t1
         res["n%d_%s" % (n, prec)] = dict(ms_per_iter=1e3 * dt / iters, est_400it_audio_s_per_s=n * 10.0 / (dt / iters * 400),
                               detect_ms=1e3 * dd, detect_audio_s_per_s=n * 10.0 / dd)
+
+
+def stage_timeline(res):
+    """Device time per kernel class inside the embed loop (events around every launch)."""
+    import numpy as np
+    import torch
+    from aware_b200.synth import synth_batch, synth_bits
+    from aware_b200.utils.watermark import PatternEncoder
+    sr = 44100
+    for n, iters, prec in ((128, 10, "tf32"), (128, 10, "bf16")):
+        eng = _engine("tf32")
+        eng.embed_precision = prec
+        x = torch.from_numpy(synth_batch(n, 10.0, sr)).cuda()
+        pat = torch.from_numpy(np.stack([PatternEncoder()(b) for b in synth_bits(n)]))
+        eng.embed(x, sr, pat, iters=2)
+        torch.cuda.synchronize()
+        eng.profile(True)
+        eng.embed(x, sr, pat, iters=iters)
+        torch.cuda.synchronize()
+        tl = eng.profile_read_named()
+        eng.profile(False)
+        tot = sum(v[1] for v in tl.values())
+        res["n%d_%s" % (n, prec)] = dict(total_ms_per_iter=tot / iters,
+                                         classes={k: [v[0], round(v[1] / iters, 4)] for k, v in
+                                                  sorted(tl.items(), key=lambda kv: -kv[1][1])})
+
+
+def stage_dual(res):
+    """Two half-batches on two streams / two contexts from two host threads: do the HBM-bound
+    elementwise kernels of one half overlap the tensor-bound GEMMs of the other?"""
+    import threading
+    import numpy as np
+    import torch
+    from aware_b200.synth import synth_batch, synth_bits
+    from aware_b200.utils.watermark import PatternEncoder
+    sr, n, iters = 44100, 128, 10
+    x = torch.from_numpy(synth_batch(n, 10.0, sr)).cuda()
+    pat = torch.from_numpy(np.stack([PatternEncoder()(b) for b in synth_bits(n)]))
+    for prec in ("tf32", "bf16"):
+        for parts in (1, 2, 4):
+            engs = [_engine("tf32") for _ in range(parts)]
+            streams = [torch.cuda.Stream() for _ in range(parts)]
+            h = n // parts
+
+            def work(i, it):
+                with torch.cuda.stream(streams[i]):
+                    engs[i].embed_precision = prec
+                    engs[i].embed(x[i * h:(i + 1) * h], sr, pat[i * h:(i + 1) * h], iters=it)
+
+            def run(it):
+                th = [threading.Thread(target=work, args=(i, it)) for i in range(parts)]
+                [t.start() for t in th]
+                [t.join() for t in th]
+                torch.cuda.synchronize()
+
+            run(2)
+            t0 = time.time()
+            run(iters)
+            dt = time.time() - t0
+            res["%s_parts%d" % (prec, parts)] = dict(ms_per_iter=1e3 * dt / iters)
+            del engs
 
 
 def run_stage(name):
