@@ -70,7 +70,7 @@ struct aw_ctx {
   bool no_fuse_norm = true;   // AW_B200_FUSE_NORM=1 opts into the in-GEMM InstanceNorm application
   Buf ready;                  // [6 fused launches][clips][4] finished-row-tile counters (gemm.cuh FUSE)
   bool legacy_spec = false;   // AW_B200_LEGACY_SPEC=1: separate synthesis / analysis kernels
-  Buf scal;
+  Buf scal, zoob;
   Buf accum, peakx, mag, ph_u, ph_q, c0, c, m, v, cbest, dA, yoob, y, dpad, M, cs, sigma;
   Buf act[5], ga, gb, dh4, dp0, part, stat[5], bstat, values, best, improved, pattern, itc, steps;
   int ws_rows = 0;
@@ -322,7 +322,7 @@ extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
                  &ctx->act[4], &ctx->ga, &ctx->gb, &ctx->dh4, &ctx->dp0, &ctx->part, &ctx->stat[0],
                  &ctx->stat[1], &ctx->stat[2], &ctx->stat[3], &ctx->stat[4], &ctx->bstat,
                  &ctx->values, &ctx->best, &ctx->improved, &ctx->pattern, &ctx->itc, &ctx->steps,
-                 &ctx->scal, &ctx->ready};
+                 &ctx->scal, &ctx->ready, &ctx->zoob};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   delete ctx;
@@ -939,6 +939,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       ensure(ctx->c, sp * 4) || ensure(ctx->m, sp * 4) || ensure(ctx->v, sp * 4) ||
       ensure(ctx->cbest, sp * 4) || ensure(ctx->dA, sp * 4) ||
       ensure(ctx->yoob, (size_t)d.n * d.L * 4) || ensure(ctx->y, (size_t)d.n * d.L * 4) ||
+      ensure(ctx->zoob, (size_t)d.n * d.L * 4) ||
       ensure(ctx->dpad, (size_t)d.n * (d.L + AW_NFFT) * 4) ||
       ensure(ctx->pattern, (size_t)d.n * AW_NBITS * 4) || ensure(ctx->scal, (size_t)d.n * sizeof(ClipScal)) ||
       ensure(ctx->steps, (size_t)(iters > 0 ? iters : 1) * sizeof(NadamStep)))
@@ -981,6 +982,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
     s0.amp = (float*)ctx->c0.p; s0.ph = (float2*)ctx->ph_u.p; s0.scale = 1.0f / AW_NFFT;
     s0.x = x; s0.x_stride = stride; s0.peak_x = (unsigned long long*)ctx->peakx.p;
     s0.y_oob = (float*)ctx->yoob.p;
+    s0.z_oob = ctx->legacy_spec ? nullptr : (float*)ctx->zoob.p;
     if (launch_syn<SYN_OOB>(ctx, dw, s0, st)) return 1;
 
     // ---- optimisation loop (multibit_embedder.py:95-122)
@@ -990,7 +992,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       SpecArgs f;
       memset(&f, 0, sizeof(f));
       f.amp = (float*)ctx->c.p; f.ph = (float2*)ctx->ph_u.p;
-      f.y_oob = (float*)ctx->yoob.p; f.peak_y = acc.peak_y;
+      f.z_oob = (float*)ctx->zoob.p; f.peak_y = acc.peak_y;
       f.mag = (float*)ctx->mag.p; f.q = (float2*)ctx->ph_q.p;
       if (launch_spec<SPEC_FWD>(ctx, dw, f, st)) return 1;
       float* lp = d_losses ? d_losses + w0 : nullptr;

@@ -351,6 +351,7 @@ struct SynArgs {
   // SYN_OOB: y_oob = x/(peak_x+1e-8) - ola/env
   const float* x; long long x_stride; const unsigned long long* peak_x;
   float* y_oob;                // [clip][L]   (OOB: out; WAVE: in)
+  float* z_oob;                // [clip][L]   (OOB: optional out) y_oob * envelope, for spec.cuh
   // SYN_WAVE: y = ola/env + y_oob, peak_y
   float* y;                    // [clip][L]   (WAVE: out; ADJ: in)
   unsigned long long* peak_y;  // [clip]      (WAVE: atomicMax out; ADJ: in)
@@ -523,8 +524,13 @@ __global__ void __launch_bounds__(128, 2) k_synthesis(SynArgs a) {
         float yb[4] = {o4.x * e4.x, o4.y * e4.y, o4.z * e4.z, o4.w * e4.w};
         if (MODE == SYN_OOB) {
           const float* xp = a.x + (long long)clip * a.x_stride + (m_lo - AW_HALF) + i;
-          *reinterpret_cast<float4*>(a.y_oob + ob + i) =
-              make_float4(xp[0] * rdx - yb[0], xp[1] * rdx - yb[1], xp[2] * rdx - yb[2], xp[3] * rdx - yb[3]);
+          const float yo[4] = {xp[0] * rdx - yb[0], xp[1] * rdx - yb[1], xp[2] * rdx - yb[2], xp[3] * rdx - yb[3]};
+          *reinterpret_cast<float4*>(a.y_oob + ob + i) = make_float4(yo[0], yo[1], yo[2], yo[3]);
+          if (a.z_oob) {
+            const float4 v4 = *reinterpret_cast<const float4*>(a.env256 + (i & 255));
+            *reinterpret_cast<float4*>(a.z_oob + ob + i) =
+                make_float4(yo[0] * v4.x, yo[1] * v4.y, yo[2] * v4.z, yo[3] * v4.w);
+          }
         } else {
           const float4 q4 = *reinterpret_cast<const float4*>(a.y_oob + ob + i);
           const float yy[4] = {yb[0] + q4.x, yb[1] + q4.y, yb[2] + q4.z, yb[3] + q4.w};
@@ -541,7 +547,9 @@ __global__ void __launch_bounds__(128, 2) k_synthesis(SynArgs a) {
         const float yb = s_ola[m - AW_HOP * f0] * ola_inv_envelope(m, T, s_win, a.env256);
         const long long o = (long long)clip * L + n;
         if (MODE == SYN_OOB) {
-          a.y_oob[o] = a.x[(long long)clip * a.x_stride + n] * rdx - yb;
+          const float yo = a.x[(long long)clip * a.x_stride + n] * rdx - yb;
+          a.y_oob[o] = yo;
+          if (a.z_oob) a.z_oob[o] = __fdiv_rn(yo, ola_inv_envelope(m, T, s_win, a.env256));
         } else {
           const float yy = yb + a.y_oob[o];
           a.y[o] = yy;

@@ -211,6 +211,19 @@ __global__ void __launch_bounds__(128) k_clip_scalars(const unsigned long long* 
   out[clip] = cs;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// whole-CTA L2 prefetch of [base, base + bytes)
+__device__ __forceinline__ void prefetch_l2(const void* base, long long bytes, int tid, int nthreads) {
+  const char* p = reinterpret_cast<const char*>(base);
+  for (long long o = (long long)tid * 128; o < bytes; o += (long long)nthreads * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+}
+
 // ---------------------------------------------------------------------------
 enum { SPEC_FWD = 0, SPEC_BWD = 1 };
 
@@ -222,7 +235,7 @@ struct SpecArgs {
   const float* amp;            // [clip][T][nbins]  FWD: c       BWD: dA~
   const float2* ph;            // [clip][T][nbins]  FWD: u       BWD: q
   // FWD
-  const float* y_oob;          // [clip][L]
+  const float* z_oob;          // [clip][L]  y_oob * overlap-add envelope (k_synthesis<SYN_OOB>)
   unsigned long long* peak_y;  // [clip] (atomicMax, pack_peak_s)
   float* mag;                  // [clip][T][nbins] out: |S~| of the un-normalised y
   float2* q;                   // [clip][T][nbins] out
@@ -287,34 +300,92 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
     const long long fbase = (long long)clip * T;
     __syncthreads();                                     // tables / previous item done with s_buf
 
+    // L2 prefetch of the NEXT item's operands (one whole tile ahead of their first use)
+    {
+      const int nitem = item + gridDim.x;
+      if (nitem < n_items) {
+        const int nclip = nitem / a.tiles, ntile = nitem - nclip * a.tiles;
+        int nt0 = ntile * AW_SP_FA;
+        if (short_last && ntile == a.tiles - 1) nt0 = T - 8;
+        const int f0 = max(nt0 - 3, 0), f1 = min(nt0 + AW_SP_FA + 3, T);
+        const long long eo = ((long long)nclip * T + f0) * nb;
+        const long long en = (long long)(f1 - f0) * nb;
+        prefetch_l2(a.amp + eo, en * 4, tid, 32 * AW_SP_WARPS);
+        prefetch_l2(a.ph + eo, en * 8, tid, 32 * AW_SP_WARPS);
+        if (MODE == SPEC_BWD) {
+          const long long wo = ((long long)nclip * T + nt0) * nb;
+          const long long wn = (long long)(min(nt0 + AW_SP_FA, T) - nt0) * nb;
+          prefetch_l2(a.u + wo, wn * 8, tid, 32 * AW_SP_WARPS);
+          prefetch_l2(a.m + wo, wn * 4, tid, 32 * AW_SP_WARPS);
+          prefetch_l2(a.v + wo, wn * 4, tid, 32 * AW_SP_WARPS);
+          prefetch_l2(a.c + wo, wn * 4, tid, 32 * AW_SP_WARPS);
+          prefetch_l2(a.c0 + wo, wn * 4, tid, 32 * AW_SP_WARPS);
+        }
+      }
+    }
+
     // ---------------- phase 1: inverse transforms + streaming overlap-add ----------------
     {
       const int fs = ta0 - 3 + 8 * warp;                 // this warp's first synthesis frame
+      if (MODE == SPEC_FWD) {
+        // The constant out-of-band waveform (pre-multiplied by the overlap-add envelope) is
+        // copied asynchronously into exactly the 8 hops this warp will store, and the stores
+        // below accumulate onto it: no global load sits on the sample-wise phase.
+        const float* zo = a.z_oob + (long long)clip * L;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int hr = fs - ta0 + i;                   // hop inside s_buf
+          if (hr < 0 || hr >= AW_SP_HOPS) continue;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int r = hr * AW_HOP + (lane + 32 * k) * 4;
+            const int n = m0 + r - AW_HALF;
+            if (n >= 0 && n + 3 < L) cp_async16(s_buf + r, zo + n);
+          }
+        }
+      }
       float acc[3][8];
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
       const float scale = MODE == SPEC_FWD ? 1.0f / AW_NFFT : 0.5f;
+      constexpr int NK = K2HI - K2LO + 1;
+      // operands of the next frame pair are fetched while the current pair is transformed
+      float pa_[NK], pb_[NK];
+      float2 qa_[NK], qb_[NK];
+      auto fetch = [&](int pr) {
+        const int ta = fs + 2 * pr, tb = ta + 1;
+        const bool va = ta >= 0 && ta < T, vb = tb >= 0 && tb < T;
+        const long long oa = (fbase + (va ? ta : 0)) * nb, ob = (fbase + (vb ? tb : 0)) * nb;
+#pragma unroll
+        for (int k2 = K2LO; k2 <= K2HI; ++k2) {
+          const int b = lane + 32 * k2 - a.bin0;
+          const int bc = (b >= 0 && b < nb) ? b : 0;
+          pa_[k2 - K2LO] = a.amp[oa + bc]; pb_[k2 - K2LO] = a.amp[ob + bc];
+          qa_[k2 - K2LO] = a.ph[oa + bc]; qb_[k2 - K2LO] = a.ph[ob + bc];
+        }
+      };
+      constexpr bool PF = NK <= 3;                       // wide bands: no registers to spare
+      if (PF) fetch(0);
 #pragma unroll 1
       for (int pr = 0; pr < 4; ++pr) {
         const int ta = fs + 2 * pr, tb = ta + 1;
         const bool va = ta >= 0 && ta < T, vb = tb >= 0 && tb < T;
+        if (!PF) fetch(pr);
         float re[32], im[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) { re[j] = 0.f; im[j] = 0.f; }
-        if (va || vb) {                                  // warp-uniform
-          const long long oa = (fbase + (va ? ta : 0)) * nb, ob = (fbase + (vb ? tb : 0)) * nb;
+        {
           const float sa = va ? scale : 0.f, sb = vb ? scale : 0.f;
-          float mr[K2HI - K2LO + 2], mi[K2HI - K2LO + 2];
-          mr[K2HI - K2LO + 1] = 0.f; mi[K2HI - K2LO + 1] = 0.f;
+          float mr[NK + 1], mi[NK + 1];
+          mr[NK] = 0.f; mi[NK] = 0.f;
 #pragma unroll
           for (int k2 = K2LO; k2 <= K2HI; ++k2) {
             const int b = lane + 32 * k2 - a.bin0;
             const bool ok = b >= 0 && b < nb;
-            const int bc = ok ? b : 0;
-            const float s0 = ok ? sa * a.amp[oa + bc] : 0.f, s1 = ok ? sb * a.amp[ob + bc] : 0.f;
-            const float2 p0 = a.ph[oa + bc], p1 = a.ph[ob + bc];
+            const float s0 = ok ? sa * pa_[k2 - K2LO] : 0.f, s1 = ok ? sb * pb_[k2 - K2LO] : 0.f;
+            const float2 p0 = qa_[k2 - K2LO], p1 = qb_[k2 - K2LO];
             const float ar = s0 * p0.x, ai = s0 * p0.y, br = s1 * p1.x, bi = s1 * p1.y;
             re[k2] = ar - bi;                            // Z[k] = Xa + i Xb
             im[k2] = ai + br;
@@ -331,33 +402,42 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
             re[31 - j] = lane ? r_hi : r_l0;
             im[31 - j] = lane ? i_hi : i_l0;
           }
-          warp_fft1024_p<1, GROUPS, 0xffffffffu>(re, im, my_tr, s_tw, lane);
-#pragma unroll
-          for (int p = 0; p < 32; ++p) {
-            const float w = s_win[lane + 32 * brev5(p)];
-            re[p] *= w;
-            im[p] *= w;
-          }
         }
-        // sliding overlap-add: frame A = re (t = ta), frame B = im (t = ta + 1); sample
-        // n = lane + 32 q sits in register brev5(q); quarter i of a frame is q in [8i, 8i+8)
+        if (PF && pr < 3) fetch(pr + 1);
+        if (va || vb)                                    // warp-uniform
+          warp_fft1024_p<1, GROUPS, 0xffffffffu>(re, im, my_tr, s_tw, lane);
+        // sliding overlap-add with the synthesis window folded into the accumulation:
+        // frame A = re (t = ta), frame B = im (t = ta + 1); sample n = lane + 32 q sits in
+        // register brev5(q); quarter i of a frame is q in [8i, 8i+8)
         float o0[8], o1[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          o0[e] = acc[0][e] + re[brev5(e)];
-          o1[e] = (acc[1][e] + re[brev5(8 + e)]) + im[brev5(e)];
-          acc[0][e] = (acc[2][e] + re[brev5(16 + e)]) + im[brev5(8 + e)];
-          acc[1][e] = re[brev5(24 + e)] + im[brev5(16 + e)];
-          acc[2][e] = im[brev5(24 + e)];
+          const float w0 = s_win[lane + 32 * e], w1 = s_win[lane + 32 * (8 + e)];
+          const float w2 = s_win[lane + 32 * (16 + e)], w3 = s_win[lane + 32 * (24 + e)];
+          o0[e] = fmaf(re[brev5(e)], w0, acc[0][e]);
+          o1[e] = fmaf(im[brev5(e)], w0, fmaf(re[brev5(8 + e)], w1, acc[1][e]));
+          acc[0][e] = fmaf(im[brev5(8 + e)], w1, fmaf(re[brev5(16 + e)], w2, acc[2][e]));
+          acc[1][e] = fmaf(im[brev5(16 + e)], w2, re[brev5(24 + e)] * w3);
+          acc[2][e] = im[brev5(24 + e)] * w3;
+        }
+        if (MODE == SPEC_FWD && pr == 0) {
+          cp_async_wait_all();
+          __syncwarp();
         }
         const int h0r = ta - ta0, h1r = h0r + 1;         // hop index inside s_buf
         if (h0r >= 0 && h0r < AW_SP_HOPS) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) s_buf[h0r * AW_HOP + lane + 32 * e] = o0[e];
+          for (int e = 0; e < 8; ++e) {
+            float* d = s_buf + h0r * AW_HOP + lane + 32 * e;
+            *d = MODE == SPEC_FWD ? *d + o0[e] : o0[e];
+          }
         }
         if (h1r >= 0 && h1r < AW_SP_HOPS) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) s_buf[h1r * AW_HOP + lane + 32 * e] = o1[e];
+          for (int e = 0; e < 8; ++e) {
+            float* d = s_buf + h1r * AW_HOP + lane + 32 * e;
+            *d = MODE == SPEC_FWD ? *d + o1[e] : o1[e];
+          }
         }
       }
       __syncthreads();
@@ -396,7 +476,6 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
       }
       float best = 0.f;
       int best_n = -1;
-      const float* yo = MODE == SPEC_FWD ? a.y_oob + (long long)clip * L : nullptr;
       for (int r4 = tid * 4; r4 < AW_SP_BUF; r4 += 4 * 32 * AW_SP_WARPS) {
         const int m = m0 + r4, n = m - AW_HALF, hop = m >> 8;
         float4 s4 = *reinterpret_cast<float4*>(s_buf + r4);
@@ -411,11 +490,9 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
             for (int k = 0; k < 4; ++k) ie[k] = ola_inv_envelope(m + k, T, s_win, a.env256);
           }
           if (MODE == SPEC_FWD) {
-            const float4 q4 = *reinterpret_cast<const float4*>(yo + n);
-            const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              vv[k] = vv[k] * ie[k] + qq[k];
+              vv[k] = vv[k] * ie[k];                     // (ola + y_oob * env) / env
               if (fabsf(vv[k]) > fabsf(best) || best_n < 0) { best = vv[k]; best_n = n + k; }
             }
           } else {
@@ -474,53 +551,87 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
       }
       warp_fft1024_p<-1, 0xffffffffu, NEED_OUT>(re, im, my_tr, s_tw, lane);
       const bool wa = ta >= t_lo, wb = tb < t_hi;
+      constexpr int NK = K2HI - K2LO + 1;
+      constexpr int G = NK < 3 ? NK : 3;                 // bin groups handled per batch
 #pragma unroll
-      for (int k2 = K2LO; k2 <= K2HI; ++k2) {
-        // Z[k], k = lane + 32 k2, is register brev5(k2); its mirror Z[1024-k] is register
-        // brev5(31-k2) of lane 32-lane (lane > 0) or register brev5(32-k2) of lane 0
-        float mr = __shfl_sync(0xffffffffu, re[brev5(31 - k2)], lm);
-        float mi = __shfl_sync(0xffffffffu, im[brev5(31 - k2)], lm);
-        if (k2 >= 1 && lane == 0) {
-          mr = re[brev5((32 - k2) & 31)];
-          mi = im[brev5((32 - k2) & 31)];
-        }
-        const int b = lane + 32 * k2 - a.bin0;
-        if (b < 0 || b >= nb) continue;
-        const float zr = re[brev5(k2)], zi = im[brev5(k2)];
-        const float fr[2] = {0.5f * (zr + mr), 0.5f * (zi + mi)};
-        const float fi[2] = {0.5f * (zi - mi), 0.5f * (mr - zr)};
+      for (int g0 = K2LO; g0 <= K2HI; g0 += G) {
+        float fr[G][2], fi[G][2];
+        bool okb[G];
+        long long ob_[G];
 #pragma unroll
-        for (int f = 0; f < 2; ++f) {
-          if (f == 0 ? !wa : !wb) continue;
-          const long long o = (fbase + ta + f) * nb + b;
-          const float sr = fr[f], si = fi[f];
-          if (MODE == SPEC_FWD) {
-            const float mag = sqrtf(sr * sr + si * si);
-            a.mag[o] = mag;
-            const float iv = mag > 0.f ? 1.0f / mag : 0.f;
-            a.q[o] = make_float2(sr * iv, si * iv);
-          } else {
-            // dX = (2/N) DFT(.) ; g = Re(dX conj(u))     (multibit_embedder.py:111)
-            const float2 uu = a.u[o];
-            const float g = (2.0f / AW_NFFT) * (sr * uu.x + si * uu.y);
-            // NAdam (torch/optim/nadam.py), clamp (:116-117), best (:120-122)
-            float mm = a.m[o], vv = a.v[o], cc = a.c[o];
-            const float c0 = a.c0[o];
-            mm = __fadd_rn(mm, __fmul_rn(0.1f, __fsub_rn(g, mm)));
-            vv = __fmul_rn(vv, 0.999f);
-            vv = __fadd_rn(vv, __fmul_rn(__fmul_rn(0.001f, g), g));
-            const float den = __fadd_rn(__fsqrt_rn(__fmul_rn(vv, st.inv_bc2)), 1e-8f);
-            const float rden = __frcp_rn(den);
-            cc = __fadd_rn(cc, __fmul_rn(__fmul_rn(st.a_g, g), rden));
-            cc = __fadd_rn(cc, __fmul_rn(__fmul_rn(st.a_m, mm), rden));
-            const float dl = __fmul_rn(c0, a.tol_ratio);
-            const float lo = fmaxf(0.f, __fsub_rn(c0, dl)), hi = __fadd_rn(c0, dl);
-            cc = fminf(fmaxf(cc, lo), hi);
-            a.m[o] = mm;
-            a.v[o] = vv;
-            a.c[o] = cc;
-            if (improved) a.cbest[o] = cc;
+        for (int gi = 0; gi < G; ++gi) {
+          const int k2 = g0 + gi;
+          okb[gi] = false;
+          fr[gi][0] = fr[gi][1] = fi[gi][0] = fi[gi][1] = 0.f;
+          ob_[gi] = 0;
+          if (k2 > K2HI) continue;
+          // Z[k], k = lane + 32 k2, is register brev5(k2); its mirror Z[1024-k] is register
+          // brev5(31-k2) of lane 32-lane (lane > 0) or register brev5(32-k2) of lane 0
+          float mr = __shfl_sync(0xffffffffu, re[brev5(31 - k2)], lm);
+          float mi = __shfl_sync(0xffffffffu, im[brev5(31 - k2)], lm);
+          if (k2 >= 1 && lane == 0) {
+            mr = re[brev5((32 - k2) & 31)];
+            mi = im[brev5((32 - k2) & 31)];
           }
+          const int b = lane + 32 * k2 - a.bin0;
+          okb[gi] = b >= 0 && b < nb;
+          ob_[gi] = (fbase + ta) * nb + (okb[gi] ? b : 0);
+          const float zr = re[brev5(k2)], zi = im[brev5(k2)];
+          // frame a: (Z[k] + conj Z[N-k]) / 2 ; frame b: (Z[k] - conj Z[N-k]) / (2i)
+          fr[gi][0] = 0.5f * (zr + mr); fr[gi][1] = 0.5f * (zi + mi);
+          fi[gi][0] = 0.5f * (zi - mi); fi[gi][1] = 0.5f * (mr - zr);
+        }
+        if (MODE == SPEC_FWD) {
+#pragma unroll
+          for (int gi = 0; gi < G; ++gi)
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+              if (!okb[gi] || (f == 0 ? !wa : !wb)) continue;
+              const long long o = ob_[gi] + (long long)f * nb;
+              const float sr = fr[gi][f], si = fi[gi][f];
+              const float mag = sqrtf(sr * sr + si * si);
+              a.mag[o] = mag;
+              const float iv = mag > 0.f ? 1.0f / mag : 0.f;
+              a.q[o] = make_float2(sr * iv, si * iv);
+            }
+        } else {
+          // all state of the batch is requested before any of it is consumed
+          float2 uu[G][2];
+          float mm[G][2], vv[G][2], cc[G][2], c0[G][2];
+#pragma unroll
+          for (int gi = 0; gi < G; ++gi)
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+              const bool on = okb[gi] && (f == 0 ? wa : wb);
+              const long long o = on ? ob_[gi] + (long long)f * nb : fbase * nb;   // any valid address
+              uu[gi][f] = a.u[o]; mm[gi][f] = a.m[o]; vv[gi][f] = a.v[o];
+              cc[gi][f] = a.c[o]; c0[gi][f] = a.c0[o];
+            }
+#pragma unroll
+          for (int gi = 0; gi < G; ++gi)
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+              if (!okb[gi] || (f == 0 ? !wa : !wb)) continue;
+              const long long o = ob_[gi] + (long long)f * nb;
+              // dX = (2/N) DFT(.) ; g = Re(dX conj(u))     (multibit_embedder.py:111)
+              const float g = (2.0f / AW_NFFT) * (fr[gi][f] * uu[gi][f].x + fi[gi][f] * uu[gi][f].y);
+              // NAdam (torch/optim/nadam.py), clamp (:116-117), best (:120-122)
+              float m1 = mm[gi][f], v1 = vv[gi][f], c1 = cc[gi][f];
+              m1 = __fadd_rn(m1, __fmul_rn(0.1f, __fsub_rn(g, m1)));
+              v1 = __fmul_rn(v1, 0.999f);
+              v1 = __fadd_rn(v1, __fmul_rn(__fmul_rn(0.001f, g), g));
+              const float den = __fadd_rn(__fsqrt_rn(__fmul_rn(v1, st.inv_bc2)), 1e-8f);
+              const float rden = __frcp_rn(den);
+              c1 = __fadd_rn(c1, __fmul_rn(__fmul_rn(st.a_g, g), rden));
+              c1 = __fadd_rn(c1, __fmul_rn(__fmul_rn(st.a_m, m1), rden));
+              const float dl = __fmul_rn(c0[gi][f], a.tol_ratio);
+              const float lo = fmaxf(0.f, __fsub_rn(c0[gi][f], dl)), hi = __fadd_rn(c0[gi][f], dl);
+              c1 = fminf(fmaxf(c1, lo), hi);
+              a.m[o] = m1;
+              a.v[o] = v1;
+              a.c[o] = c1;
+              if (improved) a.cbest[o] = c1;
+            }
         }
       }
     }
