@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libaware_b200.so")
 
-PREC_TF32, PREC_FP32, PREC_BF16 = 0, 1, 2
+PREC_TF32, PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2, 3
 
 
 class AwModel(C.Structure):

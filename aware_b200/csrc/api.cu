@@ -2,6 +2,7 @@
 // detect / embed / attack pipelines built from the kernels in this directory.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -57,6 +58,8 @@ struct aw_ctx {
   float* d_wt[4] = {};   // transposed       [kCp[l]][kCp[l+1]]
   __nv_bfloat16* d_w16[4] = {};    // bf16 copies (embed loop in bf16)
   __nv_bfloat16* d_wt16[4] = {};
+  __half* d_w16h[4] = {};          // fp16 copies (AW_PREC_FP16)
+  __half* d_wt16h[4] = {};
   int num_sms = 148;
   float* d_window = nullptr;
   float2* d_twiddle = nullptr;   // [k1][lane] = exp(2 pi i lane k1 / 1024)
@@ -65,7 +68,7 @@ struct aw_ctx {
   float band_lo = 500.f, band_hi = 4000.f, tol_db = 6.f, threshold = 0.f;
   std::vector<MelCfg> mels;
   PFN_encodeTiled encode = nullptr;
-  CUtensorMap tm_w[4], tm_wt[4], tm_w16[4], tm_wt16[4];
+  CUtensorMap tm_w[4], tm_wt[4], tm_w16[4], tm_wt16[4], tm_w16h[4], tm_wt16h[4];
   // workspace (grow-only)
   bool no_fuse_norm = true;   // AW_B200_FUSE_NORM=1 opts into the in-GEMM InstanceNorm application
   Buf ready;                  // [6 fused launches][clips][4] finished-row-tile counters (gemm.cuh FUSE)
@@ -275,6 +278,16 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
     AW_CUDA(cudaMemcpy(ctx->d_wt16[l], wt16.data(), wt16.size() * 2, cudaMemcpyHostToDevice));
     if (make_map(ctx, &ctx->tm_w16[l], ctx->d_w16[l], cop, cip, bn_for(cop), true)) return 1;
     if (make_map(ctx, &ctx->tm_wt16[l], ctx->d_wt16[l], cip, cop, bn_for(cip), true)) return 1;
+    // fp16 copies; the tensor maps only move bytes, so the 16-bit (bf16-typed) encoding serves both
+    std::vector<__half> w16h(w.size()), wt16h(wt.size());
+    for (size_t i = 0; i < w.size(); ++i) w16h[i] = __float2half_rn(w[i]);
+    for (size_t i = 0; i < wt.size(); ++i) wt16h[i] = __float2half_rn(wt[i]);
+    AW_CUDA(cudaMalloc(&ctx->d_w16h[l], w16h.size() * 2));
+    AW_CUDA(cudaMalloc(&ctx->d_wt16h[l], wt16h.size() * 2));
+    AW_CUDA(cudaMemcpy(ctx->d_w16h[l], w16h.data(), w16h.size() * 2, cudaMemcpyHostToDevice));
+    AW_CUDA(cudaMemcpy(ctx->d_wt16h[l], wt16h.data(), wt16h.size() * 2, cudaMemcpyHostToDevice));
+    if (make_map(ctx, &ctx->tm_w16h[l], ctx->d_w16h[l], cop, cip, bn_for(cop), true)) return 1;
+    if (make_map(ctx, &ctx->tm_wt16h[l], ctx->d_wt16h[l], cip, cop, bn_for(cip), true)) return 1;
   }
   ctx->num_sms = prop.multiProcessorCount;
   AW_CUDA(cudaMalloc(&ctx->d_window, 1024 * 4));
@@ -308,6 +321,8 @@ extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
     cudaFree(ctx->d_wt[l]);
     cudaFree(ctx->d_w16[l]);
     cudaFree(ctx->d_wt16[l]);
+    cudaFree(ctx->d_w16h[l]);
+    cudaFree(ctx->d_wt16h[l]);
   }
   cudaFree(ctx->d_window);
   cudaFree(ctx->d_twiddle);
@@ -331,7 +346,7 @@ extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
 
 extern "C" int aw_ctx_set_precision(aw_ctx* ctx, int prec) {
   AW_REQUIRE(ctx, "null ctx");
-  AW_REQUIRE(prec == AW_PREC_TF32 || prec == AW_PREC_FP32 || prec == AW_PREC_BF16,
+  AW_REQUIRE(prec == AW_PREC_TF32 || prec == AW_PREC_FP32 || prec == AW_PREC_BF16 || prec == AW_PREC_FP16,
              "unknown precision %d", prec);
   ctx->prec = prec;
   return 0;
@@ -604,8 +619,45 @@ int gemm_layer<__nv_bfloat16, EPI_BWD>(aw_ctx* ctx, const CUtensorMap& ma, const
   return launch_tc<__nv_bfloat16, __nv_bfloat16, 256, EPI_BWD>(ctx, ma, mb, rows, n, k, ep, st);
 }
 
-template <typename AT> struct ModeOf { static constexpr int B = 0; };
-template <> struct ModeOf<__nv_bfloat16> { static constexpr int B = 1; };
+template <>
+int gemm_layer<__half, EPI_FWD>(aw_ctx* ctx, const CUtensorMap& ma, const void*, const CUtensorMap& mb,
+                                const void*, int rows, int n, int k, const EpiArgsT<__half>& ep, cudaStream_t st) {
+  if (n >= 256) return launch_tc<__half, __half, 256, EPI_FWD>(ctx, ma, mb, rows, n, k, ep, st);
+  return launch_tc<__half, __half, 64, EPI_FWD>(ctx, ma, mb, rows, n, k, ep, st);
+}
+template <>
+int gemm_layer<__half, EPI_BWD>(aw_ctx* ctx, const CUtensorMap& ma, const void*, const CUtensorMap& mb,
+                                const void*, int rows, int n, int k, const EpiArgsT<__half>& ep, cudaStream_t st) {
+  return launch_tc<__half, __half, 256, EPI_BWD>(ctx, ma, mb, rows, n, k, ep, st);
+}
+
+// B: activation tensor-map view (0 = 4-byte, 1 = 2-byte elements); weight copies per type
+template <typename AT> struct ModeOf {
+  static constexpr int B = 0;
+  static const CUtensorMap& w(aw_ctx* c, int l) { return c->tm_w[l]; }
+  static const CUtensorMap& wt(aw_ctx* c, int l) { return c->tm_wt[l]; }
+  static const void* wp(aw_ctx* c, int l) { return c->d_w[l]; }
+  static const void* wtp(aw_ctx* c, int l) { return c->d_wt[l]; }
+  static constexpr float GSCALE = 1.0f;
+};
+template <> struct ModeOf<__nv_bfloat16> {
+  static constexpr int B = 1;
+  static const CUtensorMap& w(aw_ctx* c, int l) { return c->tm_w16[l]; }
+  static const CUtensorMap& wt(aw_ctx* c, int l) { return c->tm_wt16[l]; }
+  static const void* wp(aw_ctx* c, int l) { return c->d_w16[l]; }
+  static const void* wtp(aw_ctx* c, int l) { return c->d_wt16[l]; }
+  static constexpr float GSCALE = 1.0f;
+};
+template <> struct ModeOf<__half> {
+  static constexpr int B = 1;
+  static const CUtensorMap& w(aw_ctx* c, int l) { return c->tm_w16h[l]; }
+  static const CUtensorMap& wt(aw_ctx* c, int l) { return c->tm_wt16h[l]; }
+  static const void* wp(aw_ctx* c, int l) { return c->d_w16h[l]; }
+  static const void* wtp(aw_ctx* c, int l) { return c->d_wt16h[l]; }
+  // gradients are ~1e-4 .. 1e-8: a static power-of-two loss scale keeps them in fp16's normal
+  // range (removed again where dP0 is consumed); overflow would need |dH| > 16
+  static constexpr float GSCALE = 4096.0f;
+};
 
 template <typename AT>
 static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseMel& sm,
@@ -635,8 +687,8 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
     ep.ready = fuse ? (int*)ctx->ready.p + (size_t)l * d.n * 4 : nullptr;
     ep.tiles_per_clip = d.tiles; ep.Tp = d.Tp;
     ep.stat = (float*)ctx->stat[l + 1].p; ep.round_tf32 = tf && l < 3;
-    const CUtensorMap& mw = B ? ctx->tm_w16[l] : ctx->tm_w[l];
-    const void* w = B ? (const void*)ctx->d_w16[l] : (const void*)ctx->d_w[l];
+    const CUtensorMap& mw = ModeOf<AT>::w(ctx, l);
+    const void* w = ModeOf<AT>::wp(ctx, l);
     if (gemm_layer<AT, EPI_FWD>(ctx, ctx->tm_act[B][l], ctx->act[l].p, mw, w, d.rows, cout, cin, ep, st))
       return 1;
     if (fuse) continue;   // statistics + normalise + LeakyReLU already applied inside the GEMM kernel
@@ -679,8 +731,8 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
     ep.ready = fuse ? (int*)ctx->ready.p + (size_t)(3 + s) * d.n * 4 : nullptr;
     ep.tiles_per_clip = d.tiles; ep.Tp = d.Tp;
     ep.stat = (float*)ctx->stat[l].p; ep.round_tf32 = tf;
-    const CUtensorMap& mw = B ? ctx->tm_wt16[l] : ctx->tm_wt[l];
-    const void* w = B ? (const void*)ctx->d_wt16[l] : (const void*)ctx->d_wt[l];
+    const CUtensorMap& mw = ModeOf<AT>::wt(ctx, l);
+    const void* w = ModeOf<AT>::wtp(ctx, l);
     if (gemm_layer<AT, EPI_BWD>(ctx, *steps[s].ma, steps[s].a, mw, w, d.rows, n, k, ep, st)) return 1;
     if (fuse) continue;   // InstanceNorm adjoint already applied inside the GEMM kernel
     dim3 g((n + 127) / 128, d.n);
@@ -705,7 +757,7 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
     ep.out = (float*)ctx->dp0.p; ep.ldo = 128;
     ep.part = nullptr; ep.ldp = 0; ep.act = nullptr;
     if (B) {
-      if (launch_tc<__nv_bfloat16, float, 128, EPI_PLAIN>(ctx, ctx->tm_ga512[1], ctx->tm_wt16[0], d.rows, 128, 512, ep, st))
+      if (launch_tc<AT, float, 128, EPI_PLAIN>(ctx, ctx->tm_ga512[1], ModeOf<AT>::wt(ctx, 0), d.rows, 128, 512, ep, st))
         return 1;
     } else if (ctx->prec == AW_PREC_FP32) {
       if (launch_exact<EPI_PLAIN>(ctx, (const float*)ga, ctx->d_wt[0], d.rows, 128, 512, ep, st)) return 1;
@@ -717,7 +769,7 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
   dim3 g1((2 * d.Tp + AW_P0B_FRAMES - 1) / AW_P0B_FRAMES, d.n);
   prof_mark(ctx, st, "p0_bwd_reduce");
   k_p0_bwd_reduce<<<g1, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
-                                      (ChanStats*)ctx->cs.p, acc.bpart);
+                                      (ChanStats*)ctx->cs.p, acc.bpart, 1.0f / ModeOf<AT>::GSCALE);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   dim3 g2((d.T + AW_P0A_FRAMES - 1) / AW_P0A_FRAMES, d.n);
@@ -725,7 +777,8 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
   k_p0_bwd_apply<<<g2, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
                                      (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p, acc.bpart,
                                      acc.p0b_blocks, sm, d.nb, (float*)ctx->dA.p,
-                                     euler_s2 ? (const float*)ctx->mag.p : nullptr, acc.s2_part);
+                                     euler_s2 ? (const float*)ctx->mag.p : nullptr, acc.s2_part,
+                                     1.0f / ModeOf<AT>::GSCALE);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
@@ -742,6 +795,7 @@ static int run_head(aw_ctx* ctx, const Dims& d, const float* pattern, float* val
   h.dH4 = backward ? (AT*)ctx->dh4.p : nullptr;
   h.it_ptr = (int*)ctx->itc.p; h.n_clips = n_total;
   h.round_tf32 = ctx->prec == AW_PREC_TF32;
+  h.gscale = ModeOf<AT>::GSCALE;
   prof_mark(ctx, st, "head");
   k_head<AT><<<d.n, 256, 0, st>>>(h);
   ctx->launches++;
@@ -881,6 +935,12 @@ extern "C" int aw_detect_batch(aw_ctx* ctx, const float* d_audio, int n_clips, i
     prof_mark(ctx, st, nullptr);
     return 0;
   }
+  if (ctx->prec == AW_PREC_FP16) {
+    if (net_forward<__half>(ctx, d, acc, sm, st)) return 1;
+    if (run_head<__half>(ctx, d, nullptr, d_values, nullptr, d.n, false, st)) return 1;
+    prof_mark(ctx, st, nullptr);
+    return 0;
+  }
   if (net_forward<float>(ctx, d, acc, sm, st)) return 1;
   if (run_head<float>(ctx, d, nullptr, d_values, nullptr, d.n, false, st)) return 1;
   prof_mark(ctx, st, nullptr);
@@ -1001,6 +1061,11 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
         if (run_head<__nv_bfloat16>(ctx, dw, (float*)ctx->pattern.p, (float*)ctx->values.p, lp, n_clips, true, st))
           return 1;
         if (net_backward<__nv_bfloat16>(ctx, dw, acc, sm, st, true)) return 1;
+      } else if (ctx->prec == AW_PREC_FP16) {
+        if (net_forward<__half>(ctx, dw, acc, sm, st, acc.peak_y)) return 1;
+        if (run_head<__half>(ctx, dw, (float*)ctx->pattern.p, (float*)ctx->values.p, lp, n_clips, true, st))
+          return 1;
+        if (net_backward<__half>(ctx, dw, acc, sm, st, true)) return 1;
       } else {
         if (net_forward<float>(ctx, dw, acc, sm, st, acc.peak_y)) return 1;
         if (run_head<float>(ctx, dw, (float*)ctx->pattern.p, (float*)ctx->values.p, lp, n_clips, true, st))

@@ -17,6 +17,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace aw {
@@ -178,6 +179,16 @@ template <> struct GemmElem<__nv_bfloat16> {
   }
 };
 
+// fp16 operands: same 10-bit mantissa as TF32 at half the bytes and twice the MMA rate
+template <> struct GemmElem<__half> {
+  static constexpr int BK = 64;
+  static constexpr uint32_t FMT = 0;       // F16
+  static __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc,
+                                             uint32_t acc) {
+    GemmElem<__nv_bfloat16>::mma(d, a, b, idesc, acc);   // kind::f16 covers both 16-bit formats
+  }
+};
+
 // 32 consecutive output / activation elements of one row <-> registers
 __device__ __forceinline__ void load_row32(const float* p, float (&v)[32]) {
 #pragma unroll
@@ -224,6 +235,17 @@ __device__ __forceinline__ void act_ld4g(const __nv_bfloat16* p, float (&v)[4]) 
   const uint2 t = *reinterpret_cast<const uint2*>(p);
   v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
   v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+__device__ __forceinline__ void act_ld4g(const __half* p, float (&v)[4]) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void act_st4g(__half* p, const float (&v)[4]) {
+  const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a),
+                                            *reinterpret_cast<const uint32_t*>(&b));
 }
 __device__ __forceinline__ void act_st4g(float* p, const float (&v)[4]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);

@@ -5,6 +5,7 @@
 // [clip * Tp_pad + j][C] with Tp_pad = T' rounded up to 128 rows (pad rows are 0).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace aw {
@@ -28,6 +29,20 @@ __device__ __forceinline__ void act_st4(float* p, const float (&v)[4]) {
 }
 __device__ __forceinline__ void act_st4(__nv_bfloat16* p, const float (&v)[4]) {
   const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a),
+                                            *reinterpret_cast<const uint32_t*>(&b));
+}
+
+__device__ __forceinline__ float act_ld(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ void act_st(__half* p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ void act_ld4(const __half* p, float (&v)[4]) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void act_st4(__half* p, const float (&v)[4]) {
+  const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
   *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a),
                                             *reinterpret_cast<const uint32_t*>(&b));
 }
@@ -251,6 +266,7 @@ struct HeadArgs {
   AT* dH4;                   // [rows][64] or null
   const int* it_ptr; int n_clips;
   int round_tf32;
+  float gscale;              // loss scale of the back-propagated gradient (fp16 mode), else 1
 };
 
 template <typename AT>
@@ -325,7 +341,7 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs<AT> a) {
       const float p = act_ld(P + (long long)j * 64 + c);
       const bool pos = p > 0.f;
       const float dh = pos ? dz : AW_LEAKY * dz;
-      o = rstd * (dh - a1 - (pos ? p : p * (1.0f / AW_LEAKY)) * a2);
+      o = a.gscale * (rstd * (dh - a1 - (pos ? p : p * (1.0f / AW_LEAKY)) * a2));
       if (a.round_tf32) o = to_tf32(o);
     }
     act_st(D + (long long)j * 64 + c, o);
@@ -338,13 +354,13 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs<AT> a) {
 __global__ void __launch_bounds__(128) k_p0_bwd_reduce(const float* __restrict__ dP0,
                                                        const float* __restrict__ M, int T, int Tp,
                                                        int Tp_pad, const ChanStats* __restrict__ cs,
-                                                       double* __restrict__ bpart) {
+                                                       double* __restrict__ bpart, float ginv) {
   const int clip = blockIdx.y, c = threadIdx.x, t0 = blockIdx.x * AW_P0B_FRAMES;
   const ChanStats st = cs[(long long)clip * AW_NMEL + c];
   double s1 = 0.0, s2 = 0.0;
   const int t1 = min(t0 + AW_P0B_FRAMES, 2 * Tp);
   for (int t = t0; t < t1; ++t) {
-    const float dg = 0.5f * dP0[((long long)clip * Tp_pad + (t >> 1)) * AW_NMEL + c];
+    const float dg = (0.5f * ginv) * dP0[((long long)clip * Tp_pad + (t >> 1)) * AW_NMEL + c];
     const float mh = (M[((long long)clip * T + t) * AW_NMEL + c] - st.mu) * st.rstd;
     s1 += dg;
     s2 += (double)dg * mh;
@@ -364,7 +380,7 @@ __global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ 
                                                       SparseMel sm,
                                                       int nb, float* __restrict__ dA,
                                                       const float* __restrict__ mag_un,
-                                                      double* __restrict__ s2_part) {
+                                                      double* __restrict__ s2_part, float ginv) {
   __shared__ double s_red[32];
   __shared__ float s_dm[AW_P0A_FRAMES][AW_NMEL];
   __shared__ float s_ab[3];
@@ -388,7 +404,7 @@ __global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ 
   const int nf = min(AW_P0A_FRAMES, T - t0);
   for (int f = 0; f < nf; ++f) {
     const int t = t0 + f;
-    const float dg = t < 2 * Tp ? 0.5f * dP0[((long long)clip * Tp_pad + (t >> 1)) * AW_NMEL + c] : 0.f;
+    const float dg = t < 2 * Tp ? (0.5f * ginv) * dP0[((long long)clip * Tp_pad + (t >> 1)) * AW_NMEL + c] : 0.f;
     const float mh = (M[((long long)clip * T + t) * AW_NMEL + c] - st.mu) * st.rstd;
     const float dmh = alpha * (dg - meanG) - beta * mh;
     s_dm[f][c] = st.rstd * (dmh - A1 - mh * A2);

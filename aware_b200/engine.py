@@ -60,7 +60,7 @@ class Engine:
             pass
 
     # ------------------------------------------------------------------ misc
-    _PREC = {"tf32": _lib.PREC_TF32, "fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+    _PREC = {"tf32": _lib.PREC_TF32, "fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}
 
     def set_precision(self, precision: str):
         """GEMM arithmetic of the detector stack: "tf32" (tcgen05, TF32 operands), "fp32" (CUDA

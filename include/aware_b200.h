@@ -32,7 +32,10 @@ typedef struct aw_ctx aw_ctx;
 enum {
   AW_PREC_TF32 = 0, /* tcgen05 tensor cores, TF32 operands, fp32 accumulate (default) */
   AW_PREC_FP32 = 1, /* CUDA-core GEMMs with float64 accumulation (validation yardstick)       */
-  AW_PREC_BF16 = 2  /* tcgen05, bf16 operands AND bf16 activation storage (embed loop speed) */
+  AW_PREC_BF16 = 2, /* tcgen05, bf16 operands AND bf16 activation storage (embed loop speed) */
+  AW_PREC_FP16 = 3  /* tcgen05 kind::f16 with fp16 operands and fp16 activation storage: the same
+                       10-bit mantissa as TF32 at half the bytes; back-propagated gradients carry
+                       a static 2^12 loss scale */
 };
 
 /* Model description handed over once (reference: utils/models/load_model.py:6-76,

@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 OUT = os.path.join(ROOT, "gpurun_out")
 
 STAGES = ["gradmap", "stft", "istft", "attacks", "detect_fp32", "gemm_tc", "detect_tf32", "embed1_fp32",
-          "embed1_tf32", "embed3", "embed_full", "timing", "dual", "timeline"]
+          "embed1_tf32", "embed3", "embed_full", "timing", "dual", "timeline", "gradprec"]
 
 
 def _engine(precision="fp32"):
@@ -334,7 +334,7 @@ def stage_timeline(res):
     from aware_b200.synth import synth_batch, synth_bits
     from aware_b200.utils.watermark import PatternEncoder
     sr = 44100
-    for n, iters, prec in ((128, 10, "tf32"), (128, 10, "bf16")):
+    for n, iters, prec in ((128, 10, "tf32"), (128, 10, "fp16")):
         eng = _engine("tf32")
         eng.embed_precision = prec
         x = torch.from_numpy(synth_batch(n, 10.0, sr)).cuda()
@@ -350,6 +350,28 @@ def stage_timeline(res):
         res["n%d_%s" % (n, prec)] = dict(total_ms_per_iter=tot / iters,
                                          classes={k: [v[0], round(v[1] / iters, 4)] for k, v in
                                                   sorted(tl.items(), key=lambda kv: -kv[1][1])})
+
+
+def stage_gradprec(res):
+    """First-iteration gradient (m_1 / 0.1) of each GEMM precision against the fp32 path."""
+    import numpy as np
+    import torch
+    import aware_oracle as O
+    sr = 44100
+    x = torch.from_numpy(_clips([0, 1, 2, 3], 2.0, sr)).cuda()
+    pat = torch.from_numpy(np.stack([O.encode_bits(b) for b in O.synth_bits(4)]))
+    T = 1 + x.shape[1] // 256
+    g = {}
+    for prec in ("fp32", "tf32", "fp16", "bf16"):
+        eng = _engine(prec)
+        eng.embed(x, sr, pat, iters=1)
+        g[prec] = eng.embed_state("m", 4, T, sr).cpu().numpy() / 0.1
+    ref = g["fp32"]
+    for prec in ("tf32", "fp16", "bf16"):
+        d = g[prec] - ref
+        res[prec] = dict(rel_rms=float(np.sqrt((d ** 2).mean() / (ref ** 2).mean())),
+                         finite=bool(np.isfinite(g[prec]).all()),
+                         sign_agree=float((np.sign(g[prec]) == np.sign(ref)).mean()))
 
 
 def stage_dual(res):

@@ -91,7 +91,7 @@ def test_gemm_tensor_core_and_exact(eng, rows, n, k):
 
 
 # ------------------------------------------------------------------ detect
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32", 1e-3)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32", 1e-3), ("fp16", 1e-3)])
 def test_detect_matches_oracle(eng, precision, tol):
     eng.set_precision(precision)
     try:
@@ -322,12 +322,12 @@ def test_embed_three_iterations_losses_track_oracle(eng):
     pat = np.stack([O.encode_bits(O.synth_bits(8)[1])])
     keep = {}
     O.embed(x[0], 16000, pat[0], num_iters=3, keep=keep)
-    for precision, tol in (("fp32", 2e-3), ("tf32", 1e-2)):
+    for precision, tol in (("fp32", 2e-3), ("tf32", 1e-2), ("fp16", 1e-2)):
         _, losses, _ = _embed_state(eng, x, 16000, pat, 3, precision)
         assert np.abs(losses[:3, 0] - np.array(keep["losses"])).max() <= tol, precision
 
 
-@pytest.mark.parametrize("precision", ["tf32", "fp32"])
+@pytest.mark.parametrize("precision", ["tf32", "fp32", "fp16"])
 def test_embed_full_functional_parity(model, precision):
     """400 iterations through the service API: bits recovered by the CUDA detector AND by the
     CPU oracle (cross-detection), SNR within 1.5 dB of the reference's golden run."""
