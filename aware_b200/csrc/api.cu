@@ -700,7 +700,7 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
     AW_LAUNCH_CHECK();
     prof_mark(ctx, st, "norm_act");
     {
-      dim3 gn(d.Tp_pad / AW_NORM_ROWS, (cout / 4 + 127) / 128, d.n);
+      dim3 gn(d.Tp_pad / AW_NORM_ROWS, (cout / Vec16<AT>::N + 127) / 128, d.n);
       k_norm_rows<AT, NORM_FWD><<<gn, 128, 0, st>>>((AT*)ctx->act[l + 1].p, nullptr, cout, d.Tp, d.Tp_pad,
                                                     (float*)ctx->stat[l + 1].p, nullptr, tf && l < 3);
     }
@@ -743,7 +743,7 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
     AW_LAUNCH_CHECK();
     prof_mark(ctx, st, "in_bwd_apply");
     {
-      dim3 gn(d.Tp_pad / AW_NORM_ROWS, (n / 4 + 127) / 128, d.n);
+      dim3 gn(d.Tp_pad / AW_NORM_ROWS, (n / Vec16<AT>::N + 127) / 128, d.n);
       k_norm_rows<AT, NORM_BWD><<<gn, 128, 0, st>>>(steps[s].out, (AT*)ctx->act[l].p, n, d.Tp, d.Tp_pad,
                                                     (float*)ctx->stat[l].p, (float*)ctx->bstat.p, tf);
     }
@@ -1183,6 +1183,7 @@ extern "C" int aw_decide_and_count(aw_ctx* ctx, const float* d_values, const int
                                    int n_clips, int32_t* d_bits_out, int32_t* d_err_per_clip,
                                    uint64_t* d_counters, void* stream) {
   AW_REQUIRE(ctx && d_values, "null argument");
+  prof_mark(ctx, (cudaStream_t)stream, "decide_count");
   k_decide_count<<<(n_clips + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
       d_values, d_ref_bits, ctx->threshold, n_clips, d_bits_out, d_err_per_clip,
       (unsigned long long*)d_counters);
@@ -1304,6 +1305,7 @@ extern "C" int aw_attack_pcm(aw_ctx* ctx, const float* d_in, int n_clips, int n,
   cudaStream_t st = (cudaStream_t)stream;
   if (ensure(ctx->peakx, (size_t)n_clips * 8)) return 1;
   if (launch_peak(ctx, d_in, in_stride, n, n_clips, (unsigned long long*)ctx->peakx.p, st)) return 1;
+  prof_mark(ctx, (cudaStream_t)stream, "attack_pcm");
   k_attack_pcm<<<ew_grid(n, n_clips), 256, 0, st>>>(d_in, in_stride, n,
                                                     (unsigned long long*)ctx->peakx.p, S, lo, hi,
                                                     d_out, out_stride);
@@ -1316,6 +1318,7 @@ extern "C" int aw_attack_decimate_interp(aw_ctx* ctx, const float* d_in, int n_c
                                          int64_t in_stride, int factor, float* d_out,
                                          int64_t out_stride, void* stream) {
   AW_REQUIRE(ctx && d_in && d_out && factor >= 2, "bad argument");
+  prof_mark(ctx, (cudaStream_t)stream, "attack_decim_interp");
   k_attack_decim_interp<<<ew_grid(n, n_clips), 256, 0, (cudaStream_t)stream>>>(
       d_in, in_stride, n, factor, d_out, out_stride);
   ctx->launches++;
@@ -1328,6 +1331,7 @@ extern "C" int aw_attack_upfirdn(aw_ctx* ctx, const float* d_in, int n_clips, in
                                  int down, int first_out, int n_out, float* d_out,
                                  int64_t out_stride, void* stream) {
   AW_REQUIRE(ctx && d_in && d_out && d_h_tf, "null argument");
+  prof_mark(ctx, (cudaStream_t)stream, "attack_upfirdn");
   k_upfirdn<<<ew_grid(n_out, n_clips), 256, 0, (cudaStream_t)stream>>>(
       d_in, in_stride, n_in, d_h_tf, taps_per_phase, up, down, first_out, n_out, d_out, out_stride);
   ctx->launches++;
@@ -1372,6 +1376,7 @@ extern "C" int aw_attack_lfilter(aw_ctx* ctx, const float* d_in, int n_clips, in
   iir_plan(ia, n, n_clips, warm, &g);
   ia.x32 = d_in; ia.sx32 = in_stride; ia.n_x = n;
   ia.o32 = d_out; ia.so32 = out_stride;
+  prof_mark(ctx, (cudaStream_t)stream, "attack_lfilter");
   k_iir<IIR_SRC_F32, IIR_DST_F32><<<g, 128, 0, (cudaStream_t)stream>>>(ia);
   ctx->launches++;
   AW_LAUNCH_CHECK();
@@ -1397,10 +1402,12 @@ extern "C" int aw_attack_filtfilt(aw_ctx* ctx, const float* d_in, int n_clips, i
   ia.padlen = pad; ia.use_zi = 1;
   ia.x32 = d_in; ia.sx32 = in_stride; ia.n_x = n;
   ia.o64 = (double*)ctx->ga.p; ia.so64 = next;
+  prof_mark(ctx, (cudaStream_t)stream, "attack_filtfilt_fwd");
   k_iir<IIR_SRC_ODDEXT, IIR_DST_F64><<<g, 128, 0, st>>>(ia);
   IirArgs ib = ia;
   ib.x64 = (double*)ctx->ga.p; ib.sx64 = next;
   ib.o32 = d_out; ib.so32 = out_stride;
+  prof_mark(ctx, (cudaStream_t)stream, "attack_filtfilt_bwd");
   k_iir<IIR_SRC_REV_F64, IIR_DST_REVTRIM_F32><<<g, 128, 0, st>>>(ib);
   ctx->launches += 2;
   AW_LAUNCH_CHECK();
@@ -1411,6 +1418,7 @@ extern "C" int aw_attack_delete(aw_ctx* ctx, const float* d_in, int n_clips, int
                                 const int32_t* d_start, int n_delete, float* d_out,
                                 int64_t out_stride, void* stream) {
   AW_REQUIRE(ctx && d_in && d_out && d_start && n_delete >= 0 && n_delete < n, "bad argument");
+  prof_mark(ctx, (cudaStream_t)stream, "attack_delete");
   k_attack_delete<<<ew_grid(n - n_delete, n_clips), 256, 0, (cudaStream_t)stream>>>(
       d_in, in_stride, n - n_delete, d_start, n_delete, d_out, out_stride);
   ctx->launches++;
@@ -1422,6 +1430,7 @@ extern "C" int aw_attack_suppress(aw_ctx* ctx, const float* d_in, int n_clips, i
                                   int64_t in_stride, const int32_t* d_start, int n_zero,
                                   float* d_out, int64_t out_stride, void* stream) {
   AW_REQUIRE(ctx && d_in && d_out && d_start, "bad argument");
+  prof_mark(ctx, (cudaStream_t)stream, "attack_suppress");
   k_attack_suppress<<<ew_grid(n, n_clips), 256, 0, (cudaStream_t)stream>>>(
       d_in, in_stride, n, d_start, n_zero, d_out, out_stride);
   ctx->launches++;
@@ -1432,6 +1441,7 @@ extern "C" int aw_attack_suppress(aw_ctx* ctx, const float* d_in, int n_clips, i
 extern "C" int aw_attack_cropout(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t in_stride,
                                  int n_drop, float* d_out, int64_t out_stride, void* stream) {
   AW_REQUIRE(ctx && d_in && d_out && n_drop >= 0 && n_drop < n, "bad argument");
+  prof_mark(ctx, (cudaStream_t)stream, "attack_affine");
   k_attack_affine<<<ew_grid(n - n_drop, n_clips), 256, 0, (cudaStream_t)stream>>>(
       d_in + n_drop, in_stride, n - n_drop, 1.0f, nullptr, 0, 0.f, d_out, out_stride);
   ctx->launches++;
@@ -1443,6 +1453,7 @@ extern "C" int aw_attack_affine(aw_ctx* ctx, const float* d_in, int n_clips, int
                                 float gain, const float* d_noise, int64_t noise_stride, float sigma,
                                 float* d_out, int64_t out_stride, void* stream) {
   AW_REQUIRE(ctx && d_in && d_out, "null argument");
+  prof_mark(ctx, (cudaStream_t)stream, "attack_affine");
   k_attack_affine<<<ew_grid(n, n_clips), 256, 0, (cudaStream_t)stream>>>(
       d_in, in_stride, n, gain, d_noise, noise_stride, sigma, d_out, out_stride);
   ctx->launches++;

@@ -525,64 +525,71 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
         const int c0 = half * (BN / 2) + c * 32;    // column inside the tile
-        float v[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0), v);
-        if (c == CHUNKS - 1) {                      // accumulator fully read: hand it back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tempty + ab)) : "memory");
+        {
+          float v[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0), v);
+          if (c == CHUNKS - 1) {                    // accumulator fully read: hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tempty + ab)) : "memory");
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(s_st + lane * AW_EPI_STRIDE + 4 * i) =
+                make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
-        float hh[32];
+        __syncwarp();
+        // from here on a lane owns columns cg..cg+3 of rows 4 i + sr: the layout of the
+        // coalesced global accesses, so the activation / gradient math needs no second transpose
+        float w[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 t4 = *reinterpret_cast<const float4*>(s_st + (4 * i + sr) * AW_EPI_STRIDE + cg);
+          w[i][0] = t4.x; w[i][1] = t4.y; w[i][2] = t4.z; w[i][3] = t4.w;
+        }
+        __syncwarp();
+        float s1c[4] = {0.f, 0.f, 0.f, 0.f}, s2c[4] = {0.f, 0.f, 0.f, 0.f};
         if (EPI == EPI_BWD) {
           // d(IN out) = dP * LeakyReLU'(P);  IN out recovered from P
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(s_st + (4 * i + sr) * AW_EPI_STRIDE + cg) =
-                make_float4(ga[i][0], ga[i][1], ga[i][2], ga[i][3]);
-          __syncwarp();
-          float pa[32];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 t4 = *reinterpret_cast<const float4*>(s_st + lane * AW_EPI_STRIDE + 4 * i);
-            pa[4 * i] = t4.x; pa[4 * i + 1] = t4.y; pa[4 * i + 2] = t4.z; pa[4 * i + 3] = t4.w;
-          }
-          __syncwarp();
+            for (int k = 0; k < 4; ++k) {
+              const float pv = ga[i][k];
+              const bool pos = pv > 0.f;
+              const float g = pos ? w[i][k] : AW_LEAKY * w[i][k];
+              w[i][k] = g;
+              s1c[k] += g;
+              s2c[k] = fmaf(pos ? pv : pv * (1.0f / AW_LEAKY), g, s2c[k]);
+            }
           if (c + 1 < CHUNKS) {                     // prefetch the next chunk's activations
 #pragma unroll
             for (int i = 0; i < 8; ++i) act_ld4g(abase + (c + 1) * 32 + (long long)(4 * i) * ep.ldo, ga[i]);
           }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const bool pos = pa[i] > 0.f;
-            v[i] = pos ? v[i] : AW_LEAKY * v[i];
-            hh[i] = (pos ? pa[i] : pa[i] * (1.0f / AW_LEAKY)) * v[i];
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<float4*>(s_st + lane * AW_EPI_STRIDE + 4 * i) =
-              make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 t4 = *reinterpret_cast<const float4*>(s_st + (4 * i + sr) * AW_EPI_STRIDE + cg);
-          const float o4[4] = {t4.x, t4.y, t4.z, t4.w};
-          act_st4g(obase + c * 32 + (long long)(4 * i) * ep.ldo, o4);
-        }
-        __syncwarp();
-        if (EPI == EPI_BWD) {
-          const float s1 = warp_colsum32(v, lane);
-          const float s2 = warp_colsum32(hh, lane);
-          sp[(0 * 4 + q) * BN + c0 + lane] = s1;
-          sp[(1 * 4 + q) * BN + c0 + lane] = s2;
         } else if (EPI == EPI_FWD) {
-          float sq[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
-          const float s1 = warp_colsum32(v, lane);
-          const float s2 = warp_colsum32(sq, lane);
-          sp[(0 * 4 + q) * BN + c0 + lane] = s1;
-          sp[(1 * 4 + q) * BN + c0 + lane] = s2;
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              s1c[k] += w[i][k];
+              s2c[k] = fmaf(w[i][k], w[i][k], s2c[k]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) act_st4g(obase + c * 32 + (long long)(4 * i) * ep.ldo, w[i]);
+        if (EPI != EPI_PLAIN) {
+          // the 4 lanes that share (lane & 7) hold the same columns for different rows
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            s1c[k] += __shfl_xor_sync(0xffffffffu, s1c[k], 8);
+            s2c[k] += __shfl_xor_sync(0xffffffffu, s2c[k], 8);
+            s1c[k] += __shfl_xor_sync(0xffffffffu, s1c[k], 16);
+            s2c[k] += __shfl_xor_sync(0xffffffffu, s2c[k], 16);
+          }
+          if (sr == 0) {
+            *reinterpret_cast<float4*>(sp + (0 * 4 + q) * BN + c0 + cg) = make_float4(s1c[0], s1c[1], s1c[2], s1c[3]);
+            *reinterpret_cast<float4*>(sp + (1 * 4 + q) * BN + c0 + cg) = make_float4(s2c[0], s2c[1], s2c[2], s2c[3]);
+          }
         }
       }
       if (EPI != EPI_PLAIN) {

@@ -201,53 +201,93 @@ __global__ void __launch_bounds__(128) k_finalize_bwd(const float* __restrict__ 
 // grid = (Tp_pad / AW_NORM_ROWS, C / (4 * 128) rounded up, n_clips), block = 128.
 enum { NORM_FWD = 0, NORM_BWD = 1 };
 #define AW_NORM_ROWS 32
+// 16 bytes per access for every storage type: 4 floats or 8 half / bf16 values
+template <typename AT> struct Vec16 { static constexpr int N = 16 / sizeof(AT); };
+__device__ __forceinline__ void ld16(const float* p, float (&v)[4]) { act_ld4(p, v); }
+__device__ __forceinline__ void st16(float* p, const float (&v)[4]) { act_st4(p, v); }
+__device__ __forceinline__ void ld16(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = __uint_as_float(w[j] << 16);
+    v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void st16(__nv_bfloat16* p, const float (&v)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    w[j] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ void ld16(const __half* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+    v[2 * j] = f.x; v[2 * j + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void st16(__half* p, const float (&v)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    w[j] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 template <typename AT, int MODE>
 __global__ void __launch_bounds__(128) k_norm_rows(AT* __restrict__ X, const AT* __restrict__ P, int C,
                                                    int Tp, int Tp_pad, const float* __restrict__ stat,
                                                    const float* __restrict__ bstat, int round_tf32) {
+  constexpr int V = Vec16<AT>::N;
   const int clip = blockIdx.z;
-  const int c = (blockIdx.y * 128 + threadIdx.x) * 4;
+  const int c = (blockIdx.y * 128 + threadIdx.x) * V;
   if (c >= C) return;
   const int j0 = blockIdx.x * AW_NORM_ROWS;
-  float mu[4], rs[4], a1[4], a2[4];
-  {
-    const float4 s01 = *reinterpret_cast<const float4*>(stat + ((long long)clip * C + c) * 2);
-    const float4 s23 = *reinterpret_cast<const float4*>(stat + ((long long)clip * C + c) * 2 + 4);
-    mu[0] = s01.x; rs[0] = s01.y; mu[1] = s01.z; rs[1] = s01.w;
-    mu[2] = s23.x; rs[2] = s23.y; mu[3] = s23.z; rs[3] = s23.w;
+  float mu[V], rs[V], a1[V], a2[V];
+#pragma unroll
+  for (int k = 0; k < V; k += 2) {
+    const float4 s01 = *reinterpret_cast<const float4*>(stat + ((long long)clip * C + c + k) * 2);
+    mu[k] = s01.x; rs[k] = s01.y; mu[k + 1] = s01.z; rs[k + 1] = s01.w;
     if (MODE == NORM_BWD) {
-      const float4 b01 = *reinterpret_cast<const float4*>(bstat + ((long long)clip * C + c) * 2);
-      const float4 b23 = *reinterpret_cast<const float4*>(bstat + ((long long)clip * C + c) * 2 + 4);
-      a1[0] = b01.x; a2[0] = b01.y; a1[1] = b01.z; a2[1] = b01.w;
-      a1[2] = b23.x; a2[2] = b23.y; a1[3] = b23.z; a2[3] = b23.w;
+      const float4 b01 = *reinterpret_cast<const float4*>(bstat + ((long long)clip * C + c + k) * 2);
+      a1[k] = b01.x; a2[k] = b01.y; a1[k + 1] = b01.z; a2[k + 1] = b01.w;
     }
   }
   AT* x = X + ((long long)clip * Tp_pad + j0) * C + c;
   const AT* p = MODE == NORM_BWD ? P + ((long long)clip * Tp_pad + j0) * C + c : nullptr;
-  constexpr int NB = 8;
+  constexpr int NB = V == 4 ? 8 : 4;                     // 16-byte loads in flight per tensor
 #pragma unroll 1
   for (int r0 = 0; r0 < AW_NORM_ROWS; r0 += NB) {
-    float h[NB][4], a[NB][4];
+    float h[NB][V], a[MODE == NORM_BWD ? NB : 1][V];
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
-      act_ld4(x + (long long)(r0 + i) * C, h[i]);
-      if (MODE == NORM_BWD) act_ld4(p + (long long)(r0 + i) * C, a[i]);
+      ld16(x + (long long)(r0 + i) * C, h[i]);
+      if (MODE == NORM_BWD) ld16(p + (long long)(r0 + i) * C, a[i]);
     }
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
-      float o[4];
+      float o[V];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < V; ++k) {
         if (MODE == NORM_FWD) {
           o[k] = leaky((h[i][k] - mu[k]) * rs[k]);
         } else {
-          const float hh = a[i][k] > 0.f ? a[i][k] : a[i][k] * (1.0f / AW_LEAKY);
+          const float av = a[MODE == NORM_BWD ? i : 0][k];
+          const float hh = av > 0.f ? av : av * (1.0f / AW_LEAKY);
           o[k] = rs[k] * (h[i][k] - a1[k] - hh * a2[k]);
         }
         if (round_tf32) o[k] = to_tf32(o[k]);
         if (j0 + r0 + i >= Tp) o[k] = 0.f;
       }
-      act_st4(x + (long long)(r0 + i) * C, o);
+      st16(x + (long long)(r0 + i) * C, o);
     }
   }
 }

@@ -18,7 +18,8 @@ class AWAREEmbedder:
                  win_length: int = 1024, pattern_mode: str = "bits2bipolar", embedding_bands=(500, 4000),
                  tolerance_db: float = 6.0, num_iterations: int = 400, detection_net_cfg: dict = None,
                  optimizer_cfg: dict = None, scheduler_cfg: dict = None, loss: str = "push_extremes",
-                 verbose: bool = True, precision: str = "tf32", wave_clips: int = 0):
+                 verbose: bool = True, precision: str = "tf32", wave_clips: int = 0,
+                 embed_precision: str = "fp16"):
         if (frame_length, hop_length, win_length, window) != (1024, 256, 1024, "hann"):
             raise ValueError("aware_b200 kernels are specialised for n_fft=1024, hop=256, hann")
         optimizer_cfg = optimizer_cfg or {"name": "nadam", "params": {"lr": 0.1}}
@@ -40,7 +41,10 @@ class AWAREEmbedder:
         self.scheduler_name, self.scheduler_params = scheduler_cfg["name"], scheduler_cfg["params"]
         self.loss = loss
         self.verbose = verbose
-        self.precision = precision
+        self.precision = precision              # detector GEMMs
+        # GEMMs inside the 400-step optimisation loop: "fp16" = tcgen05 kind::f16 with fp32
+        # accumulation -- TF32's 10-bit mantissa at half the bytes (measured: not less accurate)
+        self.embed_precision = embed_precision
         self.wave_clips = wave_clips
         self.threshold = 0.0
         self._engine = None
@@ -70,7 +74,7 @@ class AWAREEmbedder:
             logger.info(f"Starting optimization with {nb * (1 + x.shape[1] // 256)} variables per clip, "
                         f"{x.shape[0]} clip(s), {self.num_iterations} iterations")
         return self.engine.embed(x, sample_rate, wm.contiguous(), iters=self.num_iterations, scale=scale,
-                                 wave_clips=self.wave_clips)
+                                 wave_clips=self.wave_clips, precision=self.embed_precision)
 
     def embed(self, audio: np.ndarray, sample_rate: int, watermark: np.ndarray) -> np.ndarray:
         x = to_tensor(audio).reshape(1, -1)

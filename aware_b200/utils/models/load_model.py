@@ -29,7 +29,8 @@ def load(config_path=None):
             scheduler_cfg=config.get("scheduler_cfg", {"name": "reduce_lr_on_plateau",
                                                        "params": {"factor": 0.9, "patience": 500}}),
             loss=config.get("loss", "push_extremes"), verbose=config.get("verbose", True),
-            precision=config.get("precision", "tf32"), wave_clips=config.get("wave_clips", 0))
+            precision=config.get("precision", "tf32"), wave_clips=config.get("wave_clips", 0),
+            embed_precision=config.get("embed_precision", "fp16"))
         embedder.enforce_16k = bool(config.get("enforce_16k", True))
         embedder.threshold = config.get("threshold", 0.0)
     except Exception as e:                                   # noqa: BLE001

@@ -41,7 +41,9 @@ def parse():
     ap.add_argument("--sr", type=int, default=44100)
     ap.add_argument("--iters", type=int, default=400)
     ap.add_argument("--wave", type=int, default=0, help="clips per optimisation wave (0 = all)")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "tf32", "fp32", "bf16"],
+                    help="GEMM arithmetic of the embed loop (detector GEMMs stay TF32)")
+    ap.add_argument("--no-alt", action="store_true", help="skip the one-step TF32 cross-check run")
     ap.add_argument("--no-attacks", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -182,10 +184,12 @@ def build_suite(A, n, sr, rng, n_clips):
     for p in (0.1, 0.15, 0.2):
         suite.append(A.DeleteSamples(p, start=rng.integers(0, n - int(p * n), size=n_clips)))
     suite.append(A.Resample())
-    suite.append(A.RandomBandstop(f_low=float(rng.uniform(300.0, 3800.0))))
+    suite.append(A.RandomBandstop(f_low=float(rng.uniform(300.0, 3800.0)), fast=True))
     for p in (0.1, 0.25):
         suite.append(A.SampleSupression(p, start=rng.integers(0, n - int(p * sr), size=n_clips)))
-    suite += [A.LowPassFilter(), A.HighPassFilter()]
+    # fast=True: chunk-parallel float64 recurrence with look-back (<= 1e-6 from scipy's sequential
+    # lfilter, tests/test_gpu_parity.py); the bit-exact sequential mode runs one thread per clip
+    suite += [A.LowPassFilter(fast=True), A.HighPassFilter(fast=True)]
     return suite
 
 
@@ -213,7 +217,7 @@ def main():
     emb, det = load()
     emb.verbose = False
     emb.num_iterations = args.iters
-    emb.precision = args.precision
+    emb.embed_precision = args.precision
     emb.wave_clips = args.wave
     eng = emb.engine
     A.set_engine(eng)
@@ -236,12 +240,15 @@ def main():
 
     def step(x):
         scale = x.max(dim=1).values                       # service/embed.py:69 signed max
-        y = eng.embed(x, sr, pat, iters=args.iters, scale=scale, wave_clips=args.wave)
+        y = eng.embed(x, sr, pat, iters=args.iters, scale=scale, wave_clips=args.wave,
+                      precision=step_prec[0])
         eng.decide(eng.detect(y, sr), bits, counters[0])
         for i, att in enumerate(suite):
             z = att.apply_batch(y, sr, engine=eng)
             eng.decide(eng.detect(z, sr), bits, counters[i + 1])
         return y
+
+    step_prec = [args.precision]
 
     def sync_all():
         torch.cuda.synchronize()
@@ -268,6 +275,7 @@ def main():
     launches = eng.launch_count() - l0
     eng.profile(False)
     prof = eng.profile_read()
+    timeline = eng.profile_read_named()
     clk = clocks.stop() if clocks else None
     cnt = counters.clone()
     if dist is not None:
@@ -304,28 +312,84 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel: the 1024x1024 tcgen05 GEMM ----------------------
+    # ---- kernel-class shares and rooflines (events around every launch, on the launching stream)
     pk = peaks()
     T = 1 + N // 256
     Tp = T // 2
+    _, nb = eng.band_bins(sr)
+    tl_ms = sum(v[1] for v in timeline.values())
+    classes = {k: {"launches": v[0], "ms": round(v[1], 3), "share_of_step": round(v[1] / ms_total, 4)}
+               for k, v in sorted(timeline.items(), key=lambda kv: -kv[1][1])}
+    n_w = n_clips if args.wave in (0, n_clips) else args.wave
+
+    def hbm_roof(name, label, bytes_per_launch, note):
+        if label not in timeline or not timeline[label][0]:
+            return None
+        cnt_, ms_ = timeline[label]
+        ach = bytes_per_launch / (ms_ / cnt_ * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": "%s copy bandwidth" % pk["src"],
+                "launches": cnt_, "avg_ms": ms_ / cnt_, "share_of_step": ms_ / ms_total,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "note": note}
+
+    # fused spectral kernels: algorithmic bytes per clip
+    spec_note = ("FP32-issue-bound, not HBM-bound: a 1024-point FFT per 256 new samples is ~25 FLOP/B against a "
+                 "machine balance of ~11 FLOP/B; ncu (profiles/): issue slots 64-69 % busy, DRAM 13-20 %")
+    roof_fwd = hbm_roof("k_spec<FWD> (c,u -> iSTFT -> +y_oob -> STFT -> |S|,q ; y stays in shared memory)",
+                        "spec_fwd", n_w * (24.0 * nb * T + 4.0 * L), spec_note)
+    roof_bwd = hbm_roof("k_spec<BWD> (dA,q -> STFT^T -> normaliser^T -> iSTFT^T -> NAdam/clamp/best)",
+                        "spec_bwd", n_w * 48.0 * nb * T, spec_note)
+    elt = {"fp16": 2, "bf16": 2}.get(args.precision, 4)
+    roof_norm = hbm_roof("k_norm_rows<BWD> (InstanceNorm adjoint, in place)", "in_bwd_apply",
+                         n_w * ((Tp + 127) // 128 * 128) * ((1024 + 1024 + 512) / 3.0) * 3 * elt,
+                         "3 launches per iteration (1024, 1024, 512 channels): read dHhat, read P, write dH")
     dom = [p for p in prof if p[0] == 1024 and p[1] == 1024]
-    roof = None
-    if dom and args.precision == "tf32":
+    roof_gemm = None
+    if dom:
         launches_d = sum(p[3] for p in dom)
         ms_d = sum(p[4] for p in dom)
-        flops = 2.0 * n_clips * Tp * 1024 * 1024 if args.wave in (0, n_clips) else None
-        if flops is None:
-            flops = 2.0 * args.wave * Tp * 1024 * 1024
+        flops = 2.0 * n_w * Tp * 1024 * 1024
         ach = flops / (ms_d / launches_d * 1e-3) / 1e12
         gemm_ms = sum(p[4] for p in prof)
-        roof = {"kernel": "k_gemm_tc<256,*> N=1024 K=1024 (tcgen05 kind::tf32, conv block 2 fwd + input-grad)",
-                "bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
-                "frac": ach / pk["tflops"], "traffic": None,
-                "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json); TF32 runs at half the bf16 rate, so "
-                               "frac 0.5 is this kernel's ceiling" % pk["src"],
-                "launches": launches_d, "avg_ms": ms_d / launches_d,
-                "share_of_step": ms_d / ms_total, "all_gemm_share_of_step": gemm_ms / ms_total,
-                "algorithmic_flops_per_launch": flops}
+        half_rate = args.precision == "tf32"
+        roof_gemm = {"kernel": "k_gemm_tc<256,*> N=1024 K=1024 (tcgen05 kind::%s, conv block 2 fwd + input-grad)"
+                               % ("tf32" if half_rate else "f16"),
+                     "bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
+                     "frac": ach / pk["tflops"], "traffic": None,
+                     "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)%s" % (
+                         pk["src"], "; TF32 runs at half the bf16 rate, so frac 0.5 is this kernel's ceiling"
+                         if half_rate else ""),
+                     "launches": launches_d, "avg_ms": ms_d / launches_d,
+                     "share_of_step": ms_d / ms_total, "all_gemm_share_of_step": gemm_ms / ms_total,
+                     "algorithmic_flops_per_launch": flops}
+    # `roofline` = the kernel class with the largest share of the step
+    cands = [r for r in (roof_fwd, roof_bwd, roof_norm, roof_gemm) if r]
+    roof = max(cands, key=lambda r: r["share_of_step"]) if cands else None
+    ncu_traffic = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if roof and os.path.exists(ncu_traffic):
+        try:
+            tr = json.load(open(ncu_traffic))
+            for r in cands:
+                key = r["kernel"].split(" ")[0]
+                if key in tr:       # dram bytes per launch per clip from one ncu --set full capture
+                    r["traffic"] = tr[key]["dram_bytes_per_clip"] * n_w
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---- cross-check: one step with TF32 GEMMs in the loop ------------------------------------
+    alt = None
+    if not args.no_alt and args.precision != "tf32":
+        step_prec[0] = "tf32"
+        step(x_dev)
+        sync_all()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        step(x_dev)
+        a1.record()
+        torch.cuda.synchronize()
+        alt = {"embed_precision": "tf32", "value": n_clips * args.seconds / (a0.elapsed_time(a1) / 1e3),
+               "unit": UNIT, "steps": 1, "n_gpus": 1, "note": "rank 0 only, same step with TF32 loop GEMMs"}
+        step_prec[0] = args.precision
 
     # ---- CPU baseline beside it (oracle port, bounded sample) ----------------------------
     cpu = None
@@ -347,9 +411,12 @@ def main():
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+        "dtype": {"fp16": "fp16 (tcgen05 kind::f16, fp32 accumulate; FFT/DSP fp32)", "tf32": "tf32",
+                  "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
         "config": workload_config(args), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roof, "cpu_baseline": cpu, "ber_percent": ber,
+        "roofline": roof, "rooflines_all": [r for r in cands if r is not roof], "kernel_classes": classes,
+        "timeline_ms_per_step": tl_ms / args.steps, "alt_precision": alt,
+        "cpu_baseline": cpu, "ber_percent": ber,
         "gemm_classes": [{"n": p[0], "k": p[1], "epi": p[2], "launches": p[3], "ms": p[4]} for p in prof]}))
     if dist is not None:
         dist.destroy_process_group()

@@ -336,12 +336,15 @@ def test_embed_full_functional_parity(model, precision):
     g = np.load(os.path.join(GOLDEN, "embed_full.npz"))
     x = O.synth_clip(1, 2.0, 16000)
     emb.engine.set_precision(precision)
+    prev = emb.embed_precision
+    emb.embed_precision = precision
     emb.num_iterations = 400
     try:
         y = embed_watermark(x, 16000, g["bits"], emb)
         got = detect_watermark(y, 16000, det)
     finally:
         emb.engine.set_precision("tf32")
+        emb.embed_precision = prev
     assert y.shape == g["wave"].shape and y.dtype == np.float32
     np.testing.assert_array_equal(got, g["bits"])                       # BER 0, as the reference
     np.testing.assert_array_equal(O.detect_watermark(y, 16000), g["bits"])
