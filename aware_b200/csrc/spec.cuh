@@ -57,43 +57,80 @@ __host__ __device__ constexpr uint32_t need_before(uint32_t need, int half) {
   return o;
 }
 
-template <int SIGN, int HALF, uint32_t NZ, uint32_t NEED, int I>
+__host__ __device__ constexpr int brevn(int x, int bits) {
+  int r = 0;
+  for (int i = 0; i < bits; ++i)
+    if ((x >> i) & 1) r |= 1 << (bits - 1 - i);
+  return r;
+}
+// cos / sin(2 pi e / 32) and their ratios as compile-time constants
+__host__ __device__ constexpr double tw_cos(int e) {
+  constexpr double c[16] = {1.0, 0.98078528040323043, 0.92387953251128674, 0.83146961230254524,
+                            0.70710678118654757, 0.55557023301960229, 0.38268343236508984, 0.19509032201612833,
+                            0.0, -0.19509032201612819, -0.38268343236508973, -0.55557023301960196,
+                            -0.70710678118654746, -0.83146961230254535, -0.92387953251128674, -0.98078528040323043};
+  return c[e];
+}
+__host__ __device__ constexpr double tw_sin(int e) {
+  constexpr double s[16] = {0.0, 0.19509032201612825, 0.38268343236508978, 0.55557023301960218,
+                            0.70710678118654746, 0.83146961230254524, 0.92387953251128674, 0.98078528040323043,
+                            1.0, 0.98078528040323043, 0.92387953251128674, 0.83146961230254546,
+                            0.70710678118654757, 0.55557023301960218, 0.38268343236508989, 0.19509032201612861};
+  return s[e];
+}
+
+// One butterfly of the decimation-in-time network with natural-order input and bit-reversed
+// output: stage S pairs registers half = 16 >> S apart inside 2^S groups, and every butterfly of
+// group g uses the same twiddle W = exp(SIGN i 2 pi e / 32), e = brev_S(g) * (16 >> S):
+//     (a, b) -> (a + W b, a - W b).
+// Because W multiplies b BEFORE the add, a non-trivial butterfly is 6 FMAs (Linzer-Feig:
+// W b = c (b + i t b) with t = s / c, or the cotangent form when |s| > |c|) instead of the
+// 8 operations of the decimation-in-frequency form.
+template <int SIGN, int S, uint32_t NZ, uint32_t NEED, int I>
 __device__ __forceinline__ void bfly_p(float (&re)[32], float (&im)[32]) {
-  constexpr int g = (I / HALF) * (2 * HALF), j = I % HALF;
-  constexpr int i0 = g + j, i1 = i0 + HALF;
+  constexpr int HALF = 16 >> S;
+  constexpr int g = I / HALF, j = I % HALF;
+  constexpr int i0 = g * 2 * HALF + j, i1 = i0 + HALF;
   constexpr bool anz = (NZ >> i0) & 1u, bnz = (NZ >> i1) & 1u;
   constexpr bool n0 = (NEED >> i0) & 1u, n1 = (NEED >> i1) & 1u;
-  constexpr int tw = j * (16 / HALF);
+  constexpr int e = brevn(g, S) * (16 >> S);
+  constexpr float c = (float)tw_cos(e), sn = (float)(SIGN * tw_sin(e));
   if constexpr ((anz || bnz) && (n0 || n1)) {
-    float dr, di;          // (a - b), with the sign folded into the twiddle when a == 0
-    float tsign = 1.f;
-    if constexpr (anz && bnz) {
-      const float ar = re[i0], ai = im[i0], br = re[i1], bi = im[i1];
-      if constexpr (n0) { re[i0] = ar + br; im[i0] = ai + bi; }
-      dr = ar - br; di = ai - bi;
-    } else if constexpr (anz) {
-      dr = re[i0]; di = im[i0];                       // sum = a stays in place
+    if constexpr (!bnz) {                               // b == 0: both outputs are a
+      if constexpr (n1) { re[i1] = re[i0]; im[i1] = im[i0]; }
+    } else if constexpr (!anz) {                        // a == 0: outputs are +-W b
+      const float br = re[i1], bi = im[i1];
+      float tr, ti;
+      if constexpr (e == 0) { tr = br; ti = bi; }
+      else if constexpr (e == 8) { tr = -SIGN * bi; ti = SIGN * br; }
+      else { tr = br * c - bi * sn; ti = br * sn + bi * c; }
+      if constexpr (n0) { re[i0] = tr; im[i0] = ti; }
+      if constexpr (n1) { re[i1] = -tr; im[i1] = -ti; }
     } else {
-      dr = re[i1]; di = im[i1];                       // sum = b, difference = -b
-      if constexpr (n0) { re[i0] = dr; im[i0] = di; }
-      tsign = -1.f;
-    }
-    if constexpr (n1) {
-      if constexpr (tw == 0) {
-        re[i1] = tsign * dr; im[i1] = tsign * di;
-      } else if constexpr (tw == 8) {                 // W = SIGN * i
-        re[i1] = -SIGN * tsign * di; im[i1] = SIGN * tsign * dr;
-      } else {
-        const float c = tsign * c_cos32[tw], s = tsign * SIGN * c_sin32[tw];
-        re[i1] = dr * c - di * s;
-        im[i1] = dr * s + di * c;
+      const float ar = re[i0], ai = im[i0], br = re[i1], bi = im[i1];
+      if constexpr (e == 0) {
+        if constexpr (n0) { re[i0] = ar + br; im[i0] = ai + bi; }
+        if constexpr (n1) { re[i1] = ar - br; im[i1] = ai - bi; }
+      } else if constexpr (e == 8) {                    // W = SIGN i
+        if constexpr (n0) { re[i0] = ar - SIGN * bi; im[i0] = ai + SIGN * br; }
+        if constexpr (n1) { re[i1] = ar + SIGN * bi; im[i1] = ai - SIGN * br; }
+      } else if constexpr (e <= 4 || e >= 12) {         // |s| <= |c|: tangent form
+        constexpr float t = (float)(SIGN * tw_sin(e) / tw_cos(e));
+        const float t1 = fmaf(-t, bi, br), t2 = fmaf(t, br, bi);
+        if constexpr (n0) { re[i0] = fmaf(c, t1, ar); im[i0] = fmaf(c, t2, ai); }
+        if constexpr (n1) { re[i1] = fmaf(-c, t1, ar); im[i1] = fmaf(-c, t2, ai); }
+      } else {                                          // cotangent form
+        constexpr float ct = (float)(tw_cos(e) / (SIGN * tw_sin(e)));
+        const float t1 = fmaf(ct, br, -bi), t2 = fmaf(ct, bi, br);
+        if constexpr (n0) { re[i0] = fmaf(sn, t1, ar); im[i0] = fmaf(sn, t2, ai); }
+        if constexpr (n1) { re[i1] = fmaf(-sn, t1, ar); im[i1] = fmaf(-sn, t2, ai); }
       }
     }
   }
 }
-template <int SIGN, int HALF, uint32_t NZ, uint32_t NEED, int... I>
+template <int SIGN, int S, uint32_t NZ, uint32_t NEED, int... I>
 __device__ __forceinline__ void stage_p(float (&re)[32], float (&im)[32], std::integer_sequence<int, I...>) {
-  (bfly_p<SIGN, HALF, NZ, NEED, I>(re, im), ...);
+  (bfly_p<SIGN, S, NZ, NEED, I>(re, im), ...);
 }
 // 32-point DFT, natural order in, bit-reversed order out (register p holds X[brev5(p)]).
 // NZ = non-zero inputs (natural index), NEED = needed outputs (register index, i.e. brev5 of
@@ -103,12 +140,12 @@ __device__ __forceinline__ void fft32_p(float (&re)[32], float (&im)[32]) {
   constexpr uint32_t Z1 = nz_after(NZ, 16), Z2 = nz_after(Z1, 8), Z3 = nz_after(Z2, 4), Z4 = nz_after(Z3, 2);
   constexpr uint32_t N4 = need_before(NEED, 1), N3 = need_before(N4, 2), N2 = need_before(N3, 4),
                      N1 = need_before(N2, 8);
-  using S = std::make_integer_sequence<int, 16>;
-  stage_p<SIGN, 16, NZ, N1>(re, im, S{});
-  stage_p<SIGN, 8, Z1, N2>(re, im, S{});
-  stage_p<SIGN, 4, Z2, N3>(re, im, S{});
-  stage_p<SIGN, 2, Z3, N4>(re, im, S{});
-  stage_p<SIGN, 1, Z4, NEED>(re, im, S{});
+  using Q = std::make_integer_sequence<int, 16>;
+  stage_p<SIGN, 0, NZ, N1>(re, im, Q{});
+  stage_p<SIGN, 1, Z1, N2>(re, im, Q{});
+  stage_p<SIGN, 2, Z2, N3>(re, im, Q{});
+  stage_p<SIGN, 3, Z3, N4>(re, im, Q{});
+  stage_p<SIGN, 4, Z4, NEED>(re, im, Q{});
 }
 
 // natural-index set of the 32-bin groups that hold the band and its hermitian mirror:

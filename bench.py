@@ -381,7 +381,7 @@ def main():
     if not args.no_alt and args.precision != "tf32":
         step_prec[0] = "tf32"
         step(x_dev)
-        sync_all()
+        torch.cuda.synchronize()                          # rank 0 only from here on: no collectives
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         step(x_dev)
