@@ -73,7 +73,7 @@ struct aw_ctx {
   bool no_fuse_norm = true;   // AW_B200_FUSE_NORM=1 opts into the in-GEMM InstanceNorm application
   Buf ready;                  // [6 fused launches][clips][4] finished-row-tile counters (gemm.cuh FUSE)
   bool legacy_spec = false;   // AW_B200_LEGACY_SPEC=1: separate synthesis / analysis kernels
-  Buf scal, zoob;
+  Buf scal, zoob, p0coef, p0scal;
   Buf accum, peakx, mag, ph_u, ph_q, c0, c, m, v, cbest, dA, yoob, y, dpad, M, cs, sigma;
   Buf act[5], ga, gb, dh4, dp0, part, stat[5], bstat, values, best, improved, pattern, itc, steps;
   int ws_rows = 0;
@@ -337,7 +337,7 @@ extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
                  &ctx->act[4], &ctx->ga, &ctx->gb, &ctx->dh4, &ctx->dp0, &ctx->part, &ctx->stat[0],
                  &ctx->stat[1], &ctx->stat[2], &ctx->stat[3], &ctx->stat[4], &ctx->bstat,
                  &ctx->values, &ctx->best, &ctx->improved, &ctx->pattern, &ctx->itc, &ctx->steps,
-                 &ctx->scal, &ctx->ready, &ctx->zoob};
+                 &ctx->scal, &ctx->ready, &ctx->zoob, &ctx->p0coef, &ctx->p0scal};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   delete ctx;
@@ -545,6 +545,7 @@ static int ensure_net_ws(aw_ctx* ctx, const Dims& d, bool backward) {
   if (ensure(ctx->M, n * d.T * AW_NMEL * 4)) return 1;
   if (ensure(ctx->cs, n * AW_NMEL * sizeof(ChanStats))) return 1;
   if (ensure(ctx->sigma, n * 4)) return 1;
+  if (ensure(ctx->p0coef, n * AW_NMEL * sizeof(P0BwdCoef)) || ensure(ctx->p0scal, n * sizeof(P0BwdScal))) return 1;
   bool remap = false;
   for (int l = 0; l < 5; ++l) {
     void* before = ctx->act[l].p;
@@ -672,9 +673,14 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
     ctx->launches++;
     AW_LAUNCH_CHECK();
     dim3 g2((d.Tp_pad + AW_P0_ROWS - 1) / AW_P0_ROWS, d.n);
+    prof_mark(ctx, st, "mel_stats");
+    k_mel_stats<<<d.n, 128, 0, st>>>(acc.chan_part, acc.mel_blocks, d.T, (ChanStats*)ctx->cs.p,
+                                     (float*)ctx->sigma.p);
+    ctx->launches++;
+    AW_LAUNCH_CHECK();
     prof_mark(ctx, st, "p0");
-    k_p0<AT><<<g2, 128, 0, st>>>((float*)ctx->M.p, d.T, d.Tp, d.Tp_pad, acc.chan_part, acc.mel_blocks,
-                                 (AT*)ctx->act[0].p, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p, tf);
+    k_p0<AT><<<g2, 128, 0, st>>>((float*)ctx->M.p, d.T, d.Tp, d.Tp_pad, (ChanStats*)ctx->cs.p,
+                                 (float*)ctx->sigma.p, (AT*)ctx->act[0].p, tf);
     ctx->launches++;
     AW_LAUNCH_CHECK();
   }
@@ -773,10 +779,15 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
   ctx->launches++;
   AW_LAUNCH_CHECK();
   dim3 g2((d.T + AW_P0A_FRAMES - 1) / AW_P0A_FRAMES, d.n);
+  prof_mark(ctx, st, "p0_bwd_coef");
+  k_p0_bwd_coef<<<d.n, 128, 0, st>>>(acc.bpart, acc.p0b_blocks, d.T, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p,
+                                     (P0BwdCoef*)ctx->p0coef.p, (P0BwdScal*)ctx->p0scal.p);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
   prof_mark(ctx, st, "p0_bwd_apply");
   k_p0_bwd_apply<<<g2, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
-                                     (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p, acc.bpart,
-                                     acc.p0b_blocks, sm, d.nb, (float*)ctx->dA.p,
+                                     (ChanStats*)ctx->cs.p, (P0BwdCoef*)ctx->p0coef.p,
+                                     (P0BwdScal*)ctx->p0scal.p, sm, d.nb, (float*)ctx->dA.p,
                                      euler_s2 ? (const float*)ctx->mag.p : nullptr, acc.s2_part,
                                      1.0f / ModeOf<AT>::GSCALE);
   ctx->launches++;

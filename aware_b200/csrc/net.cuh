@@ -113,15 +113,12 @@ __device__ __forceinline__ void sum_partials(const double* __restrict__ part, in
 // GlobalStandardize statistics are taken analytically from the channel
 // statistics: after InstanceNorm every channel has mean 0 and second moment
 // var/(var+eps), so mean_g = 0 and std_g^2 = T * sum_c var_c/(var_c+eps) / (128 T - 1).
-#define AW_P0_ROWS 32
-template <typename AT>
-__global__ void __launch_bounds__(128) k_p0(const float* __restrict__ M, int T, int Tp, int Tp_pad,
-                                            const double* __restrict__ chan_part, int nblk,
-                                            AT* __restrict__ P0, ChanStats* __restrict__ cs,
-                                            float* __restrict__ sigma_out, int round_tf32) {
+// k_mel_stats reduces the per-block partials ONCE per clip (one CTA per clip, thread = channel);
+// k_p0 then only streams.
+__global__ void __launch_bounds__(128) k_mel_stats(const double* __restrict__ chan_part, int nblk, int T,
+                                                   ChanStats* __restrict__ cs, float* __restrict__ sigma_out) {
   __shared__ double s_red[32];
-  __shared__ float s_inv;
-  const int clip = blockIdx.y, c = threadIdx.x, j0 = blockIdx.x * AW_P0_ROWS;
+  const int clip = blockIdx.x, c = threadIdx.x;
   double s1, s2;
   sum_partials(chan_part, clip, nblk, c, s1, s2);
   const double mu = s1 / T;
@@ -130,19 +127,25 @@ __global__ void __launch_bounds__(128) k_p0(const float* __restrict__ M, int T, 
   const double rstd = 1.0 / sqrt(var + AW_IN_EPS);
   const double vr = var / (var + AW_IN_EPS);
   const double tot = block_sum(vr, s_red);
+  ChanStats st;
+  st.mu = (float)mu; st.rstd = (float)rstd; st.varratio = (float)vr; st.pad = 0.f;
+  cs[(long long)clip * AW_NMEL + c] = st;
   if (threadIdx.x == 0) {
     const double n = 128.0 * T;
-    const double sigma = sqrt((double)T * tot / (n - 1.0));
-    s_inv = (float)(1.0 / (sigma + 1e-8));
-    if (blockIdx.x == 0) sigma_out[clip] = (float)sigma;
+    sigma_out[clip] = (float)sqrt((double)T * tot / (n - 1.0));
   }
-  __syncthreads();
-  if (blockIdx.x == 0) {
-    ChanStats st;
-    st.mu = (float)mu; st.rstd = (float)rstd; st.varratio = (float)vr; st.pad = 0.f;
-    cs[(long long)clip * AW_NMEL + c] = st;
-  }
-  const float fmu = (float)mu, fr = (float)rstd, inv = s_inv;
+}
+
+#define AW_P0_ROWS 32
+template <typename AT>
+__global__ void __launch_bounds__(128) k_p0(const float* __restrict__ M, int T, int Tp, int Tp_pad,
+                                            const ChanStats* __restrict__ cs,
+                                            const float* __restrict__ sigma_in,
+                                            AT* __restrict__ P0, int round_tf32) {
+  const int clip = blockIdx.y, c = threadIdx.x, j0 = blockIdx.x * AW_P0_ROWS;
+  const ChanStats st = cs[(long long)clip * AW_NMEL + c];
+  const float fmu = st.mu, fr = st.rstd;
+  const float inv = (float)(1.0 / ((double)sigma_in[clip] + 1e-8));
   const float* Mc = M + (long long)clip * T * AW_NMEL + c;
   for (int j = j0; j < min(j0 + AW_P0_ROWS, Tp_pad); ++j) {
     float p = 0.f;
@@ -410,21 +413,17 @@ __global__ void __launch_bounds__(128) k_p0_bwd_reduce(const float* __restrict__
   p[1] = s2;
 }
 
-// pass 2: dM, then dA~[t][b] = sum_c mel[c][b] dM[t][c]
-#define AW_P0A_FRAMES 16
-__global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ dP0,
-                                                      const float* __restrict__ M, int T, int Tp,
-                                                      int Tp_pad, const ChanStats* __restrict__ cs,
-                                                      const float* __restrict__ sigma_in,
-                                                      const double* __restrict__ bpart, int nblk,
-                                                      SparseMel sm,
-                                                      int nb, float* __restrict__ dA,
-                                                      const float* __restrict__ mag_un,
-                                                      double* __restrict__ s2_part, float ginv) {
+// pass 1b: per clip, once: the scalars and per-channel coefficients of the three adjoints
+struct P0BwdCoef { float A1, A2; };
+struct P0BwdScal { float alpha, beta, meanG, pad; };
+__global__ void __launch_bounds__(128) k_p0_bwd_coef(const double* __restrict__ bpart, int nblk, int T,
+                                                     const ChanStats* __restrict__ cs,
+                                                     const float* __restrict__ sigma_in,
+                                                     P0BwdCoef* __restrict__ coef,
+                                                     P0BwdScal* __restrict__ scal) {
   __shared__ double s_red[32];
-  __shared__ float s_dm[AW_P0A_FRAMES][AW_NMEL];
   __shared__ float s_ab[3];
-  const int clip = blockIdx.y, c = threadIdx.x, t0 = blockIdx.x * AW_P0A_FRAMES;
+  const int clip = blockIdx.x, c = threadIdx.x;
   double S1, S2;
   sum_partials(bpart, clip, nblk, c, S1, S2);
   const double tS1 = block_sum(S1, s_red);
@@ -435,12 +434,38 @@ __global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ 
     s_ab[0] = (float)(1.0 / (sg + 1e-8));                                      // alpha
     s_ab[1] = (float)(tS2 / ((n - 1.0) * sg * (sg + 1e-8) * (sg + 1e-8)));      // beta
     s_ab[2] = (float)(tS1 / n);                                                 // mean dG
+    P0BwdScal o;
+    o.alpha = s_ab[0]; o.beta = s_ab[1]; o.meanG = s_ab[2]; o.pad = 0.f;
+    scal[clip] = o;
   }
   __syncthreads();
   const float alpha = s_ab[0], beta = s_ab[1], meanG = s_ab[2];
   const ChanStats st = cs[(long long)clip * AW_NMEL + c];
-  const float A1 = alpha * ((float)(S1 / T) - meanG);
-  const float A2 = alpha * (float)(S2 / T) - beta * st.varratio;
+  P0BwdCoef k;
+  k.A1 = alpha * ((float)(S1 / T) - meanG);
+  k.A2 = alpha * (float)(S2 / T) - beta * st.varratio;
+  coef[(long long)clip * AW_NMEL + c] = k;
+}
+
+// pass 2: dM, then dA~[t][b] = sum_c mel[c][b] dM[t][c]
+#define AW_P0A_FRAMES 16
+__global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ dP0,
+                                                      const float* __restrict__ M, int T, int Tp,
+                                                      int Tp_pad, const ChanStats* __restrict__ cs,
+                                                      const P0BwdCoef* __restrict__ coef,
+                                                      const P0BwdScal* __restrict__ scal,
+                                                      SparseMel sm,
+                                                      int nb, float* __restrict__ dA,
+                                                      const float* __restrict__ mag_un,
+                                                      double* __restrict__ s2_part, float ginv) {
+  __shared__ double s_red[32];
+  __shared__ float s_dm[AW_P0A_FRAMES][AW_NMEL];
+  const int clip = blockIdx.y, c = threadIdx.x, t0 = blockIdx.x * AW_P0A_FRAMES;
+  const P0BwdScal sc = scal[clip];
+  const float alpha = sc.alpha, beta = sc.beta, meanG = sc.meanG;
+  const ChanStats st = cs[(long long)clip * AW_NMEL + c];
+  const P0BwdCoef k = coef[(long long)clip * AW_NMEL + c];
+  const float A1 = k.A1, A2 = k.A2;
   const int nf = min(AW_P0A_FRAMES, T - t0);
   for (int f = 0; f < nf; ++f) {
     const int t = t0 + f;

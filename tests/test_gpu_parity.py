@@ -405,3 +405,27 @@ def test_full_size_batch_properties(model):
     assert torch.equal(y_wave, y_all)
     v = eng.detect(y_all, sr)
     assert v.shape == (6, 20) and torch.isfinite(v).all()
+
+
+def test_long_clips_config4_and_config5_shapes(eng):
+    """BASELINE configs[3] clip length (30 s) and a long-form clip (5 min, the configs[4] code path
+    with T = 51 681 frames on one GPU): detector outputs against the oracle, a one-iteration embed
+    against the oracle at 30 s, and finite / deterministic long-form embedding."""
+    sr = 44100
+    x30 = _clips([5], 30.0, sr)
+    v = eng.detect(torch.from_numpy(x30).cuda(), sr).cpu().numpy()[0]
+    assert np.abs(v - O.detect(x30[0], sr)).max() <= 1e-3
+    pat = np.stack([O.encode_bits(O.synth_bits(8)[5])])
+    out, _, _ = _embed_state(eng, x30, sr, pat, 1, "fp32")
+    y = O.embed(x30[0], sr, pat[0], num_iters=1)
+    assert out.shape == (1, 256 * (x30.shape[1] // 256))
+    # 418 k coefficients: a handful of sign flips of the NAdam first step (|g| ~ 0) are expected
+    assert _snr(out[0], y) >= 75 and np.abs(out[0] - y).max() <= 3e-3
+    x300 = np.tile(_clips([6], 30.0, sr), (1, 10))                  # 5 min
+    xd = torch.from_numpy(x300).cuda()
+    v = eng.detect(xd, sr).cpu().numpy()[0]
+    assert np.abs(v - O.detect(x300[0], sr)).max() <= 1e-3
+    ya = eng.embed(xd, sr, torch.from_numpy(pat), iters=3)
+    yb = eng.embed(xd, sr, torch.from_numpy(pat), iters=3)
+    assert ya.shape == (1, 256 * (x300.shape[1] // 256)) and torch.isfinite(ya).all()
+    assert torch.equal(ya, yb)
