@@ -72,9 +72,8 @@ struct aw_ctx {
   // workspace (grow-only)
   bool no_fuse_norm = true;   // AW_B200_FUSE_NORM=1 opts into the in-GEMM InstanceNorm application
   Buf ready;                  // [6 fused launches][clips][4] finished-row-tile counters (gemm.cuh FUSE)
-  bool legacy_spec = false;   // AW_B200_LEGACY_SPEC=1: separate synthesis / analysis kernels
   Buf scal, zoob, p0coef, p0scal;
-  Buf accum, peakx, mag, ph_u, ph_q, c0, c, m, v, cbest, dA, yoob, y, dpad, M, cs, sigma;
+  Buf accum, peakx, mag, ph_u, ph_q, c0, c, m, v, cbest, dA, yoob, y, M, cs, sigma;
   Buf act[5], ga, gb, dh4, dp0, part, stat[5], bstat, values, best, improved, pattern, itc, steps;
   int ws_rows = 0;
   // activation tensor maps, [0] = float32 view, [1] = bf16 view of the same buffers
@@ -237,8 +236,7 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
   ctx->threshold = model->threshold;
   ctx->h_mel.assign(model->mel_basis, model->mel_basis + AW_NMEL * 513);
   {
-    const char* e = getenv("AW_B200_LEGACY_SPEC");
-    ctx->legacy_spec = e && e[0] == '1';
+    const char* e;
     // measured on B200 (128 x 10 s clips, TF32): 5.44 ms/iteration fused vs 5.50 ms unfused, detect
     // 2.33 vs 2.10 ms -- the 4 normaliser warps per SM are latency-bound, so the L2-hot
     // re-read buys nothing.  Kept as an opt-in experiment (single stream only: the kernel's
@@ -332,7 +330,7 @@ extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
     cudaFree(mc.colptr); cudaFree(mc.row); cudaFree(mc.valT);
   }
   Buf* bufs[] = {&ctx->accum, &ctx->peakx, &ctx->mag, &ctx->ph_u, &ctx->ph_q, &ctx->c0, &ctx->c,
-                 &ctx->m, &ctx->v, &ctx->cbest, &ctx->dA, &ctx->yoob, &ctx->y, &ctx->dpad, &ctx->M,
+                 &ctx->m, &ctx->v, &ctx->cbest, &ctx->dA, &ctx->yoob, &ctx->y, &ctx->M,
                  &ctx->cs, &ctx->sigma, &ctx->act[0], &ctx->act[1], &ctx->act[2], &ctx->act[3],
                  &ctx->act[4], &ctx->ga, &ctx->gb, &ctx->dh4, &ctx->dp0, &ctx->part, &ctx->stat[0],
                  &ctx->stat[1], &ctx->stat[2], &ctx->stat[3], &ctx->stat[4], &ctx->bstat,
@@ -522,7 +520,7 @@ static int mel_blocks(const Dims& d) { return (d.T + AW_MEL_FRAMES - 1) / AW_MEL
 static int syn_tiles(const Dims& d) { return (d.T + 3 + AW_SYN_HOPS - 1) / AW_SYN_HOPS; }
 static int p0b_blocks(const Dims& d) { return (2 * d.Tp + AW_P0B_FRAMES - 1) / AW_P0B_FRAMES; }
 static int p0a_blocks(const Dims& d) { return (d.T + AW_P0A_FRAMES - 1) / AW_P0A_FRAMES; }
-static int s2_slots(const Dims& d) { return std::max(syn_tiles(d), p0a_blocks(d)); }
+static int s2_slots(const Dims& d) { return p0a_blocks(d); }
 static size_t acc_doubles(const Dims& d) {
   return (size_t)d.n * (1 + s2_slots(d) + 256 * (size_t)mel_blocks(d) + 256 * (size_t)p0b_blocks(d));
 }
@@ -838,7 +836,7 @@ static int launch_ana_k(aw_ctx* ctx, const Dims& d, const AnaArgs& a, cudaStream
     attr_set = true;
   }
   dim3 g((d.T + AW_ANA_FRAMES - 1) / AW_ANA_FRAMES, d.n);
-  prof_mark(ctx, st, MODE == ANA_MAG ? "analysis_mag" : (MODE == ANA_INIT ? "analysis_init" : "analysis_legacy"));
+  prof_mark(ctx, st, MODE == ANA_MAG ? "analysis_mag" : "analysis_init");
   k_analysis<MODE, K2LO, K2HI><<<g, 128, AW_ANA_SMEM, st>>>(a);
   ctx->launches++;
   AW_LAUNCH_CHECK();
@@ -862,7 +860,7 @@ static int launch_syn_k(aw_ctx* ctx, const Dims& d, const SynArgs& s, cudaStream
     attr_set = true;
   }
   dim3 g((d.T + 3 + AW_SYN_HOPS - 1) / AW_SYN_HOPS, d.n);
-  prof_mark(ctx, st, MODE == SYN_OOB ? "synthesis_oob" : (MODE == SYN_WAVE ? "synthesis_wave" : "synthesis_legacy"));
+  prof_mark(ctx, st, MODE == SYN_OOB ? "synthesis_oob" : "synthesis_wave");
   k_synthesis<MODE, K2LO, K2HI><<<g, 128, AW_SYN_SMEM, st>>>(s);
   ctx->launches++;
   AW_LAUNCH_CHECK();
@@ -1011,7 +1009,6 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       ensure(ctx->cbest, sp * 4) || ensure(ctx->dA, sp * 4) ||
       ensure(ctx->yoob, (size_t)d.n * d.L * 4) || ensure(ctx->y, (size_t)d.n * d.L * 4) ||
       ensure(ctx->zoob, (size_t)d.n * d.L * 4) ||
-      ensure(ctx->dpad, (size_t)d.n * (d.L + AW_NFFT) * 4) ||
       ensure(ctx->pattern, (size_t)d.n * AW_NBITS * 4) || ensure(ctx->scal, (size_t)d.n * sizeof(ClipScal)) ||
       ensure(ctx->steps, (size_t)(iters > 0 ? iters : 1) * sizeof(NadamStep)))
     return 1;
@@ -1053,11 +1050,11 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
     s0.amp = (float*)ctx->c0.p; s0.ph = (float2*)ctx->ph_u.p; s0.scale = 1.0f / AW_NFFT;
     s0.x = x; s0.x_stride = stride; s0.peak_x = (unsigned long long*)ctx->peakx.p;
     s0.y_oob = (float*)ctx->yoob.p;
-    s0.z_oob = ctx->legacy_spec ? nullptr : (float*)ctx->zoob.p;
+    s0.z_oob = (float*)ctx->zoob.p;
     if (launch_syn<SYN_OOB>(ctx, dw, s0, st)) return 1;
 
     // ---- optimisation loop (multibit_embedder.py:95-122)
-    for (int it = 0; it < iters && !ctx->legacy_spec; ++it) {
+    for (int it = 0; it < iters; ++it) {
       // fused spectral passes (spec.cuh): y and dpad never leave shared memory
       if (begin_pass(ctx, dw.n, itc, st)) return 1;
       SpecArgs f;
@@ -1098,43 +1095,6 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       b.tol_ratio = (float)pow(10.0, -(double)ctx->tol_db / 20.0);
       if (launch_spec<SPEC_BWD>(ctx, dw, b, st)) return 1;
     }
-    for (int it = 0; it < iters && ctx->legacy_spec; ++it) {
-      if (begin_pass(ctx, dw.n, itc, st)) return 1;
-      SynArgs s1 = syn_base(ctx, dw);
-      s1.amp = (float*)ctx->c.p; s1.ph = (float2*)ctx->ph_u.p; s1.scale = 1.0f / AW_NFFT;
-      s1.y_oob = (float*)ctx->yoob.p; s1.y = (float*)ctx->y.p; s1.peak_y = acc.peak_y;
-      if (launch_syn<SYN_WAVE>(ctx, dw, s1, st)) return 1;
-      AnaArgs a1 = ana_base(ctx, dw);
-      a1.sig = (float*)ctx->y.p; a1.sig_stride = dw.L; a1.len = dw.L; a1.peak = acc.peak_y;
-      a1.mag = (float*)ctx->mag.p; a1.ph = (float2*)ctx->ph_q.p;
-      if (launch_ana<ANA_LOOP>(ctx, dw, a1, st)) return 1;
-      float* lp = d_losses ? d_losses + w0 : nullptr;
-      if (ctx->prec == AW_PREC_BF16) {
-        if (net_forward<__nv_bfloat16>(ctx, dw, acc, sm, st)) return 1;
-        if (run_head<__nv_bfloat16>(ctx, dw, (float*)ctx->pattern.p, (float*)ctx->values.p, lp, n_clips, true, st))
-          return 1;
-        if (net_backward<__nv_bfloat16>(ctx, dw, acc, sm, st)) return 1;
-      } else {
-        if (net_forward<float>(ctx, dw, acc, sm, st)) return 1;
-        if (run_head<float>(ctx, dw, (float*)ctx->pattern.p, (float*)ctx->values.p, lp, n_clips, true, st))
-          return 1;
-        if (net_backward<float>(ctx, dw, acc, sm, st)) return 1;
-      }
-      SynArgs s2 = syn_base(ctx, dw);
-      s2.amp = (float*)ctx->dA.p; s2.ph = (float2*)ctx->ph_q.p; s2.scale = 0.5f;
-      s2.y = (float*)ctx->y.p; s2.peak_y = acc.peak_y;
-      s2.dpad = (float*)ctx->dpad.p; s2.s2_part = acc.s2_part;
-      if (launch_syn<SYN_ADJ>(ctx, dw, s2, st)) return 1;
-      AnaArgs a2 = ana_base(ctx, dw);
-      a2.sig = (float*)ctx->dpad.p; a2.sig_stride = dw.L + AW_NFFT; a2.len = dw.L;
-      a2.peak = acc.peak_y;
-      a2.c = (float*)ctx->c.p; a2.m = (float*)ctx->m.p; a2.v = (float*)ctx->v.p;
-      a2.cbest = (float*)ctx->cbest.p; a2.c0 = (float*)ctx->c0.p; a2.u = (float2*)ctx->ph_u.p;
-      a2.y = (float*)ctx->y.p; a2.s2_part = acc.s2_part; a2.s2_tiles = acc.syn_tiles; a2.improved = (int*)ctx->improved.p;
-      a2.steps = (NadamStep*)ctx->steps.p; a2.it_ptr = itc;
-      if (launch_ana<ANA_ADJ>(ctx, dw, a2, st)) return 1;
-    }
-
     // ---- final synthesis from the best coefficients (multibit_embedder.py:173-192)
     if (begin_pass(ctx, dw.n, nullptr, st)) return 1;
     SynArgs sf = syn_base(ctx, dw);
@@ -1167,8 +1127,7 @@ extern "C" int aw_embed_state(aw_ctx* ctx, int which, float* d_dst, int64_t capa
     const void* p = nullptr;
     size_t words = 0;
     switch (which) {
-      case 10: p = ctx->y.p; words = n * L; break;
-      case 11: p = ctx->dpad.p; words = n * (L + AW_NFFT); break;
+      case 10: p = ctx->y.p; words = n * L; break;                // final synthesis only
       case 12: p = ctx->accum.p; words = n * 2; break;            // packed peak (u64 per clip)
       case 13: p = ctx->dA.p; words = cnt; break;
       case 14: p = ctx->mag.p; words = cnt; break;

@@ -1,5 +1,7 @@
-// Shared-memory-staged radix FFT kernels for the band-limited STFT / iSTFT and
-// their adjoints (SURVEY K2,K3,K4,K13,K14; reference utils/audio/stft.py:28,48,55,62).
+// Shared-memory-staged radix FFT kernels for the band-limited STFT / iSTFT
+// (SURVEY K2,K3,K4,K13; reference utils/audio/stft.py:28,48,55,62): the one-off passes
+// around the optimisation loop -- detector STFT, initial STFT + state, out-of-band waveform,
+// final synthesis.  The loop's own transforms and their adjoints are fused in spec.cuh.
 //
 // One warp transforms TWO real frames at once as one 1024-point complex FFT
 // (z = a + i b), decomposed 32 x 32: a radix-32 pass held entirely in registers,
@@ -135,30 +137,22 @@ struct NadamStep {
 // ---------------------------------------------------------------------------
 // analysis: frames -> band spectrum
 // ---------------------------------------------------------------------------
-enum { ANA_MAG = 0, ANA_INIT = 1, ANA_LOOP = 2, ANA_ADJ = 3 };
+enum { ANA_MAG = 0, ANA_INIT = 1 };   // the loop passes live in spec.cuh
 
 struct AnaArgs {
-  const float* sig;            // per clip signal (x, y or dpad)
+  const float* sig;            // per clip signal x
   long long sig_stride;
-  int len;                     // signal length (N for x, L for y / dy)
+  int len;                     // signal length N
   int T, bin0, nbins;
-  const unsigned long long* peak;   // [clip] packed peak of sig (MAG/INIT: of x; LOOP/ADJ: of y)
+  const unsigned long long* peak;   // [clip] packed peak of x
   const float* window;         // [1024] device
   const float2* twiddle;       // [1024] device, layout [k1][lane]
-  const float* env256;         // [256] interior window envelope
+  const float* env256;         // [512] interior window envelope and its reciprocal
   // outputs
-  float* mag;                  // [clip][T][nbins]  (MAG, INIT -> c0, LOOP -> A~)
-  float2* ph;                  // [clip][T][nbins]  (INIT -> u, LOOP -> q)
-  // embed state (INIT writes, ADJ updates)
+  float* mag;                  // [clip][T][nbins]  (MAG; INIT -> c0)
+  float2* ph;                  // [clip][T][nbins]  (INIT -> u)
+  // embed state initialised by INIT
   float* c; float* m; float* v; float* cbest;
-  const float* c0;             // ADJ: bounds are recomputed from c0
-  const float2* u;             // ADJ
-  const float* y;              // ADJ: y (to read sign of the peak sample)
-  const double* s2_part;       // ADJ: [clip][s2_tiles] per-tile partial sums of dy2*y2
-  int s2_tiles;
-  const int* improved;         // ADJ: [clip] loss < best this iteration
-  const NadamStep* steps;      // ADJ: [iters]
-  const int* it_ptr;           // ADJ: device iteration counter
   float tol_ratio;             // 10^(-tolerance_db/20) as float32
 };
 
@@ -173,7 +167,6 @@ __global__ void __launch_bounds__(128, 3) k_analysis(AnaArgs a) {
   float* s_win = s_sig + AW_ANA_SIG;
   float2* s_tw = reinterpret_cast<float2*>(s_win + 1024);
   float2* s_tr = s_tw + 1024;
-  __shared__ float s_scal[4];
 
   const int clip = blockIdx.y;
   const int t0 = blockIdx.x * AW_ANA_FRAMES;
@@ -184,20 +177,7 @@ __global__ void __launch_bounds__(128, 3) k_analysis(AnaArgs a) {
     s_win[i] = a.window[i];
     s_tw[i] = a.twiddle[i];
   }
-  if (MODE == ANA_ADJ && tid == 0) {
-    // per-clip scalars of the two peak normalisers' sub-gradient (waveform.py:19, twice)
-    const unsigned long long pk = a.peak[clip];
-    const float p1 = peak_value(pk);
-    const float d1 = p1 + 1e-8f;
-    const float d2 = __fdiv_rn(p1, d1) + 1e-8f;
-    double s2d = 0.0;                       // fixed-order sum of the synthesis tiles' partials
-    for (int i = 0; i < a.s2_tiles; ++i) s2d += a.s2_part[(long long)clip * a.s2_tiles + i];
-    const float s2 = (float)s2d;
-    const float s1 = s2 * 1e-8f / d2;
-    const float ystar = a.y[(long long)clip * L + (int)peak_index(pk)];
-    s_scal[0] = (ystar > 0.f ? 1.f : (ystar < 0.f ? -1.f : 0.f)) * (s2 / d2 + s1) / d1;
-  }
-  __syncthreads();   // tables (the ADJ loader needs s_win) and s_scal
+  __syncthreads();   // tables
 
   // ---- stage the (scaled / padded) signal segment -------------------------
   const float* sig = a.sig + (long long)clip * a.sig_stride;
@@ -206,41 +186,9 @@ __global__ void __launch_bounds__(128, 3) k_analysis(AnaArgs a) {
   const float p1 = peak_value(pk);
   const float d1 = p1 + 1e-8f;
   const float d2 = __fdiv_rn(p1, d1) + 1e-8f;
-  if (MODE == ANA_ADJ) {
-    const int nstar = (int)peak_index(pk);
-    const float corr = s_scal[0];
-    const float inv = __fdiv_rn(__fdiv_rn(1.0f, d2), d1);
-    const int m0 = AW_HOP * t0;
-    // interior tiles: no reflect-fold terms, interior envelope, everything in range
-    const bool interior = (m0 - AW_HALF > AW_HALF) && (m0 + AW_ANA_SIG - AW_HALF < L - 513) &&
-                          (t0 >= 3) && (t0 + AW_ANA_FRAMES + 3 <= T - 1);
-    if (interior) {
-      for (int j = tid; j < AW_ANA_SIG; j += 128) {
-        const int m = m0 + j;
-        float dy = sig[m] * inv;
-        if (m - AW_HALF == nstar) dy -= corr;
-        s_sig[j] = dy * a.env256[256 + (m & 255)];
-      }
-    } else {
-      for (int j = tid; j < AW_ANA_SIG; j += 128) {
-        const int m = m0 + j;
-        const int n = m - AW_HALF;
-        float val = 0.f;
-        if (n >= 0 && n < L && m < m_end) {
-          float dy2 = sig[m];
-          if (n >= 1 && n <= AW_HALF) dy2 += sig[AW_HALF - n];
-          if (n >= L - 513 && n <= L - 2) dy2 += sig[AW_HALF + 2 * (L - 1) - n];
-          float dy = dy2 * inv;
-          if (n == nstar) dy -= corr;
-          val = dy * ola_inv_envelope(m, T, s_win, a.env256);
-        }
-        s_sig[j] = val;
-      }
-    }
-  } else {
-    // x / d1 (and / d2 in the loop: the two stacked normalisers) as one multiply by the
-    // correctly rounded reciprocal: <= 1.5 ulp from the divisions, far inside tolerance.
-    const float inv = MODE == ANA_LOOP ? __fdiv_rn(__fdiv_rn(1.0f, d1), d2) : __fdiv_rn(1.0f, d1);
+  {
+    // x / d1 as one multiply by the correctly rounded reciprocal (<= 1 ulp from the division)
+    const float inv = __fdiv_rn(1.0f, d1);
     for (int j = tid; j < AW_ANA_SIG; j += 128) {
       const int m = AW_HOP * t0 + j;
       float val = 0.f;
@@ -251,13 +199,6 @@ __global__ void __launch_bounds__(128, 3) k_analysis(AnaArgs a) {
   __syncthreads();
 
   float2* my_tr = s_tr + warp * (32 * AW_TR_STRIDE);
-
-  NadamStep st;
-  bool improved = false;
-  if (MODE == ANA_ADJ) {
-    st = a.steps[*a.it_ptr];
-    improved = a.improved[clip] != 0;
-  }
 
   for (int p = warp; p < AW_ANA_FRAMES / 2; p += 4) {
     const int ta = t0 + 2 * p, tb = ta + 1;
@@ -295,31 +236,10 @@ __global__ void __launch_bounds__(128, 3) k_analysis(AnaArgs a) {
         if (f == 1 && !has_b) break;
         const long long o = ((long long)clip * T + (ta + f)) * a.nbins + b;
         const float sr = fr[f], si = fi[f];
-        if (MODE == ANA_ADJ) {
-          // dX = (2/N) DFT(.) ; g = Re(dX conj(u))     (multibit_embedder.py:111)
-          const float2 uu = a.u[o];
-          const float g = (2.0f / AW_NFFT) * (sr * uu.x + si * uu.y);
-          // NAdam (torch/optim/nadam.py), clamp (:116-117), best (:120-122)
-          float mm = a.m[o], vv = a.v[o], cc = a.c[o];
-          mm = __fadd_rn(mm, __fmul_rn(0.1f, __fsub_rn(g, mm)));
-          vv = __fmul_rn(vv, 0.999f);
-          vv = __fadd_rn(vv, __fmul_rn(__fmul_rn(0.001f, g), g));
-          const float den = __fadd_rn(__fsqrt_rn(__fmul_rn(vv, st.inv_bc2)), 1e-8f);
-          const float rden = __frcp_rn(den);     // one reciprocal for both addcdiv terms (<= 1 ulp)
-          cc = __fadd_rn(cc, __fmul_rn(__fmul_rn(st.a_g, g), rden));
-          cc = __fadd_rn(cc, __fmul_rn(__fmul_rn(st.a_m, mm), rden));
-          const float c0 = a.c0[o];
-          const float dl = __fmul_rn(c0, a.tol_ratio);
-          const float lo = fmaxf(0.f, __fsub_rn(c0, dl)), hi = __fadd_rn(c0, dl);
-          cc = fminf(fmaxf(cc, lo), hi);
-          a.m[o] = mm;
-          a.v[o] = vv;
-          a.c[o] = cc;
-          if (improved) a.cbest[o] = cc;
-        } else {
+        {
           const float mag = sqrtf(sr * sr + si * si);
           a.mag[o] = mag;
-          if (MODE == ANA_INIT || MODE == ANA_LOOP) {
+          if (MODE == ANA_INIT) {
             const float inv = mag > 0.f ? 1.0f / mag : 0.f;
             a.ph[o] = make_float2(sr * inv, si * inv);
           }
@@ -338,13 +258,13 @@ __global__ void __launch_bounds__(128, 3) k_analysis(AnaArgs a) {
 // ---------------------------------------------------------------------------
 // synthesis: band spectrum -> windowed overlap-add
 // ---------------------------------------------------------------------------
-enum { SYN_OOB = 0, SYN_WAVE = 1, SYN_ADJ = 2 };
+enum { SYN_OOB = 0, SYN_WAVE = 1 };   // the loop passes live in spec.cuh
 
 struct SynArgs {
   const float* amp;            // [clip][T][nbins] real factor (c / cbest / dA~)
   const float2* ph;            // [clip][T][nbins] unit phasor (u / q)
   int T, L, bin0, nbins;
-  float scale;                 // 1/N (irfft) or 1/2 (STFT adjoint)
+  float scale;                 // 1/N (irfft)
   const float* window;
   const float2* twiddle;       // layout [k1][lane]
   const float* env256;
@@ -353,11 +273,8 @@ struct SynArgs {
   float* y_oob;                // [clip][L]   (OOB: out; WAVE: in)
   float* z_oob;                // [clip][L]   (OOB: optional out) y_oob * envelope, for spec.cuh
   // SYN_WAVE: y = ola/env + y_oob, peak_y
-  float* y;                    // [clip][L]   (WAVE: out; ADJ: in)
-  unsigned long long* peak_y;  // [clip]      (WAVE: atomicMax out; ADJ: in)
-  // SYN_ADJ: dpad = ola (padded axis), s2 partial = sum dpad * y2[reflect]
-  float* dpad;                 // [clip][L + 1024]
-  double* s2_part;             // [clip][gridDim.x]
+  float* y;                    // [clip][L]   (WAVE: out)
+  unsigned long long* peak_y;  // [clip]      (WAVE: atomicMax out)
 };
 
 #define AW_SYN_FRAMES 32
@@ -438,7 +355,6 @@ __global__ void __launch_bounds__(128, 2) k_synthesis(SynArgs a) {
   float2* s_tw = reinterpret_cast<float2*>(s_win + 1024);
   float2* s_tr = s_tw + 1024;
   __shared__ unsigned long long s_pk[4];
-  __shared__ double s_red[32];
 
   const int clip = blockIdx.y;
   const int h0 = blockIdx.x * AW_SYN_HOPS;        // first output hop (padded axis)
@@ -493,22 +409,7 @@ __global__ void __launch_bounds__(128, 2) k_synthesis(SynArgs a) {
   int m_hi = m_lo + AW_HOP * AW_SYN_HOPS;
   if (m_hi > m_total) m_hi = m_total;
 
-  if (MODE == SYN_ADJ) {
-    const float p1 = peak_value(a.peak_y[clip]);
-    const float d1 = p1 + 1e-8f;
-    const float d2 = __fdiv_rn(p1, d1) + 1e-8f;
-    const float inv = __fdiv_rn(__fdiv_rn(1.0f, d1), d2);
-    const float* y = a.y + (long long)clip * L;
-    float* dpad = a.dpad + (long long)clip * (L + AW_NFFT);
-    double acc = 0.0;
-    for (int m = m_lo + tid; m < m_hi; m += 128) {
-      const float d = s_ola[m - AW_HOP * f0];
-      dpad[m] = d;
-      acc += (double)(d * (y[reflect_idx(m - AW_HALF, L)] * inv));
-    }
-    acc = block_sum(acc, s_red);
-    if (tid == 0) a.s2_part[(long long)clip * gridDim.x + blockIdx.x] = acc;
-  } else {
+  {
     float best = -1.f;
     int best_n = 0;
     float rdx = 1.f;
