@@ -27,14 +27,16 @@ def synth_bits(n_clips: int) -> np.ndarray:
     return np.random.default_rng(7).integers(0, 2, (n_clips, N_BITS), dtype=np.int32)
 
 
-def synth_batch(n_clips: int, seconds: float, sr: int, unique: int = 16) -> np.ndarray:
-    """[n_clips, N] batch.  Generating thousands of distinct clips on the host is slow, so
-    only `unique` distinct clips are synthesised; the rest are those clips circularly
-    shifted and re-scaled (clip-dependent), which keeps every clip's content distinct."""
-    base = np.stack([synth_clip(i, seconds, sr) for i in range(min(unique, n_clips))])
+def synth_batch(n_clips: int, seconds: float, sr: int, unique: int = 16, first: int = 0) -> np.ndarray:
+    """Clips [first, first + n_clips) of the global synthetic set, as [n_clips, N].  Generating
+    thousands of distinct clips on the host is slow, so only `unique` distinct clips are
+    synthesised; the rest are those clips circularly shifted and re-scaled (clip-dependent),
+    which keeps every clip's content distinct.  `first` lets a rank build only its own shard."""
+    base = np.stack([synth_clip(i, seconds, sr) for i in range(min(unique, first + n_clips))])
     out = np.empty((n_clips, base.shape[1]), dtype=np.float32)
-    for i in range(n_clips):
+    for j in range(n_clips):
+        i = first + j
         b = base[i % len(base)]
         k = i // len(base)
-        out[i] = np.roll(b, 997 * k) * np.float32(1.0 - 0.01 * (k % 7)) if k else b
+        out[j] = np.roll(b, 997 * k) * np.float32(1.0 - 0.01 * (k % 7)) if k else b
     return out

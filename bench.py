@@ -225,7 +225,7 @@ def main():
     sr, n_clips = args.sr, args.clips
 
     # this rank's shard: clips [rank*n_clips, (rank+1)*n_clips) of the global synthetic set
-    x_host = torch.from_numpy(synth_batch(n_clips * world, args.seconds, sr)[rank * n_clips:(rank + 1) * n_clips])
+    x_host = torch.from_numpy(synth_batch(n_clips, args.seconds, sr, first=rank * n_clips))
     x_host = x_host.contiguous().pin_memory()
     bits_np = synth_bits(n_clips * world)[rank * n_clips:(rank + 1) * n_clips]
     bits = torch.from_numpy(bits_np).to(dev)
