@@ -116,6 +116,31 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Asynchronous TMEM load (no wait) and a wait that names the destination registers as in/out
+// operands, so the compiler cannot schedule their consumers above it.
+__device__ __forceinline__ void tc_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+                 "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]),
+                 "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]),
+                 "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]),
+                 "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
 // K-major, 128B-swizzled shared tile descriptor (cute::UMMA::SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) = 1 | SBO>>4 [32,46) = 1024>>4 | version=1 [46,48)
 // | layout_type = SWIZZLE_128B (2) [61,64)
@@ -522,12 +547,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       }
       mbar_wait(tfull + ab, (it >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
+      // the TMEM load of chunk c+1 is in flight while chunk c is processed
+      uint32_t vbuf[2][32];
+      tc_ld32_async(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + half * (BN / 2)), vbuf[0]);
+#pragma unroll
       for (int c = 0; c < CHUNKS; ++c) {
         const int c0 = half * (BN / 2) + c * 32;    // column inside the tile
         {
-          float v[32];
-          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0), v);
+          uint32_t (&v)[32] = vbuf[c & 1];
+          tc_wait_ld(v);
+          if (c + 1 < CHUNKS)
+            tc_ld32_async(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0 + 32), vbuf[(c + 1) & 1]);
           if (c == CHUNKS - 1) {                    // accumulator fully read: hand it back
             tc_fence_before();
             __syncwarp();
@@ -535,8 +565,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(s_st + lane * AW_EPI_STRIDE + 4 * i) =
-                make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            *reinterpret_cast<uint4*>(s_st + lane * AW_EPI_STRIDE + 4 * i) =
+                make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
         __syncwarp();
         // from here on a lane owns columns cg..cg+3 of rows 4 i + sr: the layout of the
