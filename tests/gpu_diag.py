@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 OUT = os.path.join(ROOT, "gpurun_out")
 
-STAGES = ["gradmap", "stft", "istft", "attacks", "detect_fp32", "gemm_tc", "detect_tf32", "embed1_fp32",
+STAGES = ["stft", "istft", "attacks", "detect_fp32", "gemm_tc", "detect_tf32", "embed1_fp32",
           "embed1_tf32", "embed3", "embed_full", "timing", "dual", "timeline", "gradprec"]
 
 
@@ -204,69 +204,6 @@ def stage_embed1_fp32(res):
 
 def stage_embed1_tf32(res):
     _embed_iters(res, "tf32", 1)
-
-
-def stage_gradmap(res):
-    """Structure of the 1-iteration gradient error vs the float64 kernel model."""
-    import numpy as np
-    import torch
-    import aware_oracle as O
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from kernel_model import Model
-    eng = _engine("fp32")
-    for sr, secs in ((44100, 0.8), (16000, 1.0), (44100, 1.37)):
-        x = _clips([0], secs, sr)
-        pat = np.stack([O.encode_bits(O.synth_bits(8)[0])])
-        eng.embed(torch.from_numpy(x).cuda(), sr, torch.from_numpy(pat), iters=1)
-        T = 1 + x.shape[1] // 256
-        g = eng.embed_state("m", 1, T, sr).cpu().numpy()[0] / 0.1
-        keep = {}
-        O.embed(x[0], sr, pat[0], num_iters=1, keep=keep)
-        fi, _ = O.band_indices(sr)
-        B = len(fi)
-        g_ref = keep["grads"][0].numpy().reshape(B, T).T
-        mdl = Model(O.make_weights(), O.mel_basis(), fi)
-        mdl.forward(mdl.init(x[0]), pat[0].astype(np.float64))
-        g64 = mdl.backward(pat[0].astype(np.float64))
-        L = 256 * (T - 1)
-        eng.embed(torch.from_numpy(x).cuda(), sr, torch.from_numpy(pat), iters=0)   # y(c0), its peak
-        y_gpu = eng.debug_buffer(10, L).cpu().numpy()
-        pk = eng.debug_buffer(12, 2).cpu().numpy().view(np.uint32)
-        nstar_gpu = int(0xffffffff - int(pk[0]))
-        y_mod = mdl.s["y"]
-        order = np.argsort(-np.abs(y_mod))[:4]
-        extra = dict(nstar_gpu=nstar_gpu, nstar_model=int(mdl.s["nstar"]), y_maxdiff=float(np.abs(y_gpu - y_mod).max()),
-                     top_abs_y_model=[(int(i), float(abs(y_mod[i]))) for i in order],
-                     top_abs_y_gpu=[(int(i), float(abs(y_gpu[i]))) for i in np.argsort(-np.abs(y_gpu))[:4]])
-        # forward re-STFT and back-propagated dA of iteration 0, against the float64 model
-        eng.embed(torch.from_numpy(x).cuda(), sr, torch.from_numpy(pat), iters=1)
-        mag_gpu = eng.debug_buffer(14, T * B).cpu().numpy().reshape(T, B)
-        q_gpu = eng.debug_buffer(16, T * B * 2).cpu().numpy().reshape(T, B, 2)
-        dA_gpu = eng.debug_buffer(13, T * B).cpu().numpy().reshape(T, B)
-        from kernel_model import analysis as _ana
-        S64 = _ana(mdl.s["y2"], T, np.asarray(fi), "reflect")
-        S_gpu = mag_gpu * (q_gpu[..., 0] + 1j * q_gpu[..., 1])
-        relS = np.abs(S_gpu - S64) / np.abs(S64)
-        iS = np.argsort(-relS.ravel())[:6]
-        St = O.stft(torch.from_numpy(mdl.s["y2"].astype(np.float32))).numpy()[fi].T
-        relT = np.abs(St - S64) / np.abs(S64)
-        extra.update(relS_gpu_top=[(int(i // B), int(i % B), float(relS.ravel()[i]), float(np.abs(S64).ravel()[i])) for i in iS],
-                     relS_gpu_median=float(np.median(relS)), relS_torch_median=float(np.median(relT)),
-                     relS_torch_max=float(relT.max()), absS_err_gpu_max=float(np.abs(S_gpu - S64).max()),
-                     absS_err_torch_max=float(np.abs(St - S64).max()))
-        e = np.abs(g - g64)
-        er = np.abs(g_ref - g64)
-        med = float(np.median(np.abs(g64)))
-        by_t = e.max(1)
-        by_b = e.max(0)
-        top_t = np.argsort(-by_t)[:8]
-        top_b = np.argsort(-by_b)[:8]
-        res["sr%d_s%g" % (sr, secs)] = dict(
-            T=T, B=B, median_abs_g=med, rms_err_gpu=float(np.sqrt((e ** 2).mean())),
-            rms_err_torch=float(np.sqrt((er ** 2).mean())), max_err_gpu=float(e.max()), max_err_torch=float(er.max()),
-            top_frames=[(int(t), float(by_t[t])) for t in top_t], top_bins=[(int(b), float(by_b[b])) for b in top_b],
-            median_err_gpu=float(np.median(e)), median_err_torch=float(np.median(er)),
-            nstar_frame=int(mdl.s["nstar"] // 256), **extra)
 
 
 def stage_embed3(res):
