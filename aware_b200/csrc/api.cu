@@ -72,7 +72,7 @@ struct aw_ctx {
   // workspace (grow-only)
   bool no_fuse_norm = true;   // AW_B200_FUSE_NORM=1 opts into the in-GEMM InstanceNorm application
   Buf ready;                  // [6 fused launches][clips][4] finished-row-tile counters (gemm.cuh FUSE)
-  Buf scal, zoob, p0coef, p0scal;
+  Buf scal, zoob, p0coef, p0scal, hpart, hcoef, red_a, red_b, red_c;
   Buf accum, peakx, mag, ph_u, ph_q, c0, c, m, v, cbest, dA, yoob, y, M, cs, sigma;
   Buf act[5], ga, gb, dh4, dp0, part, stat[5], bstat, values, best, improved, pattern, itc, steps;
   int ws_rows = 0;
@@ -130,6 +130,22 @@ static int ensure(Buf& b, size_t bytes) {
   b.cap = 0;
   AW_CUDA(cudaMalloc(&b.p, bytes));
   b.cap = bytes;
+  return 0;
+}
+
+// Long clips produce thousands of per-block partial sums per clip; reduce them in groups first so
+// the per-clip consumers (one CTA per clip) stay short.  Returns the array / block count to read.
+static int reduce_if_long(aw_ctx* ctx, Buf& scratch, const double*& part, int& nblk, int n_clips, int W,
+                          cudaStream_t st) {
+  if (nblk <= 512) return 0;
+  const int G = 64, nob = (nblk + G - 1) / G;
+  if (ensure(scratch, (size_t)n_clips * nob * W * sizeof(double))) return 1;
+  prof_mark(ctx, st, "reduce_partials");
+  k_reduce_partials<<<dim3((W + 255) / 256, nob, n_clips), 256, 0, st>>>(part, nblk, W, G, (double*)scratch.p);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  part = (const double*)scratch.p;
+  nblk = nob;
   return 0;
 }
 
@@ -335,7 +351,7 @@ extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
                  &ctx->act[4], &ctx->ga, &ctx->gb, &ctx->dh4, &ctx->dp0, &ctx->part, &ctx->stat[0],
                  &ctx->stat[1], &ctx->stat[2], &ctx->stat[3], &ctx->stat[4], &ctx->bstat,
                  &ctx->values, &ctx->best, &ctx->improved, &ctx->pattern, &ctx->itc, &ctx->steps,
-                 &ctx->scal, &ctx->ready, &ctx->zoob, &ctx->p0coef, &ctx->p0scal};
+                 &ctx->scal, &ctx->ready, &ctx->zoob, &ctx->p0coef, &ctx->p0scal, &ctx->hpart, &ctx->hcoef, &ctx->red_a, &ctx->red_b, &ctx->red_c};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   delete ctx;
@@ -543,6 +559,7 @@ static int ensure_net_ws(aw_ctx* ctx, const Dims& d, bool backward) {
   if (ensure(ctx->M, n * d.T * AW_NMEL * 4)) return 1;
   if (ensure(ctx->cs, n * AW_NMEL * sizeof(ChanStats))) return 1;
   if (ensure(ctx->sigma, n * 4)) return 1;
+  if (ensure(ctx->hpart, n * d.tiles * 64 * 3 * sizeof(double)) || ensure(ctx->hcoef, n * 64 * 4 * sizeof(float))) return 1;
   if (ensure(ctx->p0coef, n * AW_NMEL * sizeof(P0BwdCoef)) || ensure(ctx->p0scal, n * sizeof(P0BwdScal))) return 1;
   bool remap = false;
   for (int l = 0; l < 5; ++l) {
@@ -671,9 +688,11 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
     ctx->launches++;
     AW_LAUNCH_CHECK();
     dim3 g2((d.Tp_pad + AW_P0_ROWS - 1) / AW_P0_ROWS, d.n);
+    const double* cp = acc.chan_part;
+    int cb = acc.mel_blocks;
+    if (reduce_if_long(ctx, ctx->red_a, cp, cb, d.n, 2 * AW_NMEL, st)) return 1;
     prof_mark(ctx, st, "mel_stats");
-    k_mel_stats<<<d.n, 128, 0, st>>>(acc.chan_part, acc.mel_blocks, d.T, (ChanStats*)ctx->cs.p,
-                                     (float*)ctx->sigma.p);
+    k_mel_stats<<<d.n, 128, 0, st>>>(cp, cb, d.T, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p);
     ctx->launches++;
     AW_LAUNCH_CHECK();
     prof_mark(ctx, st, "p0");
@@ -696,10 +715,10 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
     if (gemm_layer<AT, EPI_FWD>(ctx, ctx->tm_act[B][l], ctx->act[l].p, mw, w, d.rows, cout, cin, ep, st))
       return 1;
     if (fuse) continue;   // statistics + normalise + LeakyReLU already applied inside the GEMM kernel
-    dim3 g((cout + 127) / 128, d.n);
+    dim3 g((cout + 31) / 32, d.n);
     prof_mark(ctx, st, "finalize_fwd");
-    k_finalize_fwd<<<g, 128, 0, st>>>((float*)ctx->part.p, cout, d.tiles, cout, d.Tp,
-                                      (float*)ctx->stat[l + 1].p);
+    k_finalize<false><<<g, 256, 0, st>>>((float*)ctx->part.p, cout, d.tiles, cout, d.Tp,
+                                         (float*)ctx->stat[l + 1].p);
     ctx->launches++;
     AW_LAUNCH_CHECK();
     prof_mark(ctx, st, "norm_act");
@@ -739,10 +758,10 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
     const void* w = ModeOf<AT>::wtp(ctx, l);
     if (gemm_layer<AT, EPI_BWD>(ctx, *steps[s].ma, steps[s].a, mw, w, d.rows, n, k, ep, st)) return 1;
     if (fuse) continue;   // InstanceNorm adjoint already applied inside the GEMM kernel
-    dim3 g((n + 127) / 128, d.n);
+    dim3 g((n + 31) / 32, d.n);
     prof_mark(ctx, st, "finalize_bwd");
-    k_finalize_bwd<<<g, 128, 0, st>>>((float*)ctx->part.p, n, d.tiles, n, d.Tp,
-                                      (float*)ctx->bstat.p);
+    k_finalize<true><<<g, 256, 0, st>>>((float*)ctx->part.p, n, d.tiles, n, d.Tp,
+                                        (float*)ctx->bstat.p);
     ctx->launches++;
     AW_LAUNCH_CHECK();
     prof_mark(ctx, st, "in_bwd_apply");
@@ -777,8 +796,11 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
   ctx->launches++;
   AW_LAUNCH_CHECK();
   dim3 g2((d.T + AW_P0A_FRAMES - 1) / AW_P0A_FRAMES, d.n);
+  const double* bp = acc.bpart;
+  int bb = acc.p0b_blocks;
+  if (reduce_if_long(ctx, ctx->red_b, bp, bb, d.n, 2 * AW_NMEL, st)) return 1;
   prof_mark(ctx, st, "p0_bwd_coef");
-  k_p0_bwd_coef<<<d.n, 128, 0, st>>>(acc.bpart, acc.p0b_blocks, d.T, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p,
+  k_p0_bwd_coef<<<d.n, 128, 0, st>>>(bp, bb, d.T, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p,
                                      (P0BwdCoef*)ctx->p0coef.p, (P0BwdScal*)ctx->p0scal.p);
   ctx->launches++;
   AW_LAUNCH_CHECK();
@@ -805,9 +827,16 @@ static int run_head(aw_ctx* ctx, const Dims& d, const float* pattern, float* val
   h.it_ptr = (int*)ctx->itc.p; h.n_clips = n_total;
   h.round_tf32 = ctx->prec == AW_PREC_TF32;
   h.gscale = ModeOf<AT>::GSCALE;
+  h.hpart = (double*)ctx->hpart.p;
+  h.hcoef = (float*)ctx->hcoef.p;
   prof_mark(ctx, st, "head");
-  k_head<AT><<<d.n, 256, 0, st>>>(h);
-  ctx->launches++;
+  k_head_partial<AT><<<dim3(d.tiles, d.n), 256, 0, st>>>(h);
+  k_head_final<AT><<<d.n, 64, 0, st>>>(h, d.tiles);
+  ctx->launches += 2;
+  if (backward && pattern) {
+    k_head_seed<AT><<<dim3(d.tiles, d.n), 256, 0, st>>>(h);
+    ctx->launches++;
+  }
   AW_LAUNCH_CHECK();
   return 0;
 }
@@ -902,7 +931,7 @@ static int launch_spec(aw_ctx* ctx, const Dims& d, SpecArgs& a, cudaStream_t st)
 static int launch_peak(aw_ctx* ctx, const float* x, int64_t stride, int n, int n_clips,
                        unsigned long long* peak, cudaStream_t st) {
   AW_CUDA(cudaMemsetAsync(peak, 0, (size_t)n_clips * 8, st));
-  dim3 g(std::min((n + 2047) / 2048, 64), n_clips);
+  dim3 g(std::min((n + 2047) / 2048, std::max(64, 8192 / n_clips)), n_clips);
   prof_mark(ctx, st, "peak");
   k_peak<<<g, 256, 0, st>>>(x, stride, n, peak);
   ctx->launches++;
@@ -1080,9 +1109,12 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
           return 1;
         if (net_backward<float>(ctx, dw, acc, sm, st, true)) return 1;
       }
+      const double* sp2 = acc.s2_part;
+      int sb2 = p0a_blocks(dw);
+      if (reduce_if_long(ctx, ctx->red_c, sp2, sb2, dw.n, 1, st)) return 1;
+      if (sb2 > 512 && reduce_if_long(ctx, ctx->red_a, sp2, sb2, dw.n, 1, st)) return 1;   // 1 h: 38 760 -> 606 -> 10
       prof_mark(ctx, st, "clip_scalars");
-      k_clip_scalars<<<(dw.n + 127) / 128, 128, 0, st>>>(acc.peak_y, acc.s2_part, p0a_blocks(dw), dw.n,
-                                                         (ClipScal*)ctx->scal.p);
+      k_clip_scalars<<<(dw.n + 127) / 128, 128, 0, st>>>(acc.peak_y, sp2, sb2, dw.n, (ClipScal*)ctx->scal.p);
       ctx->launches++;
       AW_LAUNCH_CHECK();
       SpecArgs b;
@@ -1101,7 +1133,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
     sf.amp = (float*)ctx->cbest.p; sf.ph = (float2*)ctx->ph_u.p; sf.scale = 1.0f / AW_NFFT;
     sf.y_oob = (float*)ctx->yoob.p; sf.y = (float*)ctx->y.p; sf.peak_y = acc.peak_y;
     if (launch_syn<SYN_WAVE>(ctx, dw, sf, st)) return 1;
-    dim3 g(std::min((dw.L + 2047) / 2048, 64), dw.n);
+    dim3 g(std::min((dw.L + 2047) / 2048, std::max(64, 8192 / dw.n)), dw.n);
     prof_mark(ctx, st, "final_normalize");
     k_final_normalize<<<g, 256, 0, st>>>((float*)ctx->y.p, dw.L, acc.peak_y,
                                          d_scale ? d_scale + w0 : nullptr,

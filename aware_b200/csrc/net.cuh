@@ -97,6 +97,20 @@ __global__ void __launch_bounds__(128) k_mel(const float* __restrict__ mag, int 
   p[1] = s2;
 }
 
+// Second-level reduction for long clips: [clip][nblk][W] doubles -> [clip][ceil(nblk/G)][W],
+// each output the fixed-order sum of G consecutive blocks (deterministic).  W = 256 for the
+// per-channel (sum, sum-of-squares) pairs, 1 for scalar partials.
+__global__ void __launch_bounds__(256) k_reduce_partials(const double* __restrict__ in, int nblk, int W,
+                                                         int G, double* __restrict__ out) {
+  const int clip = blockIdx.z, ob = blockIdx.y, nob = gridDim.y;
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  const int b0 = ob * G, b1 = min(b0 + G, nblk);
+  double s = 0.0;
+  for (int b = b0; b < b1; ++b) s += in[((long long)clip * nblk + b) * W + w];
+  out[((long long)clip * nob + ob) * W + w] = s;
+}
+
 // sum of `nblk` per-block partials [clip][nblk][128][2] for channel c, in block order
 __device__ __forceinline__ void sum_partials(const double* __restrict__ part, int clip, int nblk, int c,
                                              double& s1, double& s2) {
@@ -161,38 +175,39 @@ __global__ void __launch_bounds__(128) k_p0(const float* __restrict__ M, int T, 
 
 // ---- InstanceNorm statistics from per-tile partials --------------------------
 // part: [clip * tiles + tile][ldp][2] ; stat: [clip][C][2] = (mean, rstd)
-__global__ void __launch_bounds__(128) k_finalize_fwd(const float* __restrict__ part, int ldp,
-                                                      int tiles, int C, int Tp,
-                                                      float* __restrict__ stat) {
-  const int clip = blockIdx.y, c = blockIdx.x * 128 + threadIdx.x;
-  if (c >= C) return;
+// block = 32 channels x 8 tile slices: slice s sums tiles s, s+8, ... and the 8 slice sums are
+// combined in fixed order, so long clips (thousands of tiles) are not serialised per channel.
+template <bool BWD>
+__global__ void __launch_bounds__(256) k_finalize(const float* __restrict__ part, int ldp, int tiles,
+                                                  int C, int Tp, float* __restrict__ stat) {
+  __shared__ double s_s[8][32][2];
+  const int clip = blockIdx.y, cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0;
-  for (int t = 0; t < tiles; ++t) {
-    const float* p = part + (((long long)clip * tiles + t) * ldp + c) * 2;
-    s1 += p[0];
-    s2 += p[1];
+  if (c < C) {
+    for (int t = sl; t < tiles; t += 8) {
+      const float2 p = *reinterpret_cast<const float2*>(part + (((long long)clip * tiles + t) * ldp + c) * 2);
+      s1 += p.x;
+      s2 += p.y;
+    }
   }
-  const double mu = s1 / Tp;
-  double var = s2 / Tp - mu * mu;
-  if (var < 0.0) var = 0.0;
-  stat[((long long)clip * C + c) * 2] = (float)mu;
-  stat[((long long)clip * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + AW_IN_EPS));
-}
-
-// bstat: [clip][C][2] = (mean_j dHhat, mean_j dHhat*Hhat)
-__global__ void __launch_bounds__(128) k_finalize_bwd(const float* __restrict__ part, int ldp,
-                                                      int tiles, int C, int Tp,
-                                                      float* __restrict__ bstat) {
-  const int clip = blockIdx.y, c = blockIdx.x * 128 + threadIdx.x;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int t = 0; t < tiles; ++t) {
-    const float* p = part + (((long long)clip * tiles + t) * ldp + c) * 2;
-    s1 += p[0];
-    s2 += p[1];
+  s_s[sl][cl][0] = s1;
+  s_s[sl][cl][1] = s2;
+  __syncthreads();
+  if (sl != 0 || c >= C) return;
+#pragma unroll
+  for (int k = 1; k < 8; ++k) { s1 += s_s[k][cl][0]; s2 += s_s[k][cl][1]; }
+  if (BWD) {
+    // bstat: (mean_j dHhat, mean_j dHhat*Hhat)
+    stat[((long long)clip * C + c) * 2] = (float)(s1 / Tp);
+    stat[((long long)clip * C + c) * 2 + 1] = (float)(s2 / Tp);
+  } else {
+    const double mu = s1 / Tp;
+    double var = s2 / Tp - mu * mu;
+    if (var < 0.0) var = 0.0;
+    stat[((long long)clip * C + c) * 2] = (float)mu;
+    stat[((long long)clip * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + AW_IN_EPS));
   }
-  bstat[((long long)clip * C + c) * 2] = (float)(s1 / Tp);
-  bstat[((long long)clip * C + c) * 2 + 1] = (float)(s2 / Tp);
 }
 
 // ---- row-wise InstanceNorm application, in place --------------------------------
@@ -296,7 +311,15 @@ __global__ void __launch_bounds__(128) k_norm_rows(AT* __restrict__ X, const AT*
 }
 
 // ---- BRH head + loss + seed of the backward pass -------------------------------
-// one CTA (256 threads) per clip.  P4: [rows][64] (40 live channels).
+// P4: [rows][64] (40 live channels) = LeakyReLU(Hhat).  Three kernels so that a long clip is
+// not serialised on one CTA:
+//   k_head_partial (grid = row tiles x clips): per 128-row tile and channel,
+//        S_pos = sum_{P>0} P,  S_neg = sum_{P<=0} P / 0.2 (= Hhat),  n_pos
+//   k_head_final   (grid = clips): z = (S_pos + 0.2 S_neg)/T', v = tanh(z_even - z_odd), loss,
+//        best / improved, dz, and the InstanceNorm-adjoint means -- both follow from the SAME
+//        partial sums because dHhat = LeakyReLU'(P) dz is constant per channel and sign:
+//        a1 = dz (n_pos + 0.2 n_neg)/T',  a2 = mean(dHhat Hhat) = dz z
+//   k_head_seed    (grid = row tiles x clips): dH4 = gscale rstd (dHhat - a1 - Hhat a2)
 template <typename AT>
 struct HeadArgs {
   const AT* P4; int Tp, Tp_pad;
@@ -310,34 +333,57 @@ struct HeadArgs {
   const int* it_ptr; int n_clips;
   int round_tf32;
   float gscale;              // loss scale of the back-propagated gradient (fp16 mode), else 1
+  double* hpart;             // [clip][tiles][64][3] partial sums
+  float* hcoef;              // [clip][64][4] = (dz, a1, a2, rstd)
 };
 
 template <typename AT>
-__global__ void __launch_bounds__(256) k_head(HeadArgs<AT> a) {
-  __shared__ double s_acc[4][64];
-  __shared__ float s_z[64], s_dz[64], s_a1[64], s_a2[64];
-  const int clip = blockIdx.x, tid = threadIdx.x;
+__global__ void __launch_bounds__(256) k_head_partial(HeadArgs<AT> a) {
+  __shared__ double s_acc[4][64][3];
+  const int tile = blockIdx.x, clip = blockIdx.y, tid = threadIdx.x;
   const int c = tid & 63, g = tid >> 6;
-  const AT* P = a.P4 + (long long)clip * a.Tp_pad * 64;
-  double acc = 0.0;
-  for (int j = g; j < a.Tp; j += 4) acc += act_ld(P + (long long)j * 64 + c);
-  s_acc[g][c] = acc;
+  const AT* P = a.P4 + ((long long)clip * a.Tp_pad + tile * 128) * 64;
+  const int rows = min(128, a.Tp - tile * 128);
+  double sp = 0.0, sn = 0.0, np_ = 0.0;
+  for (int j = g; j < rows; j += 4) {
+    const float p = act_ld(P + (long long)j * 64 + c);
+    if (p > 0.f) { sp += p; np_ += 1.0; } else { sn += (double)(p * (1.0f / AW_LEAKY)); }
+  }
+  s_acc[g][c][0] = sp; s_acc[g][c][1] = sn; s_acc[g][c][2] = np_;
   __syncthreads();
-  if (tid < 64) s_z[tid] = (float)((s_acc[0][tid] + s_acc[1][tid] + s_acc[2][tid] + s_acc[3][tid]) / a.Tp);
+  if (tid < 64) {
+    double* o = a.hpart + (((long long)clip * gridDim.x + tile) * 64 + tid) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[k] = s_acc[0][tid][k] + s_acc[1][tid][k] + s_acc[2][tid][k] + s_acc[3][tid][k];
+  }
+}
+
+template <typename AT>
+__global__ void __launch_bounds__(64) k_head_final(HeadArgs<AT> a, int tiles) {
+  __shared__ float s_z[64], s_dz[64];
+  const int clip = blockIdx.x, c = threadIdx.x;
+  double sp = 0.0, sn = 0.0, np_ = 0.0;
+  for (int t = 0; t < tiles; ++t) {
+    const double* o = a.hpart + (((long long)clip * tiles + t) * 64 + c) * 3;
+    sp += o[0]; sn += o[1]; np_ += o[2];
+  }
+  const float z = (float)((sp + (double)AW_LEAKY * sn) / a.Tp);
+  s_z[c] = z;
+  s_dz[c] = 0.f;
   __syncthreads();
-  if (tid < 32) {
+  if (c < 32) {
     float v = 0.f, p = 0.f;
-    if (tid < AW_NBITS) {
-      v = tanhf(s_z[2 * tid] - s_z[2 * tid + 1]);
-      a.values[(long long)clip * AW_NBITS + tid] = v;
-      if (a.pattern) p = a.pattern[(long long)clip * AW_NBITS + tid];
+    if (c < AW_NBITS) {
+      v = tanhf(s_z[2 * c] - s_z[2 * c + 1]);
+      a.values[(long long)clip * AW_NBITS + c] = v;
+      if (a.pattern) p = a.pattern[(long long)clip * AW_NBITS + c];
     }
     if (a.pattern) {
-      const float se = tid < AW_NBITS ? (v - p) * (v - p) : 0.f;
-      const float ab = tid < AW_NBITS ? fabsf(v) : 0.f;
+      const float se = c < AW_NBITS ? (v - p) * (v - p) : 0.f;
+      const float ab = c < AW_NBITS ? fabsf(v) : 0.f;
       const float mse = warp_sum(se) / AW_NBITS, pen = 0.1f * (warp_sum(ab) / AW_NBITS);
       const float loss = mse - pen;
-      if (tid == 0) {
+      if (c == 0) {
         const int it = a.it_ptr ? *a.it_ptr : 0;
         if (a.losses) a.losses[(long long)it * a.n_clips + clip] = loss;
         const float b = a.best[clip];
@@ -345,42 +391,36 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs<AT> a) {
         a.improved[clip] = imp;
         if (imp) a.best[clip] = loss;
       }
-      if (tid < AW_NBITS) {
+      if (c < AW_NBITS) {
         const float sg = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
         const float dv = 2.f * (v - p) / AW_NBITS - 0.1f * sg / AW_NBITS;
         const float dd = dv * (1.f - v * v);
-        s_dz[2 * tid] = dd / a.Tp;
-        s_dz[2 * tid + 1] = -dd / a.Tp;
+        s_dz[2 * c] = dd / a.Tp;
+        s_dz[2 * c + 1] = -dd / a.Tp;
       }
     }
   }
   if (!a.pattern || !a.dH4) return;
-  if (tid >= 2 * AW_NBITS && tid < 64) s_dz[tid] = 0.f;
   __syncthreads();
-  // a1 = mean_j dHhat, a2 = mean_j dHhat * Hhat
-  double q1 = 0.0, q2 = 0.0;
   const float dz = s_dz[c];
-  for (int j = g; j < a.Tp; j += 4) {
-    const float p = act_ld(P + (long long)j * 64 + c);
-    const bool pos = p > 0.f;
-    const float dh = pos ? dz : AW_LEAKY * dz;
-    q1 += dh;
-    q2 += (double)dh * (pos ? p : p * (1.0f / AW_LEAKY));
-  }
-  s_acc[g][c] = q1;
-  __syncthreads();
-  if (tid < 64) s_a1[tid] = (float)((s_acc[0][tid] + s_acc[1][tid] + s_acc[2][tid] + s_acc[3][tid]) / a.Tp);
-  __syncthreads();
-  s_acc[g][c] = q2;
-  __syncthreads();
-  if (tid < 64) s_a2[tid] = (float)((s_acc[0][tid] + s_acc[1][tid] + s_acc[2][tid] + s_acc[3][tid]) / a.Tp);
-  __syncthreads();
-  const float rstd = a.stat4[((long long)clip * 64 + c) * 2 + 1];
-  const float a1 = s_a1[c], a2 = s_a2[c];
-  AT* D = a.dH4 + (long long)clip * a.Tp_pad * 64;
-  for (int j = g; j < a.Tp_pad; j += 4) {
+  const double nneg = (double)a.Tp - np_;
+  const float a1 = (float)((double)dz * (np_ + (double)AW_LEAKY * nneg) / a.Tp);
+  const float a2 = dz * z;
+  *reinterpret_cast<float4*>(a.hcoef + ((long long)clip * 64 + c) * 4) =
+      make_float4(dz, a1, a2, a.stat4[((long long)clip * 64 + c) * 2 + 1]);
+}
+
+template <typename AT>
+__global__ void __launch_bounds__(256) k_head_seed(HeadArgs<AT> a) {
+  const int tile = blockIdx.x, clip = blockIdx.y, tid = threadIdx.x;
+  const int c = tid & 63, g = tid >> 6;
+  const float4 k = *reinterpret_cast<const float4*>(a.hcoef + ((long long)clip * 64 + c) * 4);
+  const float dz = k.x, a1 = k.y, a2 = k.z, rstd = k.w;
+  const AT* P = a.P4 + ((long long)clip * a.Tp_pad + tile * 128) * 64;
+  AT* D = a.dH4 + ((long long)clip * a.Tp_pad + tile * 128) * 64;
+  for (int j = g; j < 128; j += 4) {
     float o = 0.f;
-    if (j < a.Tp && c < 2 * AW_NBITS) {
+    if (tile * 128 + j < a.Tp && c < 2 * AW_NBITS) {
       const float p = act_ld(P + (long long)j * 64 + c);
       const bool pos = p > 0.f;
       const float dh = pos ? dz : AW_LEAKY * dz;

@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 OUT = os.path.join(ROOT, "gpurun_out")
 
 STAGES = ["stft", "istft", "attacks", "detect_fp32", "gemm_tc", "detect_tf32", "embed1_fp32",
-          "embed1_tf32", "embed3", "embed_full", "timing", "dual", "timeline", "gradprec"]
+          "embed1_tf32", "embed3", "embed_full", "timing", "dual", "timeline", "gradprec", "longform"]
 
 
 def _engine(precision="fp32"):
@@ -309,6 +309,40 @@ def stage_gradprec(res):
         res[prec] = dict(rel_rms=float(np.sqrt((d ** 2).mean() / (ref ** 2).mean())),
                          finite=bool(np.isfinite(g[prec]).all()),
                          sign_agree=float((np.sign(g[prec]) == np.sign(ref)).mean()))
+
+
+def stage_longform(res):
+    """BASELINE configs[0] (one 10 s clip) and configs[4] (one 1 h clip) on a single GPU."""
+    import numpy as np
+    import torch
+    from aware_b200.synth import synth_batch, synth_bits
+    from aware_b200.utils.watermark import PatternEncoder
+    sr = 44100
+    pat = torch.from_numpy(np.stack([PatternEncoder()(b) for b in synth_bits(1)]))
+    for name, secs, iters in (("1x10s", 10.0, 100), ("1x3600s", 3600.0, 5)):
+        eng = _engine("tf32")
+        eng.embed_precision = "fp16"
+        base = synth_batch(1, min(secs, 60.0), sr)
+        x = torch.from_numpy(np.tile(base, (1, int(round(secs / min(secs, 60.0)))))).cuda()
+        eng.embed(x, sr, pat, iters=2)
+        torch.cuda.synchronize()
+        eng.profile(True)
+        t0 = time.time()
+        out = eng.embed(x, sr, pat, iters=iters)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        tl = eng.profile_read_named()
+        eng.profile(False)
+        t1 = time.time()
+        v = eng.detect(out, sr)
+        torch.cuda.synchronize()
+        dd = time.time() - t1
+        res[name] = dict(ms_per_iter=1e3 * dt / iters, est_400it_audio_s_per_s=secs / (dt / iters * 400),
+                         detect_ms=1e3 * dd, finite=bool(torch.isfinite(out).all()),
+                         classes={k: round(v_[1] / iters, 4) for k, v_ in
+                                  sorted(tl.items(), key=lambda kv: -kv[1][1])[:10]})
+        del eng, x, out
+        torch.cuda.empty_cache()
 
 
 def stage_dual(res):
