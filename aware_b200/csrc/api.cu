@@ -73,6 +73,11 @@ struct aw_ctx {
   bool no_fuse_norm = true;   // AW_B200_FUSE_NORM=1 opts into the in-GEMM InstanceNorm application
   Buf ready;                  // [6 fused launches][clips][4] finished-row-tile counters (gemm.cuh FUSE)
   Buf scal, zoob, p0coef, p0scal, hpart, hcoef, red_a, red_b, red_c;
+  // CUDA-graph replay of the optimisation iteration (AW_B200_NO_GRAPH=1 disables): the ~50 launches
+  // of one iteration are captured once on a context-owned stream and replayed iters-1 times
+  bool graphs = true;
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   Buf accum, peakx, mag, ph_u, ph_q, c0, c, m, v, cbest, dA, yoob, y, M, cs, sigma;
   Buf act[5], ga, gb, dh4, dp0, part, stat[5], bstat, values, best, improved, pattern, itc, steps;
   int ws_rows = 0;
@@ -257,6 +262,8 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
     // 2.33 vs 2.10 ms -- the 4 normaliser warps per SM are latency-bound, so the L2-hot
     // re-read buys nothing.  Kept as an opt-in experiment (single stream only: the kernel's
     // CTAs wait on one another).
+    e = getenv("AW_B200_NO_GRAPH");
+    ctx->graphs = !(e && e[0] == '1');
     e = getenv("AW_B200_FUSE_NORM");
     ctx->no_fuse_norm = !(e && e[0] == '1');
   }
@@ -323,6 +330,9 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
   }
   AW_CUDA(cudaMalloc(&ctx->d_env256, 512 * 4));
   AW_CUDA(cudaMemcpy(ctx->d_env256, env.data(), 512 * 4, cudaMemcpyHostToDevice));
+  AW_CUDA(cudaStreamCreateWithFlags(&ctx->gstream, cudaStreamNonBlocking));
+  AW_CUDA(cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming));
+  AW_CUDA(cudaEventCreateWithFlags(&ctx->ev_out, cudaEventDisableTiming));
   *out = ctx;
   return 0;
 }
@@ -338,6 +348,9 @@ extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
     cudaFree(ctx->d_w16h[l]);
     cudaFree(ctx->d_wt16h[l]);
   }
+  if (ctx->gstream) cudaStreamDestroy(ctx->gstream);
+  if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+  if (ctx->ev_out) cudaEventDestroy(ctx->ev_out);
   cudaFree(ctx->d_window);
   cudaFree(ctx->d_twiddle);
   cudaFree(ctx->d_env256);
@@ -1025,8 +1038,16 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
                               float* d_best_loss, float* d_losses, int wave_clips, void* stream) {
   AW_REQUIRE(ctx && d_audio && d_pattern && d_out, "aw_embed_batch: null argument");
   AW_REQUIRE(iters >= 0, "aw_embed_batch: iters < 0");
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t user_stream = (cudaStream_t)stream, st = user_stream;
   AW_CUDA(cudaSetDevice(ctx->device));
+  // Graph replay needs a capturable stream (the caller's may be the legacy default stream): the
+  // whole call runs on the context's stream, ordered after / before the caller's by two events.
+  const bool use_graph = ctx->graphs && !ctx->prof_on && iters >= 4;
+  if (use_graph) {
+    AW_CUDA(cudaEventRecord(ctx->ev_in, user_stream));
+    AW_CUDA(cudaStreamWaitEvent(ctx->gstream, ctx->ev_in, 0));
+    st = ctx->gstream;
+  }
   if (wave_clips <= 0 || wave_clips > n_clips) wave_clips = n_clips;
   Dims d;
   if (make_dims(ctx, wave_clips, n_samples, sample_rate, &d)) return 1;
@@ -1083,7 +1104,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
     if (launch_syn<SYN_OOB>(ctx, dw, s0, st)) return 1;
 
     // ---- optimisation loop (multibit_embedder.py:95-122)
-    for (int it = 0; it < iters; ++it) {
+    auto iteration = [&]() -> int {
       // fused spectral passes (spec.cuh): y and dpad never leave shared memory
       if (begin_pass(ctx, dw.n, itc, st)) return 1;
       SpecArgs f;
@@ -1126,6 +1147,41 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       b.improved = (int*)ctx->improved.p; b.steps = (NadamStep*)ctx->steps.p; b.it_ptr = itc;
       b.tol_ratio = (float)pow(10.0, -(double)ctx->tol_db / 20.0);
       if (launch_spec<SPEC_BWD>(ctx, dw, b, st)) return 1;
+      return 0;
+    };
+    if (use_graph) {
+      // iteration 0 runs eagerly (function attributes, scratch sizes), iteration 1 is captured
+      // without executing, and the graph is replayed for iterations 1 .. iters-1; the iteration
+      // index and all per-clip state live on the device, so every replay is identical work
+      const int64_t l0 = ctx->launches;
+      if (iteration()) return 1;
+      const int64_t per_iter = ctx->launches - l0;
+      AW_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+      const int rc = iteration();
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc ? 1 : set_error("aw_embed_batch: stream capture failed: %s", cudaGetErrorString(ce));
+      }
+      cudaGraphExec_t exec = nullptr;
+      if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        return set_error("aw_embed_batch: cudaGraphInstantiate failed: %s", cudaGetErrorString(cudaGetLastError()));
+      }
+      for (int it = 1; it < iters; ++it) {
+        if (cudaGraphLaunch(exec, st) != cudaSuccess) {
+          cudaGraphExecDestroy(exec);
+          cudaGraphDestroy(graph);
+          return set_error("aw_embed_batch: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+      }
+      ctx->launches += per_iter * (iters - 2);      // the captured pass was counted once already
+      cudaGraphExecDestroy(exec);
+      cudaGraphDestroy(graph);
+    } else {
+      for (int it = 0; it < iters; ++it)
+        if (iteration()) return 1;
     }
     // ---- final synthesis from the best coefficients (multibit_embedder.py:173-192)
     if (begin_pass(ctx, dw.n, nullptr, st)) return 1;
@@ -1146,6 +1202,10 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
     ctx->last_n = dw.n; ctx->last_T = dw.T; ctx->last_nb = dw.nb;
   }
   prof_mark(ctx, st, nullptr);
+  if (use_graph) {
+    AW_CUDA(cudaEventRecord(ctx->ev_out, st));
+    AW_CUDA(cudaStreamWaitEvent(user_stream, ctx->ev_out, 0));
+  }
   return 0;
 }
 

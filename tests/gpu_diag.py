@@ -270,8 +270,7 @@ def stage_timeline(res):
     import torch
     from aware_b200.synth import synth_batch, synth_bits
     from aware_b200.utils.watermark import PatternEncoder
-    sr = 44100
-    for n, iters, prec in ((128, 10, "tf32"), (128, 10, "fp16")):
+    for n, iters, prec, sr in ((128, 10, "tf32", 44100), (128, 10, "fp16", 44100), (256, 10, "fp16", 16000)):
         eng = _engine("tf32")
         eng.embed_precision = prec
         x = torch.from_numpy(synth_batch(n, 10.0, sr)).cuda()
@@ -284,7 +283,7 @@ def stage_timeline(res):
         tl = eng.profile_read_named()
         eng.profile(False)
         tot = sum(v[1] for v in tl.values())
-        res["n%d_%s" % (n, prec)] = dict(total_ms_per_iter=tot / iters,
+        res["n%d_%s_%d" % (n, prec, sr)] = dict(total_ms_per_iter=tot / iters,
                                          classes={k: [v[0], round(v[1] / iters, 4)] for k, v in
                                                   sorted(tl.items(), key=lambda kv: -kv[1][1])})
 
