@@ -462,3 +462,36 @@ def test_embed_tile_edges_match_oracle(eng, n_samples):
     assert big.mean() > 0.5 and np.isfinite(out).all()
     assert _snr(out[0], y) >= (25 if T <= 6 else 55)
     assert c1_ref.shape == st["c"][0].shape
+
+
+@pytest.mark.gpu
+def test_evaluation_driver_ragged_clips(model):
+    """aware_b200.evaluate (batched scripts/test.py): clips of different lengths and rates are
+    resampled to 16 kHz on the GPU bit-exactly like scipy.signal.resample_poly, bucketed by
+    length, embedded, attacked and detected; the decoded bits equal the CPU oracle's on the same
+    watermarked audio and the clean BER is 0."""
+    from scipy.signal import resample_poly
+    from aware_b200.evaluate import evaluate_clips, resample_poly_batch
+    emb, det = model
+    eng = emb.engine
+    clips = [O.synth_clip(0, 2.0, 16000), O.synth_clip(1, 2.0, 16000), O.synth_clip(2, 1.5, 44100),
+             O.synth_clip(3, 1.25, 32000), O.synth_clip(4, 1.5, 44100)]
+    rates = [16000, 16000, 44100, 32000, 44100]
+    for x, sr in ((clips[2], 44100), (clips[3], 32000)):
+        want = resample_poly(x, 16000, sr)
+        got = resample_poly_batch(torch.from_numpy(x[None]).cuda(), 16000, sr, eng).cpu().numpy()[0]
+        np.testing.assert_array_equal(got, want.astype(np.float32))
+    prev = emb.num_iterations
+    emb.num_iterations = 200
+    try:
+        res = evaluate_clips(clips, rates, emb, det, seed=3, keep_audio=True)
+    finally:
+        emb.num_iterations = prev
+    assert res["n_clips"] == 5 and set(res["decoded"]) == set(range(5))
+    assert res["ber_percent"]["orig"] == 0.0
+    assert {"pcm_8", "delete_0.1", "resample_16000", "low_pass", "high_pass"} <= set(res["ber_percent"])
+    assert all(0.0 <= v <= 60.0 for v in res["ber_percent"].values())
+    assert 15.0 < res["snr_db_mean"] < 45.0
+    for i in range(5):
+        np.testing.assert_array_equal(res["decoded"][i], res["bits"][i])
+        np.testing.assert_array_equal(O.detect_watermark(res["audio"][i], 16000), res["bits"][i])

@@ -156,3 +156,31 @@ def test_warm_up_length_bounds_filter_memory():
             noise = np.abs(full - sosfilt(sos, x)).max()
             late = lfilter(b, a, x[2000:])                    # zero state, starts 2000 samples later
             assert np.abs(full[2000 + w:] - late[w:]).max() <= 10 * noise + 1e-12, (btype, sr, w, noise)
+
+
+def test_wav_io_and_length_buckets(tmp_path):
+    """aware_b200.evaluate: PCM WAV reader (16/24-bit, stereo mix-down like librosa mono=True) and
+    the length bucketing that turns a ragged set of clips into equal-length launches."""
+    import wave
+    from aware_b200.evaluate import bucket_by_length, read_wav, write_wav
+    rng = np.random.default_rng(5)
+    x = (0.8 * rng.uniform(-1, 1, 4000)).astype(np.float32)
+    p16 = str(tmp_path / "a.wav")
+    write_wav(p16, x, 16000)
+    y, sr = read_wav(p16)
+    assert sr == 16000 and y.dtype == np.float32 and np.abs(y - x).max() <= 2.0 / 32768   # write x32767, read /32768
+    # 24-bit stereo written by hand
+    l = np.round(x * 8388607).astype(np.int32)
+    r = np.round(-0.5 * x * 8388607).astype(np.int32)
+    inter = np.stack([l, r], axis=1).reshape(-1)
+    raw = bytearray()
+    for v in inter:
+        raw += int(v & 0xFFFFFF).to_bytes(3, "little")
+    p24 = str(tmp_path / "b.wav")
+    with wave.open(p24, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(3); w.setframerate(44100); w.writeframes(bytes(raw))
+    y, sr = read_wav(p24)
+    assert sr == 44100 and y.shape == (4000,)
+    assert np.abs(y - 0.25 * x).max() <= 2e-7                       # mean of x and -x/2
+    assert bucket_by_length([5, 7, 5, 9, 7, 5]) == {5: [0, 2, 5], 7: [1, 4], 9: [3]}
+    assert bucket_by_length([]) == {}
