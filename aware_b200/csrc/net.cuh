@@ -80,16 +80,28 @@ __global__ void __launch_bounds__(128) k_mel(const float* __restrict__ mag, int 
     const float d2 = __fdiv_rn(p1, d1) + 1e-8f;
     inv = __fdiv_rn(__fdiv_rn(1.0f, d1), d2);
   }
-  for (int i = threadIdx.x; i < nf * nb; i += 128) s_a[i] = src[i] * inv;
+  for (int i = threadIdx.x; i < AW_MEL_FRAMES * nb; i += 128) s_a[i] = i < nf * nb ? src[i] * inv : 0.f;
   __syncthreads();
+  // filter taps outermost: each (weight, bin) pair of this channel is fetched once and applied to
+  // all 32 staged frames (most channels have 2-5 taps inside the band, many have none)
   const int e0 = sm.rowptr[c], e1 = sm.rowptr[c + 1];
+  float acc[AW_MEL_FRAMES];
+#pragma unroll
+  for (int f = 0; f < AW_MEL_FRAMES; ++f) acc[f] = 0.f;
+  for (int e = e0; e < e1; ++e) {
+    const float w = sm.val[e];
+    const float* col = s_a + sm.col[e];
+#pragma unroll
+    for (int f = 0; f < AW_MEL_FRAMES; ++f) acc[f] = fmaf(w, col[f * nb], acc[f]);
+  }
   double s1 = 0.0, s2 = 0.0;
-  for (int f = 0; f < nf; ++f) {
-    float acc = 0.f;
-    for (int e = e0; e < e1; ++e) acc = fmaf(sm.val[e], s_a[f * nb + sm.col[e]], acc);
-    M[((long long)clip * T + t0 + f) * AW_NMEL + c] = acc;
-    s1 += acc;
-    s2 += (double)acc * acc;
+#pragma unroll
+  for (int f = 0; f < AW_MEL_FRAMES; ++f) {
+    if (f < nf) {
+      M[((long long)clip * T + t0 + f) * AW_NMEL + c] = acc[f];
+      s1 += acc[f];
+      s2 += (double)acc[f] * acc[f];
+    }
   }
   // per-block partial sums, reduced in fixed order by the consumers (deterministic)
   double* p = chan_part + (((long long)clip * gridDim.x + blockIdx.x) * AW_NMEL + c) * 2;
@@ -514,15 +526,29 @@ __global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ 
     const float dmh = alpha * (dg - meanG) - beta * mh;
     s_dm[f][c] = st.rstd * (dmh - A1 - mh * A2);
   }
+  for (int f = nf; f < AW_P0A_FRAMES; ++f) s_dm[f][c] = 0.f;
   __syncthreads();
+  // one thread per band bin: its (weight, channel) taps are fetched once and applied to all frames
   double s2 = 0.0;
-  for (int i = threadIdx.x; i < nf * nb; i += 128) {
-    const int f = i / nb, b = i - f * nb;
-    float acc = 0.f;
-    for (int e = sm.colptr[b]; e < sm.colptr[b + 1]; ++e) acc = fmaf(sm.valT[e], s_dm[f][sm.row[e]], acc);
-    const long long o = ((long long)clip * T + t0 + f) * nb + b;
-    dA[o] = acc;
-    if (mag_un) s2 += (double)(acc * mag_un[o]);
+  for (int b = threadIdx.x; b < nb; b += 128) {
+    const int e0 = sm.colptr[b], e1 = sm.colptr[b + 1];
+    float acc[AW_P0A_FRAMES];
+#pragma unroll
+    for (int f = 0; f < AW_P0A_FRAMES; ++f) acc[f] = 0.f;
+    for (int e = e0; e < e1; ++e) {
+      const float w = sm.valT[e];
+      const int r = sm.row[e];
+#pragma unroll
+      for (int f = 0; f < AW_P0A_FRAMES; ++f) acc[f] = fmaf(w, s_dm[f][r], acc[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < AW_P0A_FRAMES; ++f) {
+      if (f < nf) {
+        const long long o = ((long long)clip * T + t0 + f) * nb + b;
+        dA[o] = acc[f];
+        if (mag_un) s2 += (double)(acc[f] * mag_un[o]);
+      }
+    }
   }
   if (mag_un) {
     // Euler: sum_n dy2[n] y2[n] = sum_{t,b} dA~ A~ (|STFT| is 1-homogeneous); the factor

@@ -495,3 +495,30 @@ def test_evaluation_driver_ragged_clips(model):
     for i in range(5):
         np.testing.assert_array_equal(res["decoded"][i], res["bits"][i])
         np.testing.assert_array_equal(O.detect_watermark(res["audio"][i], 16000), res["bits"][i])
+
+
+@pytest.mark.parametrize("sr", [22050, 32000, 48000])
+def test_other_sample_rates_use_generic_band_kernels(eng, sr):
+    """Rates whose 500-4000 Hz band does not fall in the two specialised 32-bin group ranges
+    (22.05 kHz: bins 24..185, 32 kHz: 16..128) run the generic <0,15> kernel instantiations;
+    48 kHz (bins 11..85) shares the 44.1 kHz one.  Detector and one optimisation step vs the oracle."""
+    x = _clips([2], 1.2, sr)
+    eng.set_precision("fp32")
+    try:
+        v = eng.detect(torch.from_numpy(x).cuda(), sr).cpu().numpy()[0]
+    finally:
+        eng.set_precision("tf32")
+    assert np.abs(v - O.detect(x[0], sr)).max() <= 1e-5
+    pat = np.stack([O.encode_bits(O.synth_bits(8)[2])])
+    out, losses, st = _embed_state(eng, x, sr, pat, 2, "fp32")
+    keep = {}
+    y = O.embed(x[0], sr, pat[0], num_iters=2, keep=keep)
+    T = 1 + x.shape[1] // 256
+    B = st["c"].shape[2]
+    fi, _ = O.band_indices(sr)
+    assert B == len(fi)
+    c0_ref = keep["c0"].numpy().reshape(B, T).T
+    assert np.abs(st["c0"][0] - c0_ref).max() <= 1e-5 * np.abs(c0_ref).max()
+    assert abs(losses[0, 0] - keep["losses"][0]) <= 2e-5
+    assert abs(losses[1, 0] - keep["losses"][1]) <= 5e-3
+    assert _snr(out[0], y) >= 55
