@@ -166,8 +166,10 @@ def workload_config(args, secs_override=None, clips_override=None):
     secs = args.seconds if secs_override is None else secs_override
     clips = args.clips if clips_override is None else clips_override
     n = int(round(secs * args.sr))
-    return {"workload": "BASELINE configs[1]: %d x %g s @ %d Hz mono per GPU, embed (%d NAdam it) -> detect -> BER%s"
-                        % (clips, secs, args.sr, args.iters,
+    label = "BASELINE configs[1]" if (clips, secs) == (256, 10.0) else (
+        "BASELINE configs[3] shape (4096 x 30 s over 8 GPUs)" if (clips, secs) == (512, 30.0) else "custom")
+    return {"workload": "%s: %d x %g s @ %d Hz mono per GPU, embed (%d NAdam it) -> detect -> BER%s"
+                        % (label, clips, secs, args.sr, args.iters,
                            "" if args.no_attacks else " + 13-attack suite (pcm 8/12/16/24, delete .1/.15/.2, resample, "
                                                       "bandstop, suppress .1/.25, lowpass, highpass) -> detect -> BER"),
             "clips_per_gpu": clips, "clip_seconds": secs, "sample_rate": args.sr, "iterations": args.iters,
