@@ -683,10 +683,16 @@ template <> struct ModeOf<__half> {
   static const CUtensorMap& wt(aw_ctx* c, int l) { return c->tm_wt16h[l]; }
   static const void* wp(aw_ctx* c, int l) { return c->d_w16h[l]; }
   static const void* wtp(aw_ctx* c, int l) { return c->d_wt16h[l]; }
-  // gradients are ~1e-4 .. 1e-8: a static power-of-two loss scale keeps them in fp16's normal
-  // range (removed again where dP0 is consumed); overflow would need |dH| > 16
+  // gradients are ~1e-4 .. 1e-8 at T' = 861 and shrink like 1/T' (the head seeds dz / T'): a
+  // power-of-two loss scale proportional to T' keeps them in fp16's normal range for any clip
+  // length (removed again where dP0 is consumed); overflow would need |dH| > 16 at T' = 861
   static constexpr float GSCALE = 4096.0f;
 };
+template <typename AT>
+static float grad_scale(const Dims& d) {
+  if (ModeOf<AT>::GSCALE == 1.0f) return 1.0f;
+  return exp2f(roundf(log2f(ModeOf<AT>::GSCALE * (float)d.Tp / 861.0f)));
+}
 
 template <typename AT>
 static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseMel& sm,
@@ -805,7 +811,7 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
   dim3 g1((2 * d.Tp + AW_P0B_FRAMES - 1) / AW_P0B_FRAMES, d.n);
   prof_mark(ctx, st, "p0_bwd_reduce");
   k_p0_bwd_reduce<<<g1, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
-                                      (ChanStats*)ctx->cs.p, acc.bpart, 1.0f / ModeOf<AT>::GSCALE);
+                                      (ChanStats*)ctx->cs.p, acc.bpart, 1.0f / grad_scale<AT>(d));
   ctx->launches++;
   AW_LAUNCH_CHECK();
   dim3 g2((d.T + AW_P0A_FRAMES - 1) / AW_P0A_FRAMES, d.n);
@@ -822,7 +828,7 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
                                      (ChanStats*)ctx->cs.p, (P0BwdCoef*)ctx->p0coef.p,
                                      (P0BwdScal*)ctx->p0scal.p, sm, d.nb, (float*)ctx->dA.p,
                                      euler_s2 ? (const float*)ctx->mag.p : nullptr, acc.s2_part,
-                                     1.0f / ModeOf<AT>::GSCALE);
+                                     1.0f / grad_scale<AT>(d));
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
@@ -839,7 +845,7 @@ static int run_head(aw_ctx* ctx, const Dims& d, const float* pattern, float* val
   h.dH4 = backward ? (AT*)ctx->dh4.p : nullptr;
   h.it_ptr = (int*)ctx->itc.p; h.n_clips = n_total;
   h.round_tf32 = ctx->prec == AW_PREC_TF32;
-  h.gscale = ModeOf<AT>::GSCALE;
+  h.gscale = grad_scale<AT>(d);
   h.hpart = (double*)ctx->hpart.p;
   h.hcoef = (float*)ctx->hcoef.p;
   prof_mark(ctx, st, "head");

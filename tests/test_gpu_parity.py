@@ -429,6 +429,14 @@ def test_long_clips_config4_and_config5_shapes(eng):
     yb = eng.embed(xd, sr, torch.from_numpy(pat), iters=3)
     assert ya.shape == (1, 256 * (x300.shape[1] // 256)) and torch.isfinite(ya).all()
     assert torch.equal(ya, yb)
+    # the fp16 loop's gradient loss scale grows with the clip length (gradients shrink like 1/T'):
+    # its loss trajectory stays on the TF32 loop's
+    traj = {}
+    for prec in ("tf32", "fp16"):
+        _, _, losses = eng.embed(xd, sr, torch.from_numpy(pat), iters=12, return_losses=True, precision=prec)
+        traj[prec] = losses[:12, 0].cpu().numpy()
+    assert traj["tf32"][-1] < traj["tf32"][0] - 0.05                 # the optimiser makes progress
+    assert np.abs(traj["fp16"] - traj["tf32"]).max() <= 2e-2, traj
 
 
 @pytest.mark.parametrize("n_samples", [1100, 2048, 2303, 58 * 256 + 7, 59 * 256 + 1, 65 * 256, 115 * 256 + 13,
