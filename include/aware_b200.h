@@ -35,7 +35,7 @@ enum {
   AW_PREC_BF16 = 2, /* tcgen05, bf16 operands AND bf16 activation storage (embed loop speed) */
   AW_PREC_FP16 = 3  /* tcgen05 kind::f16 with fp16 operands and fp16 activation storage: the same
                        10-bit mantissa as TF32 at half the bytes; back-propagated gradients carry
-                       a static 2^12 loss scale */
+                       a power-of-two loss scale proportional to the clip length */
 };
 
 /* Model description handed over once (reference: utils/models/load_model.py:6-76,
