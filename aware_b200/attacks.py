@@ -251,6 +251,35 @@ class Gain(Attack):
         return _eng(engine).attack_affine(x, self.gain)
 
 
+class FIRFilter(Attack):
+    """Windowed-sinc FIR low / high / band-pass (the brief's "lowpass/highpass/bandpass FIR"; the
+    reference itself only has Butterworth IIRs).  Defined as `scipy.signal.upfirdn(h, x)[:n]` with
+    `h = firwin(numtaps, cutoff, pass_zero=..., fs=sr)` cast to float32 -- a causal FIR, the same
+    single-pass polyphase kernel as `Resample` with up = down = 1, so it is bit-exact against
+    scipy's float32 upfirdn (parity pinned to scipy, not to the reference)."""
+
+    def __init__(self, kind="lowpass", cutoff=4000.0, numtaps=101):
+        if kind not in ("lowpass", "highpass", "bandpass"):
+            raise ValueError("kind must be lowpass, highpass or bandpass")
+        self.kind, self.cutoff, self.numtaps = kind, cutoff, int(numtaps) | 1
+        self.name = f"fir_{kind}"
+        self._taps = {}
+
+    def taps(self, sr):
+        from scipy.signal import firwin
+        pass_zero = {"lowpass": True, "highpass": False, "bandpass": False}[self.kind]
+        return firwin(self.numtaps, self.cutoff, pass_zero=pass_zero, fs=sr).astype(np.float32)
+
+    def apply_batch(self, x, sr, rng=None, engine=None):
+        eng = _eng(engine)
+        key = (sr, eng.device.index)
+        if key not in self._taps:
+            h = self.taps(sr)
+            self._taps[key] = (torch.from_numpy(np.ascontiguousarray(h[::-1])).to(eng.device), len(h))
+        h_tf, n_taps = self._taps[key]
+        return eng.attack_upfirdn(x, h_tf, n_taps, 1, 1, 0, x.shape[1])
+
+
 def reference_suite():
     """The in-scope part of scripts/test.py's attack_list (test.py:15-18)."""
     return [PCMBitDepthConversion(8), PCMBitDepthConversion(12), PCMBitDepthConversion(16),

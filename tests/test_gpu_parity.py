@@ -530,3 +530,21 @@ def test_other_sample_rates_use_generic_band_kernels(eng, sr):
     assert abs(losses[0, 0] - keep["losses"][0]) <= 2e-5
     assert abs(losses[1, 0] - keep["losses"][1]) <= 5e-3
     assert _snr(out[0], y) >= 55
+
+
+@pytest.mark.parametrize("kind,cutoff", [("lowpass", 4000.0), ("highpass", 500.0), ("bandpass", [500.0, 4000.0])])
+def test_fir_attack_matches_scipy_upfirdn(model, kind, cutoff):
+    """FIR extension (no reference counterpart): bit-exact against scipy's float32 upfirdn."""
+    from scipy.signal import upfirdn
+    from aware_b200 import attacks as A
+    emb, _ = model
+    A.set_engine(emb.engine)
+    sr = 44100
+    x = _clips([0, 1], 1.0, sr)
+    att = A.FIRFilter(kind, cutoff, numtaps=129)
+    got = att.apply_batch(torch.from_numpy(x).cuda(), sr).cpu().numpy()
+    h = att.taps(sr)
+    for i in range(len(x)):
+        want = upfirdn(h, x[i], 1, 1)[:x.shape[1]]
+        assert want.dtype == np.float32
+        np.testing.assert_array_equal(got[i], want)
