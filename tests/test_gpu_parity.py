@@ -548,3 +548,30 @@ def test_fir_attack_matches_scipy_upfirdn(model, kind, cutoff):
         want = upfirdn(h, x[i], 1, 1)[:x.shape[1]]
         assert want.dtype == np.float32
         np.testing.assert_array_equal(got[i], want)
+
+
+def test_service_stereo_equals_two_mono_calls(model):
+    """service/embed.py:37-59 and detect.py:23-43 semantics: a stereo clip is two independent mono
+    embeds (each rescaled by its own signed max) and the decoder takes, per bit, the channel with
+    the larger |v|."""
+    from aware_b200.service import detect_watermark, embed_watermark
+    emb, det = model
+    prev = emb.num_iterations
+    emb.num_iterations = 80
+    try:
+        left, right = O.synth_clip(7, 1.5, 16000), 0.6 * O.synth_clip(8, 1.5, 16000)
+        bits = O.synth_bits(8)[7]
+        st = embed_watermark(np.column_stack((left, right)), 16000, bits, emb)
+        ml, mr = embed_watermark(left, 16000, bits, emb), embed_watermark(right, 16000, bits, emb)
+    finally:
+        emb.num_iterations = prev
+    assert st.shape == (len(ml), 2)
+    np.testing.assert_array_equal(st[:, 0], ml)
+    np.testing.assert_array_equal(st[:, 1], mr)
+    got = detect_watermark(st, 16000, det)
+    vl, vr = det.detect(st[:, 0], 16000), det.detect(st[:, 1], 16000)
+    want = (np.where(np.abs(vl) > np.abs(vr), vl, vr) > 0).astype(np.int32)
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(got, bits)
+    with pytest.raises(ValueError):
+        detect_watermark(st[:, :1], 16000, det)              # (N, 1) is rejected by detect (detect.py:44,55)
