@@ -337,6 +337,16 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
   return 0;
 }
 
+static std::vector<Buf*> all_bufs(aw_ctx* ctx) {
+  return {&ctx->accum, &ctx->peakx, &ctx->mag, &ctx->ph_u, &ctx->ph_q, &ctx->c0, &ctx->c,
+                 &ctx->m, &ctx->v, &ctx->cbest, &ctx->dA, &ctx->yoob, &ctx->y, &ctx->M,
+                 &ctx->cs, &ctx->sigma, &ctx->act[0], &ctx->act[1], &ctx->act[2], &ctx->act[3],
+                 &ctx->act[4], &ctx->ga, &ctx->gb, &ctx->dh4, &ctx->dp0, &ctx->part, &ctx->stat[0],
+                 &ctx->stat[1], &ctx->stat[2], &ctx->stat[3], &ctx->stat[4], &ctx->bstat,
+                 &ctx->values, &ctx->best, &ctx->improved, &ctx->pattern, &ctx->itc, &ctx->steps,
+                 &ctx->scal, &ctx->ready, &ctx->zoob, &ctx->p0coef, &ctx->p0scal, &ctx->hpart, &ctx->hcoef, &ctx->red_a, &ctx->red_b, &ctx->red_c};
+}
+
 extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
@@ -358,14 +368,7 @@ extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
     cudaFree(mc.rowptr); cudaFree(mc.col); cudaFree(mc.val);
     cudaFree(mc.colptr); cudaFree(mc.row); cudaFree(mc.valT);
   }
-  Buf* bufs[] = {&ctx->accum, &ctx->peakx, &ctx->mag, &ctx->ph_u, &ctx->ph_q, &ctx->c0, &ctx->c,
-                 &ctx->m, &ctx->v, &ctx->cbest, &ctx->dA, &ctx->yoob, &ctx->y, &ctx->M,
-                 &ctx->cs, &ctx->sigma, &ctx->act[0], &ctx->act[1], &ctx->act[2], &ctx->act[3],
-                 &ctx->act[4], &ctx->ga, &ctx->gb, &ctx->dh4, &ctx->dp0, &ctx->part, &ctx->stat[0],
-                 &ctx->stat[1], &ctx->stat[2], &ctx->stat[3], &ctx->stat[4], &ctx->bstat,
-                 &ctx->values, &ctx->best, &ctx->improved, &ctx->pattern, &ctx->itc, &ctx->steps,
-                 &ctx->scal, &ctx->ready, &ctx->zoob, &ctx->p0coef, &ctx->p0scal, &ctx->hpart, &ctx->hcoef, &ctx->red_a, &ctx->red_b, &ctx->red_c};
-  for (Buf* b : bufs)
+  for (Buf* b : all_bufs(ctx))
     if (b->p) cudaFree(b->p);
   delete ctx;
   return 0;
@@ -1054,7 +1057,26 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
     AW_CUDA(cudaStreamWaitEvent(ctx->gstream, ctx->ev_in, 0));
     st = ctx->gstream;
   }
-  if (wave_clips <= 0 || wave_clips > n_clips) wave_clips = n_clips;
+  if (wave_clips <= 0 || wave_clips > n_clips) {
+    // default: the whole batch in one wave, unless its workspace would not fit in device memory
+    // (then the largest wave that fits in 85 % of what is free plus what this context already holds)
+    wave_clips = n_clips;
+    Dims d1;
+    if (make_dims(ctx, 1, n_samples, sample_rate, &d1)) return 1;
+    const double per_clip = (double)d1.T * d1.nb * (7 * 4 + 2 * 8) + 3.0 * d1.L * 4 + (double)d1.T * AW_NMEL * 4 +
+                            (double)d1.Tp_pad * ((128 + 512 + 1024 + 1024 + 64) * 4 + 2 * 1024 * 4 + 64 * 4 + 128 * 4) +
+                            (double)d1.tiles * (1024 * 8 + 64 * 24) + 64 * 1024;
+    size_t free_b = 0, total_b = 0;
+    AW_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    double held = 0.0;
+    for (Buf* b : all_bufs(ctx)) held += (double)b->cap;
+    const double budget = 0.85 * ((double)free_b + held);
+    if (per_clip * n_clips > budget) {
+      wave_clips = (int)std::max(1.0, floor(budget / per_clip));
+      AW_REQUIRE(per_clip <= budget, "aw_embed_batch: one %d-sample clip needs %.1f GB of workspace, %.1f GB available",
+                 n_samples, per_clip / 1e9, budget / 1e9);
+    }
+  }
   Dims d;
   if (make_dims(ctx, wave_clips, n_samples, sample_rate, &d)) return 1;
   AW_REQUIRE(out_stride >= d.L, "aw_embed_batch: out_stride %lld < %d", (long long)out_stride, d.L);
