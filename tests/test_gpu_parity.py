@@ -575,3 +575,29 @@ def test_service_stereo_equals_two_mono_calls(model):
     np.testing.assert_array_equal(got, bits)
     with pytest.raises(ValueError):
         detect_watermark(st[:, :1], 16000, det)              # (N, 1) is rejected by detect (detect.py:44,55)
+
+
+def test_degenerate_inputs_stay_finite(eng):
+    """All-zero clips, a clip that is silent for most of its length, and a full-scale square wave
+    (many samples tie at the peak): detect and embed stay finite, a silent clip stays silent and
+    the oracle agrees on the detector outputs."""
+    sr = 16000
+    n = 2 * sr
+    sq = np.sign(np.sin(2 * np.pi * 440.0 * np.arange(n) / sr)).astype(np.float32)
+    half = O.synth_clip(9, 2.0, sr).copy()
+    half[: n * 3 // 4] = 0.0
+    x = np.stack([np.zeros(n, np.float32), half, sq])
+    xd = torch.from_numpy(x).cuda()
+    eng.set_precision("fp32")
+    try:
+        v = eng.detect(xd, sr).cpu().numpy()
+    finally:
+        eng.set_precision("tf32")
+    assert np.isfinite(v).all() and np.all(v[0] == 0.0)
+    for i in (1, 2):
+        assert np.abs(v[i] - O.detect(x[i], sr)).max() <= 2e-5
+    pat = torch.from_numpy(np.stack([O.encode_bits(b) for b in O.synth_bits(3)]))
+    for prec in ("fp16", "tf32"):
+        y = eng.embed(xd, sr, pat, iters=12, precision=prec).cpu().numpy()
+        assert np.isfinite(y).all() and np.all(y[0] == 0.0), prec
+        assert np.abs(y[1:]).max() <= 1.0
