@@ -70,8 +70,6 @@ struct aw_ctx {
   PFN_encodeTiled encode = nullptr;
   CUtensorMap tm_w[4], tm_wt[4], tm_w16[4], tm_wt16[4], tm_w16h[4], tm_wt16h[4];
   // workspace (grow-only)
-  bool no_fuse_norm = true;   // AW_B200_FUSE_NORM=1 opts into the in-GEMM InstanceNorm application
-  Buf ready;                  // [6 fused launches][clips][4] finished-row-tile counters (gemm.cuh FUSE)
   Buf scal, zoob, p0coef, p0scal, hpart, hcoef, red_a, red_b, red_c;
   // CUDA-graph replay of the optimisation iteration (AW_B200_NO_GRAPH=1 disables): the ~50 launches
   // of one iteration are captured once on a context-owned stream and replayed iters-1 times
@@ -172,12 +170,12 @@ static int make_map(aw_ctx* ctx, CUtensorMap* map, const void* ptr, uint64_t row
 
 static int bn_for(int n) { return n >= 256 ? 256 : (n >= 128 ? 128 : 64); }
 
-template <typename T, typename OT, int BN, int EPI, bool FUSE = false>
+template <typename T, typename OT, int BN, int EPI>
 static int launch_tc(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, int rows, int n,
                      int k, const EpiArgsT<OT>& ep, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    AW_CUDA(cudaFuncSetAttribute(k_gemm_tc<T, OT, BN, EPI, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AW_CUDA(cudaFuncSetAttribute(k_gemm_tc<T, OT, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  gemm_tc_smem<BN>()));
     attr_set = true;
   }
@@ -191,8 +189,8 @@ static int launch_tc(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, 
     cudaEventRecord(pr.a, st);
   }
   prof_mark(ctx, st, gemm_label(EPI, n, k));
-  k_gemm_tc<T, OT, BN, EPI, FUSE><<<grid, FUSE ? AW_GEMM_THREADS_FUSED : AW_GEMM_THREADS,
-                                    gemm_tc_smem<BN>(), st>>>(ma, mb, k, n_row_tiles, n_col_tiles, ep);
+  k_gemm_tc<T, OT, BN, EPI><<<grid, AW_GEMM_THREADS, gemm_tc_smem<BN>(), st>>>(ma, mb, k, n_row_tiles,
+                                                                              n_col_tiles, ep);
   if (ctx->prof_on) {
     cudaEventRecord(pr.b, st);
     ctx->prof.push_back(pr);
@@ -257,15 +255,8 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
   ctx->threshold = model->threshold;
   ctx->h_mel.assign(model->mel_basis, model->mel_basis + AW_NMEL * 513);
   {
-    const char* e;
-    // measured on B200 (128 x 10 s clips, TF32): 5.44 ms/iteration fused vs 5.50 ms unfused, detect
-    // 2.33 vs 2.10 ms -- the 4 normaliser warps per SM are latency-bound, so the L2-hot
-    // re-read buys nothing.  Kept as an opt-in experiment (single stream only: the kernel's
-    // CTAs wait on one another).
-    e = getenv("AW_B200_NO_GRAPH");
+    const char* e = getenv("AW_B200_NO_GRAPH");
     ctx->graphs = !(e && e[0] == '1');
-    e = getenv("AW_B200_FUSE_NORM");
-    ctx->no_fuse_norm = !(e && e[0] == '1');
   }
 
   void* fn = nullptr;
@@ -344,7 +335,7 @@ static std::vector<Buf*> all_bufs(aw_ctx* ctx) {
                  &ctx->act[4], &ctx->ga, &ctx->gb, &ctx->dh4, &ctx->dp0, &ctx->part, &ctx->stat[0],
                  &ctx->stat[1], &ctx->stat[2], &ctx->stat[3], &ctx->stat[4], &ctx->bstat,
                  &ctx->values, &ctx->best, &ctx->improved, &ctx->pattern, &ctx->itc, &ctx->steps,
-                 &ctx->scal, &ctx->ready, &ctx->zoob, &ctx->p0coef, &ctx->p0scal, &ctx->hpart, &ctx->hcoef, &ctx->red_a, &ctx->red_b, &ctx->red_c};
+                 &ctx->scal, &ctx->zoob, &ctx->p0coef, &ctx->p0scal, &ctx->hpart, &ctx->hcoef, &ctx->red_a, &ctx->red_b, &ctx->red_c};
 }
 
 extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
@@ -541,11 +532,10 @@ struct Acc {
 };
 static Acc acc_view(aw_ctx* ctx, const struct Dims& d);
 
-__global__ void k_iter_begin(unsigned long long* peak, int n, int* it, int* ready, int n_ready) {
+__global__ void k_iter_begin(unsigned long long* peak, int n, int* it) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) peak[i] = 0ull;
   if (i == 0 && it) *it += 1;
-  for (int j = i; j < n_ready; j += gridDim.x * blockDim.x) ready[j] = 0;
 }
 
 static int mel_blocks(const Dims& d) { return (d.T + AW_MEL_FRAMES - 1) / AW_MEL_FRAMES; }
@@ -589,7 +579,6 @@ static int ensure_net_ws(aw_ctx* ctx, const Dims& d, bool backward) {
   if (ensure(ctx->best, n * 4)) return 1;
   if (ensure(ctx->improved, n * 4)) return 1;
   if (ensure(ctx->itc, 4)) return 1;
-  if (ensure(ctx->ready, n * 6 * 4 * sizeof(int))) return 1;
   if (backward) {
     void *b0 = ctx->ga.p, *b1 = ctx->gb.p, *b2 = ctx->dh4.p;
     if (ensure(ctx->ga, R * 1024 * 4)) return 1;
@@ -627,14 +616,12 @@ template <>
 int gemm_layer<float, EPI_FWD>(aw_ctx* ctx, const CUtensorMap& ma, const void* a, const CUtensorMap& mb,
                                const void* b, int rows, int n, int k, const EpiArgsT<float>& ep, cudaStream_t st) {
   if (ctx->prec == AW_PREC_FP32) return launch_exact<EPI_FWD>(ctx, (const float*)a, (const float*)b, rows, n, k, ep, st);
-  if (ep.ready) return launch_tc<float, float, 256, EPI_FWD, true>(ctx, ma, mb, rows, n, k, ep, st);
   return launch_tc_bn<float, float, EPI_FWD>(ctx, ma, mb, rows, n, k, ep, st);
 }
 template <>
 int gemm_layer<float, EPI_BWD>(aw_ctx* ctx, const CUtensorMap& ma, const void* a, const CUtensorMap& mb,
                                const void* b, int rows, int n, int k, const EpiArgsT<float>& ep, cudaStream_t st) {
   if (ctx->prec == AW_PREC_FP32) return launch_exact<EPI_BWD>(ctx, (const float*)a, (const float*)b, rows, n, k, ep, st);
-  if (ep.ready) return launch_tc<float, float, 256, EPI_BWD, true>(ctx, ma, mb, rows, n, k, ep, st);
   return launch_tc_bn<float, float, EPI_BWD>(ctx, ma, mb, rows, n, k, ep, st);
 }
 template <>
@@ -728,15 +715,10 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
     EpiArgsT<AT> ep;
     ep.out = (AT*)ctx->act[l + 1].p; ep.ldo = cout;
     ep.part = (float*)ctx->part.p; ep.ldp = cout; ep.act = nullptr;
-    const bool fuse = !B && ctx->prec == AW_PREC_TF32 && cout >= 256 && !ctx->no_fuse_norm;
-    ep.ready = fuse ? (int*)ctx->ready.p + (size_t)l * d.n * 4 : nullptr;
-    ep.tiles_per_clip = d.tiles; ep.Tp = d.Tp;
-    ep.stat = (float*)ctx->stat[l + 1].p; ep.round_tf32 = tf && l < 3;
     const CUtensorMap& mw = ModeOf<AT>::w(ctx, l);
     const void* w = ModeOf<AT>::wp(ctx, l);
     if (gemm_layer<AT, EPI_FWD>(ctx, ctx->tm_act[B][l], ctx->act[l].p, mw, w, d.rows, cout, cin, ep, st))
       return 1;
-    if (fuse) continue;   // statistics + normalise + LeakyReLU already applied inside the GEMM kernel
     dim3 g((cout + 31) / 32, d.n);
     prof_mark(ctx, st, "finalize_fwd");
     k_finalize<false><<<g, 256, 0, st>>>((float*)ctx->part.p, cout, d.tiles, cout, d.Tp,
@@ -772,14 +754,9 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
     EpiArgsT<AT> ep;
     ep.out = steps[s].out; ep.ldo = n;
     ep.part = (float*)ctx->part.p; ep.ldp = n; ep.act = (AT*)ctx->act[l].p;
-    const bool fuse = !B && ctx->prec == AW_PREC_TF32 && n >= 256 && !ctx->no_fuse_norm;
-    ep.ready = fuse ? (int*)ctx->ready.p + (size_t)(3 + s) * d.n * 4 : nullptr;
-    ep.tiles_per_clip = d.tiles; ep.Tp = d.Tp;
-    ep.stat = (float*)ctx->stat[l].p; ep.round_tf32 = tf;
     const CUtensorMap& mw = ModeOf<AT>::wt(ctx, l);
     const void* w = ModeOf<AT>::wtp(ctx, l);
     if (gemm_layer<AT, EPI_BWD>(ctx, *steps[s].ma, steps[s].a, mw, w, d.rows, n, k, ep, st)) return 1;
-    if (fuse) continue;   // InstanceNorm adjoint already applied inside the GEMM kernel
     dim3 g((n + 31) / 32, d.n);
     prof_mark(ctx, st, "finalize_bwd");
     k_finalize<true><<<g, 256, 0, st>>>((float*)ctx->part.p, n, d.tiles, n, d.Tp,
@@ -962,9 +939,7 @@ static int launch_peak(aw_ctx* ctx, const float* x, int64_t stride, int n, int n
 }
 static int begin_pass(aw_ctx* ctx, int n, int* it, cudaStream_t st) {
   prof_mark(ctx, st, "iter_begin");
-  k_iter_begin<<<(n + 255) / 256, 256, 0, st>>>((unsigned long long*)ctx->accum.p, n, it,
-                                                (int*)ctx->ready.p,
-                                                (int)std::min<size_t>((size_t)6 * n * 4, ctx->ready.cap / 4));
+  k_iter_begin<<<(n + 255) / 256, 256, 0, st>>>((unsigned long long*)ctx->accum.p, n, it);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;

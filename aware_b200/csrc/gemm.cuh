@@ -173,7 +173,6 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 #define AW_EPI_STRIDE 36                  // words per staged row: 16-byte accesses stay conflict-free
 #define AW_EPI_STAGE_WORDS (32 * AW_EPI_STRIDE)
 #define AW_GEMM_THREADS 320               // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-#define AW_GEMM_THREADS_FUSED 448         // + warps 10..13: deferred InstanceNorm application
 
 // Operand element: float -> kind::tf32 (32 elements per 128-byte swizzle row, K=8 per MMA),
 // __nv_bfloat16 -> kind::f16 (64 elements per row, K=16 per MMA).  Either way one k-block is
@@ -249,27 +248,15 @@ struct EpiArgsT {
   float* part;           // [row_tiles][ldp][2] per-tile column partial sums (FWD/BWD)
   int ldp;
   const OT* act;         // BWD: P_{l-1} [rows][ldo] (post-LeakyReLU activations)
-  // FUSE: deferred InstanceNorm application inside the GEMM kernel (see k_gemm_tc)
-  int* ready;            // [clips][n_col_tiles] finished row tiles of a (clip, column tile)
-  int tiles_per_clip;    // row tiles per clip
-  int Tp;                // valid rows per clip (the rest of the clip's rows is padding)
-  float* stat;           // FWD: out [clip][ldp][2] = (mean, rstd);  BWD: in, this layer's forward stats
-  int round_tf32;
 };
 
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
 template <int BN>
 __host__ __device__ constexpr int gemm_stages() { return BN == 256 ? 3 : AW_GEMM_STAGES; }
 template <int BN>
 constexpr int gemm_tc_smem() {
   return gemm_stages<BN>() * (128 * 128 + BN * 128) + 1024 /*align*/ + 256 /*barriers*/ +
-         2 * 2 * 4 * BN * 4 /*double-buffered column partials*/ + BN * 8 /*fused-norm statistics*/ +
+         2 * 2 * 4 * BN * 4 /*double-buffered column partials*/ +
          8 * AW_EPI_STAGE_WORDS * 4 /*per-warp epilogue transpose tiles*/;
 }
 
@@ -278,21 +265,8 @@ constexpr int gemm_tc_smem() {
 // concurrently share A row tiles in L2).  The fp32 accumulator is double-buffered in TMEM
 // (2 x BN columns): while the 8 epilogue warps drain tile i, the MMA warp already
 // accumulates tile i+1 and the TMA warp prefetches tile i+2's operands.
-//
-// FUSE (fp32 activations, EPI_FWD / EPI_BWD): InstanceNorm needs a whole clip's column
-// statistics before any element can be normalised, which used to cost a second kernel
-// that re-read the raw GEMM output from HBM and wrote it back.  Here every finished tile
-// bumps a per-(clip, column tile) counter after its output and partial sums are globally
-// visible, and four extra warps per CTA follow the CTA's own tile sequence one step behind:
-// as soon as all row tiles of the clip have landed (they are in flight on neighbouring CTAs
-// at the same time) they reduce the partials in fixed order (float64, deterministic) and
-// normalise the CTA's own tile in place while it is still L2-resident:
-//   FWD: P = LeakyReLU((H - mean) * rstd)                      (conv1d.py:40-41)
-//   BWD: dH = rstd * (dHhat - mean(dHhat) - Hhat * mean(dHhat * Hhat))
-// The GEMM pipeline never waits on the normaliser warps, so there is no cyclic dependency;
-// the waits are bounded and trap instead of hanging.
-template <typename T, typename OT, int BN, int EPI, bool FUSE = false>
-__global__ void __launch_bounds__(FUSE ? AW_GEMM_THREADS_FUSED : AW_GEMM_THREADS, 1)
+template <typename T, typename OT, int BN, int EPI>
+__global__ void __launch_bounds__(AW_GEMM_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           int K, int n_row_tiles, int n_col_tiles, EpiArgsT<OT> ep) {
   extern __shared__ uint8_t smem_raw[];
@@ -308,8 +282,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint64_t* tempty = tfull + 2;                 // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* s_part = reinterpret_cast<float*>(smem + NSTAGE * STAGE + 256);  // [2][2][4][BN]
-  float2* s_nstat = reinterpret_cast<float2*>(s_part + 2 * 2 * 4 * BN);           // [BN] (FUSE)
-  float* s_stage = reinterpret_cast<float*>(s_nstat + BN);                        // [8 warps][32][36]
+  float* s_stage = s_part + 2 * 2 * 4 * BN;                                       // [8 warps][32][36]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = K / BK;
@@ -382,103 +355,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
         tc_commit(tfull + ab);
-      }
-    }
-  } else if (FUSE && warp >= 10) {
-    // ------------------- deferred InstanceNorm application (FUSE) -------------------
-    if constexpr (FUSE) {
-      static_assert(!FUSE || sizeof(OT) == 4, "fused InstanceNorm needs float32 activations");
-      const int t = threadIdx.x - 320;                  // 0..127
-      const int tpc = ep.tiles_per_clip;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int row_tile = tile / n_col_tiles, jt = tile % n_col_tiles, n0 = jt * BN;
-        const int clip = row_tile / tpc, r_in = row_tile - clip * tpc;
-        const int* cnt = ep.ready + clip * n_col_tiles + jt;
-        if (lane == 0) {                                // one poller per warp
-          uint32_t spins = 0;
-          while (ld_acquire(cnt) < tpc) {
-            __nanosleep(100);
-            if (++spins > (1u << 22)) {
-              printf("aware_b200: fused InstanceNorm wait timed out (block %d tile %d)\n", blockIdx.x, tile);
-              __trap();
-            }
-          }
-        }
-        __syncwarp();
-        for (int cc = t; cc < BN; cc += 128) {
-          double s1 = 0.0, s2 = 0.0;
-          for (int rt = 0; rt < tpc; ++rt) {
-            const float2 pp = __ldcg(reinterpret_cast<const float2*>(
-                ep.part + ((long long)(clip * tpc + rt) * ep.ldp + n0 + cc) * 2));
-            s1 += pp.x;
-            s2 += pp.y;
-          }
-          if (EPI == EPI_FWD) {
-            const double mu = s1 / ep.Tp;
-            double var = s2 / ep.Tp - mu * mu;
-            if (var < 0.0) var = 0.0;
-            const float2 ms = make_float2((float)mu, (float)(1.0 / sqrt(var + AW_IN_EPS)));
-            s_nstat[cc] = ms;
-            if (r_in == 0) *reinterpret_cast<float2*>(ep.stat + ((long long)clip * ep.ldp + n0 + cc) * 2) = ms;
-          } else {
-            s_nstat[cc] = make_float2((float)(s1 / ep.Tp), (float)(s2 / ep.Tp));
-          }
-        }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        // 128 threads: 64 float4 per row -> two rows per pass
-        const int c4 = (t & 63) * 4;
-        const float4 sa = *reinterpret_cast<const float4*>(&s_nstat[c4]);       // (x0,y0,x1,y1)
-        const float4 sb = *reinterpret_cast<const float4*>(&s_nstat[c4 + 2]);
-        float rs[4] = {1.f, 1.f, 1.f, 1.f};
-        if (EPI == EPI_BWD) {
-          const float4 r01 = *reinterpret_cast<const float4*>(ep.stat + ((long long)clip * ep.ldp + n0 + c4) * 2);
-          const float4 r23 = *reinterpret_cast<const float4*>(ep.stat + ((long long)clip * ep.ldp + n0 + c4) * 2 + 4);
-          rs[0] = r01.y; rs[1] = r01.w; rs[2] = r23.y; rs[3] = r23.w;
-        }
-        const float sx[4] = {sa.x, sa.z, sb.x, sb.z}, sy[4] = {sa.y, sa.w, sb.y, sb.w};
-        // Deep batches: the tile comes back from L2 (~1 us away), so every thread keeps NB
-        // independent 16-byte loads in flight (128 threads x NB x 16 B = 32 KB per SM), which
-        // is what it takes to stream at the SM's share of L2 bandwidth.
-        constexpr int NB = EPI == EPI_FWD ? 16 : 8;
-        float* base = reinterpret_cast<float*>(ep.out) + (long long)(row_tile * 128 + (t >> 6)) * ep.ldo + n0 + c4;
-        const float* abase = EPI == EPI_BWD ? reinterpret_cast<const float*>(ep.act) +
-                                                  (long long)(row_tile * 128 + (t >> 6)) * ep.ldo + n0 + c4
-                                            : nullptr;
-        const long long rstride = 2ll * ep.ldo;          // two rows per pass
-        const int j0 = r_in * 128 + (t >> 6);
-#pragma unroll 1
-        for (int pb = 0; pb < 64; pb += NB) {
-          float4 h4[NB], a4[EPI == EPI_BWD ? NB : 1];
-#pragma unroll
-          for (int i = 0; i < NB; ++i) {
-            h4[i] = ldcg4(base + (pb + i) * rstride);
-            if (EPI == EPI_BWD) a4[i] = ldcg4(abase + (pb + i) * rstride);
-          }
-#pragma unroll
-          for (int i = 0; i < NB; ++i) {
-            const int j = j0 + 2 * (pb + i);             // row inside the clip
-            const float h[4] = {h4[i].x, h4[i].y, h4[i].z, h4[i].w};
-            float o[4];
-            if (EPI == EPI_FWD) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) o[k] = leaky((h[k] - sx[k]) * sy[k]);
-            } else {
-              const float aa[4] = {a4[i].x, a4[i].y, a4[i].z, a4[i].w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float hh = aa[k] > 0.f ? aa[k] : aa[k] * (1.0f / AW_LEAKY);
-                o[k] = rs[k] * (h[k] - sx[k] - hh * sy[k]);
-              }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (ep.round_tf32) o[k] = to_tf32(o[k]);
-              if (j >= ep.Tp) o[k] = 0.f;                // pad rows of the clip stay exactly 0
-            }
-            *reinterpret_cast<float4*>(base + (pb + i) * rstride) = make_float4(o[0], o[1], o[2], o[3]);
-          }
-        }
-        asm volatile("bar.sync 2, 128;" ::: "memory");   // s_nstat is rewritten for the next tile
       }
     }
   } else {
@@ -596,15 +472,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           float* p = ep.part + ((long long)row_tile * ep.ldp + n0 + cc) * 2;
           p[0] = s1;
           p[1] = s2;
-        }
-        if constexpr (FUSE) {
-          // publish: every epilogue thread's tile / partial stores, then one counter bump
-          __threadfence();
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (t == 0) {
-            const int clip = row_tile / ep.tiles_per_clip;
-            atomicAdd(ep.ready + clip * n_col_tiles + (tile % n_col_tiles), 1);
-          }
         }
       }
     }
