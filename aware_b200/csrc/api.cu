@@ -86,6 +86,7 @@ struct aw_ctx {
   int last_n = 0, last_T = 0, last_nb = 0;
   // optional CUDA-event timing of the GEMM launches (aw_profile_*)
   struct ProfRec { int n, k, epi; cudaEvent_t a, b; };
+  std::vector<const void*> smem_attr_done;   // kernels whose dynamic-smem limit was raised on this device
   bool prof_on = false;
   std::vector<ProfRec> prof;
   // every-launch timeline: an event before each launch; a kernel's time = next mark - its mark
@@ -124,6 +125,15 @@ static const char* gemm_label(int epi, int n, int k) {
   if (used == 32) return "gemm_other";
   strcpy(table[used], buf);
   return table[used++];
+}
+
+// cudaFuncSetAttribute is per device: remember it per context, not per process
+static int raise_smem_limit(aw_ctx* ctx, const void* func, int bytes) {
+  for (const void* f : ctx->smem_attr_done)
+    if (f == func) return 0;
+  AW_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  ctx->smem_attr_done.push_back(func);
+  return 0;
 }
 
 static int ensure(Buf& b, size_t bytes) {
@@ -173,12 +183,7 @@ static int bn_for(int n) { return n >= 256 ? 256 : (n >= 128 ? 128 : 64); }
 template <typename T, typename OT, int BN, int EPI>
 static int launch_tc(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, int rows, int n,
                      int k, const EpiArgsT<OT>& ep, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AW_CUDA(cudaFuncSetAttribute(k_gemm_tc<T, OT, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 gemm_tc_smem<BN>()));
-    attr_set = true;
-  }
+  if (raise_smem_limit(ctx, (const void*)k_gemm_tc<T, OT, BN, EPI>, gemm_tc_smem<BN>())) return 1;
   const int n_row_tiles = rows / 128, n_col_tiles = n / BN;
   const int tiles = n_row_tiles * n_col_tiles;
   const int grid = std::min(tiles, ctx->num_sms);
@@ -367,6 +372,7 @@ extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
 
 extern "C" int aw_ctx_set_precision(aw_ctx* ctx, int prec) {
   AW_REQUIRE(ctx, "null ctx");
+  if (ctx) cudaSetDevice(ctx->device);
   AW_REQUIRE(prec == AW_PREC_TF32 || prec == AW_PREC_FP32 || prec == AW_PREC_BF16 || prec == AW_PREC_FP16,
              "unknown precision %d", prec);
   ctx->prec = prec;
@@ -377,6 +383,7 @@ extern "C" int64_t aw_launch_count(aw_ctx* ctx) { return ctx ? ctx->launches : 0
 
 extern "C" int aw_profile_enable(aw_ctx* ctx, int on) {
   AW_REQUIRE(ctx, "null ctx");
+  if (ctx) cudaSetDevice(ctx->device);
   ctx->prof_on = on != 0;
   return 0;
 }
@@ -385,6 +392,7 @@ extern "C" int aw_profile_enable(aw_ctx* ctx, int on) {
 extern "C" int aw_profile_read(aw_ctx* ctx, int max_classes, int* n_classes, int* cls_n, int* cls_k,
                                int* cls_epi, int64_t* cls_count, double* cls_ms) {
   AW_REQUIRE(ctx && n_classes, "null argument");
+  if (ctx) cudaSetDevice(ctx->device);
   int nc = 0;
   for (auto& r : ctx->prof) {
     AW_CUDA(cudaEventSynchronize(r.b));
@@ -413,6 +421,7 @@ extern "C" int aw_profile_read(aw_ctx* ctx, int max_classes, int* n_classes, int
 extern "C" int aw_profile_read_named(aw_ctx* ctx, int max_classes, int* n_classes, char* names,
                                      int64_t* cls_count, double* cls_ms) {
   AW_REQUIRE(ctx && n_classes && names && cls_count && cls_ms, "null argument");
+  if (ctx) cudaSetDevice(ctx->device);
   int nc = 0;
   for (size_t i = 0; i + 1 < ctx->marks.size(); ++i) {
     const aw_ctx::Mark& a = ctx->marks[i];
@@ -443,6 +452,7 @@ extern "C" int aw_profile_read_named(aw_ctx* ctx, int max_classes, int* n_classe
 // frequencies evaluated like np.fft.rfftfreq (k * (sr / 1024) in float64).
 extern "C" int aw_band_bins(aw_ctx* ctx, int sample_rate, int* bin0, int* nbins) {
   AW_REQUIRE(ctx && bin0 && nbins, "null argument");
+  if (ctx) cudaSetDevice(ctx->device);
   int lo = -1, hi = -1;
   const double val = 1.0 / (1024.0 * (1.0 / sample_rate));
   for (int k = 0; k <= 512; ++k) {
@@ -857,12 +867,7 @@ static SynArgs syn_base(aw_ctx* ctx, const Dims& d) {
 }
 template <int MODE, int K2LO, int K2HI>
 static int launch_ana_k(aw_ctx* ctx, const Dims& d, const AnaArgs& a, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AW_CUDA(cudaFuncSetAttribute(k_analysis<MODE, K2LO, K2HI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 AW_ANA_SMEM));
-    attr_set = true;
-  }
+  if (raise_smem_limit(ctx, (const void*)k_analysis<MODE, K2LO, K2HI>, AW_ANA_SMEM)) return 1;
   dim3 g((d.T + AW_ANA_FRAMES - 1) / AW_ANA_FRAMES, d.n);
   prof_mark(ctx, st, MODE == ANA_MAG ? "analysis_mag" : "analysis_init");
   k_analysis<MODE, K2LO, K2HI><<<g, 128, AW_ANA_SMEM, st>>>(a);
@@ -881,12 +886,7 @@ static int launch_ana(aw_ctx* ctx, const Dims& d, const AnaArgs& a, cudaStream_t
 }
 template <int MODE, int K2LO, int K2HI>
 static int launch_syn_k(aw_ctx* ctx, const Dims& d, const SynArgs& s, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AW_CUDA(cudaFuncSetAttribute(k_synthesis<MODE, K2LO, K2HI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 AW_SYN_SMEM));
-    attr_set = true;
-  }
+  if (raise_smem_limit(ctx, (const void*)k_synthesis<MODE, K2LO, K2HI>, AW_SYN_SMEM)) return 1;
   dim3 g((d.T + 3 + AW_SYN_HOPS - 1) / AW_SYN_HOPS, d.n);
   prof_mark(ctx, st, MODE == SYN_OOB ? "synthesis_oob" : "synthesis_wave");
   k_synthesis<MODE, K2LO, K2HI><<<g, 128, AW_SYN_SMEM, st>>>(s);
@@ -903,12 +903,7 @@ static int launch_syn(aw_ctx* ctx, const Dims& d, const SynArgs& s, cudaStream_t
 }
 template <int MODE, int K2LO, int K2HI>
 static int launch_spec_k(aw_ctx* ctx, const Dims& d, SpecArgs& a, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AW_CUDA(cudaFuncSetAttribute(k_spec<MODE, K2LO, K2HI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 AW_SP_SMEM));
-    attr_set = true;
-  }
+  if (raise_smem_limit(ctx, (const void*)k_spec<MODE, K2LO, K2HI>, AW_SP_SMEM)) return 1;
   a.n_clips = d.n; a.T = d.T; a.L = d.L; a.bin0 = d.bin0; a.nbins = d.nb;
   a.tiles = (d.T + AW_SP_FA - 1) / AW_SP_FA;
   a.window = ctx->d_window; a.twiddle = ctx->d_twiddle; a.env256 = ctx->d_env256;
@@ -1214,6 +1209,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
 
 extern "C" int aw_embed_state(aw_ctx* ctx, int which, float* d_dst, int64_t capacity, void* stream) {
   AW_REQUIRE(ctx && d_dst, "null argument");
+  if (ctx) cudaSetDevice(ctx->device);
   const size_t cnt = (size_t)ctx->last_n * ctx->last_T * ctx->last_nb;
   AW_REQUIRE(cnt > 0, "aw_embed_state: no embed has run");
   if (which >= 10) {
@@ -1248,6 +1244,7 @@ extern "C" int aw_decide_and_count(aw_ctx* ctx, const float* d_values, const int
                                    int n_clips, int32_t* d_bits_out, int32_t* d_err_per_clip,
                                    uint64_t* d_counters, void* stream) {
   AW_REQUIRE(ctx && d_values, "null argument");
+  if (ctx) cudaSetDevice(ctx->device);
   prof_mark(ctx, (cudaStream_t)stream, "decide_count");
   k_decide_count<<<(n_clips + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
       d_values, d_ref_bits, ctx->threshold, n_clips, d_bits_out, d_err_per_clip,
@@ -1261,6 +1258,7 @@ extern "C" int aw_snr_batch(aw_ctx* ctx, const float* d_out, int64_t out_stride,
                             const float* d_target, int64_t tgt_stride, int n_clips, int n,
                             double* d_snr, double* d_snr_sum, void* stream) {
   AW_REQUIRE(ctx && d_out && d_target && d_snr, "null argument");
+  if (ctx) cudaSetDevice(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (ensure(ctx->bstat, (size_t)std::max(n_clips, 1) * 16)) return 1;
   AW_CUDA(cudaMemsetAsync(ctx->bstat.p, 0, (size_t)n_clips * 16, st));
@@ -1279,6 +1277,7 @@ extern "C" int aw_stft_band(aw_ctx* ctx, const float* d_audio, int n_clips, int 
                             int64_t stride, int sample_rate, int normalize, float* d_mag,
                             float* d_phasor, void* stream) {
   AW_REQUIRE(ctx && d_audio && d_mag, "null argument");
+  if (ctx) cudaSetDevice(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   Dims d;
   if (make_dims(ctx, n_clips, n_samples, sample_rate, &d)) return 1;
@@ -1310,6 +1309,7 @@ extern "C" int aw_stft_band(aw_ctx* ctx, const float* d_audio, int n_clips, int 
 extern "C" int aw_istft_band(aw_ctx* ctx, const float* d_mag, const float* d_phasor, int n_clips,
                              int n_frames, int sample_rate, float* d_wave, void* stream) {
   AW_REQUIRE(ctx && d_mag && d_phasor && d_wave, "null argument");
+  if (ctx) cudaSetDevice(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   Dims d;
   if (make_dims(ctx, n_clips, AW_HOP * (n_frames - 1) + 1, sample_rate, &d)) return 1;
@@ -1328,6 +1328,7 @@ extern "C" int aw_istft_band(aw_ctx* ctx, const float* d_mag, const float* d_pha
 extern "C" int aw_gemm(aw_ctx* ctx, const float* d_a, const float* d_b, float* d_d, int rows, int n,
                        int k, int prec, void* stream) {
   AW_REQUIRE(ctx && d_a && d_b && d_d, "null argument");
+  if (ctx) cudaSetDevice(ctx->device);
   AW_REQUIRE(rows % 128 == 0 && k % 32 == 0 && n % 64 == 0, "aw_gemm: unsupported shape");
   AW_REQUIRE(n % bn_for(n) == 0, "aw_gemm: n must be a multiple of its tile (%d)", bn_for(n));
   cudaStream_t st = (cudaStream_t)stream;
@@ -1359,6 +1360,7 @@ static dim3 ew_grid(int n, int n_clips) { return dim3(std::min((n + 1023) / 1024
 extern "C" int aw_attack_pcm(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t in_stride,
                              int bits, float* d_out, int64_t out_stride, void* stream) {
   AW_REQUIRE(ctx && d_in && d_out, "null argument");
+  if (ctx) cudaSetDevice(ctx->device);
   float S, lo, hi;
   switch (bits) {
     case 8: S = 127.f; lo = -128.f; hi = 127.f; break;
@@ -1383,6 +1385,7 @@ extern "C" int aw_attack_decimate_interp(aw_ctx* ctx, const float* d_in, int n_c
                                          int64_t in_stride, int factor, float* d_out,
                                          int64_t out_stride, void* stream) {
   AW_REQUIRE(ctx && d_in && d_out && factor >= 2, "bad argument");
+  if (ctx) cudaSetDevice(ctx->device);
   prof_mark(ctx, (cudaStream_t)stream, "attack_decim_interp");
   k_attack_decim_interp<<<ew_grid(n, n_clips), 256, 0, (cudaStream_t)stream>>>(
       d_in, in_stride, n, factor, d_out, out_stride);
@@ -1396,6 +1399,7 @@ extern "C" int aw_attack_upfirdn(aw_ctx* ctx, const float* d_in, int n_clips, in
                                  int down, int first_out, int n_out, float* d_out,
                                  int64_t out_stride, void* stream) {
   AW_REQUIRE(ctx && d_in && d_out && d_h_tf, "null argument");
+  if (ctx) cudaSetDevice(ctx->device);
   prof_mark(ctx, (cudaStream_t)stream, "attack_upfirdn");
   k_upfirdn<<<ew_grid(n_out, n_clips), 256, 0, (cudaStream_t)stream>>>(
       d_in, in_stride, n_in, d_h_tf, taps_per_phase, up, down, first_out, n_out, d_out, out_stride);
@@ -1435,6 +1439,7 @@ extern "C" int aw_attack_lfilter(aw_ctx* ctx, const float* d_in, int n_clips, in
                                  int64_t in_stride, const double* b, const double* a, int order,
                                  int warm, float* d_out, int64_t out_stride, void* stream) {
   AW_REQUIRE(ctx && d_in && d_out && b && a, "null argument");
+  if (ctx) cudaSetDevice(ctx->device);
   IirArgs ia;
   if (fill_iir(ia, b, a, nullptr, order)) return 1;
   dim3 g;
@@ -1453,6 +1458,7 @@ extern "C" int aw_attack_filtfilt(aw_ctx* ctx, const float* d_in, int n_clips, i
                                   const double* zi, int order, int warm, float* d_out,
                                   int64_t out_stride, void* stream) {
   AW_REQUIRE(ctx && d_in && d_out && b && a && zi, "null argument");
+  if (ctx) cudaSetDevice(ctx->device);
   const int pad = 3 * (order + 1);
   AW_REQUIRE(n > pad, "The length of the input vector x must be greater than padlen, which is %d.", pad);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1483,6 +1489,7 @@ extern "C" int aw_attack_delete(aw_ctx* ctx, const float* d_in, int n_clips, int
                                 const int32_t* d_start, int n_delete, float* d_out,
                                 int64_t out_stride, void* stream) {
   AW_REQUIRE(ctx && d_in && d_out && d_start && n_delete >= 0 && n_delete < n, "bad argument");
+  if (ctx) cudaSetDevice(ctx->device);
   prof_mark(ctx, (cudaStream_t)stream, "attack_delete");
   k_attack_delete<<<ew_grid(n - n_delete, n_clips), 256, 0, (cudaStream_t)stream>>>(
       d_in, in_stride, n - n_delete, d_start, n_delete, d_out, out_stride);
@@ -1495,6 +1502,7 @@ extern "C" int aw_attack_suppress(aw_ctx* ctx, const float* d_in, int n_clips, i
                                   int64_t in_stride, const int32_t* d_start, int n_zero,
                                   float* d_out, int64_t out_stride, void* stream) {
   AW_REQUIRE(ctx && d_in && d_out && d_start, "bad argument");
+  if (ctx) cudaSetDevice(ctx->device);
   prof_mark(ctx, (cudaStream_t)stream, "attack_suppress");
   k_attack_suppress<<<ew_grid(n, n_clips), 256, 0, (cudaStream_t)stream>>>(
       d_in, in_stride, n, d_start, n_zero, d_out, out_stride);
@@ -1506,6 +1514,7 @@ extern "C" int aw_attack_suppress(aw_ctx* ctx, const float* d_in, int n_clips, i
 extern "C" int aw_attack_cropout(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t in_stride,
                                  int n_drop, float* d_out, int64_t out_stride, void* stream) {
   AW_REQUIRE(ctx && d_in && d_out && n_drop >= 0 && n_drop < n, "bad argument");
+  if (ctx) cudaSetDevice(ctx->device);
   prof_mark(ctx, (cudaStream_t)stream, "attack_affine");
   k_attack_affine<<<ew_grid(n - n_drop, n_clips), 256, 0, (cudaStream_t)stream>>>(
       d_in + n_drop, in_stride, n - n_drop, 1.0f, nullptr, 0, 0.f, d_out, out_stride);
@@ -1518,6 +1527,7 @@ extern "C" int aw_attack_affine(aw_ctx* ctx, const float* d_in, int n_clips, int
                                 float gain, const float* d_noise, int64_t noise_stride, float sigma,
                                 float* d_out, int64_t out_stride, void* stream) {
   AW_REQUIRE(ctx && d_in && d_out, "null argument");
+  if (ctx) cudaSetDevice(ctx->device);
   prof_mark(ctx, (cudaStream_t)stream, "attack_affine");
   k_attack_affine<<<ew_grid(n, n_clips), 256, 0, (cudaStream_t)stream>>>(
       d_in, in_stride, n, gain, d_noise, noise_stride, sigma, d_out, out_stride);
