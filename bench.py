@@ -375,6 +375,7 @@ def main():
                 key = r["kernel"].split(" ")[0]
                 if key in tr:       # dram bytes per launch per clip from one ncu --set full capture
                     r["traffic"] = tr[key]["dram_bytes_per_clip"] * n_w
+                    r["ncu"] = {k: v for k, v in tr[key].items() if k.endswith("_pct")}
         except Exception:  # noqa: BLE001
             pass
 
