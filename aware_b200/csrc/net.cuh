@@ -173,15 +173,30 @@ __global__ void __launch_bounds__(128) k_p0(const float* __restrict__ M, int T, 
   const float fmu = st.mu, fr = st.rstd;
   const float inv = (float)(1.0 / ((double)sigma_in[clip] + 1e-8));
   const float* Mc = M + (long long)clip * T * AW_NMEL + c;
-  for (int j = j0; j < min(j0 + AW_P0_ROWS, Tp_pad); ++j) {
-    float p = 0.f;
-    if (j < Tp) {
-      const float g0 = (Mc[(long long)(2 * j) * AW_NMEL] - fmu) * fr * inv;
-      const float g1 = (Mc[(long long)(2 * j + 1) * AW_NMEL] - fmu) * fr * inv;
-      p = 0.5f * (g0 + g1);
-      if (round_tf32) p = to_tf32(p);
+  // 8 pooled rows per batch: 16 independent loads in flight per thread (latency-bound otherwise)
+#pragma unroll 1
+  for (int jb = j0; jb < min(j0 + AW_P0_ROWS, Tp_pad); jb += 8) {
+    float a0[8], a1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = jb + i;
+      const bool ok = j < Tp;
+      a0[i] = ok ? Mc[(long long)(2 * j) * AW_NMEL] : 0.f;
+      a1[i] = ok ? Mc[(long long)(2 * j + 1) * AW_NMEL] : 0.f;
     }
-    act_st(P0 + ((long long)clip * Tp_pad + j) * AW_NMEL + c, p);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = jb + i;
+      if (j >= Tp_pad) break;
+      float p = 0.f;
+      if (j < Tp) {
+        const float g0 = (a0[i] - fmu) * fr * inv;
+        const float g1 = (a1[i] - fmu) * fr * inv;
+        p = 0.5f * (g0 + g1);
+        if (round_tf32) p = to_tf32(p);
+      }
+      act_st(P0 + ((long long)clip * Tp_pad + j) * AW_NMEL + c, p);
+    }
   }
 }
 
@@ -454,11 +469,23 @@ __global__ void __launch_bounds__(128) k_p0_bwd_reduce(const float* __restrict__
   const ChanStats st = cs[(long long)clip * AW_NMEL + c];
   double s1 = 0.0, s2 = 0.0;
   const int t1 = min(t0 + AW_P0B_FRAMES, 2 * Tp);
-  for (int t = t0; t < t1; ++t) {
-    const float dg = (0.5f * ginv) * dP0[((long long)clip * Tp_pad + (t >> 1)) * AW_NMEL + c];
-    const float mh = (M[((long long)clip * T + t) * AW_NMEL + c] - st.mu) * st.rstd;
-    s1 += dg;
-    s2 += (double)dg * mh;
+#pragma unroll 1
+  for (int tb = t0; tb < t1; tb += 8) {
+    float d8[8], m8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = tb + i;
+      const bool ok = t < t1;
+      d8[i] = ok ? dP0[((long long)clip * Tp_pad + (t >> 1)) * AW_NMEL + c] : 0.f;
+      m8[i] = ok ? M[((long long)clip * T + t) * AW_NMEL + c] : st.mu;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float dg = (0.5f * ginv) * d8[i];
+      const float mh = (m8[i] - st.mu) * st.rstd;
+      s1 += dg;
+      s2 += (double)dg * mh;
+    }
   }
   double* p = bpart + (((long long)clip * gridDim.x + blockIdx.x) * AW_NMEL + c) * 2;
   p[0] = s1;
@@ -519,14 +546,22 @@ __global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ 
   const P0BwdCoef k = coef[(long long)clip * AW_NMEL + c];
   const float A1 = k.A1, A2 = k.A2;
   const int nf = min(AW_P0A_FRAMES, T - t0);
-  for (int f = 0; f < nf; ++f) {
-    const int t = t0 + f;
-    const float dg = t < 2 * Tp ? (0.5f * ginv) * dP0[((long long)clip * Tp_pad + (t >> 1)) * AW_NMEL + c] : 0.f;
-    const float mh = (M[((long long)clip * T + t) * AW_NMEL + c] - st.mu) * st.rstd;
-    const float dmh = alpha * (dg - meanG) - beta * mh;
-    s_dm[f][c] = st.rstd * (dmh - A1 - mh * A2);
+  {
+    float d16[AW_P0A_FRAMES], m16[AW_P0A_FRAMES];          // all loads of the tile in flight together
+#pragma unroll
+    for (int f = 0; f < AW_P0A_FRAMES; ++f) {
+      const int t = t0 + f;
+      d16[f] = (f < nf && t < 2 * Tp) ? dP0[((long long)clip * Tp_pad + (t >> 1)) * AW_NMEL + c] : 0.f;
+      m16[f] = f < nf ? M[((long long)clip * T + t) * AW_NMEL + c] : st.mu;
+    }
+#pragma unroll
+    for (int f = 0; f < AW_P0A_FRAMES; ++f) {
+      const float dg = (0.5f * ginv) * d16[f];
+      const float mh = (m16[f] - st.mu) * st.rstd;
+      const float dmh = alpha * (dg - meanG) - beta * mh;
+      s_dm[f][c] = f < nf ? st.rstd * (dmh - A1 - mh * A2) : 0.f;
+    }
   }
-  for (int f = nf; f < AW_P0A_FRAMES; ++f) s_dm[f][c] = 0.f;
   __syncthreads();
   // one thread per band bin: its (weight, channel) taps are fetched once and applied to all frames
   double s2 = 0.0;
