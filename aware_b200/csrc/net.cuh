@@ -372,9 +372,17 @@ __global__ void __launch_bounds__(256) k_head_partial(HeadArgs<AT> a) {
   const AT* P = a.P4 + ((long long)clip * a.Tp_pad + tile * 128) * 64;
   const int rows = min(128, a.Tp - tile * 128);
   double sp = 0.0, sn = 0.0, np_ = 0.0;
-  for (int j = g; j < rows; j += 4) {
-    const float p = act_ld(P + (long long)j * 64 + c);
-    if (p > 0.f) { sp += p; np_ += 1.0; } else { sn += (double)(p * (1.0f / AW_LEAKY)); }
+#pragma unroll 1
+  for (int jb = g; jb < rows; jb += 32) {                  // 8 independent loads per batch
+    float p8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p8[i] = jb + 4 * i < rows ? act_ld(P + (long long)(jb + 4 * i) * 64 + c) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (jb + 4 * i >= rows) break;
+      const float p = p8[i];
+      if (p > 0.f) { sp += p; np_ += 1.0; } else { sn += (double)(p * (1.0f / AW_LEAKY)); }
+    }
   }
   s_acc[g][c][0] = sp; s_acc[g][c][1] = sn; s_acc[g][c][2] = np_;
   __syncthreads();
@@ -445,16 +453,24 @@ __global__ void __launch_bounds__(256) k_head_seed(HeadArgs<AT> a) {
   const float dz = k.x, a1 = k.y, a2 = k.z, rstd = k.w;
   const AT* P = a.P4 + ((long long)clip * a.Tp_pad + tile * 128) * 64;
   AT* D = a.dH4 + ((long long)clip * a.Tp_pad + tile * 128) * 64;
-  for (int j = g; j < 128; j += 4) {
-    float o = 0.f;
-    if (tile * 128 + j < a.Tp && c < 2 * AW_NBITS) {
-      const float p = act_ld(P + (long long)j * 64 + c);
-      const bool pos = p > 0.f;
-      const float dh = pos ? dz : AW_LEAKY * dz;
-      o = a.gscale * (rstd * (dh - a1 - (pos ? p : p * (1.0f / AW_LEAKY)) * a2));
-      if (a.round_tf32) o = to_tf32(o);
+#pragma unroll 1
+  for (int jb = g; jb < 128; jb += 32) {                   // 8 independent loads per batch
+    float p8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p8[i] = act_ld(P + (long long)(jb + 4 * i) * 64 + c);   // pad rows exist (zeros)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = jb + 4 * i;
+      float o = 0.f;
+      if (tile * 128 + j < a.Tp && c < 2 * AW_NBITS) {
+        const float p = p8[i];
+        const bool pos = p > 0.f;
+        const float dh = pos ? dz : AW_LEAKY * dz;
+        o = a.gscale * (rstd * (dh - a1 - (pos ? p : p * (1.0f / AW_LEAKY)) * a2));
+        if (a.round_tf32) o = to_tf32(o);
+      }
+      act_st(D + (long long)j * 64 + c, o);
     }
-    act_st(D + (long long)j * 64 + c, o);
   }
 }
 
