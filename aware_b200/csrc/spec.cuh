@@ -260,13 +260,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
                : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-// whole-CTA L2 prefetch of [base, base + bytes)
-__device__ __forceinline__ void prefetch_l2(const void* base, long long bytes, int tid, int nthreads) {
-  const char* p = reinterpret_cast<const char*>(base);
-  for (long long o = (long long)tid * 128; o < bytes; o += (long long)nthreads * 128)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
-}
-
 // ---------------------------------------------------------------------------
 enum { SPEC_FWD = 0, SPEC_BWD = 1 };
 
@@ -342,30 +335,6 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
     const int m0 = AW_HOP * ta0;                         // padded-axis origin of s_buf
     const long long fbase = (long long)clip * T;
     __syncthreads();                                     // tables / previous item done with s_buf
-
-    // L2 prefetch of the NEXT item's operands (one whole tile ahead of their first use)
-    {
-      const int nitem = item + gridDim.x;
-      if (nitem < n_items) {
-        const int nclip = nitem / a.tiles, ntile = nitem - nclip * a.tiles;
-        int nt0 = ntile * AW_SP_FA;
-        if (short_last && ntile == a.tiles - 1) nt0 = T - 8;
-        const int f0 = max(nt0 - 3, 0), f1 = min(nt0 + AW_SP_FA + 3, T);
-        const long long eo = ((long long)nclip * T + f0) * nb;
-        const long long en = (long long)(f1 - f0) * nb;
-        prefetch_l2(a.amp + eo, en * 4, tid, 32 * AW_SP_WARPS);
-        prefetch_l2(a.ph + eo, en * 8, tid, 32 * AW_SP_WARPS);
-        if (MODE == SPEC_BWD) {
-          const long long wo = ((long long)nclip * T + nt0) * nb;
-          const long long wn = (long long)(min(nt0 + AW_SP_FA, T) - nt0) * nb;
-          prefetch_l2(a.u + wo, wn * 8, tid, 32 * AW_SP_WARPS);
-          prefetch_l2(a.m + wo, wn * 4, tid, 32 * AW_SP_WARPS);
-          prefetch_l2(a.v + wo, wn * 4, tid, 32 * AW_SP_WARPS);
-          prefetch_l2(a.c + wo, wn * 4, tid, 32 * AW_SP_WARPS);
-          prefetch_l2(a.c0 + wo, wn * 4, tid, 32 * AW_SP_WARPS);
-        }
-      }
-    }
 
     // ---------------- phase 1: inverse transforms + streaming overlap-add ----------------
     {
