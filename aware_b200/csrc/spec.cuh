@@ -363,7 +363,6 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
         for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
       const float scale = MODE == SPEC_FWD ? 1.0f / AW_NFFT : 0.5f;
       constexpr int NK = K2HI - K2LO + 1;
-      // operands of the next frame pair are fetched while the current pair is transformed
       float pa_[NK], pb_[NK];
       float2 qa_[NK], qb_[NK];
       auto fetch = [&](int pr) {
@@ -378,13 +377,11 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
           qa_[k2 - K2LO] = a.ph[oa + bc]; qb_[k2 - K2LO] = a.ph[ob + bc];
         }
       };
-      constexpr bool PF = NK <= 3;                       // wide bands: no registers to spare
-      if (PF) fetch(0);
 #pragma unroll 1
       for (int pr = 0; pr < 4; ++pr) {
         const int ta = fs + 2 * pr, tb = ta + 1;
         const bool va = ta >= 0 && ta < T, vb = tb >= 0 && tb < T;
-        if (!PF) fetch(pr);
+        fetch(pr);
         float re[32], im[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) { re[j] = 0.f; im[j] = 0.f; }
@@ -415,7 +412,6 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
             im[31 - j] = lane ? i_hi : i_l0;
           }
         }
-        if (PF && pr < 3) fetch(pr + 1);
         if (va || vb)                                    // warp-uniform
           warp_fft1024_p<1, GROUPS, 0xffffffffu>(re, im, my_tr, s_tw, lane);
         // sliding overlap-add with the synthesis window folded into the accumulation:
