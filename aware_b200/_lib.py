@@ -13,6 +13,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libaware_b200.so")
 
 PREC_TF32, PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2, 3
+OPT_THRESHOLD, OPT_EXACT_MARGIN = 0, 1
+STAT_DETECT_CLIPS, STAT_REEVAL_CLIPS = 0, 1
+SCALE_NONE, SCALE_SIGNED_MAX = 0, 1
 
 
 class AwModel(C.Structure):
@@ -35,12 +38,15 @@ SIGNATURES = {
     "aw_ctx_set_precision": (_i, [_vp, _i]),
     "aw_band_bins": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i)]),
     "aw_launch_count": (_i64, [_vp]),
+    "aw_ctx_set_option": (_i, [_vp, _i, C.c_double]),
+    "aw_ctx_get_stat": (_i, [_vp, _i, C.POINTER(_i64)]),
+    "aw_embed_status": (_i, [_vp, _vp, _i, _vp]),
     "aw_profile_enable": (_i, [_vp, _i]),
     "aw_profile_read": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i),
                              C.POINTER(_i64), _dp]),
     "aw_profile_read_named": (_i, [_vp, _i, C.POINTER(_i), C.c_char_p, C.POINTER(_i64), _dp]),
     "aw_detect_batch": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp]),
-    "aw_embed_batch": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _i, _vp, _vp, _i64, _vp, _vp, _i, _vp]),
+    "aw_embed_batch": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _i, _vp, _i, _vp, _i64, _vp, _vp, _i, _vp]),
     "aw_embed_state": (_i, [_vp, _i, _vp, _i64, _vp]),
     "aw_decide_and_count": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "aw_snr_batch": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _vp, _vp, _vp]),

@@ -4,8 +4,10 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <math.h>
 #include <stdarg.h>
+#include <limits.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -78,6 +80,15 @@ struct aw_ctx {
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   Buf accum, peakx, mag, ph_u, ph_q, c0, c, m, v, cbest, dA, yoob, y, M, cs, sigma;
   Buf act[5], ga, gb, dh4, dp0, part, stat[5], bstat, values, best, improved, pattern, itc, steps;
+  Buf gsc;               // [clip] per-clip loss scale of the back-propagated gradient (16-bit modes)
+  Buf nonfinite;         // [n_clips of the last embed call] 1 = a non-finite gradient was skipped
+  Buf smax;              // [clip] signed max of the input, order-preserving int encoding (scale_mode 1)
+  Buf lowm;              // [1 + n_clips] low-margin count + per-clip flags (aw_detect_batch re-evaluation)
+  int* h_lowm = nullptr; // pinned host mirror of lowm
+  size_t h_lowm_cap = 0;
+  double exact_margin = 1e-3;      // AW_OPT_EXACT_MARGIN
+  int64_t stat_detect_clips = 0, stat_reeval_clips = 0;
+  int last_embed_clips = 0;
   int ws_rows = 0;
   // activation tensor maps, [0] = float32 view, [1] = bf16 view of the same buffers
   CUtensorMap tm_act[2][4], tm_dh4[2], tm_ga1024[2], tm_ga512[2], tm_gb1024[2];
@@ -340,7 +351,8 @@ static std::vector<Buf*> all_bufs(aw_ctx* ctx) {
                  &ctx->act[4], &ctx->ga, &ctx->gb, &ctx->dh4, &ctx->dp0, &ctx->part, &ctx->stat[0],
                  &ctx->stat[1], &ctx->stat[2], &ctx->stat[3], &ctx->stat[4], &ctx->bstat,
                  &ctx->values, &ctx->best, &ctx->improved, &ctx->pattern, &ctx->itc, &ctx->steps,
-                 &ctx->scal, &ctx->zoob, &ctx->p0coef, &ctx->p0scal, &ctx->hpart, &ctx->hcoef, &ctx->red_a, &ctx->red_b, &ctx->red_c};
+                 &ctx->scal, &ctx->zoob, &ctx->p0coef, &ctx->p0scal, &ctx->hpart, &ctx->hcoef, &ctx->red_a, &ctx->red_b, &ctx->red_c,
+                 &ctx->gsc, &ctx->nonfinite, &ctx->smax, &ctx->lowm};
 }
 
 extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
@@ -357,6 +369,7 @@ extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
   if (ctx->gstream) cudaStreamDestroy(ctx->gstream);
   if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
   if (ctx->ev_out) cudaEventDestroy(ctx->ev_out);
+  if (ctx->h_lowm) cudaFreeHost(ctx->h_lowm);
   cudaFree(ctx->d_window);
   cudaFree(ctx->d_twiddle);
   cudaFree(ctx->d_env256);
@@ -380,6 +393,38 @@ extern "C" int aw_ctx_set_precision(aw_ctx* ctx, int prec) {
 }
 
 extern "C" int64_t aw_launch_count(aw_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int aw_ctx_set_option(aw_ctx* ctx, int option, double value) {
+  AW_REQUIRE(ctx, "null ctx");
+  switch (option) {
+    case AW_OPT_THRESHOLD: ctx->threshold = (float)value; return 0;
+    case AW_OPT_EXACT_MARGIN:
+      AW_REQUIRE(value >= 0.0, "aw_ctx_set_option: margin must be >= 0");
+      ctx->exact_margin = value;
+      return 0;
+    default: return set_error("aw_ctx_set_option: unknown option %d", option);
+  }
+}
+
+extern "C" int aw_ctx_get_stat(aw_ctx* ctx, int which, int64_t* out) {
+  AW_REQUIRE(ctx && out, "null argument");
+  switch (which) {
+    case AW_STAT_DETECT_CLIPS: *out = ctx->stat_detect_clips; return 0;
+    case AW_STAT_REEVAL_CLIPS: *out = ctx->stat_reeval_clips; return 0;
+    default: return set_error("aw_ctx_get_stat: unknown statistic %d", which);
+  }
+}
+
+// per-clip flags of the last aw_embed_batch call: 1 = a non-finite gradient was met (its NAdam
+// update was skipped); a reduced-precision loop that flags a clip should be re-run in TF32
+extern "C" int aw_embed_status(aw_ctx* ctx, int32_t* d_flags, int n_clips, void* stream) {
+  AW_REQUIRE(ctx && d_flags, "null argument");
+  AW_REQUIRE(n_clips == ctx->last_embed_clips && ctx->nonfinite.p, "aw_embed_status: last embed had %d clips, asked for %d",
+             ctx->last_embed_clips, n_clips);
+  cudaSetDevice(ctx->device);
+  AW_CUDA(cudaMemcpyAsync(d_flags, ctx->nonfinite.p, (size_t)n_clips * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
 
 extern "C" int aw_profile_enable(aw_ctx* ctx, int on) {
   AW_REQUIRE(ctx, "null ctx");
@@ -589,6 +634,7 @@ static int ensure_net_ws(aw_ctx* ctx, const Dims& d, bool backward) {
   if (ensure(ctx->best, n * 4)) return 1;
   if (ensure(ctx->improved, n * 4)) return 1;
   if (ensure(ctx->itc, 4)) return 1;
+  if (ensure(ctx->gsc, n * 4)) return 1;
   if (backward) {
     void *b0 = ctx->ga.p, *b1 = ctx->gb.p, *b2 = ctx->dh4.p;
     if (ensure(ctx->ga, R * 1024 * 4)) return 1;
@@ -683,16 +729,15 @@ template <> struct ModeOf<__half> {
   static const CUtensorMap& wt(aw_ctx* c, int l) { return c->tm_wt16h[l]; }
   static const void* wp(aw_ctx* c, int l) { return c->d_w16h[l]; }
   static const void* wtp(aw_ctx* c, int l) { return c->d_wt16h[l]; }
-  // gradients are ~1e-4 .. 1e-8 at T' = 861 and shrink like 1/T' (the head seeds dz / T'): a
-  // power-of-two loss scale proportional to T' keeps them in fp16's normal range for any clip
-  // length (removed again where dP0 is consumed); overflow would need |dH| > 16 at T' = 861
+  // gradients are ~1e-4 .. 1e-8 at T' = 861, shrink like 1/T' (the head seeds dz / T') and shrink
+  // further as tanh saturates: k_head_final picks a per-clip power-of-two loss scale every
+  // iteration that puts the largest seeded dz at 0.5 (removed again where dP0 is consumed)
   static constexpr float GSCALE = 4096.0f;
 };
+// target magnitude of the seeded gradient for the per-clip power-of-two loss scale that
+// k_head_final chooses every iteration (0 = no scaling: fp32 / TF32 / bf16 storage)
 template <typename AT>
-static float grad_scale(const Dims& d) {
-  if (ModeOf<AT>::GSCALE == 1.0f) return 1.0f;
-  return exp2f(roundf(log2f(ModeOf<AT>::GSCALE * (float)d.Tp / 861.0f)));
-}
+static float grad_target() { return ModeOf<AT>::GSCALE == 1.0f ? 0.0f : 0.5f; }
 
 template <typename AT>
 static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseMel& sm,
@@ -801,7 +846,7 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
   dim3 g1((2 * d.Tp + AW_P0B_FRAMES - 1) / AW_P0B_FRAMES, d.n);
   prof_mark(ctx, st, "p0_bwd_reduce");
   k_p0_bwd_reduce<<<g1, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
-                                      (ChanStats*)ctx->cs.p, acc.bpart, 1.0f / grad_scale<AT>(d));
+                                      (ChanStats*)ctx->cs.p, acc.bpart, (const float*)ctx->gsc.p);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   dim3 g2((d.T + AW_P0A_FRAMES - 1) / AW_P0A_FRAMES, d.n);
@@ -818,7 +863,7 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
                                      (ChanStats*)ctx->cs.p, (P0BwdCoef*)ctx->p0coef.p,
                                      (P0BwdScal*)ctx->p0scal.p, sm, d.nb, (float*)ctx->dA.p,
                                      euler_s2 ? (const float*)ctx->mag.p : nullptr, acc.s2_part,
-                                     1.0f / grad_scale<AT>(d));
+                                     (const float*)ctx->gsc.p);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
@@ -835,7 +880,8 @@ static int run_head(aw_ctx* ctx, const Dims& d, const float* pattern, float* val
   h.dH4 = backward ? (AT*)ctx->dh4.p : nullptr;
   h.it_ptr = (int*)ctx->itc.p; h.n_clips = n_total;
   h.round_tf32 = ctx->prec == AW_PREC_TF32;
-  h.gscale = grad_scale<AT>(d);
+  h.gscale = grad_target<AT>();
+  h.gsc = (float*)ctx->gsc.p;
   h.hpart = (double*)ctx->hpart.p;
   h.hcoef = (float*)ctx->hcoef.p;
   prof_mark(ctx, st, "head");
@@ -922,12 +968,21 @@ static int launch_spec(aw_ctx* ctx, const Dims& d, SpecArgs& a, cudaStream_t st)
   if (lo >= 1 && hi <= 8) return launch_spec_k<MODE, 1, 8>(ctx, d, a, st);
   return launch_spec_k<MODE, 0, 15>(ctx, d, a, st);
 }
+__global__ void k_fill_int(int* p, int v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+// smax != null: also the signed max of every clip (order-encoded int, see k_peak)
 static int launch_peak(aw_ctx* ctx, const float* x, int64_t stride, int n, int n_clips,
-                       unsigned long long* peak, cudaStream_t st) {
+                       unsigned long long* peak, cudaStream_t st, int* smax = nullptr) {
   AW_CUDA(cudaMemsetAsync(peak, 0, (size_t)n_clips * 8, st));
-  dim3 g(std::min((n + 2047) / 2048, std::max(64, 8192 / n_clips)), n_clips);
+  if (smax) {
+    k_fill_int<<<(n_clips + 255) / 256, 256, 0, st>>>(smax, INT_MIN, n_clips);
+    ctx->launches++;
+  }
+  dim3 g(std::min((n + 4095) / 4096, std::max(64, 8192 / n_clips)), n_clips);
   prof_mark(ctx, st, "peak");
-  k_peak<<<g, 256, 0, st>>>(x, stride, n, peak);
+  k_peak<<<g, 256, 0, st>>>(x, stride, n, peak, smax);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
@@ -941,11 +996,8 @@ static int begin_pass(aw_ctx* ctx, int n, int* it, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------
-extern "C" int aw_detect_batch(aw_ctx* ctx, const float* d_audio, int n_clips, int n_samples,
-                               int64_t stride, int sample_rate, float* d_values, void* stream) {
-  AW_REQUIRE(ctx && d_audio && d_values, "aw_detect_batch: null argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  AW_CUDA(cudaSetDevice(ctx->device));
+static int detect_pipeline(aw_ctx* ctx, const float* d_audio, int n_clips, int n_samples, int64_t stride,
+                           int sample_rate, float* d_values, cudaStream_t st) {
   Dims d;
   if (make_dims(ctx, n_clips, n_samples, sample_rate, &d)) return 1;
   if (ensure_net_ws(ctx, d, false)) return 1;
@@ -961,20 +1013,81 @@ extern "C" int aw_detect_batch(aw_ctx* ctx, const float* d_audio, int n_clips, i
   if (launch_ana<ANA_MAG>(ctx, d, a, st)) return 1;
   if (ctx->prec == AW_PREC_BF16) {
     if (net_forward<__nv_bfloat16>(ctx, d, acc, sm, st)) return 1;
-    if (run_head<__nv_bfloat16>(ctx, d, nullptr, d_values, nullptr, d.n, false, st)) return 1;
-    prof_mark(ctx, st, nullptr);
-    return 0;
+    return run_head<__nv_bfloat16>(ctx, d, nullptr, d_values, nullptr, d.n, false, st);
   }
   if (ctx->prec == AW_PREC_FP16) {
     if (net_forward<__half>(ctx, d, acc, sm, st)) return 1;
-    if (run_head<__half>(ctx, d, nullptr, d_values, nullptr, d.n, false, st)) return 1;
+    return run_head<__half>(ctx, d, nullptr, d_values, nullptr, d.n, false, st);
+  }
+  if (net_forward<float>(ctx, d, acc, sm, st)) return 1;
+  return run_head<float>(ctx, d, nullptr, d_values, nullptr, d.n, false, st);
+}
+
+// flags[0] = number of clips with min_i |v_i - thr| < margin, flags[1 + clip] = 1 for those clips
+__global__ void __launch_bounds__(128) k_flag_low_margin(const float* __restrict__ values, float thr, float margin,
+                                                         int n_clips, int* __restrict__ flags) {
+  const int clip = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (clip >= n_clips) return;
+  const float dist = lane < AW_NBITS ? fabsf(values[(long long)clip * AW_NBITS + lane] - thr) : INFINITY;
+  const unsigned m = __ballot_sync(0xffffffffu, !(dist >= margin));      // NaN counts as low margin
+  if (lane == 0) {
+    flags[1 + clip] = m != 0;
+    if (m) atomicAdd(flags, 1);
+  }
+}
+
+// The tensor-core pass (TF32 / 16-bit operands) moves a detector output by up to ~2e-4, so a bit
+// whose |v - threshold| is below `exact_margin` (default 1e-3) could decode differently from the
+// reference's fp32 arithmetic (utils/watermark/decoder.py:51,63 is a strict '>').  Those clips --
+// none on watermarked audio, a few on un-watermarked or heavily attacked audio -- are evaluated
+// again through the exact CUDA-core GEMMs (float64 accumulation, <= 7e-7 from the reference), so
+// the decoded bits are the reference's.  Costs one 4-byte D2H copy + stream synchronisation per call.
+extern "C" int aw_detect_batch(aw_ctx* ctx, const float* d_audio, int n_clips, int n_samples,
+                               int64_t stride, int sample_rate, float* d_values, void* stream) {
+  AW_REQUIRE(ctx && d_audio && d_values, "aw_detect_batch: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  AW_CUDA(cudaSetDevice(ctx->device));
+  nvtxRangePushA("aw_detect_batch");
+  struct Pop { ~Pop() { nvtxRangePop(); } } pop_;
+  if (detect_pipeline(ctx, d_audio, n_clips, n_samples, stride, sample_rate, d_values, st)) return 1;
+  ctx->stat_detect_clips += n_clips;
+  if (ctx->prec == AW_PREC_FP32 || ctx->exact_margin <= 0.0) {
     prof_mark(ctx, st, nullptr);
     return 0;
   }
-  if (net_forward<float>(ctx, d, acc, sm, st)) return 1;
-  if (run_head<float>(ctx, d, nullptr, d_values, nullptr, d.n, false, st)) return 1;
+  if (ensure(ctx->lowm, (size_t)(1 + n_clips) * 4)) return 1;
+  if (ctx->h_lowm_cap < (size_t)(1 + n_clips)) {
+    if (ctx->h_lowm) cudaFreeHost(ctx->h_lowm);
+    ctx->h_lowm = nullptr;
+    AW_CUDA(cudaMallocHost((void**)&ctx->h_lowm, (size_t)(1 + n_clips) * 4));
+    ctx->h_lowm_cap = (size_t)(1 + n_clips);
+  }
+  int* flags = (int*)ctx->lowm.p;
+  AW_CUDA(cudaMemsetAsync(flags, 0, 4, st));
+  prof_mark(ctx, st, "flag_low_margin");
+  k_flag_low_margin<<<(n_clips + 3) / 4, 128, 0, st>>>(d_values, ctx->threshold, (float)ctx->exact_margin, n_clips, flags);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
   prof_mark(ctx, st, nullptr);
-  return 0;
+  AW_CUDA(cudaMemcpyAsync(ctx->h_lowm, flags, 4, cudaMemcpyDeviceToHost, st));
+  AW_CUDA(cudaStreamSynchronize(st));
+  const int n_low = ctx->h_lowm[0];
+  if (n_low == 0) return 0;
+  AW_CUDA(cudaMemcpyAsync(ctx->h_lowm + 1, flags + 1, (size_t)n_clips * 4, cudaMemcpyDeviceToHost, st));
+  AW_CUDA(cudaStreamSynchronize(st));
+  nvtxRangePushA("exact_reevaluation");
+  const int prev = ctx->prec;
+  ctx->prec = AW_PREC_FP32;
+  int rc = 0;
+  for (int i = 0; i < n_clips && !rc; ++i)
+    if (ctx->h_lowm[1 + i])
+      rc = detect_pipeline(ctx, d_audio + (size_t)i * stride, 1, n_samples, stride, sample_rate,
+                           d_values + (size_t)i * AW_NBITS, st);
+  ctx->prec = prev;
+  nvtxRangePop();
+  prof_mark(ctx, st, nullptr);
+  ctx->stat_reeval_clips += n_low;
+  return rc;
 }
 
 __global__ void k_to_bf16(const float* in, __nv_bfloat16* out, size_t n) {
@@ -1013,12 +1126,16 @@ static void nadam_table(int iters, std::vector<NadamStep>& out) {
 
 extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, int n_samples,
                               int64_t stride, int sample_rate, const int32_t* d_pattern, int iters,
-                              const float* d_scale, float* d_out, int64_t out_stride,
+                              const float* d_scale, int scale_mode, float* d_out, int64_t out_stride,
                               float* d_best_loss, float* d_losses, int wave_clips, void* stream) {
   AW_REQUIRE(ctx && d_audio && d_pattern && d_out, "aw_embed_batch: null argument");
   AW_REQUIRE(iters >= 0, "aw_embed_batch: iters < 0");
+  AW_REQUIRE(scale_mode == AW_SCALE_NONE || scale_mode == AW_SCALE_SIGNED_MAX, "aw_embed_batch: bad scale_mode %d", scale_mode);
+  AW_REQUIRE(!(d_scale && scale_mode != AW_SCALE_NONE), "aw_embed_batch: d_scale and scale_mode are exclusive");
   cudaStream_t user_stream = (cudaStream_t)stream, st = user_stream;
   AW_CUDA(cudaSetDevice(ctx->device));
+  nvtxRangePushA("aw_embed_batch");
+  struct Pop { ~Pop() { nvtxRangePop(); } } pop_;
   // Graph replay needs a capturable stream (the caller's may be the legacy default stream): the
   // whole call runs on the context's stream, ordered after / before the caller's by two events.
   const bool use_graph = ctx->graphs && !ctx->prof_on && iters >= 4;
@@ -1058,6 +1175,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       ensure(ctx->yoob, (size_t)d.n * d.L * 4) || ensure(ctx->y, (size_t)d.n * d.L * 4) ||
       ensure(ctx->zoob, (size_t)d.n * d.L * 4) ||
       ensure(ctx->pattern, (size_t)d.n * AW_NBITS * 4) || ensure(ctx->scal, (size_t)d.n * sizeof(ClipScal)) ||
+      ensure(ctx->nonfinite, (size_t)n_clips * 4) || ensure(ctx->smax, (size_t)d.n * 4) ||
       ensure(ctx->steps, (size_t)(iters > 0 ? iters : 1) * sizeof(NadamStep)))
     return 1;
   SparseMel sm;
@@ -1067,6 +1185,8 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
   if (iters > 0)
     AW_CUDA(cudaMemcpyAsync(ctx->steps.p, tab.data(), tab.size() * sizeof(NadamStep),
                             cudaMemcpyHostToDevice, st));
+  AW_CUDA(cudaMemsetAsync(ctx->nonfinite.p, 0, (size_t)n_clips * 4, st));
+  ctx->last_embed_clips = n_clips;
   AW_CUDA(cudaStreamSynchronize(st));   // `tab` is pageable host memory
 
   for (int w0 = 0; w0 < n_clips; w0 += wave_clips) {
@@ -1084,9 +1204,12 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
         d_pattern + (size_t)w0 * AW_NBITS, (float*)ctx->pattern.p, dw.n * AW_NBITS);
     ctx->launches += 3;
     AW_LAUNCH_CHECK();
-    if (launch_peak(ctx, x, stride, n_samples, dw.n, (unsigned long long*)ctx->peakx.p, st)) return 1;
+    if (launch_peak(ctx, x, stride, n_samples, dw.n, (unsigned long long*)ctx->peakx.p, st,
+                    scale_mode == AW_SCALE_SIGNED_MAX ? (int*)ctx->smax.p : nullptr))
+      return 1;
 
     // ---- pre-STFT, bounds, constant out-of-band waveform (multibit_embedder.py:143-160)
+    nvtxRangePushA("embed:init_stft_bounds_oob");
     AnaArgs a0 = ana_base(ctx, dw);
     a0.sig = x; a0.sig_stride = stride; a0.len = n_samples;
     a0.peak = (unsigned long long*)ctx->peakx.p;
@@ -1100,8 +1223,10 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
     s0.y_oob = (float*)ctx->yoob.p;
     s0.z_oob = (float*)ctx->zoob.p;
     if (launch_syn<SYN_OOB>(ctx, dw, s0, st)) return 1;
+    nvtxRangePop();
 
     // ---- optimisation loop (multibit_embedder.py:95-122)
+    nvtxRangePushA("embed:nadam_loop");
     auto iteration = [&]() -> int {
       // fused spectral passes (spec.cuh): y and dpad never leave shared memory
       if (begin_pass(ctx, dw.n, itc, st)) return 1;
@@ -1143,6 +1268,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       b.c = (float*)ctx->c.p; b.m = (float*)ctx->m.p; b.v = (float*)ctx->v.p;
       b.cbest = (float*)ctx->cbest.p; b.c0 = (float*)ctx->c0.p;
       b.improved = (int*)ctx->improved.p; b.steps = (NadamStep*)ctx->steps.p; b.it_ptr = itc;
+      b.nonfinite = (int*)ctx->nonfinite.p + w0;
       b.tol_ratio = (float)pow(10.0, -(double)ctx->tol_db / 20.0);
       if (launch_spec<SPEC_BWD>(ctx, dw, b, st)) return 1;
       return 0;
@@ -1181,16 +1307,19 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       for (int it = 0; it < iters; ++it)
         if (iteration()) return 1;
     }
+    nvtxRangePop();
     // ---- final synthesis from the best coefficients (multibit_embedder.py:173-192)
+    nvtxRangePushA("embed:final_synthesis");
     if (begin_pass(ctx, dw.n, nullptr, st)) return 1;
     SynArgs sf = syn_base(ctx, dw);
     sf.amp = (float*)ctx->cbest.p; sf.ph = (float2*)ctx->ph_u.p; sf.scale = 1.0f / AW_NFFT;
     sf.y_oob = (float*)ctx->yoob.p; sf.y = (float*)ctx->y.p; sf.peak_y = acc.peak_y;
     if (launch_syn<SYN_WAVE>(ctx, dw, sf, st)) return 1;
-    dim3 g(std::min((dw.L + 2047) / 2048, std::max(64, 8192 / dw.n)), dw.n);
+    dim3 g(std::min((dw.L + 4095) / 4096, std::max(64, 8192 / dw.n)), dw.n);
     prof_mark(ctx, st, "final_normalize");
     k_final_normalize<<<g, 256, 0, st>>>((float*)ctx->y.p, dw.L, acc.peak_y,
                                          d_scale ? d_scale + w0 : nullptr,
+                                         scale_mode == AW_SCALE_SIGNED_MAX ? (const int*)ctx->smax.p : nullptr,
                                          d_out + (size_t)w0 * out_stride, out_stride);
     ctx->launches++;
     AW_LAUNCH_CHECK();
@@ -1198,6 +1327,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       AW_CUDA(cudaMemcpyAsync(d_best_loss + w0, ctx->best.p, (size_t)dw.n * 4,
                               cudaMemcpyDeviceToDevice, st));
     ctx->last_n = dw.n; ctx->last_T = dw.T; ctx->last_nb = dw.nb;
+    nvtxRangePop();
   }
   prof_mark(ctx, st, nullptr);
   if (use_graph) {

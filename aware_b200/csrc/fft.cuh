@@ -476,37 +476,81 @@ __global__ void __launch_bounds__(128, 2) k_synthesis(SynArgs a) {
 // ---------------------------------------------------------------------------
 // per-clip peak |x| (utils/audio/waveform.py:19) and final normalise
 // ---------------------------------------------------------------------------
+// order-preserving int encoding of a float (signed max through an integer atomicMax)
+__device__ __forceinline__ int float_ordered(float f) {
+  const int b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_float(int o) {
+  return __int_as_float(o >= 0 ? o : o ^ 0x7fffffff);
+}
+// One pass over the clip: packed (|x| max, lowest index) and, with `smax`, also the SIGNED max
+// (service/embed.py:69 rescales by np.max(audio), not by the peak).  4 samples per load where the
+// row is 16-byte aligned.  smax must be pre-set to INT_MIN.
 __global__ void __launch_bounds__(256) k_peak(const float* x, long long stride, int n,
-                                              unsigned long long* peak) {
+                                              unsigned long long* peak, int* smax) {
   const int clip = blockIdx.y;
   const float* p = x + (long long)clip * stride;
   unsigned long long pk = 0ull;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  float sm = -INFINITY;
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+  const int n4 = vec ? n >> 2 : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(p)[i];
+    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned long long q = pack_peak(fabsf(e[k]), (unsigned)(4 * i + k));
+      pk = q > pk ? q : pk;
+      sm = fmaxf(sm, e[k]);
+    }
+  }
+  for (int i = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const unsigned long long q = pack_peak(fabsf(p[i]), (unsigned)i);
     pk = q > pk ? q : pk;
+    sm = fmaxf(sm, p[i]);
   }
   __shared__ unsigned long long s_pk[8];
+  __shared__ float s_sm[8];
   pk = warp_max_u64(pk);
-  if ((threadIdx.x & 31) == 0) s_pk[threadIdx.x >> 5] = pk;
+  sm = warp_max(sm);
+  if ((threadIdx.x & 31) == 0) { s_pk[threadIdx.x >> 5] = pk; s_sm[threadIdx.x >> 5] = sm; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) pk = s_pk[w] > pk ? s_pk[w] : pk;
+    for (int w = 1; w < 8; ++w) { pk = s_pk[w] > pk ? s_pk[w] : pk; sm = fmaxf(sm, s_sm[w]); }
     atomicMax(peak + clip, pk);
+    if (smax) atomicMax(smax + clip, float_ordered(sm));
   }
 }
 
 // out = y / (peak + 1e-8) [* scale[clip]]   (multibit_embedder.py:185-192, service/embed.py:73)
+// `smax` (order-encoded signed max of the input, from k_peak) takes the place of `scale`
 __global__ void __launch_bounds__(256) k_final_normalize(const float* y, int L,
                                                          const unsigned long long* peak,
-                                                         const float* scale, float* out,
+                                                         const float* scale, const int* smax, float* out,
                                                          long long out_stride) {
   const int clip = blockIdx.y;
   const float d = peak_value(peak[clip]) + 1e-8f;
-  const float s = scale ? scale[clip] : 1.f;
+  const bool scaled = scale || smax;
+  const float s = scale ? scale[clip] : (smax ? ordered_float(smax[clip]) : 1.f);
+  const float* yc = y + (long long)clip * L;
+  float* oc = out + (long long)clip * out_stride;
+  if ((out_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {      // L % 256 == 0
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (L >> 2); i += gridDim.x * blockDim.x) {
+      const float4 t = reinterpret_cast<const float4*>(yc)[i];
+      float v[4] = {__fdiv_rn(t.x, d), __fdiv_rn(t.y, d), __fdiv_rn(t.z, d), __fdiv_rn(t.w, d)};
+      if (scaled) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __fmul_rn(s, v[k]);
+      }
+      reinterpret_cast<float4*>(oc)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    return;
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
-    float v = __fdiv_rn(y[(long long)clip * L + i], d);
-    if (scale) v = __fmul_rn(s, v);
-    out[(long long)clip * out_stride + i] = v;
+    float v = __fdiv_rn(yc[i], d);
+    if (scaled) v = __fmul_rn(s, v);
+    oc[i] = v;
   }
 }
 

@@ -359,7 +359,8 @@ struct HeadArgs {
   AT* dH4;                   // [rows][64] or null
   const int* it_ptr; int n_clips;
   int round_tf32;
-  float gscale;              // loss scale of the back-propagated gradient (fp16 mode), else 1
+  float gscale;              // 16-bit modes: target magnitude of the seeded gradient (0.5), else 0
+  float* gsc;                // [clip] out: power-of-two loss scale chosen per clip and iteration
   double* hpart;             // [clip][tiles][64][3] partial sums
   float* hcoef;              // [clip][64][4] = (dz, a1, a2, rstd)
 };
@@ -437,6 +438,18 @@ __global__ void __launch_bounds__(64) k_head_final(HeadArgs<AT> a, int tiles) {
   }
   if (!a.pattern || !a.dH4) return;
   __syncthreads();
+  if (c < 32) {
+    // per-clip, per-iteration power-of-two loss scale (fp16 gradients): keeps the seeded gradient at
+    // a fixed magnitude for any clip length and however far tanh has saturated; a power of two
+    // changes no mantissa, and it is removed exactly where dP0 is consumed
+    float mx = fmaxf(fabsf(s_dz[c]), fabsf(s_dz[c + 32]));
+    mx = warp_max(mx);
+    if (c == 0) {
+      float gs = 1.0f;
+      if (a.gscale > 0.f && mx > 0.f) gs = exp2f(fminf(fmaxf(rintf(log2f(a.gscale / mx)), 0.f), 60.f));
+      a.gsc[clip] = gs;
+    }
+  }
   const float dz = s_dz[c];
   const double nneg = (double)a.Tp - np_;
   const float a1 = (float)((double)dz * (np_ + (double)AW_LEAKY * nneg) / a.Tp);
@@ -451,6 +464,7 @@ __global__ void __launch_bounds__(256) k_head_seed(HeadArgs<AT> a) {
   const int c = tid & 63, g = tid >> 6;
   const float4 k = *reinterpret_cast<const float4*>(a.hcoef + ((long long)clip * 64 + c) * 4);
   const float dz = k.x, a1 = k.y, a2 = k.z, rstd = k.w;
+  const float gscale = a.gsc[clip];
   const AT* P = a.P4 + ((long long)clip * a.Tp_pad + tile * 128) * 64;
   AT* D = a.dH4 + ((long long)clip * a.Tp_pad + tile * 128) * 64;
 #pragma unroll 1
@@ -466,7 +480,7 @@ __global__ void __launch_bounds__(256) k_head_seed(HeadArgs<AT> a) {
         const float p = p8[i];
         const bool pos = p > 0.f;
         const float dh = pos ? dz : AW_LEAKY * dz;
-        o = a.gscale * (rstd * (dh - a1 - (pos ? p : p * (1.0f / AW_LEAKY)) * a2));
+        o = gscale * (rstd * (dh - a1 - (pos ? p : p * (1.0f / AW_LEAKY)) * a2));
         if (a.round_tf32) o = to_tf32(o);
       }
       act_st(D + (long long)j * 64 + c, o);
@@ -480,8 +494,10 @@ __global__ void __launch_bounds__(256) k_head_seed(HeadArgs<AT> a) {
 __global__ void __launch_bounds__(128) k_p0_bwd_reduce(const float* __restrict__ dP0,
                                                        const float* __restrict__ M, int T, int Tp,
                                                        int Tp_pad, const ChanStats* __restrict__ cs,
-                                                       double* __restrict__ bpart, float ginv) {
+                                                       double* __restrict__ bpart,
+                                                       const float* __restrict__ gsc) {
   const int clip = blockIdx.y, c = threadIdx.x, t0 = blockIdx.x * AW_P0B_FRAMES;
+  const float ginv = 1.0f / gsc[clip];                     // exact: the scale is a power of two
   const ChanStats st = cs[(long long)clip * AW_NMEL + c];
   double s1 = 0.0, s2 = 0.0;
   const int t1 = min(t0 + AW_P0B_FRAMES, 2 * Tp);
@@ -552,12 +568,14 @@ __global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ 
                                                       SparseMel sm,
                                                       int nb, float* __restrict__ dA,
                                                       const float* __restrict__ mag_un,
-                                                      double* __restrict__ s2_part, float ginv) {
+                                                      double* __restrict__ s2_part,
+                                                      const float* __restrict__ gsc) {
   __shared__ double s_red[32];
   __shared__ float s_dm[AW_P0A_FRAMES][AW_NMEL];
   const int clip = blockIdx.y, c = threadIdx.x, t0 = blockIdx.x * AW_P0A_FRAMES;
   const P0BwdScal sc = scal[clip];
   const float alpha = sc.alpha, beta = sc.beta, meanG = sc.meanG;
+  const float ginv = 1.0f / gsc[clip];
   const ChanStats st = cs[(long long)clip * AW_NMEL + c];
   const P0BwdCoef k = coef[(long long)clip * AW_NMEL + c];
   const float A1 = k.A1, A2 = k.A2;

@@ -281,6 +281,7 @@ struct SpecArgs {
   float* c; float* m; float* v; float* cbest;
   const float* c0;
   const int* improved;         // [clip]
+  int* nonfinite;              // [clip] set to 1 when a gradient of the clip was inf / NaN (update skipped)
   const NadamStep* steps;
   const int* it_ptr;
   float tol_ratio;
@@ -625,6 +626,12 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
               const long long o = ob_[gi] + (long long)f * nb;
               // dX = (2/N) DFT(.) ; g = Re(dX conj(u))     (multibit_embedder.py:111)
               const float g = (2.0f / AW_NFFT) * (fr[gi][f] * uu[gi][f].x + fi[gi][f] * uu[gi][f].y);
+              // an overflowed reduced-precision gradient must not poison m / v (NaN would pin the
+              // coefficient to its lower bound for good): skip the step and flag the clip
+              if ((__float_as_uint(g) & 0x7f800000u) == 0x7f800000u) {
+                if (a.nonfinite) a.nonfinite[clip] = 1;
+                continue;
+              }
               // NAdam (torch/optim/nadam.py), clamp (:116-117), best (:120-122)
               float m1 = mm[gi][f], v1 = vv[gi][f], c1 = cc[gi][f];
               m1 = __fadd_rn(m1, __fmul_rn(0.1f, __fsub_rn(g, m1)));

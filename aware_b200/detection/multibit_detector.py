@@ -20,10 +20,26 @@ class AWAREDetector:
         self.win_length = self.frame_length = frame_length
         self.hop_length = hop_length
         self.detection_net = model
-        self.precision = precision
         self._engine = None
         self._engine_owner = engine_owner     # object whose .engine is shared (the embedder)
+        self._precision = precision
         self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+    @property
+    def precision(self):
+        """GEMM arithmetic of the detector stack.  With a shared engine (load()) this IS the engine's
+        setting: there is one context, so embedder and detector cannot disagree silently."""
+        if self._engine_owner is not None and self._engine_owner._engine is not None:
+            return self._engine_owner.engine.precision
+        return self._precision
+
+    @precision.setter
+    def precision(self, value):
+        self._precision = value
+        if self._engine_owner is not None:
+            self._engine_owner.engine.set_precision(value)
+        elif self._engine is not None:
+            self._engine.set_precision(value)
 
     @property
     def engine(self):
@@ -33,7 +49,7 @@ class AWAREDetector:
             from ..engine import Engine
             self._engine = Engine(self.detection_net.weights, self.detection_net.mel_filter_bank,
                                   torch.hann_window(1024).numpy(), bands=self.embedding_bands,
-                                  threshold=self.threshold, precision=self.precision)
+                                  threshold=self.threshold, precision=self._precision)
         return self._engine
 
     def detect_batch(self, audio, sample_rate: int) -> torch.Tensor:
@@ -41,8 +57,10 @@ class AWAREDetector:
         x = to_tensor(audio)
         if x.dim() != 2:
             raise ValueError("detect_batch expects [n_clips, n_samples]")
-        x = x.to(self.engine.device, non_blocking=True).contiguous()
-        return self.engine.detect(x, sample_rate)
+        eng = self.engine
+        x = x.to(eng.device, non_blocking=True).contiguous()
+        eng.set_threshold(self.threshold)       # a shared engine follows THIS detector's threshold
+        return eng.detect(x, sample_rate)
 
     def detect(self, audio: np.ndarray, sample_rate: int) -> np.ndarray:
         x = to_tensor(audio).reshape(1, -1)

@@ -46,6 +46,9 @@ class AWAREEmbedder:
         # accumulation -- TF32's 10-bit mantissa at half the bytes (measured: not less accurate)
         self.embed_precision = embed_precision
         self.wave_clips = wave_clips
+        self.vad_gate = False                   # speech / silence gate (needs webrtcvad), see load()
+        self.exact_margin = 1e-3                # detect: exact re-evaluation margin (engine option)
+        self.check_finite = True                # 16-bit loops: re-run flagged clips in TF32
         self.threshold = 0.0
         self._engine = None
         self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
@@ -58,6 +61,7 @@ class AWAREEmbedder:
                                   torch.hann_window(1024).numpy(), bands=self.embedding_bands,
                                   tolerance_db=self.tolerance_db, threshold=self.threshold,
                                   precision=self.precision)
+            self._engine.set_exact_margin(self.exact_margin)
         return self._engine
 
     def embed_batch(self, audio, sample_rate: int, watermark, scale=None) -> torch.Tensor:
@@ -73,8 +77,21 @@ class AWAREEmbedder:
             _, nb = self.engine.band_bins(sample_rate)
             logger.info(f"Starting optimization with {nb * (1 + x.shape[1] // 256)} variables per clip, "
                         f"{x.shape[0]} clip(s), {self.num_iterations} iterations")
-        return self.engine.embed(x, sample_rate, wm.contiguous(), iters=self.num_iterations, scale=scale,
-                                 wave_clips=self.wave_clips, precision=self.embed_precision)
+        eng = self.engine
+        out = eng.embed(x, sample_rate, wm.contiguous(), iters=self.num_iterations, scale=scale,
+                        wave_clips=self.wave_clips, precision=self.embed_precision)
+        if self.check_finite and (self.embed_precision or eng.precision) in ("fp16", "bf16"):
+            # a 16-bit loop skips (and flags) updates whose gradient overflowed; such a clip is
+            # embedded again with TF32 loop GEMMs instead of being returned half-optimised
+            bad = torch.nonzero(eng.embed_status()).flatten()
+            if bad.numel():
+                logger.warning(f"{bad.numel()} clip(s) met a non-finite gradient in the "
+                               f"{self.embed_precision} loop; re-embedding them with TF32 GEMMs")
+                sc = scale[bad] if isinstance(scale, torch.Tensor) else scale
+                out[bad] = eng.embed(x[bad].contiguous(), sample_rate, wm[bad].contiguous(),
+                                     iters=self.num_iterations, scale=sc, wave_clips=self.wave_clips,
+                                     precision="tf32")
+        return out
 
     def embed(self, audio: np.ndarray, sample_rate: int, watermark: np.ndarray) -> np.ndarray:
         x = to_tensor(audio).reshape(1, -1)

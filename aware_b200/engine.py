@@ -48,6 +48,7 @@ class Engine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.aw_ctx_create(C.byref(self._ctx), self.device.index, C.byref(m)))
         self.threshold = float(threshold)
+        self.exact_margin = 1e-3
         self.embed_precision = None      # None: same as `precision`; "bf16" speeds up the embed loop
         self.set_precision(precision)
 
@@ -82,6 +83,27 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self.lib.aw_launch_count(self._ctx))
+
+    def set_threshold(self, threshold: float):
+        """Decision threshold used by `decide` and by detect's low-margin test (detector.threshold)."""
+        if float(threshold) != self.threshold:
+            _lib.check(self.lib.aw_ctx_set_option(self._ctx, _lib.OPT_THRESHOLD, float(threshold)))
+            self.threshold = float(threshold)
+
+    def set_exact_margin(self, margin: float):
+        """Clips whose min |v - threshold| is below `margin` are re-evaluated by `detect` through the
+        exact fp32 GEMMs (bit decisions equal to the reference's arithmetic).  0 disables it."""
+        _lib.check(self.lib.aw_ctx_set_option(self._ctx, _lib.OPT_EXACT_MARGIN, float(margin)))
+        self.exact_margin = float(margin)
+
+    def detect_stats(self):
+        """(clips seen by detect, clips re-evaluated exactly) since the engine was created."""
+        out = []
+        for which in (_lib.STAT_DETECT_CLIPS, _lib.STAT_REEVAL_CLIPS):
+            v = C.c_int64()
+            _lib.check(self.lib.aw_ctx_get_stat(self._ctx, which, C.byref(v)))
+            out.append(int(v.value))
+        return tuple(out)
 
     def profile(self, on: bool):
         _lib.check(self.lib.aw_profile_enable(self._ctx, int(on)))
@@ -128,10 +150,11 @@ class Engine:
         return out
 
     def embed(self, audio: torch.Tensor, sample_rate: int, pattern: torch.Tensor, iters: int = 400,
-              scale: torch.Tensor | None = None, wave_clips: int = 0, return_losses: bool = False,
+              scale: torch.Tensor | str | None = None, wave_clips: int = 0, return_losses: bool = False,
               precision: str | None = None):
         """[n, N] + [n, 20] int32 (+-1) -> [n, 256*(N//256)] watermarked, peak-normalised
-        (AWAREEmbedder.embed for a batch); optionally multiplied per clip by `scale`."""
+        (AWAREEmbedder.embed for a batch); optionally multiplied per clip by `scale` (a tensor, or
+        "signed_max": each clip's signed max computed on the device, service/embed.py:69,73)."""
         x = self._audio(audio)
         n, N = x.shape
         L = HOP * (N // HOP)
@@ -141,14 +164,29 @@ class Engine:
         out = torch.empty((n, L), dtype=torch.float32, device=x.device)
         best = torch.empty((n,), dtype=torch.float32, device=x.device)
         losses = torch.zeros((max(iters, 1), n), dtype=torch.float32, device=x.device) if return_losses else None
-        sc = scale.to(device=x.device, dtype=torch.float32).contiguous() if scale is not None else None
+        mode = _lib.SCALE_NONE
+        if isinstance(scale, str):
+            if scale != "signed_max":
+                raise ValueError("scale must be a tensor, None or 'signed_max'")
+            mode, sc = _lib.SCALE_SIGNED_MAX, None
+        else:
+            sc = scale.to(device=x.device, dtype=torch.float32).contiguous() if scale is not None else None
         with self._with_precision(precision or self.embed_precision):
             _lib.check(self.lib.aw_embed_batch(self._ctx, _ptr(x), n, N, x.stride(0), int(sample_rate),
-                                               _ptr(pat), int(iters), _ptr(sc), _ptr(out), out.stride(0),
+                                               _ptr(pat), int(iters), _ptr(sc), mode, _ptr(out), out.stride(0),
                                                _ptr(best), _ptr(losses), int(wave_clips), _stream()))
+        self._last_embed_n = n
         if return_losses:
             return out, best, losses
         return out
+
+    def embed_status(self) -> torch.Tensor:
+        """int32 [n] flags of the last `embed`: 1 = the clip met a non-finite gradient in the loop
+        (its update was skipped; only possible with 16-bit loop GEMMs)."""
+        n = getattr(self, "_last_embed_n", 0)
+        flags = torch.empty((n,), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.aw_embed_status(self._ctx, _ptr(flags), n, _stream()))
+        return flags
 
     def embed_state(self, which: str, n: int, n_frames: int, sample_rate: int) -> torch.Tensor:
         """Optimisation state of the last embed wave, [n, T, nbins] (parity hooks)."""
@@ -166,9 +204,12 @@ class Engine:
         return dst
 
     def decide(self, values: torch.Tensor, ref_bits: torch.Tensor | None = None,
-               counters: torch.Tensor | None = None):
+               counters: torch.Tensor | None = None, threshold: float | None = None):
         """values [n,20] -> bits int32 [n,20] (strict '>' threshold); with ref_bits also
-        per-clip error counts, and `counters` (int64[3]: errors, bits, clips) is incremented."""
+        per-clip error counts, and `counters` (int64[3]: errors, bits, clips) is incremented.
+        `threshold` (the detector's) overrides the engine's current one."""
+        if threshold is not None:
+            self.set_threshold(threshold)
         n = values.shape[0]
         bits = torch.empty((n, N_BITS), dtype=torch.int32, device=values.device)
         errs = torch.zeros((n,), dtype=torch.int32, device=values.device) if ref_bits is not None else None

@@ -1,8 +1,8 @@
 """Metrics with the reference's call signatures (metrics/audio.py there).
 
-BER and SNR accept numpy arrays / CPU tensors like the reference, and additionally
-CUDA tensors, in which case the batched device kernels are used (BER via
-aw_decide_and_count's counters, SNR via aw_snr_batch)."""
+BER and SNR accept numpy arrays like the reference (torch tensors, host or device, are copied
+to the host first): they are the reference's per-clip host metrics.  The batched device
+versions are `Engine.decide` (BER counters, aw_decide_and_count) and `Engine.snr` (aw_snr_batch)."""
 import numpy as np
 import torch
 

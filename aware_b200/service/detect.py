@@ -34,4 +34,4 @@ def detect_watermark_batch(audio, sample_rate: int, detector, ref_bits=None, cou
     values = detector.detect_batch(audio, sample_rate)
     if ref_bits is not None and not isinstance(ref_bits, torch.Tensor):
         ref_bits = torch.as_tensor(np.asarray(ref_bits))
-    return detector.engine.decide(values, ref_bits, counters)
+    return detector.engine.decide(values, ref_bits, counters, threshold=detector.threshold)

@@ -1,18 +1,16 @@
 """Host-side audio helpers kept for interface compatibility.  The arithmetic of
 WaveformNormalizer / STFT / ISTFT lives in the CUDA kernels; only the VAD gate
-(reference utils/audio/waveform.py:22-46) is a host object, and it is pluggable:
-webrtcvad is a C extension that may be absent."""
+(reference utils/audio/waveform.py:22-46) is a host object (webrtcvad is a C extension)."""
 import numpy as np
-
-from ..logger import logger
 
 
 class SilenceChecker:
-    """True when the clip holds less than `min_speech_seconds` of voiced frames.
+    """True when the clip holds less than `min_speech_seconds` of voiced frames
+    (utils/audio/waveform.py:22-46 upstream: webrtcvad, 8/16/32/48 kHz only).
 
-    Uses webrtcvad when importable (8/16/32/48 kHz only, as upstream); otherwise the
-    gate is skipped (returns False) with a one-time warning."""
-    _warned = False
+    Upstream imports webrtcvad unconditionally, so a host without it cannot embed at all.  Here
+    the gate is switched by the model card (`vad_gate`, see cards/config.yaml): when it is ON and
+    webrtcvad is missing this raises ImportError -- it never silently reports "not silent"."""
 
     def __init__(self, sample_rate=16000, aggr=3, frame_ms=30.0, min_speech_seconds=0.01):
         self.sample_rate, self.aggr = sample_rate, aggr
@@ -21,11 +19,10 @@ class SilenceChecker:
     def __call__(self, data: np.ndarray) -> bool:
         try:
             import webrtcvad
-        except ImportError:
-            if not SilenceChecker._warned:
-                logger.warning("webrtcvad not installed: speech/silence gate skipped")
-                SilenceChecker._warned = True
-            return False
+        except ImportError as e:
+            raise ImportError("the speech / silence gate needs the `webrtcvad` package; install it or "
+                              "switch the gate off explicitly (vad_gate: false in cards/config.yaml, "
+                              "or model.vad_gate = False)") from e
         pcm = (np.asarray(data) * 32767).astype(np.int16).tobytes()
         vad = webrtcvad.Vad(self.aggr)
         step = int(self.sample_rate * self.frame_ms / 1000) * 2
@@ -34,4 +31,13 @@ class SilenceChecker:
         return voiced * (self.frame_ms / 1000.0) < self.min_speech_seconds
 
 
-__all__ = ["SilenceChecker"]
+def silent_mask(clips, sample_rate: int, model) -> np.ndarray:
+    """bool [n]: True where the VAD gate rejects the clip (all False when `model.vad_gate` is off)."""
+    n = len(clips)
+    if not getattr(model, "vad_gate", False):
+        return np.zeros(n, dtype=bool)
+    chk = SilenceChecker(sample_rate=sample_rate)
+    return np.array([bool(chk(np.asarray(c))) for c in clips], dtype=bool)
+
+
+__all__ = ["SilenceChecker", "silent_mask"]

@@ -33,6 +33,8 @@ def load(config_path=None):
             embed_precision=config.get("embed_precision", "fp16"))
         embedder.enforce_16k = bool(config.get("enforce_16k", True))
         embedder.threshold = config.get("threshold", 0.0)
+        embedder.vad_gate = bool(config.get("vad_gate", True))    # absent key = upstream behaviour (gate on)
+        embedder.exact_margin = float(config.get("exact_margin", 1e-3))
     except Exception as e:                                   # noqa: BLE001
         logger.error(f"Error creating embedder: {e}")
         return

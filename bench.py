@@ -10,6 +10,16 @@ scripts/attacks.py -> detect -> BER.  Workload = BASELINE.json configs[1]
 (256 x 10 s @ 44.1 kHz per GPU); with N GPUs every rank processes its own 256
 clips (weak scaling, no data-path collective) and NCCL only all-reduces the
 bit-error counters.  Prints ONE JSON line on rank 0.
+
+What the line carries (rank 0):
+  value / ms_per_step  K steps, inputs resident in HBM, profiling hooks OFF, CUDA-graph replay ON
+  e2e                  the same step through the service API from pinned HOST buffers (H2D + D2H inside)
+  kernel_classes       one extra INSTRUMENTED step (events around every launch; not the timed region)
+  roofline(s)          from that instrumented step
+  phases               detect-only, attack-suite -> detect, embed, full; per-attack streaming GB/s
+  parity               oracle gates on the first --parity-clips clips of THIS batch: outputs of the LAST
+                       TIMED step (fp16 loop, graph replay) and of one TF32-loop step
+  cpu_baseline         the oracle port on the box's host cores, one clip of the same length
 """
 import argparse
 import json
@@ -42,11 +52,14 @@ def parse():
     ap.add_argument("--iters", type=int, default=400)
     ap.add_argument("--wave", type=int, default=0, help="clips per optimisation wave (0 = all)")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "tf32", "fp32", "bf16"],
-                    help="GEMM arithmetic of the embed loop (detector GEMMs stay TF32)")
-    ap.add_argument("--no-alt", action="store_true", help="skip the one-step TF32 cross-check run")
+                    help="GEMM arithmetic of the embed loop (detector GEMMs stay TF32 + exact re-evaluation)")
+    ap.add_argument("--parity-clips", type=int, default=4, help="clips of the batch gated against the oracle (0 = off)")
+    ap.add_argument("--no-alt", action="store_true", help="skip the TF32-loop step (and its parity gates)")
     ap.add_argument("--no-attacks", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-phases", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the configs[3]-shape record (N > 1 only)")
     return ap.parse_args()
 
 
@@ -102,69 +115,58 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------
-# reference arm: the reference's own CPU implementation of the path (oracle port)
+# the attack suite: ONE parameter draw shared by the CUDA arm and the oracle arm
 # --------------------------------------------------------------------------------------
-def oracle_step(O, x, bits, sr, iters, attacks=True):
-    """embed -> detect -> attack suite -> detect on ONE clip; returns bit errors."""
+def suite_params(n, sr, rng, n_clips):
+    """Host-drawn randomness of the suite (the reference draws it unseeded, attacks.py:170,340,378)."""
+    p = {"delete": {}, "suppress": {}}
+    for pc in (0.1, 0.15, 0.2):
+        p["delete"][pc] = rng.integers(0, n - int(pc * n), size=n_clips)
+    p["f_low"] = float(rng.uniform(300.0, 3800.0))
+    for pc in (0.1, 0.25):
+        p["suppress"][pc] = rng.integers(0, n - int(pc * sr), size=n_clips)
+    return p
+
+
+def build_suite(A, sr, p):
+    """[(CUDA attack or None when A is None, oracle restatement taking (O, audio, clip index))].  Every
+    mode used here meets the 1e-4 waveform tolerance: the band-stop (direct-form filtfilt, round-off
+    noise up to 6e-4 between evaluation orders) runs the SEQUENTIAL scan that reproduces scipy bit for
+    bit; the well-conditioned low/high-pass run the chunk-parallel scan (<= 1e-6 from scipy, tested)."""
+    def cu(make):
+        return make(A) if A is not None else None
+    s = [(cu(lambda A_, b=b: A_.PCMBitDepthConversion(b)), (lambda O, a, i, b=b: O.attack_pcm(a, b)))
+         for b in (8, 12, 16, 24)]
+    for pc in (0.1, 0.15, 0.2):
+        st = p["delete"][pc]
+        s.append((cu(lambda A_, pc=pc, st=st: A_.DeleteSamples(pc, start=st)),
+                  (lambda O, a, i, pc=pc, st=st: O.attack_delete(a, pc, int(st[i])))))
+    s.append((cu(lambda A_: A_.Resample()), (lambda O, a, i: O.attack_resample(a, sr))))
+    s.append((cu(lambda A_: A_.RandomBandstop(f_low=p["f_low"], fast=False)),
+              (lambda O, a, i: O.attack_bandstop(a, sr, p["f_low"]))))
+    for pc in (0.1, 0.25):
+        st = p["suppress"][pc]
+        s.append((cu(lambda A_, pc=pc, st=st: A_.SampleSupression(pc, start=st)),
+                  (lambda O, a, i, pc=pc, st=st: O.attack_suppress(a, pc, sr, int(st[i])))))
+    s.append((cu(lambda A_: A_.LowPassFilter(fast=True)), (lambda O, a, i: O.attack_lowpass(a, sr))))
+    s.append((cu(lambda A_: A_.HighPassFilter(fast=True)), (lambda O, a, i: O.attack_highpass(a, sr))))
+    return s
+
+
+def oracle_step(O, x, bits, sr, iters, oracle_suite, clip_index=0, keep=None):
+    """embed -> detect -> attack suite -> detect on ONE clip through the oracle; returns bit errors.
+    keep (dict) receives the watermarked audio and the per-evaluation detector values."""
     y = O.embed_watermark(x, sr, bits, num_iters=iters)
-    errs = int(np.sum(O.detect_watermark(y, sr) != bits))
-    if attacks:
-        n = len(y)
-        rng = np.random.default_rng(99)
-        suite = [lambda a: O.attack_pcm(a, 8), lambda a: O.attack_pcm(a, 12), lambda a: O.attack_pcm(a, 16),
-                 lambda a: O.attack_pcm(a, 24)]
-        for p in (0.1, 0.15, 0.2):
-            st = int(rng.integers(0, n - int(p * n)))
-            suite.append(lambda a, p=p, st=st: O.attack_delete(a, p, st))
-        suite.append(lambda a: O.attack_resample(a, sr))
-        f_low = float(rng.uniform(300.0, 3800.0))
-        suite.append(lambda a: O.attack_bandstop(a, sr, f_low))
-        for p in (0.1, 0.25):
-            st = int(rng.integers(0, n - int(p * sr)))
-            suite.append(lambda a, p=p, st=st: O.attack_suppress(a, p, sr, st))
-        suite += [lambda a: O.attack_lowpass(a, sr), lambda a: O.attack_highpass(a, sr)]
-        for f in suite:
-            errs += int(np.sum(O.detect_watermark(np.asarray(f(y)), sr) != bits))
-    return errs
+    vals = [O.detect(y, sr)]
+    for f in oracle_suite:
+        vals.append(O.detect(np.asarray(f(O, y, clip_index), dtype=np.float32), sr))
+    if keep is not None:
+        keep["y"], keep["values"] = y, np.stack(vals)
+    return int(sum(np.sum(O.decode_values(v) != bits) for v in vals))
 
 
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import aware_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    total = args.steps + args.warmup
-    secs = float(min(args.seconds, max(1, 90 // max(total, 1))))
-    x = O.synth_clip(0, secs, args.sr)
-    bits = O.synth_bits(1)[0]
-    O.net()
-    for _ in range(args.warmup):
-        oracle_step(O, x, bits, args.sr, args.iters, not args.no_attacks)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle_step(O, x, bits, args.sr, args.iters, not args.no_attacks)
-    dt = time.perf_counter() - t0
-    value = args.steps * secs / dt
-    sample = "1 clip x %g s @ %d Hz per step, %d NAdam iterations, attack suite %s" % (
-        secs, args.sr, args.iters, "off" if args.no_attacks else "on")
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args), reference_sample=sample),     # the arm's config; one step here = the sample
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "oracle/aware_oracle.py: torch-CPU restatement of the reference (bit-identical to it on "
-                "detect and 1-3 embed iterations; its bounds set-up is vectorised, so it is faster than "
-                "the unmodified reference by ~3.7 s/clip)"}))
-
-
-def workload_config(args, secs_override=None, clips_override=None):
-    secs = args.seconds if secs_override is None else secs_override
-    clips = args.clips if clips_override is None else clips_override
+def workload_config(args):
+    secs, clips = args.seconds, args.clips
     n = int(round(secs * args.sr))
     label = "BASELINE configs[1]" if (clips, secs) == (256, 10.0) else (
         "BASELINE configs[3] shape (4096 x 30 s over 8 GPUs)" if (clips, secs) == (512, 30.0) else "custom")
@@ -178,21 +180,58 @@ def workload_config(args, secs_override=None, clips_override=None):
 
 
 # --------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path (oracle port)
+# --------------------------------------------------------------------------------------
+def run_reference(args):
+    """Same config / metric as our arm; one step = a bounded sample of the workload: ONE clip of the
+    workload's real length (10 s) through the full step, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import aware_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x = O.synth_clip(0, args.seconds, args.sr)
+    bits = O.synth_bits(1)[0]
+    L = 256 * (len(x) // 256)
+    osuite = [] if args.no_attacks else [
+        f for _, f in build_suite(None, args.sr, suite_params(L, args.sr, np.random.default_rng(99), 1))]
+    O.net()
+    for _ in range(args.warmup):
+        oracle_step(O, x, bits, args.sr, args.iters, osuite)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_step(O, x, bits, args.sr, args.iters, osuite)
+    dt = time.perf_counter() - t0
+    value = args.steps * args.seconds / dt
+    sample = "1 clip x %g s @ %d Hz per step (of the %d-clip batch), %d NAdam iterations, attack suite %s" % (
+        args.seconds, args.sr, args.clips, args.iters, "off" if args.no_attacks else "on")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle/aware_oracle.py: torch-CPU restatement of the reference (bit-identical to it on "
+                "detect and 1-3 embed iterations; its bounds set-up is vectorised, so it is faster than "
+                "the unmodified reference by ~3.7 s/clip)"}))
+
+
+# --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
-def build_suite(A, n, sr, rng, n_clips):
-    suite = [A.PCMBitDepthConversion(8), A.PCMBitDepthConversion(12), A.PCMBitDepthConversion(16),
-             A.PCMBitDepthConversion(24)]
-    for p in (0.1, 0.15, 0.2):
-        suite.append(A.DeleteSamples(p, start=rng.integers(0, n - int(p * n), size=n_clips)))
-    suite.append(A.Resample())
-    suite.append(A.RandomBandstop(f_low=float(rng.uniform(300.0, 3800.0)), fast=True))
-    for p in (0.1, 0.25):
-        suite.append(A.SampleSupression(p, start=rng.integers(0, n - int(p * sr), size=n_clips)))
-    # fast=True: chunk-parallel float64 recurrence with look-back (<= 1e-6 from scipy's sequential
-    # lfilter, tests/test_gpu_parity.py); the bit-exact sequential mode runs one thread per clip
-    suite += [A.LowPassFilter(fast=True), A.HighPassFilter(fast=True)]
-    return suite
+def timed(fn, reps=1):
+    """Device time of `reps` calls of fn (CUDA events on the current stream), ms per call."""
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
 
 
 def main():
@@ -212,6 +251,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from aware_b200 import attacks as A
+    from aware_b200.service import detect_watermark_batch, embed_watermark_batch
     from aware_b200.synth import synth_batch, synth_bits
     from aware_b200.utils.models import load
     from aware_b200.utils.watermark import PatternEncoder
@@ -221,6 +261,7 @@ def main():
     emb.num_iterations = args.iters
     emb.embed_precision = args.precision
     emb.wave_clips = args.wave
+    emb.enforce_16k = det.enforce_16k = False          # 44.1 kHz goes through the model interface
     eng = emb.engine
     A.set_engine(eng)
     dev = eng.device
@@ -234,23 +275,36 @@ def main():
     pat = torch.from_numpy(np.stack([PatternEncoder()(b) for b in bits_np])).to(dev)
     N = x_host.shape[1]
     L = 256 * (N // 256)
-    suite = [] if args.no_attacks else build_suite(A, L, sr, np.random.default_rng(99 + rank), n_clips)
+    params = suite_params(L, sr, np.random.default_rng(99 + rank), n_clips)
+    pairs = [] if args.no_attacks else build_suite(A, sr, params)
+    suite = [a for a, _ in pairs]
+    osuite = [f for _, f in pairs]
     n_eval = 1 + len(suite)
     x_dev = x_host.to(dev)
     y_host = torch.empty((n_clips, L), dtype=torch.float32).pin_memory()
     counters = torch.zeros((n_eval, 3), dtype=torch.int64, device=dev)
-
-    def step(x):
-        scale = x.max(dim=1).values                       # service/embed.py:69 signed max
-        y = eng.embed(x, sr, pat, iters=args.iters, scale=scale, wave_clips=args.wave,
-                      precision=step_prec[0])
-        eng.decide(eng.detect(y, sr), bits, counters[0])
-        for i, att in enumerate(suite):
-            z = att.apply_batch(y, sr, engine=eng)
-            eng.decide(eng.detect(z, sr), bits, counters[i + 1])
-        return y
-
     step_prec = [args.precision]
+
+    def embed_only(x):
+        # the signed max that service/embed.py:69 rescales by is taken on the device inside the embed
+        return eng.embed(x, sr, pat, iters=args.iters, scale="signed_max", wave_clips=args.wave,
+                         precision=step_prec[0])
+
+    def evaluate(y, keep=None):
+        v = eng.detect(y, sr)
+        eng.decide(v, bits, counters[0])
+        if keep is not None:
+            keep.append(v)
+        for i, att in enumerate(suite):
+            v = eng.detect(att.apply_batch(y, sr, engine=eng), sr)
+            eng.decide(v, bits, counters[i + 1])
+            if keep is not None:
+                keep.append(v)
+
+    def step(x, keep=None):
+        y = embed_only(x)
+        evaluate(y, keep)
+        return y
 
     def sync_all():
         torch.cuda.synchronize()
@@ -263,23 +317,21 @@ def main():
     counters.zero_()
     sync_all()
 
-    # ---- timed region: device-resident inputs ------------------------------------------
+    # ---- timed region: device-resident inputs, no profiling hooks, graph replay ------------------
     clocks = ClockSampler(local) if rank == 0 else None
-    eng.profile(True)
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    keep_vals = []                                          # detector outputs of the LAST timed step (parity)
     e0.record()
-    for _ in range(args.steps):
-        step(x_dev)
+    for k_ in range(args.steps):
+        y_fp = step(x_dev, keep_vals if k_ == args.steps - 1 else None)
     e1.record()
     sync_all()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     launches = eng.launch_count() - l0
-    eng.profile(False)
-    prof = eng.profile_read()
-    timeline = eng.profile_read_named()
     clk = clocks.stop() if clocks else None
     cnt = counters.clone()
+    nonfinite = int(eng.embed_status().sum().item())
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)          # max over ranks
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)          # the only collective on the path
@@ -287,7 +339,8 @@ def main():
     audio_s = world * n_clips * args.seconds * args.steps
     value = audio_s / (ms_total / 1e3)
 
-    # ---- end to end: host buffers in, watermarked audio + BER counters out ----------------
+    # ---- end to end: the service API on pinned HOST buffers; H2D of the inputs, D2H of the
+    # watermarked audio and of the BER counters inside the timed region --------------------------
     e2e = None
     if not args.no_e2e:
         sync_all()
@@ -296,8 +349,10 @@ def main():
         c_host = None
         t0.record()
         for _ in range(k_e2e):
-            xd = x_host.to(dev, non_blocking=True)                 # H2D of this step's inputs (pinned)
-            y = step(xd)
+            y = embed_watermark_batch(x_host, sr, bits_np, emb)      # H2D of this step's inputs (pinned) inside
+            detect_watermark_batch(y, sr, det, bits, counters[0])
+            for i, att in enumerate(suite):
+                detect_watermark_batch(att.apply_batch(y, sr, engine=eng), sr, det, bits, counters[i + 1])
             y_host.copy_(y, non_blocking=True)                      # D2H: watermarked audio
             c_host = counters.cpu()                                 # D2H: BER counters (blocks)
         t1.record()
@@ -306,23 +361,68 @@ def main():
         if dist is not None:
             dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
         e2e = {"value": world * n_clips * args.seconds * k_e2e / (float(ms2.item()) / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": int(x_host.numel() * 4),
-               "d2h_bytes_per_step": int(y_host.numel() * 4 + c_host.numel() * 8), "steps": k_e2e}
+               "h2d_bytes_per_step": int(x_host.numel() * 4 + bits.numel() * 4),
+               "d2h_bytes_per_step": int(y_host.numel() * 4 + c_host.numel() * 8), "steps": k_e2e,
+               "api": "aware_b200.service.embed_watermark_batch / detect_watermark_batch + Attack.apply_batch"}
+
+    # ---- secondary record at N > 1: the per-GPU shape of BASELINE configs[3] (4096 x 30 s over 8 GPUs)
+    cfg4 = None
+    if world > 1 and not args.no_config4:
+        n4, secs4 = 512, 30.0
+        x4 = torch.from_numpy(synth_batch(n4, secs4, sr, first=rank * n4)).to(dev)
+        b4 = synth_bits(n4 * world)[rank * n4:(rank + 1) * n4]
+        bits4 = torch.from_numpy(b4).to(dev)
+        pat4 = torch.from_numpy(np.stack([PatternEncoder()(b) for b in b4])).to(dev)
+        L4 = 256 * (x4.shape[1] // 256)
+        suite4 = [a for a, _ in build_suite(A, sr, suite_params(L4, sr, np.random.default_rng(199 + rank), n4))]
+        c4 = torch.zeros((1 + len(suite4), 3), dtype=torch.int64, device=dev)
+
+        def step4():
+            y4 = eng.embed(x4, sr, pat4, iters=args.iters, scale="signed_max", precision=args.precision)
+            eng.decide(eng.detect(y4, sr), bits4, c4[0])
+            for i, att in enumerate(suite4):
+                eng.decide(eng.detect(att.apply_batch(y4, sr, engine=eng), sr), bits4, c4[i + 1])
+        sync_all()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        step4()
+        f1.record()
+        sync_all()
+        ms4 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms4, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c4, op=dist.ReduceOp.SUM)
+        cfg4 = {"workload": "BASELINE configs[3] per-GPU shape: %d x %g s per GPU (%d clips over %d GPUs), full step"
+                            % (n4, secs4, n4 * world, world), "steps": 1, "warmup": 0,
+                "value": world * n4 * secs4 / (float(ms4.item()) / 1e3), "unit": UNIT,
+                "ms_per_step": float(ms4.item()),
+                "ber_percent_clean": 100.0 * int(c4[0, 0]) / max(int(c4[0, 1]), 1)}
+        del x4
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-
-    # ---- kernel-class shares and rooflines (events around every launch, on the launching stream)
+    # ======================= rank 0 only from here on: no collectives ==========================
     pk = peaks()
     T = 1 + N // 256
     Tp = T // 2
     _, nb = eng.band_bins(sr)
-    tl_ms = sum(v[1] for v in timeline.values())
-    classes = {k: {"launches": v[0], "ms": round(v[1], 3), "share_of_step": round(v[1] / ms_total, 4)}
-               for k, v in sorted(timeline.items(), key=lambda kv: -kv[1][1])}
     n_w = n_clips if args.wave in (0, n_clips) else args.wave
+
+    # ---- one INSTRUMENTED step (events around every launch, eager launches): kernel classes ----
+    eng.profile(True)
+    i0 = torch.cuda.Event(enable_timing=True); i1 = torch.cuda.Event(enable_timing=True)
+    i0.record()
+    step(x_dev)
+    i1.record()
+    torch.cuda.synchronize()
+    ms_instr = i0.elapsed_time(i1)
+    eng.profile(False)
+    prof = eng.profile_read()
+    timeline = eng.profile_read_named()
+    tl_ms = sum(v[1] for v in timeline.values())
+    classes = {k: {"launches": v[0], "ms": round(v[1], 3), "share_of_step": round(v[1] / ms_instr, 4)}
+               for k, v in sorted(timeline.items(), key=lambda kv: -kv[1][1])}
 
     def hbm_roof(name, label, bytes_per_launch, note):
         if label not in timeline or not timeline[label][0]:
@@ -331,10 +431,9 @@ def main():
         ach = bytes_per_launch / (ms_ / cnt_ * 1e-3) / 1e9
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": "%s copy bandwidth" % pk["src"],
-                "launches": cnt_, "avg_ms": ms_ / cnt_, "share_of_step": ms_ / ms_total,
+                "launches": cnt_, "avg_ms": ms_ / cnt_, "share_of_step": ms_ / ms_instr,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "note": note}
 
-    # fused spectral kernels: algorithmic bytes per clip
     spec_note = ("FP32-issue-bound, not HBM-bound: a 1024-point FFT per 256 new samples is ~25 FLOP/B against a "
                  "machine balance of ~11 FLOP/B; ncu (profiles/): issue slots 64-69 % busy, DRAM 13-20 %")
     roof_fwd = hbm_roof("k_spec<FWD> (c,u -> iSTFT -> +y_oob -> STFT -> |S|,q ; y stays in shared memory)",
@@ -362,52 +461,157 @@ def main():
                          pk["src"], "; TF32 runs at half the bf16 rate, so frac 0.5 is this kernel's ceiling"
                          if half_rate else ""),
                      "launches": launches_d, "avg_ms": ms_d / launches_d,
-                     "share_of_step": ms_d / ms_total, "all_gemm_share_of_step": gemm_ms / ms_total,
+                     "share_of_step": ms_d / ms_instr, "all_gemm_share_of_step": gemm_ms / ms_instr,
                      "algorithmic_flops_per_launch": flops}
-    # `roofline` = the kernel class with the largest share of the step
     cands = [r for r in (roof_fwd, roof_bwd, roof_norm, roof_gemm) if r]
-    roof = max(cands, key=lambda r: r["share_of_step"]) if cands else None
-    ncu_traffic = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-    if roof and os.path.exists(ncu_traffic):
-        try:
-            tr = json.load(open(ncu_traffic))
-            for r in cands:
-                key = r["kernel"].split(" ")[0]
-                if key in tr:       # dram bytes per launch per clip from one ncu --set full capture
-                    r["traffic"] = tr[key]["dram_bytes_per_clip"] * n_w
-                    r["ncu"] = {k: v for k, v in tr[key].items() if k.endswith("_pct")}
-        except Exception:  # noqa: BLE001
-            pass
+    roof = max(cands, key=lambda r: r["share_of_step"]) if cands else None     # the dominant kernel class
+    for fname in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        ncu_traffic = os.path.join(ROOT, "profiles", fname)
+        if roof and os.path.exists(ncu_traffic):
+            try:
+                tr = json.load(open(ncu_traffic))
+                for r in cands:
+                    key = r["kernel"].split(" ")[0]
+                    if key in tr and r["traffic"] is None:   # dram bytes per launch per clip, one ncu --set full capture
+                        r["traffic"] = tr[key]["dram_bytes_per_clip"] * n_w
+                        r["traffic_source"] = "profiles/" + fname
+                        r["ncu"] = {k: v for k, v in tr[key].items() if k.endswith("_pct")}
+            except Exception:  # noqa: BLE001
+                pass
 
-    # ---- cross-check: one step with TF32 GEMMs in the loop ------------------------------------
-    alt = None
+    # ---- phases (SURVEY 8d i-iv), device-timed, and the streaming attack passes ---------------------
+    phases = None
+    if not args.no_phases:
+        y_w = y_fp
+        ms_embed = timed(lambda: embed_only(x_dev))
+        ms_det = timed(lambda: eng.detect(y_w, sr), reps=5)
+        ms_suite = timed(lambda: evaluate(y_w)) if suite else None
+        aud = n_clips * args.seconds
+        phases = {"detect_only": {"value": aud / (ms_det / 1e3), "unit": UNIT, "ms": ms_det},
+                  "embed": {"value": aud / (ms_embed / 1e3), "unit": UNIT, "ms": ms_embed},
+                  "full_step": {"value": value / world, "unit": UNIT, "ms": ms_total / args.steps},
+                  "detect_stats": dict(zip(("clips_detected", "clips_reevaluated_exact"), eng.detect_stats()))}
+        if suite:
+            phases["attack_suite_to_detect"] = {
+                "value": aud * n_eval / (ms_suite / 1e3), "unit": "attacked audio-s/s (clean + %d attacks)" % len(suite),
+                "ms": ms_suite}
+            att = {}
+            for lab, n_out in (("attack_pcm", L), ("attack_decim_interp", L), ("attack_delete", None),
+                               ("attack_suppress", L), ("attack_lfilter", L), ("attack_filtfilt_fwd", None),
+                               ("attack_filtfilt_bwd", None), ("peak", 0)):
+                if lab in timeline and timeline[lab][0]:
+                    c_, m_ = timeline[lab]
+                    rec = {"launches": c_, "avg_ms": m_ / c_}
+                    if n_out is not None:
+                        by = n_clips * 4.0 * (L + n_out)
+                        rec["GBps"] = by / (m_ / c_ * 1e-3) / 1e9
+                        rec["frac_of_hbm"] = rec["GBps"] / pk["hbm_gbs"]
+                    att[lab] = rec
+            phases["attack_kernels"] = att
+        # BASELINE configs[2]: the attack sweep over 1024 clips on one GPU (watermarked audio tiled x4)
+        if suite and n_clips * 4 * L * 4 * 3 < 40e9:
+            y1k = y_w.repeat(4, 1)
+            b1k = bits.repeat(4, 1)
+            c1k = torch.zeros((n_eval, 3), dtype=torch.int64, device=dev)
+            p1k = suite_params(L, sr, np.random.default_rng(299), 4 * n_clips)
+            s1k = [a for a, _ in build_suite(A, sr, p1k)]
+
+            def sweep():
+                eng.decide(eng.detect(y1k, sr), b1k, c1k[0])
+                for i, a_ in enumerate(s1k):
+                    eng.decide(eng.detect(a_.apply_batch(y1k, sr, engine=eng), sr), b1k, c1k[i + 1])
+            sweep()
+            ms_1k = timed(sweep)
+            phases["config3_attack_sweep_1024_clips"] = {
+                "workload": "BASELINE configs[2]: %d watermarked clips x %g s, clean + %d attacks -> detect -> BER"
+                            % (4 * n_clips, args.seconds, len(s1k)),
+                "value": 4 * aud * n_eval / (ms_1k / 1e3), "unit": "attacked audio-s/s", "ms": ms_1k}
+            del y1k
+
+    # ---- one step with TF32 GEMMs in the loop (conservative precision; parity-gated below) ---------
+    alt, y_tf, vals_tf = None, None, []
     if not args.no_alt and args.precision != "tf32":
         step_prec[0] = "tf32"
         step(x_dev)
-        torch.cuda.synchronize()                          # rank 0 only from here on: no collectives
+        torch.cuda.synchronize()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
-        step(x_dev)
+        y_tf = step(x_dev, vals_tf)
         a1.record()
         torch.cuda.synchronize()
         alt = {"embed_precision": "tf32", "value": n_clips * args.seconds / (a0.elapsed_time(a1) / 1e3),
                "unit": UNIT, "steps": 1, "n_gpus": 1, "note": "rank 0 only, same step with TF32 loop GEMMs"}
         step_prec[0] = args.precision
 
-    # ---- CPU baseline beside it (oracle port, bounded sample) ----------------------------
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
+    # ---- CPU baseline + parity gates (oracle port) -----------------------------------------------
+    cpu, parity = None, None
+    n_par = min(args.parity_clips, n_clips)
+    if world == 1 and (not args.no_cpu_baseline or n_par > 0):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import aware_oracle as O
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        xs = x_host[0].numpy()
-        t0 = time.perf_counter()
-        oracle_step(O, xs, bits_np[0], sr, args.iters, not args.no_attacks)
-        dt = time.perf_counter() - t0
-        cpu = {"value": args.seconds / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "1 clip x %g s @ %d Hz, one full step (%d iterations%s), %.1f s wall"
-                         % (args.seconds, sr, args.iters, "" if args.no_attacks else " + attack suite", dt)}
+        ref = []                                  # per parity clip: oracle-embedded audio + its values
+        for i in range(max(n_par, 0 if args.no_cpu_baseline else 1)):
+            k = {}
+            t0 = time.perf_counter()
+            oracle_step(O, x_host[i].numpy(), bits_np[i], sr, args.iters, osuite, clip_index=i, keep=k)
+            dt = time.perf_counter() - t0
+            ref.append(k)
+            if i == 0 and not args.no_cpu_baseline:
+                cpu = {"value": args.seconds / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": "1 clip x %g s @ %d Hz, one full step (%d iterations%s), %.1f s wall"
+                                 % (args.seconds, sr, args.iters, "" if args.no_attacks else " + attack suite", dt)}
+        if n_par > 0:
+            parity = {"clips": n_par, "evaluations_per_clip": n_eval, "margin": 1e-3,
+                      "tolerances": "decoded bits bit-exact vs the oracle on the same audio wherever |v_oracle| >= 1e-5 "
+                                    "(below that fp32 summation order decides); functional SNR within +-1 dB of the "
+                                    "oracle's own embed; cross-detect BER 0 (SURVEY 8c protocol, F7)"}
+            x_np = x_host[:n_par].numpy()
+            y_ref = np.stack([ref[i]["y"] for i in range(n_par)])
+            # cross-detect: ORACLE-embedded audio decoded by the CUDA detector (clean + attacks)
+            yr_d = torch.from_numpy(y_ref).to(dev)
+            cross_ok, cross_ber_n, cross_flips = True, 0, 0
+            for e in range(n_eval):
+                z = yr_d if e == 0 else suite_sub(suite[e - 1], yr_d, sr, eng, n_par)
+                v = eng.detect(z, sr).cpu().numpy()
+                vo = np.stack([ref[i]["values"][e] for i in range(n_par)])
+                safe = np.abs(vo) >= 1e-5
+                cross_ok &= bool(np.array_equal((v > 0)[safe], (vo > 0)[safe]))
+                cross_flips += int(np.sum((v > 0)[safe] != (vo > 0)[safe]))
+                if e == 0:
+                    cross_ber_n = int(np.sum((v > 0).astype(np.int32) != bits_np[:n_par]))
+            parity["cross_detect"] = {"gpu_bits_equal_oracle_bits_on_oracle_audio": cross_ok, "flips": cross_flips,
+                                      "clean_bit_errors": cross_ber_n, "ok": bool(cross_ok and cross_ber_n == 0)}
+            for tag, y_g, vals_g in ((args.precision, y_fp, keep_vals), ("tf32", y_tf, vals_tf)):
+                if y_g is None:
+                    continue
+                yg = y_g[:n_par].cpu().numpy()
+                bits_ok, n_low, n_flip_low, n_flip, ber_gpu, ber_orc, worst = True, 0, 0, 0, 0, 0, 0.0
+                for e in range(n_eval):
+                    vg = vals_g[e][:n_par].cpu().numpy()
+                    for i in range(n_par):
+                        a = yg[i] if e == 0 else np.asarray(osuite[e - 1](O, yg[i], i), dtype=np.float32)
+                        vo = O.detect(a, sr)                # the oracle on the GPU-embedded (oracle-attacked) audio
+                        low = np.abs(vo) < 1e-3
+                        fl = (vg[i] > 0) != (vo > 0)
+                        n_low += int(low.sum()); n_flip_low += int((fl & low).sum()); n_flip += int(fl.sum())
+                        bits_ok &= not bool((fl & (np.abs(vo) >= 1e-5)).any())
+                        worst = max(worst, float(np.abs(vg[i] - vo).max()))
+                        if e == 0:
+                            ber_gpu += int(np.sum((vg[i] > 0).astype(np.int32) != bits_np[i]))
+                            ber_orc += int(np.sum((vo > 0).astype(np.int32) != bits_np[i]))
+                snr_g = [O.snr_db(yg[i], x_np[i][:L]) for i in range(n_par)]
+                snr_o = [O.snr_db(y_ref[i], x_np[i][:L]) for i in range(n_par)]
+                d_snr = [g - o for g, o in zip(snr_g, snr_o)]
+                parity[tag + "_loop"] = {
+                    "gpu_bits_equal_oracle_bits_on_gpu_audio": bits_ok, "values_compared": n_par * n_eval * 20,
+                    "values_below_margin": n_low, "flips_below_margin": n_flip_low, "flips_total": n_flip,
+                    "max_abs_value_diff": worst, "clean_bit_errors_gpu_detector": ber_gpu,
+                    "clean_bit_errors_oracle_detector": ber_orc, "snr_db_gpu": snr_g, "snr_db_oracle_embed": snr_o,
+                    "snr_delta_db_max_abs": max(abs(d) for d in d_snr),
+                    "ok": bool(bits_ok and ber_gpu == 0 and ber_orc == 0 and max(abs(d) for d in d_snr) <= 1.0)}
+            parity["all_ok"] = bool(all(v["ok"] for v in parity.values() if isinstance(v, dict) and "ok" in v))
 
     names = ["clean"] + [a.name for a in suite]
     ber = {nm: (100.0 * int(cnt[i, 0]) / max(int(cnt[i, 1]), 1)) for i, nm in enumerate(names)}
@@ -417,12 +621,24 @@ def main():
         "dtype": {"fp16": "fp16 (tcgen05 kind::f16, fp32 accumulate; FFT/DSP fp32)", "tf32": "tf32",
                   "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
         "config": workload_config(args), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+        "timed_region": "profiling hooks off, CUDA-graph replay on; kernel_classes / rooflines from ONE separate "
+                        "instrumented step (%.1f ms with an event per launch)" % ms_instr,
         "roofline": roof, "rooflines_all": [r for r in cands if r is not roof], "kernel_classes": classes,
-        "timeline_ms_per_step": tl_ms / args.steps, "alt_precision": alt,
+        "timeline_ms_instrumented_step": tl_ms, "phases": phases, "alt_precision": alt, "parity": parity,
+        "nonfinite_gradient_clips": nonfinite, "config4_shape": cfg4,
         "cpu_baseline": cpu, "ber_percent": ber,
         "gemm_classes": [{"n": p[0], "k": p[1], "epi": p[2], "launches": p[3], "ms": p[4]} for p in prof]}))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def suite_sub(att, y, sr, eng, n):
+    """Apply `att` (built for the whole batch) to the first n clips: per-clip parameters are sliced."""
+    import copy
+    a = copy.copy(att)
+    if getattr(a, "start", None) is not None and np.ndim(a.start) > 0:
+        a.start = np.asarray(a.start)[:n]
+    return a.apply_batch(y, sr, engine=eng)
 
 
 if __name__ == "__main__":

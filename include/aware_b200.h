@@ -60,6 +60,17 @@ int aw_ctx_set_precision(aw_ctx* ctx, int prec);
 int aw_band_bins(aw_ctx* ctx, int sample_rate, int* bin0, int* nbins);
 /* number of CUDA kernels launched by this context since creation */
 int64_t aw_launch_count(aw_ctx* ctx);
+
+/* Run-time knobs.  AW_OPT_THRESHOLD: decision threshold of aw_decide_and_count and of the
+ * low-margin test (detector.threshold, service/detect.py:17; default = aw_model.threshold).
+ * AW_OPT_EXACT_MARGIN: aw_detect_batch re-evaluates every clip with min_i |v_i - threshold| below
+ * this margin through the exact fp32 GEMM path, so decoded bits equal the reference's fp32
+ * arithmetic (default 1e-3; 0 switches the re-evaluation and its stream synchronisation off). */
+enum { AW_OPT_THRESHOLD = 0, AW_OPT_EXACT_MARGIN = 1 };
+int aw_ctx_set_option(aw_ctx* ctx, int option, double value);
+/* counters since context creation: clips seen by aw_detect_batch / clips it re-evaluated exactly */
+enum { AW_STAT_DETECT_CLIPS = 0, AW_STAT_REEVAL_CLIPS = 1 };
+int aw_ctx_get_stat(aw_ctx* ctx, int which, int64_t* out);
 /* CUDA-event timing of the tensor-core GEMM launches, on the launching stream (bench.py's
  * roofline).  aw_profile_read sums the launches recorded since the last read by
  * (n, k, epilogue kind) and clears the record. */
@@ -72,21 +83,29 @@ int aw_profile_read_named(aw_ctx* ctx, int max_classes, int* n_classes, char* na
                           int64_t* cls_count, double* cls_ms);
 
 /* ---- detection: AWAREDetector.detect (detection/multibit_detector.py:28-42) for a batch.
- * d_values: [n_clips][20] float32 tanh outputs. */
+ * d_values: [n_clips][20] float32 tanh outputs.  Tensor-core pass first; clips whose decision
+ * margin is below AW_OPT_EXACT_MARGIN are evaluated again in exact fp32 (one 4-byte D2H copy and
+ * a stream synchronisation per call; none with the margin at 0 or in AW_PREC_FP32 mode). */
 int aw_detect_batch(aw_ctx* ctx, const float* d_audio, int n_clips, int n_samples,
                     int64_t stride, int sample_rate, float* d_values, void* stream);
 
 /* ---- embedding: AWAREEmbedder.embed (embedding/multibit_embedder.py:141-197) for a batch.
  * d_pattern : [n_clips][20] int32 in {-1,+1} (utils/watermark/encoder.py:35-45)
- * d_scale   : optional [n_clips] float32; output is multiplied by it
- *             (service/embed.py:69,73 rescale by the signed max) -- may be NULL
+ * d_scale   : optional [n_clips] float32; output is multiplied by it -- may be NULL
+ * scale_mode: AW_SCALE_SIGNED_MAX multiplies every output clip by the SIGNED max of its input,
+ *             computed on the device in the same pass as the peak (service/embed.py:69,73:
+ *             `audio_mx = np.max(audio)`); exclusive with d_scale
  * d_out     : [n_clips][out_stride], each clip gets 256*(n_samples/256) samples
  * d_best_loss: optional [n_clips]; d_losses: optional [iters][n_clips]
  * wave_clips: clips processed together per optimisation wave (0 = all). */
+enum { AW_SCALE_NONE = 0, AW_SCALE_SIGNED_MAX = 1 };
 int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, int n_samples, int64_t stride,
                    int sample_rate, const int32_t* d_pattern, int iters, const float* d_scale,
-                   float* d_out, int64_t out_stride, float* d_best_loss, float* d_losses,
-                   int wave_clips, void* stream);
+                   int scale_mode, float* d_out, int64_t out_stride, float* d_best_loss,
+                   float* d_losses, int wave_clips, void* stream);
+/* per-clip status of the last aw_embed_batch call, int32 [n_clips]: 1 = the clip met a non-finite
+ * gradient inside the loop (only possible with 16-bit loop GEMMs; that NAdam update was skipped) */
+int aw_embed_status(aw_ctx* ctx, int32_t* d_flags, int n_clips, void* stream);
 /* debug/parity hooks: after aw_embed_batch, copy the optimisation state of the LAST wave.
  * which: 0 coeffs c, 1 best coeffs, 2 initial coeffs c0, 3 last gradient-free state m, 4 v
  * layout [clip][T][nbins] float32. */

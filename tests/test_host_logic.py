@@ -184,3 +184,46 @@ def test_wav_io_and_length_buckets(tmp_path):
     assert np.abs(y - 0.25 * x).max() <= 2e-7                       # mean of x and -x/2
     assert bucket_by_length([5, 7, 5, 9, 7, 5]) == {5: [0, 2, 5], 7: [1, 4], 9: [3]}
     assert bucket_by_length([]) == {}
+
+
+def test_vad_gate_is_explicit_never_silent():
+    """without webrtcvad the gate must not quietly answer "not silent".  The shipped card opts
+    out explicitly (vad_gate: false); switching it on without the package raises ImportError."""
+    from aware_b200.service import embed_watermark
+    from aware_b200.utils.audio import SilenceChecker, silent_mask
+    from aware_b200.utils.models import load
+    emb, _ = load()
+    assert emb.vad_gate is False
+    x = np.zeros(16000, dtype=np.float32)
+    assert not silent_mask([x], 16000, emb).any()                 # gate off: nothing is rejected
+    try:
+        import webrtcvad  # noqa: F401
+        pytest.skip("webrtcvad installed")
+    except ImportError:
+        pass
+    with pytest.raises(ImportError, match="webrtcvad"):
+        SilenceChecker()(x)
+    emb.vad_gate = True
+    with pytest.raises(ImportError, match="webrtcvad"):
+        embed_watermark(x, 16000, np.zeros(20, dtype=np.int32), emb)
+
+
+def test_bench_suite_is_identical_for_both_arms():
+    """bench.py draws the attack parameters once; the oracle restatement list (reference arm, parity
+    gates) and the CUDA attack list are built from the same draw, in the same order."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from aware_b200 import attacks as A
+    p = bench.suite_params(4096, 16000, np.random.default_rng(99), 3)
+    both = bench.build_suite(A, 16000, p)
+    only_oracle = bench.build_suite(None, 16000, p)
+    assert len(both) == len(only_oracle) == 13 and all(a is None for a, _ in only_oracle)
+    names = [a.name for a, _ in both]
+    assert names[:4] == ["pcm_8", "pcm_12", "pcm_16", "pcm_24"] and names[-2:] == ["low_pass", "high_pass"]
+    x = O.synth_clip(0, 4096 / 16000, 16000)
+    for (a, f), (_, g) in zip(both, only_oracle):
+        np.testing.assert_array_equal(np.asarray(f(O, x, 1)), np.asarray(g(O, x, 1)))
+    bs = [a for a, _ in both if a.name.startswith("bandstop")][0]
+    assert bs.fast is False and bs.f_low == p["f_low"]           # the bit-exact sequential mode is benched
