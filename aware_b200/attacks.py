@@ -280,6 +280,50 @@ class FIRFilter(Attack):
         return eng.attack_upfirdn(x, h_tf, n_taps, 1, 1, 0, x.shape[1])
 
 
+class CompressionApprox(Attack):
+    """The brief's "compression approximation" -- PARITY UNPINNED: upstream's MP3Compression shells out to
+    ffmpeg (attacks.py:73-148) and has no arithmetic to follow, so the attack is defined here.  It is what a
+    transform codec does to the band that carries the watermark, in closed form: STFT (1024 / 256, Hann) of
+    the input restricted to the embedding band; per frame, bins more than `floor_db` below the frame's
+    strongest band bin are dropped (masking) and the others are rounded to a `step_db` grid in
+    log-magnitude (coarse quantisation); phases are kept; the change is resynthesised (overlap-add) and
+    added to the input, so content outside the band passes through.  Output length 256 * (N // 256).
+    Pinned by `oracle_compression_approx` below (numpy restatement) in tests/test_gpu_parity.py."""
+
+    def __init__(self, step_db=1.5, floor_db=-30.0):
+        self.step_db, self.floor_db = float(step_db), float(floor_db)
+        self.name = f"compress_{step_db}dB"
+
+    def apply_batch(self, x, sr, rng=None, engine=None):
+        eng = _eng(engine)
+        L = 256 * (x.shape[1] // 256)
+        mag, ph = eng.stft_band(x, sr, normalize=False, phasor=True)
+        delta = eng.istft_band(eng.spectral_quantize(mag, self.step_db, self.floor_db), ph, sr)
+        return eng.attack_affine(x[:, :L], 1.0, delta, 1.0)
+
+
+def oracle_compression_approx(x, sr, step_db=1.5, floor_db=-30.0, bands=(500.0, 4000.0)):
+    """numpy / torch-CPU restatement of CompressionApprox for ONE clip (test infrastructure)."""
+    x = np.asarray(x, dtype=np.float32)
+    win = torch.hann_window(1024)
+    S = torch.stft(torch.from_numpy(x), n_fft=1024, hop_length=256, win_length=1024, window=win, center=True,
+                   pad_mode="reflect", return_complex=True)
+    f = np.fft.rfftfreq(1024, 1.0 / sr)
+    band = torch.from_numpy((f >= bands[0]) & (f <= bands[1]))
+    mag = S.abs()[band].numpy()                                    # [nb, T]
+    k_log = np.float32(20.0 * np.log10(2.0) / step_db)
+    k_exp = np.float32(step_db / (20.0 * np.log10(2.0)))
+    floor = mag.max(axis=0, keepdims=True) * np.float32(10.0 ** (floor_db / 20.0))
+    with np.errstate(divide="ignore"):
+        q = np.exp2(np.rint(np.log2(mag) * k_log) * k_exp).astype(np.float32)
+    q = np.where((mag >= floor) & (mag > 0), q, np.float32(0.0))
+    D = torch.zeros_like(S)
+    ph = S[band] / torch.clamp(S[band].abs(), min=1e-30)
+    D[band] = torch.from_numpy(q - mag) * ph
+    delta = torch.istft(D, n_fft=1024, hop_length=256, win_length=1024, window=win, center=True).numpy()
+    return (x[:len(delta)] + delta).astype(np.float32), mag.T, q.T
+
+
 def reference_suite():
     """The in-scope part of scripts/test.py's attack_list (test.py:15-18)."""
     return [PCMBitDepthConversion(8), PCMBitDepthConversion(12), PCMBitDepthConversion(16),

@@ -1665,3 +1665,21 @@ extern "C" int aw_attack_affine(aw_ctx* ctx, const float* d_in, int n_clips, int
   AW_LAUNCH_CHECK();
   return 0;
 }
+
+extern "C" int aw_attack_spectral_quantize(aw_ctx* ctx, const float* d_mag, int n_clips, int n_frames, int nbins,
+                                           float step_db, float floor_db, float* d_dmag, void* stream) {
+  AW_REQUIRE(ctx && d_mag && d_dmag, "null argument");
+  AW_REQUIRE(step_db > 0.f && nbins >= 1 && nbins <= AW_MAX_BINS, "bad argument");
+  if (ctx) cudaSetDevice(ctx->device);
+  // 20 log10(m) / step = log2(m) * k_log ;  10^(step * r / 20) = 2^(r * k_exp)   (float32, as the oracle)
+  const float k_log = (float)(20.0 * log10(2.0) / (double)step_db);
+  const float k_exp = (float)((double)step_db / (20.0 * log10(2.0)));
+  const float ratio = (float)pow(10.0, (double)floor_db / 20.0);
+  const long long frames = (long long)n_clips * n_frames;
+  prof_mark(ctx, (cudaStream_t)stream, "attack_spec_quant");
+  k_spectral_quantize<<<(unsigned)((frames + 3) / 4), 128, 0, (cudaStream_t)stream>>>(d_mag, frames, nbins, k_log,
+                                                                                   k_exp, ratio, d_dmag);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}

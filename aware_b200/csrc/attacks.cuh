@@ -185,4 +185,39 @@ __global__ void __launch_bounds__(256) k_attack_affine(const float* __restrict__
   }
 }
 
+// ---- X3 "compression approximation" (named by the build brief; NO reference arithmetic: upstream's
+// MP3 attack shells out to ffmpeg, attacks.py:73-148 -- parity unpinned, defined here) -------------
+// A transform codec in one line: coarse log-magnitude quantisation plus masking of weak bins, applied
+// to the embedding band of the STFT and resynthesised with the original phase.  Per frame:
+//     floor = max_b |X_b| * 10^(floor_db/20);   |X_b| < floor -> 0;
+//     else  |X_b| -> 10^(step_db * rint(20 log10|X_b| / step_db) / 20)
+// The kernel emits the magnitude CHANGE (q - |X|): the caller adds iSTFT(change * phasor) to the input,
+// so everything outside the band passes through untouched.  One warp per frame.
+__global__ void __launch_bounds__(128) k_spectral_quantize(const float* __restrict__ mag, long long frames,
+                                                           int nb, float k_log, float k_exp, float floor_ratio,
+                                                           float* __restrict__ dmag) {
+  const long long f = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (f >= frames) return;
+  const float* src = mag + f * nb;
+  float v[8];                                            // nb <= AW_MAX_BINS = 256
+  float mx = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int b = lane + 32 * i;
+    v[i] = b < nb ? src[b] : 0.f;
+    mx = fmaxf(mx, v[i]);
+  }
+  mx = warp_max(mx);
+  const float floor_v = __fmul_rn(mx, floor_ratio);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int b = lane + 32 * i;
+    if (b >= nb) continue;
+    float q = 0.f;
+    if (v[i] >= floor_v && v[i] > 0.f) q = exp2f(__fmul_rn(rintf(__fmul_rn(log2f(v[i]), k_log)), k_exp));
+    dmag[f * nb + b] = __fsub_rn(q, v[i]);
+  }
+}
+
 }  // namespace aw

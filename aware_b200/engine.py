@@ -323,3 +323,11 @@ class Engine:
         _lib.check(self.lib.aw_attack_affine(self._ctx, _ptr(x), x.shape[0], x.shape[1], x.stride(0), float(gain),
                                              _ptr(noise), ns, float(sigma), _ptr(out), out.stride(0), _stream()))
         return out
+
+    def spectral_quantize(self, mag, step_db, floor_db):
+        """[n, T, nb] band magnitudes -> (quantised - original) magnitudes (CompressionApprox attack)."""
+        n, T, nb = mag.shape
+        out = torch.empty_like(mag)
+        _lib.check(self.lib.aw_attack_spectral_quantize(self._ctx, _ptr(mag.contiguous()), n, T, nb, float(step_db),
+                                                        float(floor_db), _ptr(out), _stream()))
+        return out

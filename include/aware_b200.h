@@ -173,6 +173,14 @@ int aw_attack_affine(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t
                      float gain, const float* d_noise, int64_t noise_stride, float sigma,
                      float* d_out, int64_t out_stride, void* stream);
 
+/* "compression approximation" named by the build brief (parity unpinned: upstream's MP3 attack calls
+ * ffmpeg, attacks.py:73-148).  Per frame of a band spectrum [n_clips][n_frames][nbins] (aw_stft_band,
+ * normalize = 0): magnitudes below max * 10^(floor_db/20) are zeroed, the rest are rounded to a
+ * step_db grid in log-magnitude.  d_dmag receives (quantised - original); the caller resynthesises it
+ * with the original phasors (aw_istft_band) and adds it to the input (aw_attack_affine). */
+int aw_attack_spectral_quantize(aw_ctx* ctx, const float* d_mag, int n_clips, int n_frames, int nbins,
+                                float step_db, float floor_db, float* d_dmag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
