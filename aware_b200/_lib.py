@@ -29,6 +29,17 @@ class AwModel(C.Structure):
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _dp = C.POINTER(C.c_double)
 
+COMM_F64, COMM_I64 = 0, 1
+COMM_SUM, COMM_MAX = 0, 1
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p)
+
+
+class AwComm(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("allreduce", ALLREDUCE_FN), ("allgather", ALLGATHER_FN),
+                ("d_arena", C.c_void_p), ("arena_bytes", C.c_int64), ("rank", C.c_int), ("world", C.c_int)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/aware_b200.h
 SIGNATURES = {
     "aw_last_error": (C.c_char_p, []),
@@ -48,6 +59,9 @@ SIGNATURES = {
     "aw_detect_batch": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp]),
     "aw_embed_batch": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _i, _vp, _i, _vp, _i64, _vp, _vp, _i, _vp]),
     "aw_embed_state": (_i, [_vp, _i, _vp, _i64, _vp]),
+    "aw_detect_sharded": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, C.POINTER(AwComm), _vp, _vp]),
+    "aw_embed_sharded": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, C.POINTER(AwComm), _vp, _i64, _vp, _vp,
+                              C.POINTER(_i64), _vp]),
     "aw_decide_and_count": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "aw_snr_batch": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "aw_stft_band": (_i, [_vp, _vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp]),

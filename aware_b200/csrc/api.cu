@@ -89,6 +89,16 @@ struct aw_ctx {
   double exact_margin = 1e-3;      // AW_OPT_EXACT_MARGIN
   int64_t stat_detect_clips = 0, stat_reeval_clips = 0;
   int last_embed_clips = 0;
+  // frame-sharded long-form mode (aw_*_sharded): this context holds a halo-extended segment of ONE
+  // clip; per-clip statistics are all-reduced over the ranks through the caller's callbacks
+  struct Shard {
+    aw_comm comm;
+    int T_glob, Tp_glob;       // frames / pooled frames of the whole clip
+    int e0;                    // global index of the segment's first frame
+    int own_lo, own_hi;        // frames this rank owns, LOCAL indices into the segment
+    int64_t n_allreduce = 0, n_allgather = 0;
+  };
+  Shard* sh = nullptr;
   int ws_rows = 0;
   // activation tensor maps, [0] = float32 view, [1] = bf16 view of the same buffers
   CUtensorMap tm_act[2][4], tm_dh4[2], tm_ga1024[2], tm_ga512[2], tm_gb1024[2];
@@ -170,6 +180,86 @@ static int reduce_if_long(aw_ctx* ctx, Buf& scratch, const double*& part, int& n
   AW_LAUNCH_CHECK();
   part = (const double*)scratch.p;
   nblk = nob;
+  return 0;
+}
+
+// ---- frame-sharded mode: reductions over ranks ------------------------------------------------
+// arena layout (caller-owned device buffer): [0, 32 KB) reduction operand, [32 KB, 64 KB) halo send,
+// [64 KB, 64 KB + world * 32 KB) halo receive
+#define AW_ARENA_RED 0
+#define AW_ARENA_SEND (32 << 10)
+#define AW_ARENA_RECV (64 << 10)
+#define AW_HALO 8
+static int sh_allreduce(aw_ctx* ctx, int64_t count, int dtype, int op, cudaStream_t st) {
+  aw_ctx::Shard* sh = ctx->sh;
+  prof_mark(ctx, st, "allreduce");
+  if (sh->comm.allreduce(sh->comm.user, AW_ARENA_RED, count, dtype, op, (void*)st))
+    return set_error("frame-sharded mode: all-reduce callback failed");
+  sh->n_allreduce++;
+  prof_mark(ctx, st, nullptr);
+  return 0;
+}
+// [nblk][W] float64 partials of the single clip -> arena[0..W) (fixed order), all-reduced (sum)
+static int sh_reduce_sum(aw_ctx* ctx, Buf& scratch, const double* part, int nblk, int W, cudaStream_t st) {
+  if (reduce_if_long(ctx, scratch, part, nblk, 1, W, st)) return 1;
+  double* red = (double*)((uint8_t*)ctx->sh->comm.d_arena + AW_ARENA_RED);
+  prof_mark(ctx, st, "reduce_partials");
+  k_reduce_partials<<<dim3((W + 255) / 256, 1, 1), 256, 0, st>>>(part, nblk, W, nblk, red);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return sh_allreduce(ctx, W, AW_COMM_F64, AW_COMM_SUM, st);
+}
+static const double* sh_red(aw_ctx* ctx) { return (const double*)((uint8_t*)ctx->sh->comm.d_arena + AW_ARENA_RED); }
+// per-clip packed peak word: max over ranks (the u64 word never has bit 63 set: int64 max == u64 max)
+static int sh_peak_max(aw_ctx* ctx, unsigned long long* peak, cudaStream_t st) {
+  void* red = (uint8_t*)ctx->sh->comm.d_arena + AW_ARENA_RED;
+  AW_CUDA(cudaMemcpyAsync(red, peak, 8, cudaMemcpyDeviceToDevice, st));
+  if (sh_allreduce(ctx, 1, AW_COMM_I64, AW_COMM_MAX, st)) return 1;
+  AW_CUDA(cudaMemcpyAsync(peak, red, 8, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// boundary frames of a [T_seg][nb] float array: own frames [own_lo, own_lo+H) and [own_hi-H, own_hi)
+// -> send[2][H][nb]; after the all-gather the neighbours' pieces land in this rank's halos
+__global__ void k_halo_pack(const float* __restrict__ a, int nb, int own_lo, int own_hi, int H,
+                            float* __restrict__ send) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, per = H * nb;
+  if (i >= 2 * per) return;
+  const int side = i / per, r = i - side * per;
+  const int frame = side == 0 ? own_lo + r / nb : own_hi - H + r / nb;
+  send[i] = a[(long long)frame * nb + r % nb];
+}
+__global__ void k_halo_unpack(const float* __restrict__ recv, int nb, int own_lo, int own_hi, int H, int rank,
+                              int world, int stride_floats, float* __restrict__ a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, per = H * nb;
+  if (i >= 2 * per) return;
+  const int side = i / per, r = i - side * per;
+  if (side == 0) {                     // left halo <- left neighbour's LAST H own frames
+    if (rank == 0) return;
+    a[(long long)(own_lo - H + r / nb) * nb + r % nb] = recv[(long long)(rank - 1) * stride_floats + per + r];
+  } else {                             // right halo <- right neighbour's FIRST H own frames
+    if (rank == world - 1) return;
+    a[(long long)(own_hi + r / nb) * nb + r % nb] = recv[(long long)(rank + 1) * stride_floats + r];
+  }
+}
+static int sh_halo_exchange(aw_ctx* ctx, float* arr, int nb, cudaStream_t st) {
+  aw_ctx::Shard* sh = ctx->sh;
+  if (sh->comm.world == 1) return 0;
+  float* send = (float*)((uint8_t*)sh->comm.d_arena + AW_ARENA_SEND);
+  float* recv = (float*)((uint8_t*)sh->comm.d_arena + AW_ARENA_RECV);
+  const int per = AW_HALO * nb, tot = 2 * per;
+  prof_mark(ctx, st, "halo_pack");
+  k_halo_pack<<<(tot + 255) / 256, 256, 0, st>>>(arr, nb, sh->own_lo, sh->own_hi, AW_HALO, send);
+  prof_mark(ctx, st, "allgather");
+  if (sh->comm.allgather(sh->comm.user, AW_ARENA_SEND, AW_ARENA_RECV, (int64_t)tot * 4, (void*)st))
+    return set_error("frame-sharded mode: all-gather callback failed");
+  sh->n_allgather++;
+  prof_mark(ctx, st, "halo_unpack");
+  k_halo_unpack<<<(tot + 255) / 256, 256, 0, st>>>(recv, nb, sh->own_lo, sh->own_hi, AW_HALO, sh->comm.rank,
+                                                   sh->comm.world, tot, arr);
+  ctx->launches += 2;
+  AW_LAUNCH_CHECK();
+  prof_mark(ctx, st, nullptr);
   return 0;
 }
 
@@ -739,6 +829,24 @@ template <> struct ModeOf<__half> {
 template <typename AT>
 static float grad_target() { return ModeOf<AT>::GSCALE == 1.0f ? 0.0f : 0.5f; }
 
+// spectra are stored for the whole (halo-extended) segment; the detector net runs on the own frames
+static float* own_frames(aw_ctx* ctx, float* base, int nb) {
+  return ctx->sh ? base + (size_t)ctx->sh->own_lo * nb : base;
+}
+// frame-sharded InstanceNorm statistics: local raw sums -> all-reduce -> (mean, rstd) / adjoint means
+template <bool BWD>
+static int sh_finalize(aw_ctx* ctx, int C, int tiles, float* stat, cudaStream_t st) {
+  double* red = (double*)((uint8_t*)ctx->sh->comm.d_arena + AW_ARENA_RED);
+  k_finalize<2><<<dim3((C + 31) / 32, 1), 256, 0, st>>>((float*)ctx->part.p, C, tiles, C, 1, nullptr, red);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  if (sh_allreduce(ctx, 2 * (int64_t)C, AW_COMM_F64, AW_COMM_SUM, st)) return 1;
+  k_stat_from_sums<BWD><<<dim3((C + 255) / 256, 1), 256, 0, st>>>(red, C, ctx->sh->Tp_glob, stat);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename AT>
 static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseMel& sm,
                        cudaStream_t st, const unsigned long long* peak_scale = nullptr) {
@@ -747,16 +855,20 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
   {
     dim3 g((d.T + AW_MEL_FRAMES - 1) / AW_MEL_FRAMES, d.n);
     prof_mark(ctx, st, "mel");
-    k_mel<<<g, 128, AW_MEL_FRAMES * d.nb * 4, st>>>((float*)ctx->mag.p, d.T, d.nb, sm,
+    k_mel<<<g, 128, AW_MEL_FRAMES * d.nb * 4, st>>>(own_frames(ctx, (float*)ctx->mag.p, d.nb), d.T, d.nb, sm,
                                                     (float*)ctx->M.p, acc.chan_part, peak_scale);
     ctx->launches++;
     AW_LAUNCH_CHECK();
     dim3 g2((d.Tp_pad + AW_P0_ROWS - 1) / AW_P0_ROWS, d.n);
     const double* cp = acc.chan_part;
     int cb = acc.mel_blocks;
-    if (reduce_if_long(ctx, ctx->red_a, cp, cb, d.n, 2 * AW_NMEL, st)) return 1;
+    if (ctx->sh) {            // channel sums over the WHOLE clip
+      if (sh_reduce_sum(ctx, ctx->red_a, cp, cb, 2 * AW_NMEL, st)) return 1;
+      cp = sh_red(ctx);
+      cb = 1;
+    } else if (reduce_if_long(ctx, ctx->red_a, cp, cb, d.n, 2 * AW_NMEL, st)) return 1;
     prof_mark(ctx, st, "mel_stats");
-    k_mel_stats<<<d.n, 128, 0, st>>>(cp, cb, d.T, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p);
+    k_mel_stats<<<d.n, 128, 0, st>>>(cp, cb, ctx->sh ? ctx->sh->T_glob : d.T, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p);
     ctx->launches++;
     AW_LAUNCH_CHECK();
     prof_mark(ctx, st, "p0");
@@ -776,10 +888,14 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
       return 1;
     dim3 g((cout + 31) / 32, d.n);
     prof_mark(ctx, st, "finalize_fwd");
-    k_finalize<false><<<g, 256, 0, st>>>((float*)ctx->part.p, cout, d.tiles, cout, d.Tp,
-                                         (float*)ctx->stat[l + 1].p);
-    ctx->launches++;
-    AW_LAUNCH_CHECK();
+    if (ctx->sh) {
+      if (sh_finalize<false>(ctx, cout, d.tiles, (float*)ctx->stat[l + 1].p, st)) return 1;
+    } else {
+      k_finalize<0><<<g, 256, 0, st>>>((float*)ctx->part.p, cout, d.tiles, cout, d.Tp,
+                                       (float*)ctx->stat[l + 1].p);
+      ctx->launches++;
+      AW_LAUNCH_CHECK();
+    }
     prof_mark(ctx, st, "norm_act");
     {
       dim3 gn(d.Tp_pad / AW_NORM_ROWS, (cout / Vec16<AT>::N + 127) / 128, d.n);
@@ -814,10 +930,14 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
     if (gemm_layer<AT, EPI_BWD>(ctx, *steps[s].ma, steps[s].a, mw, w, d.rows, n, k, ep, st)) return 1;
     dim3 g((n + 31) / 32, d.n);
     prof_mark(ctx, st, "finalize_bwd");
-    k_finalize<true><<<g, 256, 0, st>>>((float*)ctx->part.p, n, d.tiles, n, d.Tp,
-                                        (float*)ctx->bstat.p);
-    ctx->launches++;
-    AW_LAUNCH_CHECK();
+    if (ctx->sh) {
+      if (sh_finalize<true>(ctx, n, d.tiles, (float*)ctx->bstat.p, st)) return 1;
+    } else {
+      k_finalize<1><<<g, 256, 0, st>>>((float*)ctx->part.p, n, d.tiles, n, d.Tp,
+                                       (float*)ctx->bstat.p);
+      ctx->launches++;
+      AW_LAUNCH_CHECK();
+    }
     prof_mark(ctx, st, "in_bwd_apply");
     {
       dim3 gn(d.Tp_pad / AW_NORM_ROWS, (n / Vec16<AT>::N + 127) / 128, d.n);
@@ -852,17 +972,21 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
   dim3 g2((d.T + AW_P0A_FRAMES - 1) / AW_P0A_FRAMES, d.n);
   const double* bp = acc.bpart;
   int bb = acc.p0b_blocks;
-  if (reduce_if_long(ctx, ctx->red_b, bp, bb, d.n, 2 * AW_NMEL, st)) return 1;
+  if (ctx->sh) {
+    if (sh_reduce_sum(ctx, ctx->red_b, bp, bb, 2 * AW_NMEL, st)) return 1;
+    bp = sh_red(ctx);
+    bb = 1;
+  } else if (reduce_if_long(ctx, ctx->red_b, bp, bb, d.n, 2 * AW_NMEL, st)) return 1;
   prof_mark(ctx, st, "p0_bwd_coef");
-  k_p0_bwd_coef<<<d.n, 128, 0, st>>>(bp, bb, d.T, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p,
+  k_p0_bwd_coef<<<d.n, 128, 0, st>>>(bp, bb, ctx->sh ? ctx->sh->T_glob : d.T, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p,
                                      (P0BwdCoef*)ctx->p0coef.p, (P0BwdScal*)ctx->p0scal.p);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   prof_mark(ctx, st, "p0_bwd_apply");
   k_p0_bwd_apply<<<g2, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
                                      (ChanStats*)ctx->cs.p, (P0BwdCoef*)ctx->p0coef.p,
-                                     (P0BwdScal*)ctx->p0scal.p, sm, d.nb, (float*)ctx->dA.p,
-                                     euler_s2 ? (const float*)ctx->mag.p : nullptr, acc.s2_part,
+                                     (P0BwdScal*)ctx->p0scal.p, sm, d.nb, own_frames(ctx, (float*)ctx->dA.p, d.nb),
+                                     euler_s2 ? (const float*)own_frames(ctx, (float*)ctx->mag.p, d.nb) : nullptr, acc.s2_part,
                                      (const float*)ctx->gsc.p);
   ctx->launches++;
   AW_LAUNCH_CHECK();
@@ -874,6 +998,7 @@ static int run_head(aw_ctx* ctx, const Dims& d, const float* pattern, float* val
                     int n_total, bool backward, cudaStream_t st) {
   HeadArgs<AT> h;
   h.P4 = (AT*)ctx->act[4].p; h.Tp = d.Tp; h.Tp_pad = d.Tp_pad;
+  h.Tp_glob = ctx->sh ? ctx->sh->Tp_glob : d.Tp;
   h.stat4 = (float*)ctx->stat[4].p;
   h.pattern = pattern; h.values = values; h.losses = losses;
   h.best = (float*)ctx->best.p; h.improved = (int*)ctx->improved.p;
@@ -886,7 +1011,14 @@ static int run_head(aw_ctx* ctx, const Dims& d, const float* pattern, float* val
   h.hcoef = (float*)ctx->hcoef.p;
   prof_mark(ctx, st, "head");
   k_head_partial<AT><<<dim3(d.tiles, d.n), 256, 0, st>>>(h);
-  k_head_final<AT><<<d.n, 64, 0, st>>>(h, d.tiles);
+  if (ctx->sh) {
+    if (sh_reduce_sum(ctx, ctx->red_a, h.hpart, d.tiles, 64 * 3, st)) return 1;
+    HeadArgs<AT> hf = h;
+    hf.hpart = const_cast<double*>(sh_red(ctx));
+    k_head_final<AT><<<d.n, 64, 0, st>>>(hf, 1);
+  } else {
+    k_head_final<AT><<<d.n, 64, 0, st>>>(h, d.tiles);
+  }
   ctx->launches += 2;
   if (backward && pattern) {
     k_head_seed<AT><<<dim3(d.tiles, d.n), 256, 0, st>>>(h);
@@ -1337,6 +1469,212 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------
+// frame-sharded long-form mode (BASELINE configs[4]): ONE long clip, frames split over
+// the ranks of a box.  Every statistic the reference takes is whole-clip (utils/audio/waveform.py:19,
+// detection/modules/globalStandardize.py:17-19, multibit_detector_net.py:50,126, modules/BRH.py:18),
+// so a rank processes a halo-extended SEGMENT of the clip as if it were a clip of its own -- the
+// pseudo-edges only contaminate halo frames, which are never used -- while (a) every per-clip sum /
+// max is reduced over the ranks between the kernel that produces its partials and the kernel that
+// consumes it, and (b) the halo frames of the optimisation variables and of the spectral gradient are
+// refreshed from their owners every iteration.  Results equal the single-GPU run up to the summation
+// order of the float64 statistics.
+// ---------------------------------------------------------------------------
+static int shard_begin(aw_ctx* ctx, aw_ctx::Shard* sh, const aw_comm* comm, int seg_samples, int seg_first_frame,
+                       int own_lo, int own_hi, int total_frames, int sample_rate, Dims* ds, Dims* dn) {
+  AW_REQUIRE(comm && comm->allreduce && comm->allgather && comm->d_arena, "sharded mode: incomplete aw_comm");
+  AW_REQUIRE(comm->world >= 1 && comm->rank >= 0 && comm->rank < comm->world, "sharded mode: bad rank %d / %d",
+             comm->rank, comm->world);
+  AW_REQUIRE(comm->arena_bytes >= AW_ARENA_RECV + (int64_t)comm->world * (32 << 10),
+             "sharded mode: arena must hold %d bytes", AW_ARENA_RECV + comm->world * (32 << 10));
+  if (make_dims(ctx, 1, seg_samples, sample_rate, ds)) return 1;
+  AW_REQUIRE(own_lo >= 0 && own_hi <= ds->T && own_hi - own_lo >= 2 * AW_HALO,
+             "sharded mode: own frames [%d,%d) of a %d-frame segment (need >= %d)", own_lo, own_hi, ds->T, 2 * AW_HALO);
+  const bool first = comm->rank == 0, last = comm->rank == comm->world - 1;
+  AW_REQUIRE(first ? (own_lo == 0 && seg_first_frame == 0) : own_lo == AW_HALO, "sharded mode: left halo must be %d frames", AW_HALO);
+  AW_REQUIRE(last ? own_hi == ds->T : own_hi == ds->T - AW_HALO, "sharded mode: right halo must be %d frames", AW_HALO);
+  AW_REQUIRE(((seg_first_frame + own_lo) & 1) == 0 && (last || ((own_hi - own_lo) & 1) == 0),
+             "sharded mode: shard boundaries must fall on even frames (AvgPool1d(2,2) pairs)");
+  AW_REQUIRE(last ? seg_first_frame + ds->T == total_frames : seg_first_frame + ds->T < total_frames + AW_HALO,
+             "sharded mode: segment does not fit the clip");
+  sh->comm = *comm;
+  sh->T_glob = total_frames;
+  sh->Tp_glob = total_frames / 2;
+  sh->e0 = seg_first_frame;
+  sh->own_lo = own_lo;
+  sh->own_hi = own_hi;
+  *dn = *ds;
+  dn->T = own_hi - own_lo;
+  dn->Tp = dn->T / 2;
+  dn->Tp_pad = (dn->Tp + AW_ROW_TILE - 1) / AW_ROW_TILE * AW_ROW_TILE;
+  dn->tiles = dn->Tp_pad / AW_ROW_TILE;
+  dn->rows = dn->Tp_pad;
+  dn->L = AW_HOP * (dn->T - 1);
+  return 0;
+}
+
+extern "C" int aw_detect_sharded(aw_ctx* ctx, const float* d_segment, int seg_samples, int seg_first_frame,
+                                 int own_lo, int own_hi, int total_frames, int sample_rate, const aw_comm* comm,
+                                 float* d_values, void* stream) {
+  AW_REQUIRE(ctx && d_segment && d_values, "aw_detect_sharded: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  AW_CUDA(cudaSetDevice(ctx->device));
+  aw_ctx::Shard sh;
+  Dims ds, dn;
+  if (shard_begin(ctx, &sh, comm, seg_samples, seg_first_frame, own_lo, own_hi, total_frames, sample_rate, &ds, &dn)) return 1;
+  if (ensure(ctx->mag, (size_t)ds.T * ds.nb * 4) || ensure_net_ws(ctx, dn, false) ||
+      ensure(ctx->accum, acc_doubles(ds) * 8) || ensure(ctx->peakx, 8))
+    return 1;
+  SparseMel sm;
+  if (get_mel(ctx, ds.bin0, ds.nb, &sm)) return 1;
+  ctx->sh = &sh;
+  struct Clear { aw_ctx* c; ~Clear() { c->sh = nullptr; } } clear_{ctx};
+  nvtxRangePushA("aw_detect_sharded");
+  struct Pop { ~Pop() { nvtxRangePop(); } } pop_;
+  const Acc acc = acc_view(ctx, dn);
+  if (begin_pass(ctx, 1, nullptr, st)) return 1;
+  if (launch_peak(ctx, d_segment, seg_samples, seg_samples, 1, (unsigned long long*)ctx->peakx.p, st)) return 1;
+  if (sh_peak_max(ctx, (unsigned long long*)ctx->peakx.p, st)) return 1;        // waveform.py:19 over the whole clip
+  AnaArgs a = ana_base(ctx, ds);
+  a.sig = d_segment; a.sig_stride = seg_samples; a.len = seg_samples;
+  a.peak = (unsigned long long*)ctx->peakx.p;
+  a.mag = (float*)ctx->mag.p;
+  if (launch_ana<ANA_MAG>(ctx, ds, a, st)) return 1;
+  int rc;
+  if (ctx->prec == AW_PREC_BF16)
+    rc = net_forward<__nv_bfloat16>(ctx, dn, acc, sm, st) || run_head<__nv_bfloat16>(ctx, dn, nullptr, d_values, nullptr, 1, false, st);
+  else if (ctx->prec == AW_PREC_FP16)
+    rc = net_forward<__half>(ctx, dn, acc, sm, st) || run_head<__half>(ctx, dn, nullptr, d_values, nullptr, 1, false, st);
+  else
+    rc = net_forward<float>(ctx, dn, acc, sm, st) || run_head<float>(ctx, dn, nullptr, d_values, nullptr, 1, false, st);
+  prof_mark(ctx, st, nullptr);
+  return rc;
+}
+
+extern "C" int aw_embed_sharded(aw_ctx* ctx, const float* d_segment, int seg_samples, int seg_first_frame,
+                                int own_lo, int own_hi, int total_frames, int sample_rate,
+                                const int32_t* d_pattern, int iters, const aw_comm* comm, float* d_out_own,
+                                int64_t out_capacity, float* d_best_loss, float* d_losses, int64_t* comm_counts,
+                                void* stream) {
+  AW_REQUIRE(ctx && d_segment && d_pattern && d_out_own, "aw_embed_sharded: null argument");
+  AW_REQUIRE(iters >= 0, "aw_embed_sharded: iters < 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  AW_CUDA(cudaSetDevice(ctx->device));
+  aw_ctx::Shard sh;
+  Dims ds, dn;
+  if (shard_begin(ctx, &sh, comm, seg_samples, seg_first_frame, own_lo, own_hi, total_frames, sample_rate, &ds, &dn)) return 1;
+  // own output samples: global [256 f0, 256 f1) cut at the clip's length 256 (T - 1)
+  const int out_lo = AW_HOP * own_lo, out_hi = std::min(AW_HOP * own_hi, ds.L);
+  AW_REQUIRE(out_capacity >= out_hi - out_lo, "aw_embed_sharded: output capacity %lld < %d", (long long)out_capacity, out_hi - out_lo);
+  const size_t sp = (size_t)ds.T * ds.nb;
+  if (ensure(ctx->mag, sp * 4) || ensure_net_ws(ctx, dn, true) || ensure(ctx->accum, acc_doubles(ds) * 8) ||
+      ensure(ctx->ph_u, sp * 8) || ensure(ctx->ph_q, sp * 8) || ensure(ctx->c0, sp * 4) ||
+      ensure(ctx->c, sp * 4) || ensure(ctx->m, sp * 4) || ensure(ctx->v, sp * 4) ||
+      ensure(ctx->cbest, sp * 4) || ensure(ctx->dA, sp * 4) ||
+      ensure(ctx->yoob, (size_t)ds.L * 4) || ensure(ctx->y, (size_t)ds.L * 4) || ensure(ctx->zoob, (size_t)ds.L * 4) ||
+      ensure(ctx->pattern, AW_NBITS * 4) || ensure(ctx->scal, sizeof(ClipScal)) || ensure(ctx->nonfinite, 4) ||
+      ensure(ctx->steps, (size_t)(iters > 0 ? iters : 1) * sizeof(NadamStep)) || ensure(ctx->peakx, 8))
+    return 1;
+  SparseMel sm;
+  if (get_mel(ctx, ds.bin0, ds.nb, &sm)) return 1;
+  std::vector<NadamStep> tab;
+  nadam_table(iters, tab);
+  if (iters > 0)
+    AW_CUDA(cudaMemcpyAsync(ctx->steps.p, tab.data(), tab.size() * sizeof(NadamStep), cudaMemcpyHostToDevice, st));
+  AW_CUDA(cudaMemsetAsync(ctx->nonfinite.p, 0, 4, st));
+  AW_CUDA(cudaMemsetAsync(ctx->dA.p, 0, sp * 4, st));
+  ctx->last_embed_clips = 1;
+  AW_CUDA(cudaStreamSynchronize(st));   // `tab` is pageable host memory
+  ctx->sh = &sh;
+  struct Clear { aw_ctx* c; ~Clear() { c->sh = nullptr; } } clear_{ctx};
+  nvtxRangePushA("aw_embed_sharded");
+  struct Pop { ~Pop() { nvtxRangePop(); } } pop_;
+
+  const Acc acc = acc_view(ctx, dn);           // peak word at the base; partial-sum arrays of the own frames
+  int* itc = (int*)ctx->itc.p;
+  const int n_base = AW_HOP * seg_first_frame;  // global index of the segment's sample 0
+  k_set_int<<<1, 1, 0, st>>>(itc, -1);
+  k_fill<<<1, 256, 0, st>>>((float*)ctx->best.p, INFINITY, 1);
+  k_pattern_to_float<<<1, 256, 0, st>>>(d_pattern, (float*)ctx->pattern.p, AW_NBITS);
+  ctx->launches += 3;
+  AW_LAUNCH_CHECK();
+  if (launch_peak(ctx, d_segment, seg_samples, seg_samples, 1, (unsigned long long*)ctx->peakx.p, st)) return 1;
+  if (sh_peak_max(ctx, (unsigned long long*)ctx->peakx.p, st)) return 1;
+
+  // ---- pre-STFT, bounds, constant out-of-band waveform of the segment
+  AnaArgs a0 = ana_base(ctx, ds);
+  a0.sig = d_segment; a0.sig_stride = seg_samples; a0.len = seg_samples;
+  a0.peak = (unsigned long long*)ctx->peakx.p;
+  a0.mag = (float*)ctx->c0.p; a0.ph = (float2*)ctx->ph_u.p;
+  a0.c = (float*)ctx->c.p; a0.m = (float*)ctx->m.p; a0.v = (float*)ctx->v.p; a0.cbest = (float*)ctx->cbest.p;
+  if (launch_ana<ANA_INIT>(ctx, ds, a0, st)) return 1;
+  SynArgs s0 = syn_base(ctx, ds);
+  s0.amp = (float*)ctx->c0.p; s0.ph = (float2*)ctx->ph_u.p; s0.scale = 1.0f / AW_NFFT;
+  s0.x = d_segment; s0.x_stride = seg_samples; s0.peak_x = (unsigned long long*)ctx->peakx.p;
+  s0.y_oob = (float*)ctx->yoob.p; s0.z_oob = (float*)ctx->zoob.p;
+  if (launch_syn<SYN_OOB>(ctx, ds, s0, st)) return 1;
+
+  auto net_pass = [&](auto tag) -> int {
+    using AT = decltype(tag);
+    if (net_forward<AT>(ctx, dn, acc, sm, st, acc.peak_y)) return 1;
+    if (run_head<AT>(ctx, dn, (float*)ctx->pattern.p, (float*)ctx->values.p, d_losses, 1, true, st)) return 1;
+    return net_backward<AT>(ctx, dn, acc, sm, st, true);
+  };
+  for (int it = 0; it < iters; ++it) {
+    if (begin_pass(ctx, 1, itc, st)) return 1;
+    SpecArgs f;
+    memset(&f, 0, sizeof(f));
+    f.amp = (float*)ctx->c.p; f.ph = (float2*)ctx->ph_u.p;
+    f.z_oob = (float*)ctx->zoob.p; f.peak_y = acc.peak_y;
+    f.mag = (float*)ctx->mag.p; f.q = (float2*)ctx->ph_q.p;
+    f.pk_lo = out_lo; f.pk_hi = out_hi; f.idx_base = n_base;
+    if (launch_spec<SPEC_FWD>(ctx, ds, f, st)) return 1;
+    if (sh_peak_max(ctx, acc.peak_y, st)) return 1;                      // max |y| over the whole clip
+    int rc;
+    if (ctx->prec == AW_PREC_BF16) rc = net_pass(__nv_bfloat16());
+    else if (ctx->prec == AW_PREC_FP16) rc = net_pass(__half());
+    else rc = net_pass(float());
+    if (rc) return 1;
+    if (sh_reduce_sum(ctx, ctx->red_c, acc.s2_part, p0a_blocks(dn), 1, st)) return 1;   // Euler sum over the clip
+    prof_mark(ctx, st, "clip_scalars");
+    k_clip_scalars<<<1, 128, 0, st>>>(acc.peak_y, sh_red(ctx), 1, 1, (ClipScal*)ctx->scal.p, n_base);
+    ctx->launches++;
+    AW_LAUNCH_CHECK();
+    if (sh_halo_exchange(ctx, (float*)ctx->dA.p, ds.nb, st)) return 1;   // spectral gradient of the halo frames
+    SpecArgs b;
+    memset(&b, 0, sizeof(b));
+    b.amp = (float*)ctx->dA.p; b.ph = (float2*)ctx->ph_q.p;
+    b.scal = (ClipScal*)ctx->scal.p; b.u = (float2*)ctx->ph_u.p;
+    b.c = (float*)ctx->c.p; b.m = (float*)ctx->m.p; b.v = (float*)ctx->v.p;
+    b.cbest = (float*)ctx->cbest.p; b.c0 = (float*)ctx->c0.p;
+    b.improved = (int*)ctx->improved.p; b.steps = (NadamStep*)ctx->steps.p; b.it_ptr = itc;
+    b.nonfinite = (int*)ctx->nonfinite.p;
+    b.tol_ratio = (float)pow(10.0, -(double)ctx->tol_db / 20.0);
+    if (launch_spec<SPEC_BWD>(ctx, ds, b, st)) return 1;
+    if (sh_halo_exchange(ctx, (float*)ctx->c.p, ds.nb, st)) return 1;    // updated coefficients of the halo frames
+  }
+  // ---- final synthesis from the best coefficients, peak over the whole clip, own samples out
+  if (sh_halo_exchange(ctx, (float*)ctx->cbest.p, ds.nb, st)) return 1;
+  if (begin_pass(ctx, 1, nullptr, st)) return 1;
+  SynArgs sf = syn_base(ctx, ds);
+  sf.amp = (float*)ctx->cbest.p; sf.ph = (float2*)ctx->ph_u.p; sf.scale = 1.0f / AW_NFFT;
+  sf.y_oob = (float*)ctx->yoob.p; sf.y = (float*)ctx->y.p; sf.peak_y = acc.peak_y;
+  sf.pk_lo = out_lo; sf.pk_hi = out_hi;
+  if (launch_syn<SYN_WAVE>(ctx, ds, sf, st)) return 1;
+  if (sh_peak_max(ctx, acc.peak_y, st)) return 1;
+  prof_mark(ctx, st, "final_normalize");
+  k_final_normalize<<<dim3(std::min((out_hi - out_lo + 4095) / 4096, 1024), 1), 256, 0, st>>>(
+      (float*)ctx->y.p + out_lo, out_hi - out_lo, acc.peak_y, nullptr, nullptr, d_out_own, out_capacity);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  if (d_best_loss) AW_CUDA(cudaMemcpyAsync(d_best_loss, ctx->best.p, 4, cudaMemcpyDeviceToDevice, st));
+  if (comm_counts) { comm_counts[0] = sh.n_allreduce; comm_counts[1] = sh.n_allgather; }
+  ctx->last_n = 1; ctx->last_T = ds.T; ctx->last_nb = ds.nb;
+  prof_mark(ctx, st, nullptr);
+  return 0;
+}
+
 extern "C" int aw_embed_state(aw_ctx* ctx, int which, float* d_dst, int64_t capacity, void* stream) {
   AW_REQUIRE(ctx && d_dst, "null argument");
   if (ctx) cudaSetDevice(ctx->device);
@@ -1485,7 +1823,8 @@ extern "C" int aw_gemm(aw_ctx* ctx, const float* d_a, const float* d_b, float* d
 // ---------------------------------------------------------------------------
 // attacks
 // ---------------------------------------------------------------------------
-static dim3 ew_grid(int n, int n_clips) { return dim3(std::min((n + 1023) / 1024, 256), n_clips); }
+// streaming passes: 4 samples per thread and access, enough CTAs to cover the 148 SMs several times
+static dim3 ew_grid(int n, int n_clips) { return dim3(std::min((n + 4095) / 4096, std::max(8, 4096 / n_clips)), n_clips); }
 
 extern "C" int aw_attack_pcm(aw_ctx* ctx, const float* d_in, int n_clips, int n, int64_t in_stride,
                              int bits, float* d_out, int64_t out_stride, void* stream) {
@@ -1577,7 +1916,10 @@ extern "C" int aw_attack_lfilter(aw_ctx* ctx, const float* d_in, int n_clips, in
   ia.x32 = d_in; ia.sx32 = in_stride; ia.n_x = n;
   ia.o32 = d_out; ia.so32 = out_stride;
   prof_mark(ctx, (cudaStream_t)stream, "attack_lfilter");
-  k_iir<IIR_SRC_F32, IIR_DST_F32><<<g, 128, 0, (cudaStream_t)stream>>>(ia);
+  if (warm <= 0)
+    k_iir_seq<IIR_SRC_F32, IIR_DST_F32><<<(n_clips + 31) / 32, 32, 0, (cudaStream_t)stream>>>(ia);
+  else
+    k_iir<IIR_SRC_F32, IIR_DST_F32><<<g, 128, 0, (cudaStream_t)stream>>>(ia);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
@@ -1604,12 +1946,18 @@ extern "C" int aw_attack_filtfilt(aw_ctx* ctx, const float* d_in, int n_clips, i
   ia.x32 = d_in; ia.sx32 = in_stride; ia.n_x = n;
   ia.o64 = (double*)ctx->ga.p; ia.so64 = next;
   prof_mark(ctx, (cudaStream_t)stream, "attack_filtfilt_fwd");
-  k_iir<IIR_SRC_ODDEXT, IIR_DST_F64><<<g, 128, 0, st>>>(ia);
+  if (warm <= 0)
+    k_iir_seq<IIR_SRC_ODDEXT, IIR_DST_F64><<<(n_clips + 31) / 32, 32, 0, st>>>(ia);
+  else
+    k_iir<IIR_SRC_ODDEXT, IIR_DST_F64><<<g, 128, 0, st>>>(ia);
   IirArgs ib = ia;
   ib.x64 = (double*)ctx->ga.p; ib.sx64 = next;
   ib.o32 = d_out; ib.so32 = out_stride;
   prof_mark(ctx, (cudaStream_t)stream, "attack_filtfilt_bwd");
-  k_iir<IIR_SRC_REV_F64, IIR_DST_REVTRIM_F32><<<g, 128, 0, st>>>(ib);
+  if (warm <= 0)
+    k_iir_seq<IIR_SRC_REV_F64, IIR_DST_REVTRIM_F32><<<(n_clips + 31) / 32, 32, 0, st>>>(ib);
+  else
+    k_iir<IIR_SRC_REV_F64, IIR_DST_REVTRIM_F32><<<g, 128, 0, st>>>(ib);
   ctx->launches += 2;
   AW_LAUNCH_CHECK();
   return 0;

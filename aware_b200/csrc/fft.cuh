@@ -275,6 +275,7 @@ struct SynArgs {
   // SYN_WAVE: y = ola/env + y_oob, peak_y
   float* y;                    // [clip][L]   (WAVE: out)
   unsigned long long* peak_y;  // [clip]      (WAVE: atomicMax out)
+  int pk_lo, pk_hi;            // WAVE: samples competing for the peak (frame-sharded mode); pk_hi = 0: all
 };
 
 #define AW_SYN_FRAMES 32
@@ -413,6 +414,7 @@ __global__ void __launch_bounds__(128, 2) k_synthesis(SynArgs a) {
     float best = -1.f;
     int best_n = 0;
     float rdx = 1.f;
+    const int pk_lo = a.pk_lo, pk_hi = a.pk_hi > 0 ? a.pk_hi : L;
     if (MODE == SYN_OOB) rdx = __fdiv_rn(1.0f, peak_value(a.peak_x[clip]) + 1e-8f);
     const bool interior = h0 >= 3 && h0 + AW_SYN_HOPS <= T - 1 && m_lo >= AW_HALF && m_hi - AW_HALF <= L;
     if (interior) {
@@ -437,8 +439,10 @@ __global__ void __launch_bounds__(128, 2) k_synthesis(SynArgs a) {
           const float yy[4] = {yb[0] + q4.x, yb[1] + q4.y, yb[2] + q4.z, yb[3] + q4.w};
           *reinterpret_cast<float4*>(a.y + ob + i) = make_float4(yy[0], yy[1], yy[2], yy[3]);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (fabsf(yy[k]) > best) { best = fabsf(yy[k]); best_n = m_lo - AW_HALF + i + k; }
+          for (int k = 0; k < 4; ++k) {
+            const int nn = m_lo - AW_HALF + i + k;
+            if (fabsf(yy[k]) > best && nn >= pk_lo && nn < pk_hi) { best = fabsf(yy[k]); best_n = nn; }
+          }
         }
       }
     } else {
@@ -454,7 +458,7 @@ __global__ void __launch_bounds__(128, 2) k_synthesis(SynArgs a) {
         } else {
           const float yy = yb + a.y_oob[o];
           a.y[o] = yy;
-          if (fabsf(yy) > best) { best = fabsf(yy); best_n = n; }
+          if (fabsf(yy) > best && n >= pk_lo && n < pk_hi) { best = fabsf(yy); best_n = n; }
         }
       }
     }

@@ -204,9 +204,12 @@ __global__ void __launch_bounds__(128) k_p0(const float* __restrict__ M, int T, 
 // part: [clip * tiles + tile][ldp][2] ; stat: [clip][C][2] = (mean, rstd)
 // block = 32 channels x 8 tile slices: slice s sums tiles s, s+8, ... and the 8 slice sums are
 // combined in fixed order, so long clips (thousands of tiles) are not serialised per channel.
-template <bool BWD>
+// MODE: 0 forward (mean, rstd), 1 backward (two means), 2 raw float64 sums [clip][C][2] written to
+// `raw` (frame-sharded long-form mode: the sums are all-reduced over ranks before k_stat_from_sums)
+template <int MODE>
 __global__ void __launch_bounds__(256) k_finalize(const float* __restrict__ part, int ldp, int tiles,
-                                                  int C, int Tp, float* __restrict__ stat) {
+                                                  int C, int Tp, float* __restrict__ stat,
+                                                  double* __restrict__ raw = nullptr) {
   __shared__ double s_s[8][32][2];
   const int clip = blockIdx.y, cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
@@ -224,8 +227,30 @@ __global__ void __launch_bounds__(256) k_finalize(const float* __restrict__ part
   if (sl != 0 || c >= C) return;
 #pragma unroll
   for (int k = 1; k < 8; ++k) { s1 += s_s[k][cl][0]; s2 += s_s[k][cl][1]; }
-  if (BWD) {
+  if (MODE == 2) {
+    raw[((long long)clip * C + c) * 2] = s1;
+    raw[((long long)clip * C + c) * 2 + 1] = s2;
+  } else if (MODE == 1) {
     // bstat: (mean_j dHhat, mean_j dHhat*Hhat)
+    stat[((long long)clip * C + c) * 2] = (float)(s1 / Tp);
+    stat[((long long)clip * C + c) * 2 + 1] = (float)(s2 / Tp);
+  } else {
+    const double mu = s1 / Tp;
+    double var = s2 / Tp - mu * mu;
+    if (var < 0.0) var = 0.0;
+    stat[((long long)clip * C + c) * 2] = (float)mu;
+    stat[((long long)clip * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + AW_IN_EPS));
+  }
+}
+
+// statistics from (all-reduced) raw sums; Tp = GLOBAL pooled frame count of the clip
+template <bool BWD>
+__global__ void __launch_bounds__(256) k_stat_from_sums(const double* __restrict__ raw, int C, int Tp,
+                                                        float* __restrict__ stat) {
+  const int clip = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s1 = raw[((long long)clip * C + c) * 2], s2 = raw[((long long)clip * C + c) * 2 + 1];
+  if (BWD) {
     stat[((long long)clip * C + c) * 2] = (float)(s1 / Tp);
     stat[((long long)clip * C + c) * 2 + 1] = (float)(s2 / Tp);
   } else {
@@ -350,6 +375,7 @@ __global__ void __launch_bounds__(128) k_norm_rows(AT* __restrict__ X, const AT*
 template <typename AT>
 struct HeadArgs {
   const AT* P4; int Tp, Tp_pad;
+  int Tp_glob;               // pooled frames of the WHOLE clip (= Tp unless the clip is frame-sharded)
   const float* stat4;        // [clip][64][2]
   const float* pattern;      // [clip][20] (+-1) or null (detect only)
   float* values;             // [clip][20]
@@ -403,7 +429,7 @@ __global__ void __launch_bounds__(64) k_head_final(HeadArgs<AT> a, int tiles) {
     const double* o = a.hpart + (((long long)clip * tiles + t) * 64 + c) * 3;
     sp += o[0]; sn += o[1]; np_ += o[2];
   }
-  const float z = (float)((sp + (double)AW_LEAKY * sn) / a.Tp);
+  const float z = (float)((sp + (double)AW_LEAKY * sn) / a.Tp_glob);
   s_z[c] = z;
   s_dz[c] = 0.f;
   __syncthreads();
@@ -431,8 +457,8 @@ __global__ void __launch_bounds__(64) k_head_final(HeadArgs<AT> a, int tiles) {
         const float sg = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
         const float dv = 2.f * (v - p) / AW_NBITS - 0.1f * sg / AW_NBITS;
         const float dd = dv * (1.f - v * v);
-        s_dz[2 * c] = dd / a.Tp;
-        s_dz[2 * c + 1] = -dd / a.Tp;
+        s_dz[2 * c] = dd / a.Tp_glob;
+        s_dz[2 * c + 1] = -dd / a.Tp_glob;
       }
     }
   }
@@ -451,8 +477,8 @@ __global__ void __launch_bounds__(64) k_head_final(HeadArgs<AT> a, int tiles) {
     }
   }
   const float dz = s_dz[c];
-  const double nneg = (double)a.Tp - np_;
-  const float a1 = (float)((double)dz * (np_ + (double)AW_LEAKY * nneg) / a.Tp);
+  const double nneg = (double)a.Tp_glob - np_;
+  const float a1 = (float)((double)dz * (np_ + (double)AW_LEAKY * nneg) / a.Tp_glob);
   const float a2 = dz * z;
   *reinterpret_cast<float4*>(a.hcoef + ((long long)clip * 64 + c) * 4) =
       make_float4(dz, a1, a2, a.stat4[((long long)clip * 64 + c) * 2 + 1]);

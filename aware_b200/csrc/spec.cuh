@@ -233,9 +233,11 @@ struct ClipScal {
 };
 
 // s2_part: [clip][nblk] partial sums of dA~ * A~(un-normalised), fixed-order reduction
+// n_base: sample index of this rank's local sample 0 in the whole clip (frame-sharded mode packs
+// GLOBAL indices into the peak word; 0 otherwise)
 __global__ void __launch_bounds__(128) k_clip_scalars(const unsigned long long* __restrict__ peak_y,
                                                       const double* __restrict__ s2_part, int nblk,
-                                                      int n_clips, ClipScal* __restrict__ out) {
+                                                      int n_clips, ClipScal* __restrict__ out, int n_base = 0) {
   const int clip = blockIdx.x * blockDim.x + threadIdx.x;
   if (clip >= n_clips) return;
   const unsigned long long pk = peak_y[clip];
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(128) k_clip_scalars(const unsigned long long* 
   const float s2 = (float)(s2d * (double)cs.inv);
   const float s1 = s2 * 1e-8f / d2;
   cs.corr = peak_s_sign(pk) * (s2 / d2 + s1) / d1;
-  cs.nstar = (int)peak_s_index(pk);
+  cs.nstar = (int)peak_s_index(pk) - n_base;
   cs.pad = 0.f;
   out[clip] = cs;
 }
@@ -285,6 +287,9 @@ struct SpecArgs {
   const NadamStep* steps;
   const int* it_ptr;
   float tol_ratio;
+  // frame-sharded long-form mode: only samples [pk_lo, pk_hi) of the local (halo-extended) segment
+  // compete for the peak, and the index packed with it is global (local + idx_base).  pk_hi = 0: all.
+  int pk_lo, pk_hi, idx_base;
 };
 
 #define AW_SP_FA 58                        // analysis frames per tile
@@ -485,6 +490,7 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
       }
       float best = 0.f;
       int best_n = -1;
+      const int pk_lo = a.pk_lo, pk_hi = a.pk_hi > 0 ? a.pk_hi : L;
       for (int r4 = tid * 4; r4 < AW_SP_BUF; r4 += 4 * 32 * AW_SP_WARPS) {
         const int m = m0 + r4, n = m - AW_HALF, hop = m >> 8;
         float4 s4 = *reinterpret_cast<float4*>(s_buf + r4);
@@ -502,7 +508,10 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               vv[k] = vv[k] * ie[k];                     // (ola + y_oob * env) / env
-              if (fabsf(vv[k]) > fabsf(best) || best_n < 0) { best = vv[k]; best_n = n + k; }
+              if ((fabsf(vv[k]) > fabsf(best) || best_n < 0) && (n + k >= pk_lo && n + k < pk_hi)) {
+                best = vv[k];
+                best_n = n + k;
+              }
             }
           } else {
 #pragma unroll
@@ -518,7 +527,7 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
         *reinterpret_cast<float4*>(s_buf + r4) = make_float4(vv[0], vv[1], vv[2], vv[3]);
       }
       if (MODE == SPEC_FWD) {
-        unsigned long long pk = best_n >= 0 ? pack_peak_s(best, (unsigned)best_n) : 0ull;
+        unsigned long long pk = best_n >= 0 ? pack_peak_s(best, (unsigned)(best_n + a.idx_base)) : 0ull;
         pk = warp_max_u64(pk);
         if (lane == 0) s_pk[warp] = pk;
       }

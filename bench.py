@@ -176,7 +176,8 @@ def workload_config(args):
                                                       "bandstop, suppress .1/.25, lowpass, highpass) -> detect -> BER"),
             "clips_per_gpu": clips, "clip_seconds": secs, "sample_rate": args.sr, "iterations": args.iters,
             "gemm_precision": args.precision, "wave_clips": args.wave,
-            "cache": "inputs %.0f MB per GPU > 126 MB L2 (no explicit flush)" % (clips * n * 4 / 1e6)}
+            "cache": ("inputs %.0f MB per GPU > 126 MB L2 (no explicit flush)" if clips * n * 4 > 126e6 else
+                      "inputs %.0f MB per GPU fit L2: reduced configuration, not a bench line") % (clips * n * 4 / 1e6)}
 
 
 # --------------------------------------------------------------------------------------
@@ -498,7 +499,7 @@ def main():
             att = {}
             for lab, n_out in (("attack_pcm", L), ("attack_decim_interp", L), ("attack_delete", None),
                                ("attack_suppress", L), ("attack_lfilter", L), ("attack_filtfilt_fwd", None),
-                               ("attack_filtfilt_bwd", None), ("peak", 0)):
+                               ("attack_filtfilt_bwd", None)):
                 if lab in timeline and timeline[lab][0]:
                     c_, m_ = timeline[lab]
                     rec = {"launches": c_, "avg_ms": m_ / c_}
@@ -565,10 +566,24 @@ def main():
         if n_par > 0:
             parity = {"clips": n_par, "evaluations_per_clip": n_eval, "margin": 1e-3,
                       "tolerances": "decoded bits bit-exact vs the oracle on the same audio wherever |v_oracle| >= 1e-5 "
-                                    "(below that fp32 summation order decides); functional SNR within +-1 dB of the "
-                                    "oracle's own embed; cross-detect BER 0 (SURVEY 8c protocol, F7)"}
+                                    "(below that fp32 summation order decides); functional SNR: MEAN over the parity clips "
+                                    "within +-1 dB of the oracle's own embeds (per-clip values are chaotic, SURVEY F7: the "
+                                    "oracle itself moves by `oracle_reproducibility.snr_delta_db` when only its thread "
+                                    "count changes); cross-detect BER 0 (SURVEY 8c protocol)"}
             x_np = x_host[:n_par].numpy()
             y_ref = np.stack([ref[i]["y"] for i in range(n_par)])
+            # the reference against itself: same clips, half the intra-op threads (only summation order changes)
+            torch.set_num_threads(max(1, cores // 2))
+            y_ref2 = [O.embed_watermark(x_np[i], sr, bits_np[i], num_iters=args.iters) for i in range(n_par)]
+            torch.set_num_threads(cores)
+            s_a = [O.snr_db(y_ref[i], x_np[i][:L]) for i in range(n_par)]
+            s_b = [O.snr_db(y_ref2[i], x_np[i][:L]) for i in range(n_par)]
+            parity["oracle_reproducibility"] = {
+                "threads": [cores, max(1, cores // 2)], "snr_db": [s_a, s_b],
+                "snr_delta_db": [a_ - b_ for a_, b_ in zip(s_a, s_b)],
+                "waveform_snr_db_between_runs": [O.snr_db(y_ref2[i], y_ref[i]) for i in range(n_par)],
+                "bits_identical": bool(all(np.array_equal(O.detect_watermark(y_ref2[i], sr), bits_np[i])
+                                           for i in range(n_par)))}
             # cross-detect: ORACLE-embedded audio decoded by the CUDA detector (clean + attacks)
             yr_d = torch.from_numpy(y_ref).to(dev)
             cross_ok, cross_ber_n, cross_flips = True, 0, 0
@@ -609,8 +624,8 @@ def main():
                     "values_below_margin": n_low, "flips_below_margin": n_flip_low, "flips_total": n_flip,
                     "max_abs_value_diff": worst, "clean_bit_errors_gpu_detector": ber_gpu,
                     "clean_bit_errors_oracle_detector": ber_orc, "snr_db_gpu": snr_g, "snr_db_oracle_embed": snr_o,
-                    "snr_delta_db_max_abs": max(abs(d) for d in d_snr),
-                    "ok": bool(bits_ok and ber_gpu == 0 and ber_orc == 0 and max(abs(d) for d in d_snr) <= 1.0)}
+                    "snr_delta_db_per_clip": d_snr, "snr_delta_db_mean": float(np.mean(d_snr)),
+                    "ok": bool(bits_ok and ber_gpu == 0 and ber_orc == 0 and abs(float(np.mean(d_snr))) <= 1.0)}
             parity["all_ok"] = bool(all(v["ok"] for v in parity.values() if isinstance(v, dict) and "ok" in v))
 
     names = ["clean"] + [a.name for a in suite]

@@ -106,6 +106,42 @@ int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, int n_samples
 /* per-clip status of the last aw_embed_batch call, int32 [n_clips]: 1 = the clip met a non-finite
  * gradient inside the loop (only possible with 16-bit loop GEMMs; that NAdam update was skipped) */
 int aw_embed_status(aw_ctx* ctx, int32_t* d_flags, int n_clips, void* stream);
+/* ---- frame-sharded long-form mode (BASELINE configs[4]: one long clip over the GPUs of a box).
+ * The reference processes a clip whole and every statistic is whole-clip (utils/audio/waveform.py:19,
+ * detection/modules/globalStandardize.py:17-19, multibit_detector_net.py:50,126, modules/BRH.py:18).
+ * Here each rank passes a SEGMENT of the clip: its own frames [own_lo, own_hi) (local indices) plus
+ * 8 halo frames per inner side; per-clip sums / maxima are reduced over the ranks and halo frames are
+ * refreshed through the caller's two collectives, both operating on a caller-owned device arena:
+ *   allreduce(user, offset, count, dtype, op, stream)  in place, `count` 8-byte elements at arena+offset
+ *   allgather(user, send_offset, recv_offset, bytes, stream)  rank-major result at arena+recv_offset
+ * (host callbacks: they ENQUEUE the collective behind the work already on `stream`; 0 = success).
+ * Geometry (T = 1 + N/256 frames of the whole clip): a rank owns global frames [f0, f1), f0 even, f1
+ * even except on the last rank (f1 = T); segment frames [e0, e1) = [max(0, f0-8), min(T, f1+8));
+ * segment samples = global samples [256 e0, ...): 256 (e1-e0-1) + 1 of them, or all remaining ones on
+ * the last rank.  Results equal the single-GPU run up to float64 summation order. */
+enum { AW_COMM_F64 = 0, AW_COMM_I64 = 1 };
+enum { AW_COMM_SUM = 0, AW_COMM_MAX = 1 };
+typedef struct aw_comm {
+  void* user;
+  int (*allreduce)(void* user, int64_t offset, int64_t count, int dtype, int op, void* stream);
+  int (*allgather)(void* user, int64_t send_offset, int64_t recv_offset, int64_t bytes, void* stream);
+  void* d_arena;         /* device scratch, >= 64 KiB + world * 32 KiB */
+  int64_t arena_bytes;
+  int rank, world;
+} aw_comm;
+/* d_values [20]: identical on every rank */
+int aw_detect_sharded(aw_ctx* ctx, const float* d_segment, int seg_samples, int seg_first_frame,
+                      int own_lo, int own_hi, int total_frames, int sample_rate, const aw_comm* comm,
+                      float* d_values, void* stream);
+/* d_out_own: this rank's samples of the watermarked clip, global [256 f0, min(256 f1, 256 (T-1))).
+ * d_losses: optional [iters] (identical on every rank); comm_counts: optional int64[2] = number of
+ * all-reduces / all-gathers issued. */
+int aw_embed_sharded(aw_ctx* ctx, const float* d_segment, int seg_samples, int seg_first_frame,
+                     int own_lo, int own_hi, int total_frames, int sample_rate,
+                     const int32_t* d_pattern, int iters, const aw_comm* comm, float* d_out_own,
+                     int64_t out_capacity, float* d_best_loss, float* d_losses, int64_t* comm_counts,
+                     void* stream);
+
 /* debug/parity hooks: after aw_embed_batch, copy the optimisation state of the LAST wave.
  * which: 0 coeffs c, 1 best coeffs, 2 initial coeffs c0, 3 last gradient-free state m, 4 v
  * layout [clip][T][nbins] float32. */
