@@ -290,7 +290,7 @@ class CompressionApprox(Attack):
     added to the input, so content outside the band passes through.  Output length 256 * (N // 256).
     Pinned by `oracle_compression_approx` below (numpy restatement) in tests/test_gpu_parity.py."""
 
-    def __init__(self, step_db=1.5, floor_db=-30.0):
+    def __init__(self, step_db=1.5, floor_db=-60.0):
         self.step_db, self.floor_db = float(step_db), float(floor_db)
         self.name = f"compress_{step_db}dB"
 
@@ -302,7 +302,7 @@ class CompressionApprox(Attack):
         return eng.attack_affine(x[:, :L], 1.0, delta, 1.0)
 
 
-def oracle_compression_approx(x, sr, step_db=1.5, floor_db=-30.0, bands=(500.0, 4000.0)):
+def oracle_compression_approx(x, sr, step_db=1.5, floor_db=-60.0, bands=(500.0, 4000.0)):
     """numpy / torch-CPU restatement of CompressionApprox for ONE clip (test infrastructure)."""
     x = np.asarray(x, dtype=np.float32)
     win = torch.hann_window(1024)

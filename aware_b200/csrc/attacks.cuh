@@ -176,14 +176,14 @@ __global__ void __launch_bounds__(128) k_iir(IirArgs a) {
 // Sequential mode, one thread per clip, software-pipelined: the recurrence itself is a chain of three
 // dependent float64 operations per sample (~30 cycles), but a naive loop also waits a full,
 // uncoalesced memory latency per sample (measured 380 ns / sample).  Here the next 32 inputs are
-// requested while the current 32 are filtered, and outputs leave in batches, so the loop runs at the
+// requested while the current 16 are filtered, and outputs leave in batches, so the loop runs at the
 // speed of the dependency chain.  The arithmetic (operation order, no FMA contraction) is unchanged:
 // bit-identical to scipy's lfilter.
 template <int SRC, int DST>
 __global__ void __launch_bounds__(32) k_iir_seq(IirArgs a) {
   const int clip = blockIdx.x * blockDim.x + threadIdx.x;
   if (clip >= a.n_clips) return;
-  constexpr int NB = 32;
+  constexpr int NB = 16;                 // 3 x 16 doubles of staging: no register spills
   double z[AW_IIR_MAXORD];
 #pragma unroll
   for (int k = 0; k < AW_IIR_MAXORD; ++k) z[k] = 0.0;

@@ -144,6 +144,7 @@ def _gpu_worker(rank, world, port, secs, iters, ret):
     with eng._with_precision("fp32"):
         out["v_fp32"] = lf.detect(x, sr)
     out["v_tf32"] = lf.detect(x, sr, precision="tf32")
+    out["y1_fp32"] = lf.embed(x, sr, pat, iters=1, precision="fp32")
     for prec in ("fp32", "fp16"):
         y, losses = lf.embed(x, sr, pat, iters=iters, precision=prec, return_losses=True)
         out["y_" + prec], out["loss_" + prec] = y, losses
@@ -156,6 +157,7 @@ def _gpu_worker(rank, world, port, secs, iters, ret):
         xd = torch.from_numpy(x[None]).cuda()
         with eng._with_precision("fp32"):
             out["ref_v_fp32"] = eng.detect(xd, sr).cpu().numpy()[0]
+        out["ref_y1_fp32"] = eng.embed(xd, sr, torch.from_numpy(pat[None]), iters=1, precision="fp32").cpu().numpy()[0]
         for prec in ("fp32", "fp16"):
             yr, _, lr = eng.embed(xd, sr, torch.from_numpy(pat[None]), iters=iters, precision=prec, return_losses=True)
             out["ref_y_" + prec], out["ref_loss_" + prec] = yr.cpu().numpy()[0], lr.cpu().numpy()[:, 0]
@@ -171,9 +173,12 @@ def _gpu_worker(rank, world, port, secs, iters, ret):
 @pytest.mark.parametrize("world,secs", [(2, 6.0), (3, 9.5)])
 def test_sharded_ranks_reproduce_the_whole_clip_run(world, secs):
     """2 and 3 ranks (sharing the one GPU, gloo collectives): halo + statistic exchange.  Detector values
-    equal the whole-clip run to 1e-6 and decode identically; three optimisation steps give the same
-    losses and waveform (the float64 statistics are summed in another order, nothing else differs);
-    every rank holds the same result; a 60-iteration sharded embed is decoded correctly."""
+    equal the whole-clip run to 1e-6 and decode identically; every rank holds the same result.  Embed: the
+    only difference to the whole-clip run is the summation order of the float64 statistics, so the first
+    loss is identical and ONE step gives the same waveform (1e-4 on >= 99.5 % of the samples: a NAdam first
+    step is sign-like, a gradient within rounding of 0 can flip); after that the iteration is chaotic
+    (reference vs reference 6e-7 after 1 step, 1.8e-3 after 3), so three steps are gated
+    loosely; a 60-iteration sharded embed is decoded correctly by the sharded detector and the CPU oracle."""
     with mp.Manager() as mgr:
         ret = mgr.dict()
         mp.spawn(_gpu_worker, args=(world, _port(), secs, 3, ret), nprocs=world, join=True)
@@ -184,15 +189,19 @@ def test_sharded_ranks_reproduce_the_whole_clip_run(world, secs):
     for k in range(1, world):
         np.testing.assert_array_equal(r["v_fp32_r%d" % k], r["v_fp32"])          # identical on every rank
         np.testing.assert_array_equal(r["y_fp32_r%d" % k], r["y_fp32"])
-    for prec, tol_l, tol_y in (("fp32", 1e-5, 2e-4), ("fp16", 2e-3, 5e-3)):
-        assert np.abs(r["loss_" + prec][:3] - r["ref_loss_" + prec][:3]).max() <= tol_l, prec
+    d1 = np.abs(r["y1_fp32"] - r["ref_y1_fp32"])
+    print("world %d: 1-iteration waveform max diff %.2e, %.4f %% within 1e-4" % (world, d1.max(), 100 * (d1 <= 1e-4).mean()))
+    assert r["y1_fp32"].shape == r["ref_y1_fp32"].shape
+    assert (d1 <= 1e-4).mean() >= 0.995 and d1.max() <= 3e-3
+    for prec, tol0, tol_l in (("fp32", 1e-6, 1e-3), ("fp16", 1e-3, 1e-2)):
+        dl = np.abs(r["loss_" + prec][:3] - r["ref_loss_" + prec][:3])
+        assert dl[0] <= tol0 and dl.max() <= tol_l, (prec, dl)
         d = np.abs(r["y_" + prec] - r["ref_y_" + prec])
         print("world %d %s: 3-iteration waveform max diff %.2e, %.4f %% within 1e-4" % (
             world, prec, d.max(), 100 * (d <= 1e-4).mean()))
-        assert r["y_" + prec].shape == r["ref_y_" + prec].shape
-        assert (d <= 1e-4).mean() >= 0.995 and d.max() <= tol_y, prec
+        assert (d <= 1e-3).mean() >= 0.97 and d.max() <= 2e-2, prec
     st = r["stats"]
-    assert st["allreduces"] == 2 + 3 * 12 and st["allgathers"] == 2 * 3 + 1
+    assert st["allreduces"] == 2 + 3 * 12 and st["allgathers"] == 2 * 3 + 1     # of the 3-iteration fp16 run
     bits = O.synth_bits(8)[5]
     np.testing.assert_array_equal((r["v_after"] > 0).astype(np.int32), bits)
     np.testing.assert_array_equal(O.detect_watermark(r["y_long"], 44100), bits)   # the CPU oracle agrees
