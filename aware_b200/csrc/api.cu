@@ -87,6 +87,7 @@ struct aw_ctx {
   int* h_lowm = nullptr; // pinned host mirror of lowm
   size_t h_lowm_cap = 0;
   double exact_margin = 1e-3;      // AW_OPT_EXACT_MARGIN
+  bool two_pass = true;            // small-K layers as statistics pass + apply pass (AW_B200_ONE_PASS=1: off)
   int64_t stat_detect_clips = 0, stat_reeval_clips = 0;
   int last_embed_clips = 0;
   // frame-sharded long-form mode (aw_*_sharded): this context holds a halo-extended segment of ONE
@@ -140,7 +141,8 @@ static const char* gemm_label(int epi, int n, int k) {
   static char table[32][32];
   static int used = 0;
   char buf[32];
-  snprintf(buf, sizeof(buf), "gemm_%s_n%d_k%d", epi == 1 ? "fwd" : (epi == 2 ? "bwd" : "plain"), n, k);
+  static const char* kind[7] = {"plain", "fwd", "bwd", "fwd_stats", "fwd_apply", "bwd_stats", "bwd_apply"};
+  snprintf(buf, sizeof(buf), "gemm_%s_n%d_k%d", epi >= 0 && epi < 7 ? kind[epi] : "other", n, k);
   for (int i = 0; i < used; ++i)
     if (strcmp(table[i], buf) == 0) return table[i];
   if (used == 32) return "gemm_other";
@@ -363,6 +365,8 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
   {
     const char* e = getenv("AW_B200_NO_GRAPH");
     ctx->graphs = !(e && e[0] == '1');
+    const char* e2 = getenv("AW_B200_ONE_PASS");
+    ctx->two_pass = !(e2 && e2[0] == '1');
   }
 
   void* fn = nullptr;
@@ -879,12 +883,18 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
   }
   for (int l = 0; l < 4; ++l) {
     const int cin = kCp[l], cout = kCp[l + 1];
-    EpiArgsT<AT> ep;
+    EpiArgsT<AT> ep{};
     ep.out = (AT*)ctx->act[l + 1].p; ep.ldo = cout;
     ep.part = (float*)ctx->part.p; ep.ldp = cout; ep.act = nullptr;
     const CUtensorMap& mw = ModeOf<AT>::w(ctx, l);
     const void* w = ModeOf<AT>::wp(ctx, l);
-    if (gemm_layer<AT, EPI_FWD>(ctx, ctx->tm_act[B][l], ctx->act[l].p, mw, w, d.rows, cout, cin, ep, st))
+    // layer 0 (K = 128): the GEMM (30 GFLOP at 256 clips) is cheaper than one round trip of its 235 MB
+    // output, so it runs twice -- column sums only, then again with InstanceNorm + LeakyReLU applied in
+    // the epilogue -- and the raw H1 never exists (exact fp32 mode keeps the one-pass form)
+    const bool two_pass = l == 0 && ctx->prec != AW_PREC_FP32 && ctx->two_pass;
+    if (two_pass) {
+      if (launch_tc<AT, AT, 256, EPI_FWD_STATS>(ctx, ctx->tm_act[B][l], mw, d.rows, cout, cin, ep, st)) return 1;
+    } else if (gemm_layer<AT, EPI_FWD>(ctx, ctx->tm_act[B][l], ctx->act[l].p, mw, w, d.rows, cout, cin, ep, st))
       return 1;
     dim3 g((cout + 31) / 32, d.n);
     prof_mark(ctx, st, "finalize_fwd");
@@ -895,6 +905,11 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
                                        (float*)ctx->stat[l + 1].p);
       ctx->launches++;
       AW_LAUNCH_CHECK();
+    }
+    if (two_pass) {
+      ep.stat = (float*)ctx->stat[l + 1].p; ep.tiles_per_clip = d.tiles; ep.Tp = d.Tp; ep.round_tf32 = tf && l < 3;
+      if (launch_tc<AT, AT, 256, EPI_FWD_APPLY>(ctx, ctx->tm_act[B][l], mw, d.rows, cout, cin, ep, st)) return 1;
+      continue;
     }
     prof_mark(ctx, st, "norm_act");
     {
@@ -922,12 +937,17 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
                          {&ctx->tm_gb1024[B], gb, 1, ga}};
   for (int s = 0; s < 3; ++s) {
     const int l = steps[s].l, k = kCp[l + 1], n = kCp[l];
-    EpiArgsT<AT> ep;
+    EpiArgsT<AT> ep{};
     ep.out = steps[s].out; ep.ldo = n;
     ep.part = (float*)ctx->part.p; ep.ldp = n; ep.act = (AT*)ctx->act[l].p;
     const CUtensorMap& mw = ModeOf<AT>::wt(ctx, l);
     const void* w = ModeOf<AT>::wtp(ctx, l);
-    if (gemm_layer<AT, EPI_BWD>(ctx, *steps[s].ma, steps[s].a, mw, w, d.rows, n, k, ep, st)) return 1;
+    // dP3 = dH4 W3 has K = 64: recomputing it is cheaper than writing dHhat3 (470 MB at 256 clips) and
+    // reading it back for the InstanceNorm adjoint -- statistics pass, then a pass that applies the adjoint
+    const bool two_pass = s == 0 && ctx->prec != AW_PREC_FP32 && ctx->two_pass;
+    if (two_pass) {
+      if (launch_tc<AT, AT, 256, EPI_BWD_STATS>(ctx, *steps[s].ma, mw, d.rows, n, k, ep, st)) return 1;
+    } else if (gemm_layer<AT, EPI_BWD>(ctx, *steps[s].ma, steps[s].a, mw, w, d.rows, n, k, ep, st)) return 1;
     dim3 g((n + 31) / 32, d.n);
     prof_mark(ctx, st, "finalize_bwd");
     if (ctx->sh) {
@@ -937,6 +957,12 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
                                        (float*)ctx->bstat.p);
       ctx->launches++;
       AW_LAUNCH_CHECK();
+    }
+    if (two_pass) {
+      ep.stat = (float*)ctx->stat[l].p; ep.bstat = (float*)ctx->bstat.p;
+      ep.tiles_per_clip = d.tiles; ep.Tp = d.Tp; ep.round_tf32 = tf;
+      if (launch_tc<AT, AT, 256, EPI_BWD_APPLY>(ctx, *steps[s].ma, mw, d.rows, n, k, ep, st)) return 1;
+      continue;
     }
     prof_mark(ctx, st, "in_bwd_apply");
     {

@@ -21,7 +21,16 @@
 
 namespace aw {
 
-enum { EPI_PLAIN = 0, EPI_FWD = 1, EPI_BWD = 2 };
+// EPI_*_STATS / EPI_*_APPLY: two-pass form for the small-K layers (K <= 128), whose GEMM is cheaper than
+// one round trip of its output.  STATS runs the GEMM for the InstanceNorm column sums only (no store);
+// APPLY runs it again and normalises in the epilogue, so the raw H / dHhat tensor never exists in HBM.
+enum { EPI_PLAIN = 0, EPI_FWD = 1, EPI_BWD = 2, EPI_FWD_STATS = 3, EPI_FWD_APPLY = 4, EPI_BWD_STATS = 5,
+       EPI_BWD_APPLY = 6 };
+__host__ __device__ constexpr bool epi_is_bwd(int e) { return e == EPI_BWD || e == EPI_BWD_STATS || e == EPI_BWD_APPLY; }
+__host__ __device__ constexpr bool epi_is_fwd(int e) { return e == EPI_FWD || e == EPI_FWD_STATS || e == EPI_FWD_APPLY; }
+__host__ __device__ constexpr bool epi_has_stats(int e) { return e == EPI_FWD || e == EPI_BWD || e == EPI_FWD_STATS || e == EPI_BWD_STATS; }
+__host__ __device__ constexpr bool epi_stores(int e) { return e != EPI_FWD_STATS && e != EPI_BWD_STATS; }
+__host__ __device__ constexpr bool epi_applies(int e) { return e == EPI_FWD_APPLY || e == EPI_BWD_APPLY; }
 
 struct EpiArgs {
   float* out;            // [rows][ldo]
@@ -248,6 +257,12 @@ struct EpiArgsT {
   float* part;           // [row_tiles][ldp][2] per-tile column partial sums (FWD/BWD)
   int ldp;
   const OT* act;         // BWD: P_{l-1} [rows][ldo] (post-LeakyReLU activations)
+  // *_APPLY: per-clip column statistics [clip][ldo][2] = (mean, rstd) / (a1, a2), rows per clip
+  const float* stat;
+  const float* bstat;
+  int tiles_per_clip;    // 128-row tiles per clip (Tp_pad / 128)
+  int Tp;                // valid pooled frames per clip: rows beyond are written as 0
+  int round_tf32;
 };
 
 
@@ -374,11 +389,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       float* s_st = s_stage + e * AW_EPI_STAGE_WORDS;
       const int sr = lane >> 3, cg = (lane & 7) * 4;  // staged access: row 4 i + sr, columns cg .. cg+3
       const long long grow = (long long)(row_tile * 128 + q * 32 + sr) * ep.ldo + n0 + half * (BN / 2) + cg;
-      OT* obase = ep.out + grow;
-      const OT* abase = EPI == EPI_BWD ? ep.act + grow : nullptr;
+      OT* obase = epi_stores(EPI) ? ep.out + grow : nullptr;
+      const OT* abase = epi_is_bwd(EPI) ? ep.act + grow : nullptr;
       float* sp = s_part + ab * (2 * 4 * BN);
       float ga[8][4];
-      if (EPI == EPI_BWD) {                           // overlaps the wait for the accumulator
+      // *_APPLY: this tile's clip, its first row inside the clip, and the statistics base
+      const int clip_ = epi_applies(EPI) ? row_tile / ep.tiles_per_clip : 0;
+      const int jrow0 = epi_applies(EPI) ? (row_tile - clip_ * ep.tiles_per_clip) * 128 + q * 32 + sr : 0;
+      const long long sbase = epi_applies(EPI) ? ((long long)clip_ * ep.ldo + n0 + half * (BN / 2) + cg) * 2 : 0;
+      if (epi_is_bwd(EPI)) {                          // overlaps the wait for the accumulator
 #pragma unroll
         for (int i = 0; i < 8; ++i) act_ld4g(abase + (long long)(4 * i) * ep.ldo, ga[i]);
       }
@@ -416,7 +435,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         }
         __syncwarp();
         float s1c[4] = {0.f, 0.f, 0.f, 0.f}, s2c[4] = {0.f, 0.f, 0.f, 0.f};
-        if (EPI == EPI_BWD) {
+        float st_mu[4], st_rs[4], st_a1[4], st_a2[4];
+        if (epi_applies(EPI)) {
+          const float4 s01 = *reinterpret_cast<const float4*>(ep.stat + sbase + c * 64);
+          const float4 s23 = *reinterpret_cast<const float4*>(ep.stat + sbase + c * 64 + 4);
+          st_mu[0] = s01.x; st_rs[0] = s01.y; st_mu[1] = s01.z; st_rs[1] = s01.w;
+          st_mu[2] = s23.x; st_rs[2] = s23.y; st_mu[3] = s23.z; st_rs[3] = s23.w;
+          if (EPI == EPI_BWD_APPLY) {
+            const float4 b01 = *reinterpret_cast<const float4*>(ep.bstat + sbase + c * 64);
+            const float4 b23 = *reinterpret_cast<const float4*>(ep.bstat + sbase + c * 64 + 4);
+            st_a1[0] = b01.x; st_a2[0] = b01.y; st_a1[1] = b01.z; st_a2[1] = b01.w;
+            st_a1[2] = b23.x; st_a2[2] = b23.y; st_a1[3] = b23.z; st_a2[3] = b23.w;
+          }
+        }
+        if (epi_is_bwd(EPI)) {
           // d(IN out) = dP * LeakyReLU'(P);  IN out recovered from P
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -425,15 +457,31 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               const float pv = ga[i][k];
               const bool pos = pv > 0.f;
               const float g = pos ? w[i][k] : AW_LEAKY * w[i][k];
-              w[i][k] = g;
-              s1c[k] += g;
-              s2c[k] = fmaf(pos ? pv : pv * (1.0f / AW_LEAKY), g, s2c[k]);
+              const float hh = pos ? pv : pv * (1.0f / AW_LEAKY);
+              if (EPI == EPI_BWD_APPLY) {               // dH = rstd (dHhat - a1 - Hhat a2), pad rows 0 (k_norm_rows<BWD>)
+                float o = st_rs[k] * (g - st_a1[k] - hh * st_a2[k]);
+                if (ep.round_tf32) o = to_tf32(o);
+                w[i][k] = jrow0 + 4 * i < ep.Tp ? o : 0.f;
+              } else {
+                w[i][k] = g;
+                s1c[k] += g;
+                s2c[k] = fmaf(hh, g, s2c[k]);
+              }
             }
           if (c + 1 < CHUNKS) {                     // prefetch the next chunk's activations
 #pragma unroll
             for (int i = 0; i < 8; ++i) act_ld4g(abase + (c + 1) * 32 + (long long)(4 * i) * ep.ldo, ga[i]);
           }
-        } else if (EPI == EPI_FWD) {
+        } else if (EPI == EPI_FWD_APPLY) {              // P = LeakyReLU((H - mean) rstd), pad rows 0 (k_norm_rows<FWD>)
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float o = leaky((w[i][k] - st_mu[k]) * st_rs[k]);
+              if (ep.round_tf32) o = to_tf32(o);
+              w[i][k] = jrow0 + 4 * i < ep.Tp ? o : 0.f;
+            }
+        } else if (epi_is_fwd(EPI)) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -442,9 +490,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               s2c[k] = fmaf(w[i][k], w[i][k], s2c[k]);
             }
         }
+        if (epi_stores(EPI)) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) act_st4g(obase + c * 32 + (long long)(4 * i) * ep.ldo, w[i]);
-        if (EPI != EPI_PLAIN) {
+          for (int i = 0; i < 8; ++i) act_st4g(obase + c * 32 + (long long)(4 * i) * ep.ldo, w[i]);
+        }
+        if (epi_has_stats(EPI)) {
           // the 4 lanes that share (lane & 7) hold the same columns for different rows
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -459,7 +509,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           }
         }
       }
-      if (EPI != EPI_PLAIN) {
+      if (epi_has_stats(EPI)) {
         asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps
         const int t = threadIdx.x - 64;                  // 0..255
         for (int cc = t; cc < BN; cc += 256) {

