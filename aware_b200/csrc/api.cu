@@ -20,6 +20,7 @@
 #include "gemm.cuh"
 #include "net.cuh"
 #include "spec.cuh"
+#include "spectc.cuh"
 
 namespace aw {
 thread_local char g_err[512] = "";
@@ -66,7 +67,7 @@ struct aw_ctx {
   float* d_window = nullptr;
   float2* d_twiddle = nullptr;   // [k1][lane] = exp(2 pi i lane k1 / 1024)
   float* d_env256 = nullptr;     // interior overlap-add envelope sum_r w^2[j + 256 r]
-  std::vector<float> h_mel;
+  std::vector<float> h_mel, h_window;
   float band_lo = 500.f, band_hi = 4000.f, tol_db = 6.f, threshold = 0.f;
   std::vector<MelCfg> mels;
   PFN_encodeTiled encode = nullptr;
@@ -88,6 +89,19 @@ struct aw_ctx {
   size_t h_lowm_cap = 0;
   double exact_margin = 1e-3;      // AW_OPT_EXACT_MARGIN
   bool two_pass = true;            // small-K layers as statistics pass + apply pass (AW_B200_ONE_PASS=1: off)
+  // tensor-core spectral path of the fp16 embed loop (spectc.cuh; AW_B200_FFT_SPEC=1: off)
+  bool tc_spec = true;
+  struct TcMats {
+    int bin0 = -1, nb = 0;
+    __half *peakB = nullptr, *compB = nullptr, *compBT = nullptr;
+    float* fix = nullptr;
+    CUtensorMap tm_peakB, tm_compB, tm_compBT;
+  } tcm;
+  Buf tc_X, tc_dS, tc_soob, tc_dX, tc_gedge, tc_dmax, tc_ones;
+  CUtensorMap tm_tcX4, tm_tcX7, tm_tcdS7;
+  void *tc_map_x = nullptr, *tc_map_ds = nullptr;
+  long long tc_map_rows = 0;
+  bool tc_active = false;          // set while an embed wave runs on the tensor-core spectral path
   int64_t stat_detect_clips = 0, stat_reeval_clips = 0;
   int last_embed_clips = 0;
   // frame-sharded long-form mode (aw_*_sharded): this context holds a halo-extended segment of ONE
@@ -141,8 +155,8 @@ static const char* gemm_label(int epi, int n, int k) {
   static char table[32][32];
   static int used = 0;
   char buf[32];
-  static const char* kind[7] = {"plain", "fwd", "bwd", "fwd_stats", "fwd_apply", "bwd_stats", "bwd_apply"};
-  snprintf(buf, sizeof(buf), "gemm_%s_n%d_k%d", epi >= 0 && epi < 7 ? kind[epi] : "other", n, k);
+  static const char* kind[9] = {"plain", "fwd", "bwd", "fwd_stats", "fwd_apply", "bwd_stats", "bwd_apply", "peak", "spec"};
+  snprintf(buf, sizeof(buf), "gemm_%s_n%d_k%d", epi >= 0 && epi < 9 ? kind[epi] : "other", n, k);
   for (int i = 0; i < used; ++i)
     if (strcmp(table[i], buf) == 0) return table[i];
   if (used == 32) return "gemm_other";
@@ -281,6 +295,20 @@ static int make_map(aw_ctx* ctx, CUtensorMap* map, const void* ptr, uint64_t row
   return 0;
 }
 
+// Toeplitz operand: rows of `nf` consecutive frame rows [P] each, row r starting at frame row r
+// (dims {P, nf, rows}, the two outer strides both one frame row): fp16, 128-byte swizzle, box 64 x 1 x 128
+static int make_map_toeplitz(aw_ctx* ctx, CUtensorMap* map, const void* ptr, uint64_t rows, uint32_t nf) {
+  cuuint64_t gdim[3] = {AW_TC_P, nf, rows};
+  cuuint64_t gstr[2] = {AW_TC_P * 2, AW_TC_P * 2};
+  cuuint32_t box[3] = {64, 1, 128};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)ptr, gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled (Toeplitz operand) failed: %d", (int)r);
+  return 0;
+}
+
 static int bn_for(int n) { return n >= 256 ? 256 : (n >= 128 ? 128 : 64); }
 
 template <typename T, typename OT, int BN, int EPI>
@@ -362,11 +390,14 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
   ctx->tol_db = model->tolerance_db;
   ctx->threshold = model->threshold;
   ctx->h_mel.assign(model->mel_basis, model->mel_basis + AW_NMEL * 513);
+  ctx->h_window.assign(model->window, model->window + 1024);
   {
     const char* e = getenv("AW_B200_NO_GRAPH");
     ctx->graphs = !(e && e[0] == '1');
     const char* e2 = getenv("AW_B200_ONE_PASS");
     ctx->two_pass = !(e2 && e2[0] == '1');
+    const char* e3 = getenv("AW_B200_FFT_SPEC");
+    ctx->tc_spec = !(e3 && e3[0] == '1');
   }
 
   void* fn = nullptr;
@@ -446,7 +477,8 @@ static std::vector<Buf*> all_bufs(aw_ctx* ctx) {
                  &ctx->stat[1], &ctx->stat[2], &ctx->stat[3], &ctx->stat[4], &ctx->bstat,
                  &ctx->values, &ctx->best, &ctx->improved, &ctx->pattern, &ctx->itc, &ctx->steps,
                  &ctx->scal, &ctx->zoob, &ctx->p0coef, &ctx->p0scal, &ctx->hpart, &ctx->hcoef, &ctx->red_a, &ctx->red_b, &ctx->red_c,
-                 &ctx->gsc, &ctx->nonfinite, &ctx->smax, &ctx->lowm};
+                 &ctx->gsc, &ctx->nonfinite, &ctx->smax, &ctx->lowm, &ctx->tc_X, &ctx->tc_dS, &ctx->tc_soob,
+                 &ctx->tc_dX, &ctx->tc_gedge, &ctx->tc_dmax, &ctx->tc_ones};
 }
 
 extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
@@ -464,6 +496,7 @@ extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
   if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
   if (ctx->ev_out) cudaEventDestroy(ctx->ev_out);
   if (ctx->h_lowm) cudaFreeHost(ctx->h_lowm);
+  cudaFree(ctx->tcm.peakB); cudaFree(ctx->tcm.compB); cudaFree(ctx->tcm.compBT); cudaFree(ctx->tcm.fix);
   cudaFree(ctx->d_window);
   cudaFree(ctx->d_twiddle);
   cudaFree(ctx->d_env256);
@@ -496,6 +529,8 @@ extern "C" int aw_ctx_set_option(aw_ctx* ctx, int option, double value) {
       AW_REQUIRE(value >= 0.0, "aw_ctx_set_option: margin must be >= 0");
       ctx->exact_margin = value;
       return 0;
+    case AW_OPT_TC_SPECTRAL: ctx->tc_spec = value != 0.0; return 0;
+    case AW_OPT_TWO_PASS: ctx->two_pass = value != 0.0; return 0;
     default: return set_error("aw_ctx_set_option: unknown option %d", option);
   }
 }
@@ -681,10 +716,15 @@ struct Acc {
 };
 static Acc acc_view(aw_ctx* ctx, const struct Dims& d);
 
-__global__ void k_iter_begin(unsigned long long* peak, int n, int* it) {
+__global__ void k_iter_begin(unsigned long long* peak, int n, int* it, unsigned* dmax = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) peak[i] = 0ull;
+  if (i < n && dmax) dmax[i] = 0u;
   if (i == 0 && it) *it += 1;
+}
+__global__ void k_fill_u64(unsigned long long* p, unsigned long long v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
 }
 
 static int mel_blocks(const Dims& d) { return (d.T + AW_MEL_FRAMES - 1) / AW_MEL_FRAMES; }
@@ -1013,7 +1053,7 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
                                      (ChanStats*)ctx->cs.p, (P0BwdCoef*)ctx->p0coef.p,
                                      (P0BwdScal*)ctx->p0scal.p, sm, d.nb, own_frames(ctx, (float*)ctx->dA.p, d.nb),
                                      euler_s2 ? (const float*)own_frames(ctx, (float*)ctx->mag.p, d.nb) : nullptr, acc.s2_part,
-                                     (const float*)ctx->gsc.p);
+                                     (const float*)ctx->gsc.p, ctx->tc_active ? (unsigned*)ctx->tc_dmax.p : nullptr);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
@@ -1111,9 +1151,9 @@ static int launch_spec_k(aw_ctx* ctx, const Dims& d, SpecArgs& a, cudaStream_t s
   a.n_clips = d.n; a.T = d.T; a.L = d.L; a.bin0 = d.bin0; a.nbins = d.nb;
   a.tiles = (d.T + AW_SP_FA - 1) / AW_SP_FA;
   a.window = ctx->d_window; a.twiddle = ctx->d_twiddle; a.env256 = ctx->d_env256;
-  const int items = a.n_clips * a.tiles;
+  const int items = a.edge_mode ? a.n_clips * 2 : a.n_clips * a.tiles;
   const int grid = std::min(items, 2 * ctx->num_sms);
-  prof_mark(ctx, st, MODE == SPEC_FWD ? "spec_fwd" : "spec_bwd");
+  prof_mark(ctx, st, a.edge_mode ? (MODE == SPEC_FWD ? "spec_edge_fwd" : "spec_edge_bwd") : (MODE == SPEC_FWD ? "spec_fwd" : "spec_bwd"));
   k_spec<MODE, K2LO, K2HI><<<grid, 32 * AW_SP_WARPS, AW_SP_SMEM, st>>>(a);
   ctx->launches++;
   AW_LAUNCH_CHECK();
@@ -1145,9 +1185,9 @@ static int launch_peak(aw_ctx* ctx, const float* x, int64_t stride, int n, int n
   AW_LAUNCH_CHECK();
   return 0;
 }
-static int begin_pass(aw_ctx* ctx, int n, int* it, cudaStream_t st) {
+static int begin_pass(aw_ctx* ctx, int n, int* it, cudaStream_t st, unsigned* dmax = nullptr) {
   prof_mark(ctx, st, "iter_begin");
-  k_iter_begin<<<(n + 255) / 256, 256, 0, st>>>((unsigned long long*)ctx->accum.p, n, it);
+  k_iter_begin<<<(n + 255) / 256, 256, 0, st>>>((unsigned long long*)ctx->accum.p, n, it, dmax);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
@@ -1216,6 +1256,7 @@ extern "C" int aw_detect_batch(aw_ctx* ctx, const float* d_audio, int n_clips, i
   if (ensure(ctx->lowm, (size_t)(1 + n_clips) * 4)) return 1;
   if (ctx->h_lowm_cap < (size_t)(1 + n_clips)) {
     if (ctx->h_lowm) cudaFreeHost(ctx->h_lowm);
+  cudaFree(ctx->tcm.peakB); cudaFree(ctx->tcm.compB); cudaFree(ctx->tcm.compBT); cudaFree(ctx->tcm.fix);
     ctx->h_lowm = nullptr;
     AW_CUDA(cudaMallocHost((void**)&ctx->h_lowm, (size_t)(1 + n_clips) * 4));
     ctx->h_lowm_cap = (size_t)(1 + n_clips);
@@ -1280,6 +1321,138 @@ static void nadam_table(int iters, std::vector<NadamStep>& out) {
     s.pad = 0.f;
     out[step - 1] = s;
   }
+}
+
+
+// ---------------------------------------------------------------------------
+// tensor-core spectral path of the fp16 embed loop (spectc.cuh)
+// ---------------------------------------------------------------------------
+static bool tc_eligible(aw_ctx* ctx, const Dims& d) {
+  return ctx->tc_spec && ctx->prec == AW_PREC_FP16 && 2 * d.nb <= AW_TC_P && d.T >= 128 && !ctx->sh;
+}
+static long long tc_rows128(const Dims& d) { return (((long long)d.n * (d.T + 6) + 127) / 128) * 128; }
+
+static int tc_prepare_mats(aw_ctx* ctx, const Dims& d, const float* h_window) {
+  aw_ctx::TcMats& m = ctx->tcm;
+  if (m.bin0 == d.bin0 && m.nb == d.nb) return 0;
+  SpecTcMats h;
+  spectc_build(h_window, d.bin0, d.nb, h);
+  cudaFree(m.peakB); cudaFree(m.compB); cudaFree(m.compBT); cudaFree(m.fix);
+  m.peakB = m.compB = m.compBT = nullptr; m.fix = nullptr;
+  AW_CUDA(cudaMalloc(&m.peakB, h.peakB.size() * 2));
+  AW_CUDA(cudaMalloc(&m.compB, h.compB.size() * 2));
+  AW_CUDA(cudaMalloc(&m.compBT, h.compBT.size() * 2));
+  AW_CUDA(cudaMalloc(&m.fix, h.fix.size() * 4));
+  AW_CUDA(cudaMemcpy(m.peakB, h.peakB.data(), h.peakB.size() * 2, cudaMemcpyHostToDevice));
+  AW_CUDA(cudaMemcpy(m.compB, h.compB.data(), h.compB.size() * 2, cudaMemcpyHostToDevice));
+  AW_CUDA(cudaMemcpy(m.compBT, h.compBT.data(), h.compBT.size() * 2, cudaMemcpyHostToDevice));
+  AW_CUDA(cudaMemcpy(m.fix, h.fix.data(), h.fix.size() * 4, cudaMemcpyHostToDevice));
+  if (make_map(ctx, &m.tm_peakB, m.peakB, 256, 4 * AW_TC_P, 256, true)) return 1;
+  if (make_map(ctx, &m.tm_compB, m.compB, AW_TC_P, 7 * AW_TC_P, AW_TC_P, true)) return 1;
+  if (make_map(ctx, &m.tm_compBT, m.compBT, AW_TC_P, 7 * AW_TC_P, AW_TC_P, true)) return 1;
+  m.bin0 = d.bin0; m.nb = d.nb;
+  return 0;
+}
+
+// buffers, Toeplitz maps, the constant out-of-band spectrum and the first frame rows of a wave
+static int tc_setup_wave(aw_ctx* ctx, const Dims& d, cudaStream_t st) {
+  const long long rows = (long long)d.n * (d.T + 6), r128 = tc_rows128(d);
+  const size_t frame_bytes = (size_t)(r128 + 8) * AW_TC_P * 2;          // + 8 rows: the Toeplitz reach of the last rows
+  if (ensure(ctx->tc_X, frame_bytes) || ensure(ctx->tc_dS, frame_bytes) ||
+      ensure(ctx->tc_soob, (size_t)d.n * d.T * d.nb * 8) || ensure(ctx->tc_dX, (size_t)r128 * AW_TC_P * 4) ||
+      ensure(ctx->tc_gedge, (size_t)d.n * 12 * d.nb * 4) || ensure(ctx->tc_dmax, (size_t)d.n * 4) ||
+      ensure(ctx->tc_ones, (size_t)d.n * 8))
+    return 1;
+  if (ctx->tc_map_x != ctx->tc_X.p || ctx->tc_map_ds != ctx->tc_dS.p || ctx->tc_map_rows != rows) {
+    if (make_map_toeplitz(ctx, &ctx->tm_tcX4, ctx->tc_X.p, rows, 4)) return 1;
+    if (make_map_toeplitz(ctx, &ctx->tm_tcX7, ctx->tc_X.p, rows, 7)) return 1;
+    if (make_map_toeplitz(ctx, &ctx->tm_tcdS7, ctx->tc_dS.p, rows, 7)) return 1;
+    ctx->tc_map_x = ctx->tc_X.p; ctx->tc_map_ds = ctx->tc_dS.p; ctx->tc_map_rows = rows;
+  }
+  AW_CUDA(cudaMemsetAsync(ctx->tc_X.p, 0, frame_bytes, st));
+  AW_CUDA(cudaMemsetAsync(ctx->tc_dS.p, 0, frame_bytes, st));
+  AW_CUDA(cudaMemsetAsync(ctx->tc_gedge.p, 0, (size_t)d.n * 12 * d.nb * 4, st));
+  // S_oob = STFT(y_oob) restricted to the band, un-normalised (peak word 1.0: x / (1 + 1e-8) == x in fp32)
+  k_fill_u64<<<(d.n + 255) / 256, 256, 0, st>>>((unsigned long long*)ctx->tc_ones.p, (unsigned long long)0x3f800000u << 32, d.n);
+  ctx->launches++;
+  AnaArgs a = ana_base(ctx, d);
+  a.sig = (const float*)ctx->yoob.p; a.sig_stride = d.L; a.len = d.L;
+  a.peak = (unsigned long long*)ctx->tc_ones.p;
+  a.ph = (float2*)ctx->tc_soob.p;
+  if (launch_ana<ANA_CPLX>(ctx, d, a, st)) return 1;
+  prof_mark(ctx, st, "tc_xprep");
+  k_tc_xprep<<<dim3(d.T, d.n), 128, 0, st>>>((const float*)ctx->c.p, (const float2*)ctx->ph_u.p, d.T, d.nb,
+                                              (__half*)ctx->tc_X.p);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
+static EpiArgsT<float> tc_epi(const Dims& d) {
+  EpiArgsT<float> ep{};
+  ep.toep_P = AW_TC_P;
+  ep.rpc = d.T + 6;
+  ep.total_rows = d.n * (d.T + 6);
+  ep.T = d.T; ep.L = d.L; ep.nb = d.nb;
+  return ep;
+}
+
+// c u (frame rows) -> max |y| -> |S|, S/|S| ; then the six edge frames per clip exactly
+static int tc_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, cudaStream_t st) {
+  const int r128 = (int)tc_rows128(d);
+  EpiArgsT<float> ep = tc_epi(d);
+  ep.aux = (const float*)ctx->yoob.p; ep.fix = ctx->tcm.fix; ep.peak = acc.peak_y;
+  if (launch_tc<__half, float, 256, EPI_PEAK>(ctx, ctx->tm_tcX4, ctx->tcm.tm_peakB, r128, 256, 4 * AW_TC_P, ep, st)) return 1;
+  EpiArgsT<float> es = tc_epi(d);
+  es.aux = (const float*)ctx->tc_soob.p; es.mag = (float*)ctx->mag.p; es.qph = (float2*)ctx->ph_q.p;
+  if (launch_tc<__half, float, AW_TC_P, EPI_SPEC>(ctx, ctx->tm_tcX7, ctx->tcm.tm_compB, r128, AW_TC_P, 7 * AW_TC_P, es, st)) return 1;
+  SpecArgs f;
+  memset(&f, 0, sizeof(f));
+  f.amp = (float*)ctx->c.p; f.ph = (float2*)ctx->ph_u.p;
+  f.z_oob = (float*)ctx->zoob.p; f.peak_y = acc.peak_y;
+  f.mag = (float*)ctx->mag.p; f.q = (float2*)ctx->ph_q.p;
+  f.edge_mode = 1;
+  return launch_spec<SPEC_FWD>(ctx, d, f, st);
+}
+
+// dA q (frame rows, edge rows zeroed) -> K^T -> + exact edge adjoint + peak sub-gradient -> NAdam
+static int tc_backward(aw_ctx* ctx, const Dims& d, int* itc, cudaStream_t st, int* nonfinite) {
+  const int r128 = (int)tc_rows128(d);
+  prof_mark(ctx, st, "tc_dsprep");
+  k_tc_dsprep<<<dim3(d.T, d.n), 128, 0, st>>>((const float*)ctx->dA.p, (const float2*)ctx->ph_q.p, d.T, d.nb,
+                                               (const unsigned*)ctx->tc_dmax.p, (__half*)ctx->tc_dS.p);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  EpiArgsT<float> ep = tc_epi(d);
+  ep.out = (float*)ctx->tc_dX.p; ep.ldo = AW_TC_P;
+  if (launch_tc<__half, float, AW_TC_P, EPI_PLAIN>(ctx, ctx->tm_tcdS7, ctx->tcm.tm_compBT, r128, AW_TC_P, 7 * AW_TC_P, ep, st)) return 1;
+  SpecArgs b;
+  memset(&b, 0, sizeof(b));
+  b.amp = (float*)ctx->dA.p; b.ph = (float2*)ctx->ph_q.p;
+  b.scal = (ClipScal*)ctx->scal.p; b.u = (float2*)ctx->ph_u.p;
+  b.c = (float*)ctx->c.p; b.m = (float*)ctx->m.p; b.v = (float*)ctx->v.p;
+  b.cbest = (float*)ctx->cbest.p; b.c0 = (float*)ctx->c0.p;
+  b.improved = (int*)ctx->improved.p; b.steps = (NadamStep*)ctx->steps.p; b.it_ptr = itc;
+  b.tol_ratio = (float)pow(10.0, -(double)ctx->tol_db / 20.0);
+  b.edge_mode = 1; b.g_edge = (float*)ctx->tc_gedge.p;
+  if (launch_spec<SPEC_BWD>(ctx, d, b, st)) return 1;
+  TcUpdateArgs u{};
+  u.T = d.T; u.nb = d.nb; u.rpc = d.T + 6;
+  u.dX = (const float*)ctx->tc_dX.p; u.dmax = (const unsigned*)ctx->tc_dmax.p;
+  u.scal = (const ClipScal*)ctx->scal.p; u.g_edge = (const float*)ctx->tc_gedge.p;
+  u.u = (const float2*)ctx->ph_u.p;
+  u.c = (float*)ctx->c.p; u.m = (float*)ctx->m.p; u.v = (float*)ctx->v.p; u.cbest = (float*)ctx->cbest.p;
+  u.c0 = (const float*)ctx->c0.p; u.improved = (const int*)ctx->improved.p;
+  u.steps = (const NadamStep*)ctx->steps.p; u.it_ptr = itc;
+  u.tol_ratio = b.tol_ratio;
+  u.window = ctx->d_window; u.env256 = ctx->d_env256; u.bin0 = d.bin0;
+  u.X = (__half*)ctx->tc_X.p;
+  u.nonfinite = nonfinite;
+  prof_mark(ctx, st, "tc_update");
+  k_tc_update<<<dim3(d.T, d.n), 128, 0, st>>>(u);
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, int n_samples,
@@ -1381,19 +1554,31 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
     s0.y_oob = (float*)ctx->yoob.p;
     s0.z_oob = (float*)ctx->zoob.p;
     if (launch_syn<SYN_OOB>(ctx, dw, s0, st)) return 1;
+    // fp16 loop at 44.1 / 48 kHz: the loop's band-limited transforms run on the tensor cores (spectc.cuh)
+    const bool tc = tc_eligible(ctx, dw);
+    if (tc) {
+      if (tc_prepare_mats(ctx, dw, ctx->h_window.data())) return 1;
+      if (tc_setup_wave(ctx, dw, st)) return 1;
+    }
+    ctx->tc_active = tc;
+    struct TcOff { aw_ctx* c; ~TcOff() { c->tc_active = false; } } tc_off_{ctx};
     nvtxRangePop();
 
     // ---- optimisation loop (multibit_embedder.py:95-122)
     nvtxRangePushA("embed:nadam_loop");
     auto iteration = [&]() -> int {
       // fused spectral passes (spec.cuh): y and dpad never leave shared memory
-      if (begin_pass(ctx, dw.n, itc, st)) return 1;
-      SpecArgs f;
-      memset(&f, 0, sizeof(f));
-      f.amp = (float*)ctx->c.p; f.ph = (float2*)ctx->ph_u.p;
-      f.z_oob = (float*)ctx->zoob.p; f.peak_y = acc.peak_y;
-      f.mag = (float*)ctx->mag.p; f.q = (float2*)ctx->ph_q.p;
-      if (launch_spec<SPEC_FWD>(ctx, dw, f, st)) return 1;
+      if (begin_pass(ctx, dw.n, itc, st, tc ? (unsigned*)ctx->tc_dmax.p : nullptr)) return 1;
+      if (tc) {
+        if (tc_forward(ctx, dw, acc, st)) return 1;
+      } else {
+        SpecArgs f;
+        memset(&f, 0, sizeof(f));
+        f.amp = (float*)ctx->c.p; f.ph = (float2*)ctx->ph_u.p;
+        f.z_oob = (float*)ctx->zoob.p; f.peak_y = acc.peak_y;
+        f.mag = (float*)ctx->mag.p; f.q = (float2*)ctx->ph_q.p;
+        if (launch_spec<SPEC_FWD>(ctx, dw, f, st)) return 1;
+      }
       float* lp = d_losses ? d_losses + w0 : nullptr;
       if (ctx->prec == AW_PREC_BF16) {
         if (net_forward<__nv_bfloat16>(ctx, dw, acc, sm, st, acc.peak_y)) return 1;
@@ -1419,6 +1604,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       k_clip_scalars<<<(dw.n + 127) / 128, 128, 0, st>>>(acc.peak_y, sp2, sb2, dw.n, (ClipScal*)ctx->scal.p);
       ctx->launches++;
       AW_LAUNCH_CHECK();
+      if (tc) return tc_backward(ctx, dw, itc, st, (int*)ctx->nonfinite.p + w0);
       SpecArgs b;
       memset(&b, 0, sizeof(b));
       b.amp = (float*)ctx->dA.p; b.ph = (float2*)ctx->ph_q.p;

@@ -137,7 +137,7 @@ struct NadamStep {
 // ---------------------------------------------------------------------------
 // analysis: frames -> band spectrum
 // ---------------------------------------------------------------------------
-enum { ANA_MAG = 0, ANA_INIT = 1 };   // the loop passes live in spec.cuh
+enum { ANA_MAG = 0, ANA_INIT = 1, ANA_CPLX = 2 };   // CPLX: complex band spectrum only (spectc.cuh's S_oob)
 
 struct AnaArgs {
   const float* sig;            // per clip signal x
@@ -236,7 +236,9 @@ __global__ void __launch_bounds__(128, 3) k_analysis(AnaArgs a) {
         if (f == 1 && !has_b) break;
         const long long o = ((long long)clip * T + (ta + f)) * a.nbins + b;
         const float sr = fr[f], si = fi[f];
-        {
+        if (MODE == ANA_CPLX) {
+          a.ph[o] = make_float2(sr, si);
+        } else {
           const float mag = sqrtf(sr * sr + si * si);
           a.mag[o] = mag;
           if (MODE == ANA_INIT) {

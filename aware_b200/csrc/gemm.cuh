@@ -24,12 +24,16 @@ namespace aw {
 // EPI_*_STATS / EPI_*_APPLY: two-pass form for the small-K layers (K <= 128), whose GEMM is cheaper than
 // one round trip of its output.  STATS runs the GEMM for the InstanceNorm column sums only (no store);
 // APPLY runs it again and normalises in the epilogue, so the raw H / dHhat tensor never exists in HBM.
+// EPI_PEAK / EPI_SPEC: epilogues of the tensor-core spectral path (spectc.cuh): the band-limited
+// iSTFT as a GEMM whose epilogue adds the constant out-of-band waveform and reduces max|y| (nothing is
+// stored), and the band-limited STFT o iSTFT composite whose epilogue adds the constant out-of-band
+// spectrum and writes |S| and S/|S|.
 enum { EPI_PLAIN = 0, EPI_FWD = 1, EPI_BWD = 2, EPI_FWD_STATS = 3, EPI_FWD_APPLY = 4, EPI_BWD_STATS = 5,
-       EPI_BWD_APPLY = 6 };
+       EPI_BWD_APPLY = 6, EPI_PEAK = 7, EPI_SPEC = 8 };
 __host__ __device__ constexpr bool epi_is_bwd(int e) { return e == EPI_BWD || e == EPI_BWD_STATS || e == EPI_BWD_APPLY; }
 __host__ __device__ constexpr bool epi_is_fwd(int e) { return e == EPI_FWD || e == EPI_FWD_STATS || e == EPI_FWD_APPLY; }
 __host__ __device__ constexpr bool epi_has_stats(int e) { return e == EPI_FWD || e == EPI_BWD || e == EPI_FWD_STATS || e == EPI_BWD_STATS; }
-__host__ __device__ constexpr bool epi_stores(int e) { return e != EPI_FWD_STATS && e != EPI_BWD_STATS; }
+__host__ __device__ constexpr bool epi_stores(int e) { return e != EPI_FWD_STATS && e != EPI_BWD_STATS && e != EPI_PEAK && e != EPI_SPEC; }
 __host__ __device__ constexpr bool epi_applies(int e) { return e == EPI_FWD_APPLY || e == EPI_BWD_APPLY; }
 
 struct EpiArgs {
@@ -83,6 +87,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
@@ -263,11 +275,32 @@ struct EpiArgsT {
   int tiles_per_clip;    // 128-row tiles per clip (Tp_pad / 128)
   int Tp;                // valid pooled frames per clip: rows beyond are written as 0
   int round_tf32;
+  // Toeplitz A operand (spectral path): map_a is a 3-D map {P, frames per row, rows} over an array of
+  // frame rows [rows + pad][P]; k-block kb of GEMM row r is elements (kb % (P/BK)) * BK .. of frame
+  // row r + kb / (P/BK).  0 = ordinary 2-D operand.
+  int toep_P;
+  // EPI_PEAK / EPI_SPEC
+  int rpc;               // GEMM rows per clip (T + 6: three zero frame rows at either end)
+  int total_rows;        // n_clips * rpc
+  int T, L, nb;
+  const float* aux;      // PEAK: y_oob [clip][L]      SPEC: S_oob [clip][T][nb] (float2)
+  const float* fix;      // PEAK: [0] interior scale, [256..512) hop-2 scale, [512..768) hop-T scale
+  unsigned long long* peak;  // PEAK: [clip] packed peak (pack_peak_s), atomicMax
+  float* mag;            // SPEC: [clip][T][nb]
+  float2* qph;           // SPEC: [clip][T][nb]
 };
+
+// packed peak word with sign: see spec.cuh (declared here for the EPI_PEAK epilogue)
+__device__ __forceinline__ unsigned long long gemm_pack_peak_s(float v, unsigned idx) {
+  return ((unsigned long long)__float_as_uint(fabsf(v)) << 32) |
+         ((unsigned long long)(0x7fffffffu - idx) << 1) | (v < 0.f ? 1ull : 0ull);
+}
 
 
 template <int BN>
 __host__ __device__ constexpr int gemm_stages() { return BN == 256 ? 3 : AW_GEMM_STAGES; }
+template <int BN>
+__host__ __device__ constexpr int gemm_tmem_cols() { return BN == 192 ? 512 : 2 * BN; }   // power of two >= 2 BN
 template <int BN>
 constexpr int gemm_tc_smem() {
   return gemm_stages<BN>() * (128 * 128 + BN * 128) + 1024 /*align*/ + 256 /*barriers*/ +
@@ -319,7 +352,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_slot)),
-                 "n"(2 * BN)
+                 "n"(gemm_tmem_cols<BN>())
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -338,7 +371,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty + s, ph ^ 1);
           mbar_expect_tx(full + s, STAGE);
-          tma_load_2d(tiles + s * STAGE, &map_a, full + s, kb * BK, row0);
+          if (ep.toep_P > 0) {
+            const int kpf = ep.toep_P / BK;                 // k-blocks per frame row
+            tma_load_3d(tiles + s * STAGE, &map_a, full + s, (kb % kpf) * BK, kb / kpf, row0);
+          } else
+            tma_load_2d(tiles + s * STAGE, &map_a, full + s, kb * BK, row0);
           tma_load_2d(tiles + s * STAGE + A_BYTES, &map_b, full + s, kb * BK, n0);
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
@@ -393,6 +430,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       const OT* abase = epi_is_bwd(EPI) ? ep.act + grow : nullptr;
       float* sp = s_part + ab * (2 * 4 * BN);
       float ga[8][4];
+      // EPI_PEAK / EPI_SPEC: GEMM row -> (clip, frame row inside the clip) of this lane's first staged row
+      const int sp_r0 = row_tile * 128 + q * 32 + sr;
+      const int sp_c0 = (EPI == EPI_PEAK || EPI == EPI_SPEC) ? sp_r0 / ep.rpc : 0;
+      const int sp_t0 = (EPI == EPI_PEAK || EPI == EPI_SPEC) ? sp_r0 - sp_c0 * ep.rpc : 0;
+      const int sp_clip0 = EPI == EPI_PEAK ? (row_tile * 128) / ep.rpc : 0;   // a 128-row tile spans <= 2 clips
+      unsigned long long sp_pk[2] = {0ull, 0ull};
       // *_APPLY: this tile's clip, its first row inside the clip, and the statistics base
       const int clip_ = epi_applies(EPI) ? row_tile / ep.tiles_per_clip : 0;
       const int jrow0 = epi_applies(EPI) ? (row_tile - clip_ * ep.tiles_per_clip) * 128 + q * 32 + sr : 0;
@@ -434,6 +477,54 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           w[i][0] = t4.x; w[i][1] = t4.y; w[i][2] = t4.z; w[i][3] = t4.w;
         }
         __syncwarp();
+        if (EPI == EPI_PEAK) {
+          // y = y_band (this GEMM, scaled) + y_oob; only max |y| with its sample index and sign survives
+          const int j0 = half * (BN / 2) + c * 32 + cg;          // sample inside the hop (N = 256: one column tile)
+          const float f0 = ep.fix[0];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            int ti = sp_t0 + 4 * i, ci = sp_c0;
+            if (ti >= ep.rpc) { ti -= ep.rpc; ++ci; }
+            if (sp_r0 + 4 * i >= ep.total_rows || ti < 2 || ti > ep.T) continue;
+            float4 sc = make_float4(f0, f0, f0, f0);
+            if (ti == 2) sc = *reinterpret_cast<const float4*>(ep.fix + 256 + j0);
+            else if (ti == ep.T) sc = *reinterpret_cast<const float4*>(ep.fix + 512 + j0);
+            const int n = AW_HOP * (ti - 2) + j0;
+            const float4 yo = *reinterpret_cast<const float4*>(ep.aux + (long long)ci * ep.L + n);
+            const float v4[4] = {fmaf(w[i][0], sc.x, yo.x), fmaf(w[i][1], sc.y, yo.y), fmaf(w[i][2], sc.z, yo.z),
+                                 fmaf(w[i][3], sc.w, yo.w)};
+            unsigned long long& dst = sp_pk[ci - sp_clip0];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const unsigned long long pw = gemm_pack_peak_s(v4[k], (unsigned)(n + k));
+              dst = pw > dst ? pw : dst;
+            }
+          }
+          continue;
+        }
+        if (EPI == EPI_SPEC) {
+          // S = S_band (this GEMM) + S_oob; |S| and the phasor S/|S| of two bins per lane and row
+          const int b0 = (half * (BN / 2) + c * 32 + cg) >> 1;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            int ti = sp_t0 + 4 * i, ci = sp_c0;
+            if (ti >= ep.rpc) { ti -= ep.rpc; ++ci; }
+            if (sp_r0 + 4 * i >= ep.total_rows || ti >= ep.T) continue;
+            const long long base = ((long long)ci * ep.T + ti) * ep.nb;
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const int b = b0 + e2;
+              if (b >= ep.nb) continue;
+              const float2 so = reinterpret_cast<const float2*>(ep.aux)[base + b];
+              const float xr = w[i][2 * e2] + so.x, xi = w[i][2 * e2 + 1] + so.y;
+              const float p2 = xr * xr + xi * xi;
+              const float iv = p2 > 0.f ? rsqrtf(p2) : 0.f;
+              ep.mag[base + b] = p2 * iv;
+              ep.qph[base + b] = make_float2(xr * iv, xi * iv);
+            }
+          }
+          continue;
+        }
         float s1c[4] = {0.f, 0.f, 0.f, 0.f}, s2c[4] = {0.f, 0.f, 0.f, 0.f};
         float st_mu[4], st_rs[4], st_a1[4], st_a2[4];
         if (epi_applies(EPI)) {
@@ -509,6 +600,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           }
         }
       }
+      if (EPI == EPI_PEAK) {
+#pragma unroll
+        for (int z = 0; z < 2; ++z) {
+          const unsigned long long pw = warp_max_u64(sp_pk[z]);
+          if (lane == 0 && pw) atomicMax(ep.peak + sp_clip0 + z, pw);
+        }
+      }
       if (epi_has_stats(EPI)) {
         asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps
         const int t = threadIdx.x - 64;                  // 0..255
@@ -529,7 +627,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(gemm_tmem_cols<BN>())
                  : "memory");
   }
 }

@@ -290,6 +290,12 @@ struct SpecArgs {
   // frame-sharded long-form mode: only samples [pk_lo, pk_hi) of the local (halo-extended) segment
   // compete for the peak, and the index packed with it is global (local + idx_base).  pk_hi = 0: all.
   int pk_lo, pk_hi, idx_base;
+  // edge mode (spectc.cuh): only the three frames at either end of every clip are evaluated -- item =
+  // (clip, side).  FWD overwrites |S|, q of frames 0..2 / T-3..T-1 (no peak).  BWD takes dA of those
+  // frames only, applies no peak correction, and writes the gradient it induces on frames 0..5 /
+  // T-6..T-1 to g_edge [clip][12][nbins] instead of stepping the optimiser.
+  int edge_mode;
+  float* g_edge;
 };
 
 #define AW_SP_FA 58                        // analysis frames per tile
@@ -321,23 +327,35 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
   if (tid < 256) s_ienv[tid] = a.env256[256 + tid];
   float* my_tr = s_tr + warp * AW_TR1_FLOATS;
   const int lm = (32 - lane) & 31;
-  const int n_items = a.n_clips * a.tiles;
+  const int n_items = a.edge_mode ? a.n_clips * 2 : a.n_clips * a.tiles;
 
   NadamStep st;
   if (MODE == SPEC_BWD) st = a.steps[*a.it_ptr];
 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int clip = item / a.tiles, tile = item - clip * a.tiles;
+    int clip = item / a.tiles, tile = item - clip * a.tiles;
     // Frames [t_lo, t_hi) are written by this tile.  The frames that touch the right-hand
     // reflect seam (t >= T-5) must sit in a tile whose buffer reaches hop T+2, so the last
     // tile always owns at least the final 8 frames: a shorter last tile is pulled back and
     // its predecessor stops at T-8.
-    const bool is_last = tile == a.tiles - 1;
+    bool is_last = tile == a.tiles - 1;
     const bool short_last = T > 8 && T - (a.tiles - 1) * AW_SP_FA < 8;
     int t_lo = tile * AW_SP_FA, t_hi = min(T, t_lo + AW_SP_FA);
     if (short_last && is_last) t_lo = T - 8;
     if (short_last && tile == a.tiles - 2) t_hi = T - 8;
-    const int ta0 = t_lo;
+    int ta0 = t_lo;
+    int e_lo = -8, e_hi = T + 8;                          // synthesis frames that carry input (edge mode)
+    if (a.edge_mode) {                                   // needs T >= 16
+      clip = item >> 1;
+      is_last = (item & 1) != 0;
+      if (!is_last) {
+        ta0 = 0; t_lo = 0; t_hi = MODE == SPEC_FWD ? 3 : 6;
+        e_hi = MODE == SPEC_FWD ? 5 : 2;
+      } else {
+        ta0 = T - 8; t_lo = MODE == SPEC_FWD ? T - 3 : T - 6; t_hi = T;
+        e_lo = MODE == SPEC_FWD ? T - 6 : T - 3;
+      }
+    }
     const int m0 = AW_HOP * ta0;                         // padded-axis origin of s_buf
     const long long fbase = (long long)clip * T;
     __syncthreads();                                     // tables / previous item done with s_buf
@@ -373,7 +391,7 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
       float2 qa_[NK], qb_[NK];
       auto fetch = [&](int pr) {
         const int ta = fs + 2 * pr, tb = ta + 1;
-        const bool va = ta >= 0 && ta < T, vb = tb >= 0 && tb < T;
+        const bool va = ta >= 0 && ta < T && ta >= e_lo && ta <= e_hi, vb = tb >= 0 && tb < T && tb >= e_lo && tb <= e_hi;
         const long long oa = (fbase + (va ? ta : 0)) * nb, ob = (fbase + (vb ? tb : 0)) * nb;
 #pragma unroll
         for (int k2 = K2LO; k2 <= K2HI; ++k2) {
@@ -386,7 +404,7 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
 #pragma unroll 1
       for (int pr = 0; pr < 4; ++pr) {
         const int ta = fs + 2 * pr, tb = ta + 1;
-        const bool va = ta >= 0 && ta < T, vb = tb >= 0 && tb < T;
+        const bool va = ta >= 0 && ta < T && ta >= e_lo && ta <= e_hi, vb = tb >= 0 && tb < T && tb >= e_lo && tb <= e_hi;
         fetch(pr);
         float re[32], im[32];
 #pragma unroll
@@ -517,7 +535,7 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               float dy = vv[k] * inv;
-              if (n + k == nstar) dy -= corr;
+              if (n + k == nstar && !a.edge_mode) dy -= corr;
               vv[k] = dy * ie[k];
             }
           }
@@ -534,7 +552,7 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
     }
     __syncthreads();
     if (MODE == SPEC_FWD) {
-      if (tid == 0) {
+      if (tid == 0 && !a.edge_mode) {
         unsigned long long pk = s_pk[0];
         for (int w = 1; w < AW_SP_WARPS; ++w) pk = s_pk[w] > pk ? s_pk[w] : pk;
         atomicMax(a.peak_y + clip, pk);
@@ -635,6 +653,12 @@ __global__ void __launch_bounds__(32 * AW_SP_WARPS, 2) k_spec(SpecArgs a) {
               const long long o = ob_[gi] + (long long)f * nb;
               // dX = (2/N) DFT(.) ; g = Re(dX conj(u))     (multibit_embedder.py:111)
               const float g = (2.0f / AW_NFFT) * (fr[gi][f] * uu[gi][f].x + fi[gi][f] * uu[gi][f].y);
+              if (a.edge_mode) {                          // gradient induced by the edge rows only, no update
+                const int t = ta + f;
+                const int er = !is_last ? t : 6 + (t - (T - 6));
+                a.g_edge[((long long)clip * 12 + er) * nb + (o - (fbase + t) * nb)] = g;
+                continue;
+              }
               // an overflowed reduced-precision gradient must not poison m / v (NaN would pin the
               // coefficient to its lower bound for good): skip the step and flag the clip
               if ((__float_as_uint(g) & 0x7f800000u) == 0x7f800000u) {

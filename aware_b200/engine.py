@@ -96,6 +96,14 @@ class Engine:
         _lib.check(self.lib.aw_ctx_set_option(self._ctx, _lib.OPT_EXACT_MARGIN, float(margin)))
         self.exact_margin = float(margin)
 
+    def set_tc_spectral(self, on: bool):
+        """fp16 embed loop at 44.1 / 48 kHz: band-limited STFT / iSTFT as tcgen05 GEMMs (default) or the
+        fp32 FFT kernels."""
+        _lib.check(self.lib.aw_ctx_set_option(self._ctx, _lib.OPT_TC_SPECTRAL, 1.0 if on else 0.0))
+
+    def set_two_pass(self, on: bool):
+        _lib.check(self.lib.aw_ctx_set_option(self._ctx, _lib.OPT_TWO_PASS, 1.0 if on else 0.0))
+
     def detect_stats(self):
         """(clips seen by detect, clips re-evaluated exactly) since the engine was created."""
         out = []

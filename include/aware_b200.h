@@ -65,8 +65,12 @@ int64_t aw_launch_count(aw_ctx* ctx);
  * low-margin test (detector.threshold, service/detect.py:17; default = aw_model.threshold).
  * AW_OPT_EXACT_MARGIN: aw_detect_batch re-evaluates every clip with min_i |v_i - threshold| below
  * this margin through the exact fp32 GEMM path, so decoded bits equal the reference's fp32
- * arithmetic (default 1e-3; 0 switches the re-evaluation and its stream synchronisation off). */
-enum { AW_OPT_THRESHOLD = 0, AW_OPT_EXACT_MARGIN = 1 };
+ * arithmetic (default 1e-3; 0 switches the re-evaluation and its stream synchronisation off).
+ * AW_OPT_TC_SPECTRAL (default 1): with fp16 loop GEMMs and a band of <= 96 bins (44.1 / 48 kHz) the
+ * embed loop's band-limited STFT / iSTFT run as tcgen05 GEMMs over Toeplitz views of the frame rows
+ * (csrc/spectc.cuh); 0 keeps the fp32 FFT kernels.  AW_OPT_TWO_PASS (default 1): the K <= 128 layers run
+ * as a statistics pass + an apply pass instead of materialising their raw output. */
+enum { AW_OPT_THRESHOLD = 0, AW_OPT_EXACT_MARGIN = 1, AW_OPT_TC_SPECTRAL = 2, AW_OPT_TWO_PASS = 3 };
 int aw_ctx_set_option(aw_ctx* ctx, int option, double value);
 /* counters since context creation: clips seen by aw_detect_batch / clips it re-evaluated exactly */
 enum { AW_STAT_DETECT_CLIPS = 0, AW_STAT_REEVAL_CLIPS = 1 };
