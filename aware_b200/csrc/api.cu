@@ -98,7 +98,7 @@ struct aw_ctx {
     CUtensorMap tm_peakB, tm_compB, tm_compBT;
   } tcm;
   Buf tc_X, tc_dS, tc_soob, tc_dX, tc_gedge, tc_dmax, tc_ones;
-  CUtensorMap tm_tcX4, tm_tcX7, tm_tcdS7;
+  CUtensorMap tm_tcX, tm_tcdS;     // plain 2-D maps of the frame-row arrays (Toeplitz by row offset per k-block)
   void *tc_map_x = nullptr, *tc_map_ds = nullptr;
   long long tc_map_rows = 0;
   bool tc_active = false;          // set while an embed wave runs on the tensor-core spectral path
@@ -292,20 +292,6 @@ static int make_map(aw_ctx* ctx, CUtensorMap* map, const void* ptr, uint64_t row
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed: %d", (int)r);
-  return 0;
-}
-
-// Toeplitz operand: rows of `nf` consecutive frame rows [P] each, row r starting at frame row r
-// (dims {P, nf, rows}, the two outer strides both one frame row): fp16, 128-byte swizzle, box 64 x 1 x 128
-static int make_map_toeplitz(aw_ctx* ctx, CUtensorMap* map, const void* ptr, uint64_t rows, uint32_t nf) {
-  cuuint64_t gdim[3] = {AW_TC_P, nf, rows};
-  cuuint64_t gstr[2] = {AW_TC_P * 2, AW_TC_P * 2};
-  cuuint32_t box[3] = {64, 1, 128};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)ptr, gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled (Toeplitz operand) failed: %d", (int)r);
   return 0;
 }
 
@@ -1364,9 +1350,8 @@ static int tc_setup_wave(aw_ctx* ctx, const Dims& d, cudaStream_t st) {
       ensure(ctx->tc_ones, (size_t)d.n * 8))
     return 1;
   if (ctx->tc_map_x != ctx->tc_X.p || ctx->tc_map_ds != ctx->tc_dS.p || ctx->tc_map_rows != rows) {
-    if (make_map_toeplitz(ctx, &ctx->tm_tcX4, ctx->tc_X.p, rows, 4)) return 1;
-    if (make_map_toeplitz(ctx, &ctx->tm_tcX7, ctx->tc_X.p, rows, 7)) return 1;
-    if (make_map_toeplitz(ctx, &ctx->tm_tcdS7, ctx->tc_dS.p, rows, 7)) return 1;
+    if (make_map(ctx, &ctx->tm_tcX, ctx->tc_X.p, r128 + 8, AW_TC_P, 128, true)) return 1;
+    if (make_map(ctx, &ctx->tm_tcdS, ctx->tc_dS.p, r128 + 8, AW_TC_P, 128, true)) return 1;
     ctx->tc_map_x = ctx->tc_X.p; ctx->tc_map_ds = ctx->tc_dS.p; ctx->tc_map_rows = rows;
   }
   AW_CUDA(cudaMemsetAsync(ctx->tc_X.p, 0, frame_bytes, st));
@@ -1381,7 +1366,7 @@ static int tc_setup_wave(aw_ctx* ctx, const Dims& d, cudaStream_t st) {
   a.ph = (float2*)ctx->tc_soob.p;
   if (launch_ana<ANA_CPLX>(ctx, d, a, st)) return 1;
   prof_mark(ctx, st, "tc_xprep");
-  k_tc_xprep<<<dim3(d.T, d.n), 128, 0, st>>>((const float*)ctx->c.p, (const float2*)ctx->ph_u.p, d.T, d.nb,
+  k_tc_xprep<<<dim3((d.T + AW_TC_FR - 1) / AW_TC_FR, d.n), 256, 0, st>>>((const float*)ctx->c.p, (const float2*)ctx->ph_u.p, d.T, d.nb,
                                               (__half*)ctx->tc_X.p);
   ctx->launches++;
   AW_LAUNCH_CHECK();
@@ -1402,10 +1387,10 @@ static int tc_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, cudaStream_t s
   const int r128 = (int)tc_rows128(d);
   EpiArgsT<float> ep = tc_epi(d);
   ep.aux = (const float*)ctx->yoob.p; ep.fix = ctx->tcm.fix; ep.peak = acc.peak_y;
-  if (launch_tc<__half, float, 256, EPI_PEAK>(ctx, ctx->tm_tcX4, ctx->tcm.tm_peakB, r128, 256, 4 * AW_TC_P, ep, st)) return 1;
+  if (launch_tc<__half, float, 256, EPI_PEAK>(ctx, ctx->tm_tcX, ctx->tcm.tm_peakB, r128, 256, 4 * AW_TC_P, ep, st)) return 1;
   EpiArgsT<float> es = tc_epi(d);
   es.aux = (const float*)ctx->tc_soob.p; es.mag = (float*)ctx->mag.p; es.qph = (float2*)ctx->ph_q.p;
-  if (launch_tc<__half, float, AW_TC_P, EPI_SPEC>(ctx, ctx->tm_tcX7, ctx->tcm.tm_compB, r128, AW_TC_P, 7 * AW_TC_P, es, st)) return 1;
+  if (launch_tc<__half, float, AW_TC_P, EPI_SPEC>(ctx, ctx->tm_tcX, ctx->tcm.tm_compB, r128, AW_TC_P, 7 * AW_TC_P, es, st)) return 1;
   SpecArgs f;
   memset(&f, 0, sizeof(f));
   f.amp = (float*)ctx->c.p; f.ph = (float2*)ctx->ph_u.p;
@@ -1419,13 +1404,13 @@ static int tc_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, cudaStream_t s
 static int tc_backward(aw_ctx* ctx, const Dims& d, int* itc, cudaStream_t st, int* nonfinite) {
   const int r128 = (int)tc_rows128(d);
   prof_mark(ctx, st, "tc_dsprep");
-  k_tc_dsprep<<<dim3(d.T, d.n), 128, 0, st>>>((const float*)ctx->dA.p, (const float2*)ctx->ph_q.p, d.T, d.nb,
+  k_tc_dsprep<<<dim3((d.T + AW_TC_FR - 1) / AW_TC_FR, d.n), 256, 0, st>>>((const float*)ctx->dA.p, (const float2*)ctx->ph_q.p, d.T, d.nb,
                                                (const unsigned*)ctx->tc_dmax.p, (__half*)ctx->tc_dS.p);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   EpiArgsT<float> ep = tc_epi(d);
   ep.out = (float*)ctx->tc_dX.p; ep.ldo = AW_TC_P;
-  if (launch_tc<__half, float, AW_TC_P, EPI_PLAIN>(ctx, ctx->tm_tcdS7, ctx->tcm.tm_compBT, r128, AW_TC_P, 7 * AW_TC_P, ep, st)) return 1;
+  if (launch_tc<__half, float, AW_TC_P, EPI_PLAIN>(ctx, ctx->tm_tcdS, ctx->tcm.tm_compBT, r128, AW_TC_P, 7 * AW_TC_P, ep, st)) return 1;
   SpecArgs b;
   memset(&b, 0, sizeof(b));
   b.amp = (float*)ctx->dA.p; b.ph = (float2*)ctx->ph_q.p;
@@ -1449,7 +1434,7 @@ static int tc_backward(aw_ctx* ctx, const Dims& d, int* itc, cudaStream_t st, in
   u.X = (__half*)ctx->tc_X.p;
   u.nonfinite = nonfinite;
   prof_mark(ctx, st, "tc_update");
-  k_tc_update<<<dim3(d.T, d.n), 128, 0, st>>>(u);
+  k_tc_update<<<dim3((d.T + AW_TC_FR - 1) / AW_TC_FR, d.n), 256, 0, st>>>(u);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;

@@ -275,9 +275,9 @@ struct EpiArgsT {
   int tiles_per_clip;    // 128-row tiles per clip (Tp_pad / 128)
   int Tp;                // valid pooled frames per clip: rows beyond are written as 0
   int round_tf32;
-  // Toeplitz A operand (spectral path): map_a is a 3-D map {P, frames per row, rows} over an array of
-  // frame rows [rows + pad][P]; k-block kb of GEMM row r is elements (kb % (P/BK)) * BK .. of frame
-  // row r + kb / (P/BK).  0 = ordinary 2-D operand.
+  // Toeplitz A operand (spectral path): map_a is the plain 2-D map of an array of frame rows
+  // [rows + pad][P]; k-block kb of GEMM row r is elements (kb % (P/BK)) * BK .. of frame row
+  // r + kb / (P/BK), i.e. GEMM row r is the concatenation of K / P consecutive frame rows.  0 = ordinary.
   int toep_P;
   // EPI_PEAK / EPI_SPEC
   int rpc;               // GEMM rows per clip (T + 6: three zero frame rows at either end)
@@ -372,8 +372,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           mbar_wait(empty + s, ph ^ 1);
           mbar_expect_tx(full + s, STAGE);
           if (ep.toep_P > 0) {
+            // Toeplitz operand: GEMM row r, k-block kb = the ordinary 2-D box of the frame-row array at
+            // frame row r + kb / kpf, columns (kb % kpf) * BK .. -- a row offset per k-block, nothing else
             const int kpf = ep.toep_P / BK;                 // k-blocks per frame row
-            tma_load_3d(tiles + s * STAGE, &map_a, full + s, (kb % kpf) * BK, kb / kpf, row0);
+            tma_load_2d(tiles + s * STAGE, &map_a, full + s, (kb % kpf) * BK, row0 + kb / kpf);
           } else
             tma_load_2d(tiles + s * STAGE, &map_a, full + s, kb * BK, row0);
           tma_load_2d(tiles + s * STAGE + A_BYTES, &map_b, full + s, kb * BK, n0);

@@ -14,7 +14,7 @@
 // with P = 192 (2B = 162 padded), K_d = A_w E S_w shifted by d hops: analysis basis x 1/envelope x
 // synthesis basis, built once on the host in float64 (spectc_build).  The A operands are TOEPLITZ views
 // of the frame-row arrays X / dS ([T + 6][P] fp16 per clip, three zero rows at either end), expressed as
-// 3-D TMA tensor maps -- nothing is gathered or copied.  All three GEMMs run on k_gemm_tc (tcgen05,
+// a row offset per k-block into the plain 2-D TMA map of the frame rows -- nothing is gathered or copied.  All three GEMMs run on k_gemm_tc (tcgen05,
 // kind::f16, fp32 accumulation in TMEM).
 //
 // What is NOT Toeplitz: the three frames at either end of a clip (edge envelope, reflect padding).  Those
@@ -109,15 +109,18 @@ static void spectc_build(const float* window, int bin0, int nb, SpecTcMats& m) {
 
 // ---- frame-row arrays ---------------------------------------------------------------------------------
 // X rows: [clip][T + 6][P] fp16, row t + 3 = (Re, Im) of c u interleaved per bin; other rows / columns 0.
-__global__ void __launch_bounds__(128) k_tc_xprep(const float* __restrict__ c, const float2* __restrict__ u, int T,
+#define AW_TC_FR 16            // frames per block of the element-wise kernels (16 x 81 elements, 256 threads)
+__global__ void __launch_bounds__(256) k_tc_xprep(const float* __restrict__ c, const float2* __restrict__ u, int T,
                                                   int nb, __half* __restrict__ X) {
-  const int clip = blockIdx.y, t = blockIdx.x;
-  const long long src = ((long long)clip * T + t) * nb;
-  __half2* dst = reinterpret_cast<__half2*>(X + ((long long)clip * (T + 6) + t + 3) * AW_TC_P);
-  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-    const float cv = c[src + b];
-    const float2 uv = u[src + b];
-    dst[b] = __floats2half2_rn(cv * uv.x, cv * uv.y);
+  const int clip = blockIdx.y, t0 = blockIdx.x * AW_TC_FR;
+  const int nf = min(AW_TC_FR, T - t0);
+  const long long src = ((long long)clip * T + t0) * nb;            // frames t0.. are contiguous in [T][nb]
+  for (int e = threadIdx.x; e < nf * nb; e += blockDim.x) {
+    const int f = e / nb, b = e - f * nb;
+    const float cv = c[src + e];
+    const float2 uv = u[src + e];
+    reinterpret_cast<__half2*>(X + ((long long)clip * (T + 6) + t0 + f + 3) * AW_TC_P)[b] =
+        __floats2half2_rn(cv * uv.x, cv * uv.y);
   }
 }
 
@@ -131,22 +134,22 @@ __device__ __forceinline__ float tc_grad_scale(unsigned dmax_bits) {
 
 // dS rows: [clip][T + 6][P] fp16, row t + 3 = scale * dA q; the three frames at either end of the clip are
 // written as 0 (their adjoint is evaluated exactly by the edge kernel)
-__global__ void __launch_bounds__(128) k_tc_dsprep(const float* __restrict__ dA, const float2* __restrict__ q, int T,
+__global__ void __launch_bounds__(256) k_tc_dsprep(const float* __restrict__ dA, const float2* __restrict__ q, int T,
                                                    int nb, const unsigned* __restrict__ dmax,
                                                    __half* __restrict__ dS) {
-  const int clip = blockIdx.y, t = blockIdx.x;
-  const long long src = ((long long)clip * T + t) * nb;
-  __half2* dst = reinterpret_cast<__half2*>(dS + ((long long)clip * (T + 6) + t + 3) * AW_TC_P);
-  const bool edge = t < 3 || t >= T - 3;
+  const int clip = blockIdx.y, t0 = blockIdx.x * AW_TC_FR;
+  const int nf = min(AW_TC_FR, T - t0);
+  const long long src = ((long long)clip * T + t0) * nb;
   const float s = tc_grad_scale(dmax[clip]);
-  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+  for (int e = threadIdx.x; e < nf * nb; e += blockDim.x) {
+    const int f = e / nb, b = e - f * nb, t = t0 + f;
     float2 v = make_float2(0.f, 0.f);
-    if (!edge) {
-      const float g = dA[src + b] * s;
-      const float2 qv = q[src + b];
+    if (t >= 3 && t < T - 3) {
+      const float g = dA[src + e] * s;
+      const float2 qv = q[src + e];
       v = make_float2(g * qv.x, g * qv.y);
     }
-    dst[b] = __floats2half2_rn(v.x, v.y);
+    reinterpret_cast<__half2*>(dS + ((long long)clip * (T + 6) + t + 3) * AW_TC_P)[b] = __floats2half2_rn(v.x, v.y);
   }
 }
 
@@ -171,24 +174,26 @@ struct TcUpdateArgs {
   __half* X;                   // next iteration's frame rows
 };
 
-__global__ void __launch_bounds__(128) k_tc_update(TcUpdateArgs a) {
-  const int clip = blockIdx.y, t = blockIdx.x, T = a.T, nb = a.nb;
+__global__ void __launch_bounds__(256) k_tc_update(TcUpdateArgs a) {
+  const int clip = blockIdx.y, t0 = blockIdx.x * AW_TC_FR, T = a.T, nb = a.nb;
+  const int nf = min(AW_TC_FR, T - t0);
   const NadamStep st = a.steps[*a.it_ptr];
   const ClipScal cs = a.scal[clip];
   const float gs = cs.inv / tc_grad_scale(a.dmax[clip]);
   const bool improved = a.improved[clip] != 0;
-  const long long o0 = ((long long)clip * T + t) * nb;
-  const float* dx = a.dX + ((long long)clip * a.rpc + t) * AW_TC_P;
-  __half2* xrow = reinterpret_cast<__half2*>(a.X + ((long long)clip * a.rpc + t + 3) * AW_TC_P);
-  // peak-normaliser sub-gradient (waveform.py:19 twice): dy[n*] -= corr reaches the (at most four) frames
-  // that cover sample n*; through the iSTFT adjoint it is one windowed complex exponential per frame
-  const int mstar = cs.nstar + AW_HALF, nn = mstar - AW_HOP * t;
-  const bool has_corr = cs.corr != 0.f && nn >= 0 && nn < AW_NFFT && cs.nstar >= 0;
-  float cw = 0.f;
-  if (has_corr) cw = (2.0f / AW_NFFT) * a.window[nn] * (-cs.corr * ola_inv_envelope(mstar, T, a.window, a.env256));
-  const int er = t < 6 ? t : (t >= T - 6 ? 6 + (t - (T - 6)) : -1);      // row of g_edge, or -1
-  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-    const long long o = o0 + b;
+  const int mstar = cs.nstar + AW_HALF;
+  for (int e = threadIdx.x; e < nf * nb; e += blockDim.x) {
+    const int f = e / nb, b = e - f * nb, t = t0 + f;
+    const long long o = ((long long)clip * T + t0) * nb + e;
+    const float* dx = a.dX + ((long long)clip * a.rpc + t) * AW_TC_P;
+    __half2* xrow = reinterpret_cast<__half2*>(a.X + ((long long)clip * a.rpc + t + 3) * AW_TC_P);
+    // peak-normaliser sub-gradient (waveform.py:19 twice): dy[n*] -= corr reaches the (at most four) frames
+    // that cover sample n*; through the iSTFT adjoint it is one windowed complex exponential per frame
+    const int nn = mstar - AW_HOP * t;
+    const bool has_corr = cs.corr != 0.f && nn >= 0 && nn < AW_NFFT && cs.nstar >= 0;
+    float cw = 0.f;
+    if (has_corr) cw = (2.0f / AW_NFFT) * a.window[nn] * (-cs.corr * ola_inv_envelope(mstar, T, a.window, a.env256));
+    const int er = t < 6 ? t : (t >= T - 6 ? 6 + (t - (T - 6)) : -1);      // row of g_edge, or -1
     const float2 uv = a.u[o];
     const float2 d2 = *reinterpret_cast<const float2*>(dx + 2 * b);
     float g = gs * (d2.x * uv.x + d2.y * uv.y);
