@@ -1231,6 +1231,7 @@ extern "C" int aw_detect_batch(aw_ctx* ctx, const float* d_audio, int n_clips, i
   AW_REQUIRE(ctx && d_audio && d_values, "aw_detect_batch: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   AW_CUDA(cudaSetDevice(ctx->device));
+  AW_ENTRY("aw_detect_batch");
   nvtxRangePushA("aw_detect_batch");
   struct Pop { ~Pop() { nvtxRangePop(); } } pop_;
   if (detect_pipeline(ctx, d_audio, n_clips, n_samples, stride, sample_rate, d_values, st)) return 1;
@@ -1450,6 +1451,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
   AW_REQUIRE(!(d_scale && scale_mode != AW_SCALE_NONE), "aw_embed_batch: d_scale and scale_mode are exclusive");
   cudaStream_t user_stream = (cudaStream_t)stream, st = user_stream;
   AW_CUDA(cudaSetDevice(ctx->device));
+  AW_ENTRY("aw_embed_batch");
   nvtxRangePushA("aw_embed_batch");
   struct Pop { ~Pop() { nvtxRangePop(); } } pop_;
   // Graph replay needs a capturable stream (the caller's may be the legacy default stream): the

@@ -36,6 +36,15 @@ int set_error(const char* fmt, ...);
                            cudaGetErrorString(e__));                               \
   } while (0)
 
+// at API entry: an error left behind by an earlier, unchecked call must not be blamed on this one
+#define AW_ENTRY(name)                                                             \
+  do {                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                          \
+    if (e__ != cudaSuccess)                                                        \
+      return aw::set_error("%s: CUDA error pending from an earlier call -> %s", name, \
+                           cudaGetErrorString(e__));                               \
+  } while (0)
+
 #define AW_REQUIRE(cond, ...)                                                      \
   do {                                                                             \
     if (!(cond)) return aw::set_error(__VA_ARGS__);                                \

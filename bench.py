@@ -464,7 +464,27 @@ def main():
                      "launches": launches_d, "avg_ms": ms_d / launches_d,
                      "share_of_step": ms_d / ms_instr, "all_gemm_share_of_step": gemm_ms / ms_instr,
                      "algorithmic_flops_per_launch": flops}
-    cands = [r for r in (roof_fwd, roof_bwd, roof_norm, roof_gemm) if r]
+    def tensor_roof(name, label, flops, note):
+        if label not in timeline or not timeline[label][0]:
+            return None
+        cnt_, ms_ = timeline[label]
+        ach = flops / (ms_ / cnt_ * 1e-3) / 1e12
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
+                "frac": ach / pk["tflops"], "traffic": None,
+                "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % pk["src"], "launches": cnt_,
+                "avg_ms": ms_ / cnt_, "share_of_step": ms_ / ms_instr, "algorithmic_flops_per_launch": flops,
+                "note": note}
+
+    # tensor-core spectral path (csrc/spectc.cuh): useful FLOPs = the un-padded contraction (2B = 162 of P = 192)
+    tc_note = ("band-limited STFT / iSTFT of the fp16 loop as tcgen05 GEMMs over Toeplitz views of the frame rows; "
+               "FLOPs counted without the padding of 2B = %d to P = 192" % (2 * nb))
+    roof_tc_spec = tensor_roof("k_gemm_tc<half,float,192,EPI_SPEC> (STFT o iSTFT composite, K = 7P; + S_oob, |S|, S/|S|)",
+                               "gemm_spec_n192_k1344", 2.0 * n_w * T * (2 * nb) * (7 * 2 * nb), tc_note)
+    roof_tc_adj = tensor_roof("k_gemm_tc<half,float,192,EPI_PLAIN> (adjoint composite, K = 7P, fp32 out)",
+                              "gemm_plain_n192_k1344", 2.0 * n_w * T * (2 * nb) * (7 * 2 * nb), tc_note)
+    roof_tc_peak = tensor_roof("k_gemm_tc<half,float,256,EPI_PEAK> (band-limited iSTFT, K = 4P; + y_oob, max|y|; y never stored)",
+                               "gemm_peak_n256_k768", 2.0 * n_w * (T - 1) * 256 * (4 * 2 * nb), tc_note)
+    cands = [r for r in (roof_fwd, roof_bwd, roof_norm, roof_gemm, roof_tc_spec, roof_tc_adj, roof_tc_peak) if r]
     roof = max(cands, key=lambda r: r["share_of_step"]) if cands else None     # the dominant kernel class
     for fname in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
         ncu_traffic = os.path.join(ROOT, "profiles", fname)

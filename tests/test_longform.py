@@ -117,12 +117,14 @@ def test_sharded_path_with_one_rank_equals_the_batch_path():
     assert np.abs(v - v_ref).max() <= 1e-6
     np.testing.assert_allclose(v, O.detect(x, sr), atol=1e-5)
     pat = O.encode_bits(O.synth_bits(8)[5])
+    eng.set_tc_spectral(False)          # the sharded mode runs the fp32 FFT spectral kernels: compare like with like
     for prec in ("fp32", "fp16"):
         y_ref = eng.embed(torch.from_numpy(x[None]).cuda(), sr, torch.from_numpy(pat[None]), iters=3,
                           precision=prec).cpu().numpy()[0]
         y = lf.embed(x, sr, pat, iters=3, precision=prec)
         assert y.shape == y_ref.shape
         assert np.abs(y - y_ref).max() <= 1e-5, prec
+    eng.set_tc_spectral(True)
     assert lf.last_stats["allgathers"] == 0 and lf.last_stats["allreduces"] == 2 + 3 * 12
 
 
@@ -153,7 +155,8 @@ def _gpu_worker(rank, world, port, secs, iters, ret):
     out["v_after"] = lf.detect(yl, sr)
     out["y_long"] = yl
     if rank == 0:
-        # the whole-clip path on the same GPU, same process
+        # the whole-clip path on the same GPU, same process (fp32 FFT spectral kernels, as the sharded mode)
+        eng.set_tc_spectral(False)
         xd = torch.from_numpy(x[None]).cuda()
         with eng._with_precision("fp32"):
             out["ref_v_fp32"] = eng.detect(xd, sr).cpu().numpy()[0]
