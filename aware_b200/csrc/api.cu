@@ -1242,8 +1242,7 @@ extern "C" int aw_detect_batch(aw_ctx* ctx, const float* d_audio, int n_clips, i
   }
   if (ensure(ctx->lowm, (size_t)(1 + n_clips) * 4)) return 1;
   if (ctx->h_lowm_cap < (size_t)(1 + n_clips)) {
-    if (ctx->h_lowm) cudaFreeHost(ctx->h_lowm);
-  cudaFree(ctx->tcm.peakB); cudaFree(ctx->tcm.compB); cudaFree(ctx->tcm.compBT); cudaFree(ctx->tcm.fix);
+    if (ctx->h_lowm) AW_CUDA(cudaFreeHost(ctx->h_lowm));
     ctx->h_lowm = nullptr;
     AW_CUDA(cudaMallocHost((void**)&ctx->h_lowm, (size_t)(1 + n_clips) * 4));
     ctx->h_lowm_cap = (size_t)(1 + n_clips);
