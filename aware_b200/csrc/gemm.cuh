@@ -480,49 +480,72 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         }
         __syncwarp();
         if (EPI == EPI_PEAK) {
-          // y = y_band (this GEMM, scaled) + y_oob; only max |y| with its sample index and sign survives
+          // y = y_band (this GEMM, scaled) + y_oob; only max |y| with its sample index and sign survives.
+          // All loads of the chunk are issued first (read-only path): one exposed memory latency per
+          // chunk instead of one per row.
           const int j0 = half * (BN / 2) + c * 32 + cg;          // sample inside the hop (N = 256: one column tile)
-          const float f0 = ep.fix[0];
+          const float f0 = __ldg(ep.fix);
+          float4 yo[8], sc[8];
+          int nn[8], slot[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             int ti = sp_t0 + 4 * i, ci = sp_c0;
             if (ti >= ep.rpc) { ti -= ep.rpc; ++ci; }
-            if (sp_r0 + 4 * i >= ep.total_rows || ti < 2 || ti > ep.T) continue;
-            float4 sc = make_float4(f0, f0, f0, f0);
-            if (ti == 2) sc = *reinterpret_cast<const float4*>(ep.fix + 256 + j0);
-            else if (ti == ep.T) sc = *reinterpret_cast<const float4*>(ep.fix + 512 + j0);
-            const int n = AW_HOP * (ti - 2) + j0;
-            const float4 yo = *reinterpret_cast<const float4*>(ep.aux + (long long)ci * ep.L + n);
-            const float v4[4] = {fmaf(w[i][0], sc.x, yo.x), fmaf(w[i][1], sc.y, yo.y), fmaf(w[i][2], sc.z, yo.z),
-                                 fmaf(w[i][3], sc.w, yo.w)};
-            unsigned long long& dst = sp_pk[ci - sp_clip0];
+            const bool ok = sp_r0 + 4 * i < ep.total_rows && ti >= 2 && ti <= ep.T;
+            slot[i] = ok ? ci - sp_clip0 : -1;
+            nn[i] = AW_HOP * (ti - 2) + j0;
+            yo[i] = ok ? __ldg(reinterpret_cast<const float4*>(ep.aux + (long long)ci * ep.L + nn[i]))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            sc[i] = make_float4(f0, f0, f0, f0);
+            if (ok && ti == 2) sc[i] = __ldg(reinterpret_cast<const float4*>(ep.fix + 256 + j0));
+            if (ok && ti == ep.T) sc[i] = __ldg(reinterpret_cast<const float4*>(ep.fix + 512 + j0));
+          }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const unsigned long long pw = gemm_pack_peak_s(v4[k], (unsigned)(n + k));
-              dst = pw > dst ? pw : dst;
-            }
+          for (int i = 0; i < 8; ++i) {
+            if (slot[i] < 0) continue;
+            const float v4[4] = {fmaf(w[i][0], sc[i].x, yo[i].x), fmaf(w[i][1], sc[i].y, yo[i].y),
+                                 fmaf(w[i][2], sc[i].z, yo[i].z), fmaf(w[i][3], sc[i].w, yo[i].w)};
+            // largest |v| of the four first (lowest index wins ties), then ONE packed compare
+            float bv = v4[0];
+            int bk = 0;
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+              if (fabsf(v4[k]) > fabsf(bv)) { bv = v4[k]; bk = k; }
+            const unsigned long long pw = gemm_pack_peak_s(bv, (unsigned)(nn[i] + bk));
+            if (slot[i] == 0) sp_pk[0] = pw > sp_pk[0] ? pw : sp_pk[0];
+            else sp_pk[1] = pw > sp_pk[1] ? pw : sp_pk[1];
           }
           continue;
         }
         if (EPI == EPI_SPEC) {
-          // S = S_band (this GEMM) + S_oob; |S| and the phasor S/|S| of two bins per lane and row
+          // S = S_band (this GEMM) + S_oob; |S| and the phasor S/|S| of two bins per lane and row.
+          // Loads of the whole chunk first, through the read-only path (no aliasing with the stores).
           const int b0 = (half * (BN / 2) + c * 32 + cg) >> 1;
+          const float2* aux2 = reinterpret_cast<const float2*>(ep.aux);
+          float2 so[8][2];
+          long long base[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             int ti = sp_t0 + 4 * i, ci = sp_c0;
             if (ti >= ep.rpc) { ti -= ep.rpc; ++ci; }
-            if (sp_r0 + 4 * i >= ep.total_rows || ti >= ep.T) continue;
-            const long long base = ((long long)ci * ep.T + ti) * ep.nb;
+            const bool ok = sp_r0 + 4 * i < ep.total_rows && ti < ep.T;
+            base[i] = ok ? ((long long)ci * ep.T + ti) * ep.nb : -1;
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2)
+              so[i][e2] = (ok && b0 + e2 < ep.nb) ? __ldg(aux2 + base[i] + b0 + e2) : make_float2(0.f, 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (base[i] < 0) continue;
 #pragma unroll
             for (int e2 = 0; e2 < 2; ++e2) {
               const int b = b0 + e2;
               if (b >= ep.nb) continue;
-              const float2 so = reinterpret_cast<const float2*>(ep.aux)[base + b];
-              const float xr = w[i][2 * e2] + so.x, xi = w[i][2 * e2 + 1] + so.y;
+              const float xr = w[i][2 * e2] + so[i][e2].x, xi = w[i][2 * e2 + 1] + so[i][e2].y;
               const float p2 = xr * xr + xi * xi;
               const float iv = p2 > 0.f ? rsqrtf(p2) : 0.f;
-              ep.mag[base + b] = p2 * iv;
-              ep.qph[base + b] = make_float2(xr * iv, xi * iv);
+              ep.mag[base[i] + b] = p2 * iv;
+              ep.qph[base[i] + b] = make_float2(xr * iv, xi * iv);
             }
           }
           continue;

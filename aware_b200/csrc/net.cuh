@@ -655,9 +655,15 @@ __global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ 
     s2 = block_sum(s2, s_red);
     if (threadIdx.x == 0) s2_part[(long long)clip * gridDim.x + blockIdx.x] = s2;
   }
-  if (dmax) {
+  if (dmax) {                                            // one atomic per block
+    __shared__ float s_amax[4];
     amax = warp_max(amax);
-    if ((threadIdx.x & 31) == 0 && amax > 0.f && amax < INFINITY) atomicMax(dmax + clip, __float_as_uint(amax));
+    if ((threadIdx.x & 31) == 0) s_amax[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      amax = fmaxf(fmaxf(s_amax[0], s_amax[1]), fmaxf(s_amax[2], s_amax[3]));
+      if (amax > 0.f && amax < INFINITY) atomicMax(dmax + clip, __float_as_uint(amax));
+    }
   }
 }
 

@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(256) k_tc_xprep(const float* __restrict__ c, c
   const long long src = ((long long)clip * T + t0) * nb;            // frames t0.. are contiguous in [T][nb]
   for (int e = threadIdx.x; e < nf * nb; e += blockDim.x) {
     const int f = e / nb, b = e - f * nb;
-    const float cv = c[src + e];
-    const float2 uv = u[src + e];
+    const float cv = __ldg(c + src + e);
+    const float2 uv = __ldg(u + src + e);
     reinterpret_cast<__half2*>(X + ((long long)clip * (T + 6) + t0 + f + 3) * AW_TC_P)[b] =
         __floats2half2_rn(cv * uv.x, cv * uv.y);
   }
@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(256) k_tc_dsprep(const float* __restrict__ dA,
     const int f = e / nb, b = e - f * nb, t = t0 + f;
     float2 v = make_float2(0.f, 0.f);
     if (t >= 3 && t < T - 3) {
-      const float g = dA[src + e] * s;
-      const float2 qv = q[src + e];
+      const float g = __ldg(dA + src + e) * s;
+      const float2 qv = __ldg(q + src + e);
       v = make_float2(g * qv.x, g * qv.y);
     }
     reinterpret_cast<__half2*>(dS + ((long long)clip * (T + 6) + t + 3) * AW_TC_P)[b] = __floats2half2_rn(v.x, v.y);
@@ -194,17 +194,17 @@ __global__ void __launch_bounds__(256) k_tc_update(TcUpdateArgs a) {
     float cw = 0.f;
     if (has_corr) cw = (2.0f / AW_NFFT) * a.window[nn] * (-cs.corr * ola_inv_envelope(mstar, T, a.window, a.env256));
     const int er = t < 6 ? t : (t >= T - 6 ? 6 + (t - (T - 6)) : -1);      // row of g_edge, or -1
-    const float2 uv = a.u[o];
-    const float2 d2 = *reinterpret_cast<const float2*>(dx + 2 * b);
+    const float2 uv = __ldg(a.u + o);
+    const float2 d2 = __ldg(reinterpret_cast<const float2*>(dx + 2 * b));
     float g = gs * (d2.x * uv.x + d2.y * uv.y);
-    if (er >= 0) g += a.g_edge[((long long)clip * 12 + er) * nb + b];
+    if (er >= 0) g += __ldg(a.g_edge + ((long long)clip * 12 + er) * nb + b);
     if (has_corr) {
       float sn, cn;
       sincospif((float)(((a.bin0 + b) * nn) & (AW_NFFT - 1)) * (2.0f / AW_NFFT), &sn, &cn);
       g += cw * (cn * uv.x - sn * uv.y);
     }
     float m1 = a.m[o], v1 = a.v[o], c1 = a.c[o];
-    const float c0 = a.c0[o];
+    const float c0 = __ldg(a.c0 + o);
     if ((__float_as_uint(g) & 0x7f800000u) == 0x7f800000u) {
       if (a.nonfinite) a.nonfinite[clip] = 1;
     } else {
