@@ -1039,7 +1039,7 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
                                      (ChanStats*)ctx->cs.p, (P0BwdCoef*)ctx->p0coef.p,
                                      (P0BwdScal*)ctx->p0scal.p, sm, d.nb, own_frames(ctx, (float*)ctx->dA.p, d.nb),
                                      euler_s2 ? (const float*)own_frames(ctx, (float*)ctx->mag.p, d.nb) : nullptr, acc.s2_part,
-                                     (const float*)ctx->gsc.p, ctx->tc_active ? (unsigned*)ctx->tc_dmax.p : nullptr);
+                                     (const float*)ctx->gsc.p);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
@@ -1346,7 +1346,7 @@ static int tc_setup_wave(aw_ctx* ctx, const Dims& d, cudaStream_t st) {
   const size_t frame_bytes = (size_t)(r128 + 8) * AW_TC_P * 2;          // + 8 rows: the Toeplitz reach of the last rows
   if (ensure(ctx->tc_X, frame_bytes) || ensure(ctx->tc_dS, frame_bytes) ||
       ensure(ctx->tc_soob, (size_t)d.n * d.T * d.nb * 8) || ensure(ctx->tc_dX, (size_t)r128 * AW_TC_P * 4) ||
-      ensure(ctx->tc_gedge, (size_t)d.n * 12 * d.nb * 4) || ensure(ctx->tc_dmax, (size_t)d.n * 4) ||
+      ensure(ctx->tc_gedge, (size_t)d.n * 12 * d.nb * 4) || ensure(ctx->tc_dmax, (size_t)d.n * 8) ||
       ensure(ctx->tc_ones, (size_t)d.n * 8))
     return 1;
   if (ctx->tc_map_x != ctx->tc_X.p || ctx->tc_map_ds != ctx->tc_dS.p || ctx->tc_map_rows != rows) {
@@ -1357,6 +1357,7 @@ static int tc_setup_wave(aw_ctx* ctx, const Dims& d, cudaStream_t st) {
   AW_CUDA(cudaMemsetAsync(ctx->tc_X.p, 0, frame_bytes, st));
   AW_CUDA(cudaMemsetAsync(ctx->tc_dS.p, 0, frame_bytes, st));
   AW_CUDA(cudaMemsetAsync(ctx->tc_gedge.p, 0, (size_t)d.n * 12 * d.nb * 4, st));
+  AW_CUDA(cudaMemsetAsync(ctx->tc_dmax.p, 0, (size_t)d.n * 8, st));
   // S_oob = STFT(y_oob) restricted to the band, un-normalised (peak word 1.0: x / (1 + 1e-8) == x in fp32)
   k_fill_u64<<<(d.n + 255) / 256, 256, 0, st>>>((unsigned long long*)ctx->tc_ones.p, (unsigned long long)0x3f800000u << 32, d.n);
   ctx->launches++;
@@ -1401,11 +1402,16 @@ static int tc_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, cudaStream_t s
 }
 
 // dA q (frame rows, edge rows zeroed) -> K^T -> + exact edge adjoint + peak sub-gradient -> NAdam
-static int tc_backward(aw_ctx* ctx, const Dims& d, int* itc, cudaStream_t st, int* nonfinite) {
+static int tc_backward(aw_ctx* ctx, const Dims& d, int* itc, cudaStream_t st, int* nonfinite, bool first) {
   const int r128 = (int)tc_rows128(d);
+  if (first) {            // the first iteration has no predecessor to take the scale from
+    prof_mark(ctx, st, "tc_absmax");
+    k_tc_absmax<<<dim3(32, d.n), 256, 0, st>>>((const float*)ctx->dA.p, (long long)d.T * d.nb, (unsigned*)ctx->tc_dmax.p);
+    ctx->launches++;
+  }
   prof_mark(ctx, st, "tc_dsprep");
   k_tc_dsprep<<<dim3((d.T + AW_TC_FR - 1) / AW_TC_FR, d.n), 256, 0, st>>>((const float*)ctx->dA.p, (const float2*)ctx->ph_q.p, d.T, d.nb,
-                                               (const unsigned*)ctx->tc_dmax.p, (__half*)ctx->tc_dS.p);
+                                               (unsigned*)ctx->tc_dmax.p, itc, d.n, (__half*)ctx->tc_dS.p);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   EpiArgsT<float> ep = tc_epi(d);
@@ -1423,7 +1429,7 @@ static int tc_backward(aw_ctx* ctx, const Dims& d, int* itc, cudaStream_t st, in
   if (launch_spec<SPEC_BWD>(ctx, d, b, st)) return 1;
   TcUpdateArgs u{};
   u.T = d.T; u.nb = d.nb; u.rpc = d.T + 6;
-  u.dX = (const float*)ctx->tc_dX.p; u.dmax = (const unsigned*)ctx->tc_dmax.p;
+  u.dX = (const float*)ctx->tc_dX.p; u.dmax = (const unsigned*)ctx->tc_dmax.p; u.n_clips = d.n;
   u.scal = (const ClipScal*)ctx->scal.p; u.g_edge = (const float*)ctx->tc_gedge.p;
   u.u = (const float2*)ctx->ph_u.p;
   u.c = (float*)ctx->c.p; u.m = (float*)ctx->m.p; u.v = (float*)ctx->v.p; u.cbest = (float*)ctx->cbest.p;
@@ -1552,9 +1558,9 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
 
     // ---- optimisation loop (multibit_embedder.py:95-122)
     nvtxRangePushA("embed:nadam_loop");
-    auto iteration = [&]() -> int {
+    auto iteration = [&](bool first) -> int {
       // fused spectral passes (spec.cuh): y and dpad never leave shared memory
-      if (begin_pass(ctx, dw.n, itc, st, tc ? (unsigned*)ctx->tc_dmax.p : nullptr)) return 1;
+      if (begin_pass(ctx, dw.n, itc, st)) return 1;
       if (tc) {
         if (tc_forward(ctx, dw, acc, st)) return 1;
       } else {
@@ -1587,10 +1593,11 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       if (reduce_if_long(ctx, ctx->red_c, sp2, sb2, dw.n, 1, st)) return 1;
       if (sb2 > 512 && reduce_if_long(ctx, ctx->red_a, sp2, sb2, dw.n, 1, st)) return 1;   // 1 h: 38 760 -> 606 -> 10
       prof_mark(ctx, st, "clip_scalars");
-      k_clip_scalars<<<(dw.n + 127) / 128, 128, 0, st>>>(acc.peak_y, sp2, sb2, dw.n, (ClipScal*)ctx->scal.p);
+      k_clip_scalars<<<(dw.n + 127) / 128, 128, 0, st>>>(acc.peak_y, sp2, sb2, dw.n, (ClipScal*)ctx->scal.p, 0,
+                                                         tc ? (unsigned*)ctx->tc_dmax.p : nullptr, itc);
       ctx->launches++;
       AW_LAUNCH_CHECK();
-      if (tc) return tc_backward(ctx, dw, itc, st, (int*)ctx->nonfinite.p + w0);
+      if (tc) return tc_backward(ctx, dw, itc, st, (int*)ctx->nonfinite.p + w0, first);
       SpecArgs b;
       memset(&b, 0, sizeof(b));
       b.amp = (float*)ctx->dA.p; b.ph = (float2*)ctx->ph_q.p;
@@ -1608,10 +1615,10 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       // without executing, and the graph is replayed for iterations 1 .. iters-1; the iteration
       // index and all per-clip state live on the device, so every replay is identical work
       const int64_t l0 = ctx->launches;
-      if (iteration()) return 1;
-      const int64_t per_iter = ctx->launches - l0;
+      if (iteration(true)) return 1;
+      const int64_t per_iter = ctx->launches - l0 - (tc ? 1 : 0);
       AW_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-      const int rc = iteration();
+      const int rc = iteration(false);
       cudaGraph_t graph = nullptr;
       const cudaError_t ce = cudaStreamEndCapture(st, &graph);
       if (rc || ce != cudaSuccess || !graph) {
@@ -1635,7 +1642,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       cudaGraphDestroy(graph);
     } else {
       for (int it = 0; it < iters; ++it)
-        if (iteration()) return 1;
+        if (iteration(it == 0)) return 1;
     }
     nvtxRangePop();
     // ---- final synthesis from the best coefficients (multibit_embedder.py:173-192)

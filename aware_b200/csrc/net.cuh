@@ -595,8 +595,7 @@ __global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ 
                                                       int nb, float* __restrict__ dA,
                                                       const float* __restrict__ mag_un,
                                                       double* __restrict__ s2_part,
-                                                      const float* __restrict__ gsc,
-                                                      unsigned* __restrict__ dmax = nullptr) {
+                                                      const float* __restrict__ gsc) {
   __shared__ double s_red[32];
   __shared__ float s_dm[AW_P0A_FRAMES][AW_NMEL];
   const int clip = blockIdx.y, c = threadIdx.x, t0 = blockIdx.x * AW_P0A_FRAMES;
@@ -626,7 +625,6 @@ __global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ 
   __syncthreads();
   // one thread per band bin: its (weight, channel) taps are fetched once and applied to all frames
   double s2 = 0.0;
-  float amax = 0.f;                                      // max |dA| of the clip (spectc.cuh's fp16 scale)
   for (int b = threadIdx.x; b < nb; b += 128) {
     const int e0 = sm.colptr[b], e1 = sm.colptr[b + 1];
     float acc[AW_P0A_FRAMES];
@@ -643,7 +641,6 @@ __global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ 
       if (f < nf) {
         const long long o = ((long long)clip * T + t0 + f) * nb + b;
         dA[o] = acc[f];
-        amax = fmaxf(amax, fabsf(acc[f]));
         if (mag_un) s2 += (double)(acc[f] * mag_un[o]);
       }
     }
@@ -654,16 +651,6 @@ __global__ void __launch_bounds__(128) k_p0_bwd_apply(const float* __restrict__ 
     __syncthreads();
     s2 = block_sum(s2, s_red);
     if (threadIdx.x == 0) s2_part[(long long)clip * gridDim.x + blockIdx.x] = s2;
-  }
-  if (dmax) {                                            // one atomic per block
-    __shared__ float s_amax[4];
-    amax = warp_max(amax);
-    if ((threadIdx.x & 31) == 0) s_amax[threadIdx.x >> 5] = amax;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      amax = fmaxf(fmaxf(s_amax[0], s_amax[1]), fmaxf(s_amax[2], s_amax[3]));
-      if (amax > 0.f && amax < INFINITY) atomicMax(dmax + clip, __float_as_uint(amax));
-    }
   }
 }
 

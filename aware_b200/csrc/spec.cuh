@@ -237,9 +237,13 @@ struct ClipScal {
 // GLOBAL indices into the peak word; 0 otherwise)
 __global__ void __launch_bounds__(128) k_clip_scalars(const unsigned long long* __restrict__ peak_y,
                                                       const double* __restrict__ s2_part, int nblk,
-                                                      int n_clips, ClipScal* __restrict__ out, int n_base = 0) {
+                                                      int n_clips, ClipScal* __restrict__ out, int n_base = 0,
+                                                      unsigned* __restrict__ dmax2 = nullptr,
+                                                      const int* __restrict__ it_ptr = nullptr) {
   const int clip = blockIdx.x * blockDim.x + threadIdx.x;
   if (clip >= n_clips) return;
+  // spectc.cuh: the slot that this iteration's k_tc_dsprep accumulates max |dA| into (next iteration's scale)
+  if (dmax2) dmax2[(size_t)((*it_ptr + 1) & 1) * n_clips + clip] = 0u;
   const unsigned long long pk = peak_y[clip];
   const float p1 = peak_value(pk);
   const float d1 = p1 + 1e-8f;

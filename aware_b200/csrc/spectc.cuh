@@ -125,7 +125,12 @@ __global__ void __launch_bounds__(256) k_tc_xprep(const float* __restrict__ c, c
 }
 
 // per-clip power-of-two scale that brings the largest |dA| of the clip to ~2^9 (fp16 normal range for
-// everything within 2^-23 of it); dmax holds the float bits of max |dA| (atomicMax on non-negative floats)
+// everything within 2^-23 of it, 2^7 of headroom); dmax holds the float bits of max |dA| (atomicMax on
+// non-negative floats) in TWO slots [2][n_clips]: iteration `it` scales by slot it & 1, which iteration
+// it - 1 accumulated while it wrote its own dS (the first iteration fills slot 0 with k_tc_absmax), and
+// accumulates into slot (it + 1) & 1, which k_clip_scalars has just cleared.  |dA| drifts slowly; should
+// it ever jump by more than 2^7 between two iterations the overflow shows up as a non-finite gradient,
+// the update is skipped and the clip flagged (aw_embed_status).
 __device__ __forceinline__ float tc_grad_scale(unsigned dmax_bits) {
   const float mx = __uint_as_float(dmax_bits);
   if (!(mx > 0.f) || !(mx < INFINITY)) return 1.0f;
@@ -134,22 +139,46 @@ __device__ __forceinline__ float tc_grad_scale(unsigned dmax_bits) {
 
 // dS rows: [clip][T + 6][P] fp16, row t + 3 = scale * dA q; the three frames at either end of the clip are
 // written as 0 (their adjoint is evaluated exactly by the edge kernel)
+__global__ void __launch_bounds__(256) k_tc_absmax(const float* __restrict__ dA, long long per_clip,
+                                                   unsigned* __restrict__ dmax) {
+  const int clip = blockIdx.y;
+  const float* p = dA + (long long)clip * per_clip;
+  float mx = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_clip; i += (long long)gridDim.x * blockDim.x)
+    mx = fmaxf(mx, fabsf(p[i]));
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0 && mx > 0.f && mx < INFINITY) atomicMax(dmax + clip, __float_as_uint(mx));
+}
+
 __global__ void __launch_bounds__(256) k_tc_dsprep(const float* __restrict__ dA, const float2* __restrict__ q, int T,
-                                                   int nb, const unsigned* __restrict__ dmax,
-                                                   __half* __restrict__ dS) {
+                                                   int nb, unsigned* __restrict__ dmax2, const int* __restrict__ it_ptr,
+                                                   int n_clips, __half* __restrict__ dS) {
+  __shared__ float s_mx[8];
   const int clip = blockIdx.y, t0 = blockIdx.x * AW_TC_FR;
   const int nf = min(AW_TC_FR, T - t0);
   const long long src = ((long long)clip * T + t0) * nb;
-  const float s = tc_grad_scale(dmax[clip]);
+  const int slot = *it_ptr & 1;
+  const float s = tc_grad_scale(dmax2[(size_t)slot * n_clips + clip]);
+  float mx = 0.f;
   for (int e = threadIdx.x; e < nf * nb; e += blockDim.x) {
     const int f = e / nb, b = e - f * nb, t = t0 + f;
     float2 v = make_float2(0.f, 0.f);
+    const float a0 = __ldg(dA + src + e);
+    mx = fmaxf(mx, fabsf(a0));
     if (t >= 3 && t < T - 3) {
-      const float g = __ldg(dA + src + e) * s;
+      const float g = a0 * s;
       const float2 qv = __ldg(q + src + e);
       v = make_float2(g * qv.x, g * qv.y);
     }
     reinterpret_cast<__half2*>(dS + ((long long)clip * (T + 6) + t + 3) * AW_TC_P)[b] = __floats2half2_rn(v.x, v.y);
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_mx[w]);
+    if (mx > 0.f && mx < INFINITY) atomicMax(dmax2 + (size_t)(slot ^ 1) * n_clips + clip, __float_as_uint(mx));
   }
 }
 
@@ -157,7 +186,8 @@ __global__ void __launch_bounds__(256) k_tc_dsprep(const float* __restrict__ dA,
 struct TcUpdateArgs {
   int T, nb, rpc;
   const float* dX;             // [rows][P] fp32: scale * K^T dS (interleaved Re, Im)
-  const unsigned* dmax;        // [clip]
+  const unsigned* dmax;        // [2][n_clips]: this iteration's scale sits in slot it & 1
+  int n_clips;
   const ClipScal* scal;        // [clip] inv, corr, nstar
   const float* g_edge;         // [clip][12][nb]: exact adjoint of the six edge rows, frames 0..5 and T-6..T-1
   const float2* u;
@@ -177,9 +207,10 @@ struct TcUpdateArgs {
 __global__ void __launch_bounds__(256) k_tc_update(TcUpdateArgs a) {
   const int clip = blockIdx.y, t0 = blockIdx.x * AW_TC_FR, T = a.T, nb = a.nb;
   const int nf = min(AW_TC_FR, T - t0);
-  const NadamStep st = a.steps[*a.it_ptr];
+  const int it = *a.it_ptr;
+  const NadamStep st = a.steps[it];
   const ClipScal cs = a.scal[clip];
-  const float gs = cs.inv / tc_grad_scale(a.dmax[clip]);
+  const float gs = cs.inv / tc_grad_scale(a.dmax[(size_t)(it & 1) * a.n_clips + clip]);
   const bool improved = a.improved[clip] != 0;
   const int mstar = cs.nstar + AW_HALF;
   for (int e = threadIdx.x; e < nf * nb; e += blockDim.x) {

@@ -29,5 +29,53 @@ def big_detect():
                 print("  detect n=%d FAILED: %s" % (n, e), flush=True)
 
 
-if __name__ == "__main__":
-    {"big_detect": big_detect}[sys.argv[1]]()
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "big_detect":
+    big_detect()
+
+
+def tl(tag=""):
+    """per-kernel-class timeline of a few embed iterations (128 clips), TC spectral path on / off"""
+    from aware_b200.synth import synth_batch, synth_bits
+    from aware_b200.utils.models import load
+    emb, det = load(); emb.verbose = False
+    eng = emb.engine
+    sr = 44100
+    n = int(os.environ.get("CLIPS", "256"))
+    x = torch.from_numpy(synth_batch(n, 10.0, sr)).cuda()
+    pat = torch.from_numpy(2 * synth_bits(n) - 1)
+    for tc in (True, False):
+        eng.set_tc_spectral(tc)
+        eng.embed(x, sr, pat, iters=4, precision="fp16")
+        eng.profile(True)
+        eng.embed(x, sr, pat, iters=10, precision="fp16")
+        torch.cuda.synchronize()
+        eng.profile(False)
+        eng.profile_read()
+        t = eng.profile_read_named()
+        tot = sum(v[1] for v in t.values())
+        print("tc=%s total %.2f ms per iteration" % (tc, tot / 10))
+        for k, v in sorted(t.items(), key=lambda kv: -kv[1][1])[:40]:
+            print("   %-28s %4d launches %8.3f ms/iter" % (k, v[0], v[1] / 10))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "tl":
+    tl()
+
+
+def tcprof():
+    """short fp16 embed on the TC spectral path for ncu (64 clips x 10 s, 6 iterations, eager launches)"""
+    from aware_b200.synth import synth_batch, synth_bits
+    from aware_b200.utils.models import load
+    emb, det = load(); emb.verbose = False
+    eng = emb.engine
+    sr = 44100
+    n = int(os.environ.get("CLIPS", "64"))
+    x = torch.from_numpy(synth_batch(n, 10.0, sr)).cuda()
+    pat = torch.from_numpy(2 * synth_bits(n) - 1)
+    eng.embed(x, sr, pat, iters=int(os.environ.get("ITERS", "6")), precision="fp16")
+    torch.cuda.synchronize()
+    print("tcprof ok", eng.launch_count())
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "tcprof":
+    tcprof()
