@@ -432,12 +432,33 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       const OT* abase = epi_is_bwd(EPI) ? ep.act + grow : nullptr;
       float* sp = s_part + ab * (2 * 4 * BN);
       float ga[8][4];
-      // EPI_PEAK / EPI_SPEC: GEMM row -> (clip, frame row inside the clip) of this lane's first staged row
-      const int sp_r0 = row_tile * 128 + q * 32 + sr;
-      const int sp_c0 = (EPI == EPI_PEAK || EPI == EPI_SPEC) ? sp_r0 / ep.rpc : 0;
-      const int sp_t0 = (EPI == EPI_PEAK || EPI == EPI_SPEC) ? sp_r0 - sp_c0 * ep.rpc : 0;
+      // EPI_PEAK / EPI_SPEC: everything that depends only on the ROW is computed once per tile (the
+      // epilogue warps are few -- two per scheduler -- so their instruction count is what bounds these
+      // epilogues): GEMM row -> (clip, frame row), validity, the row's base pointer / offset
       const int sp_clip0 = EPI == EPI_PEAK ? (row_tile * 128) / ep.rpc : 0;   // a 128-row tile spans <= 2 clips
-      unsigned long long sp_pk[2] = {0ull, 0ull};
+      const float* sp_yrow[8];       // PEAK: y_oob + clip * L + 256 (hop - 2), or null when the row is not a valid hop
+      int sp_n0[8], sp_kind[8];      // PEAK: sample index of the hop's first sample; 0 interior, 1 hop 2, 2 hop T
+      long long sp_base[8];          // SPEC: (clip * T + t) * nb, or -1
+      float sp_bv[2] = {0.f, 0.f};   // PEAK: signed value with the largest |.| per clip slot, and its sample index
+      int sp_bn[2] = {-1, -1};
+      if (EPI == EPI_PEAK || EPI == EPI_SPEC) {
+        const int r0 = row_tile * 128 + q * 32 + sr;
+        const int c0_ = r0 / ep.rpc, t0_ = r0 - c0_ * ep.rpc;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int ti = t0_ + 4 * i, ci = c0_;
+          if (ti >= ep.rpc) { ti -= ep.rpc; ++ci; }
+          const bool in = r0 + 4 * i < ep.total_rows;
+          if (EPI == EPI_PEAK) {
+            const bool ok = in && ti >= 2 && ti <= ep.T;
+            sp_n0[i] = AW_HOP * (ti - 2);
+            sp_yrow[i] = ok ? ep.aux + (long long)ci * ep.L + sp_n0[i] : nullptr;
+            sp_kind[i] = (ti == 2 ? 1 : (ti == ep.T ? 2 : 0)) | ((ci - sp_clip0) << 4);
+          } else {
+            sp_base[i] = in && ti < ep.T ? ((long long)ci * ep.T + ti) * ep.nb : -1;
+          }
+        }
+      }
       // *_APPLY: this tile's clip, its first row inside the clip, and the statistics base
       const int clip_ = epi_applies(EPI) ? row_tile / ep.tiles_per_clip : 0;
       const int jrow0 = epi_applies(EPI) ? (row_tile - clip_ * ep.tiles_per_clip) * 128 + q * 32 + sr : 0;
@@ -481,39 +502,31 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         __syncwarp();
         if (EPI == EPI_PEAK) {
           // y = y_band (this GEMM, scaled) + y_oob; only max |y| with its sample index and sign survives.
-          // All loads of the chunk are issued first (read-only path): one exposed memory latency per
-          // chunk instead of one per row.
+          // The chunk's loads are issued first, through the read-only path.
           const int j0 = half * (BN / 2) + c * 32 + cg;          // sample inside the hop (N = 256: one column tile)
           const float f0 = __ldg(ep.fix);
-          float4 yo[8], sc[8];
-          int nn[8], slot[8];
+          const float4 fl = __ldg(reinterpret_cast<const float4*>(ep.fix + 256 + j0));
+          const float4 fr = __ldg(reinterpret_cast<const float4*>(ep.fix + 512 + j0));
+          float4 yo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            yo[i] = sp_yrow[i] ? __ldg(reinterpret_cast<const float4*>(sp_yrow[i] + j0)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            int ti = sp_t0 + 4 * i, ci = sp_c0;
-            if (ti >= ep.rpc) { ti -= ep.rpc; ++ci; }
-            const bool ok = sp_r0 + 4 * i < ep.total_rows && ti >= 2 && ti <= ep.T;
-            slot[i] = ok ? ci - sp_clip0 : -1;
-            nn[i] = AW_HOP * (ti - 2) + j0;
-            yo[i] = ok ? __ldg(reinterpret_cast<const float4*>(ep.aux + (long long)ci * ep.L + nn[i]))
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-            sc[i] = make_float4(f0, f0, f0, f0);
-            if (ok && ti == 2) sc[i] = __ldg(reinterpret_cast<const float4*>(ep.fix + 256 + j0));
-            if (ok && ti == ep.T) sc[i] = __ldg(reinterpret_cast<const float4*>(ep.fix + 512 + j0));
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (slot[i] < 0) continue;
-            const float v4[4] = {fmaf(w[i][0], sc[i].x, yo[i].x), fmaf(w[i][1], sc[i].y, yo[i].y),
-                                 fmaf(w[i][2], sc[i].z, yo[i].z), fmaf(w[i][3], sc[i].w, yo[i].w)};
-            // largest |v| of the four first (lowest index wins ties), then ONE packed compare
-            float bv = v4[0];
+            if (!sp_yrow[i]) continue;
+            const int kind = sp_kind[i] & 3, slot = sp_kind[i] >> 4;
+            const float4 sc = kind == 0 ? make_float4(f0, f0, f0, f0) : (kind == 1 ? fl : fr);
+            const float v4[4] = {fmaf(w[i][0], sc.x, yo[i].x), fmaf(w[i][1], sc.y, yo[i].y),
+                                 fmaf(w[i][2], sc.z, yo[i].z), fmaf(w[i][3], sc.w, yo[i].w)};
+            float bv = v4[0];                                   // largest |v| of the four, lowest index on ties
             int bk = 0;
 #pragma unroll
             for (int k = 1; k < 4; ++k)
               if (fabsf(v4[k]) > fabsf(bv)) { bv = v4[k]; bk = k; }
-            const unsigned long long pw = gemm_pack_peak_s(bv, (unsigned)(nn[i] + bk));
-            if (slot[i] == 0) sp_pk[0] = pw > sp_pk[0] ? pw : sp_pk[0];
-            else sp_pk[1] = pw > sp_pk[1] ? pw : sp_pk[1];
+            const int n = sp_n0[i] + j0 + bk;
+            float& cv = slot == 0 ? sp_bv[0] : sp_bv[1];
+            int& cn = slot == 0 ? sp_bn[0] : sp_bn[1];
+            if (fabsf(bv) > fabsf(cv) || cn < 0 || (fabsf(bv) == fabsf(cv) && n < cn)) { cv = bv; cn = n; }
           }
           continue;
         }
@@ -522,30 +535,27 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           // Loads of the whole chunk first, through the read-only path (no aliasing with the stores).
           const int b0 = (half * (BN / 2) + c * 32 + cg) >> 1;
           const float2* aux2 = reinterpret_cast<const float2*>(ep.aux);
+          const bool v0 = b0 < ep.nb, v1 = b0 + 1 < ep.nb;
           float2 so[8][2];
-          long long base[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            int ti = sp_t0 + 4 * i, ci = sp_c0;
-            if (ti >= ep.rpc) { ti -= ep.rpc; ++ci; }
-            const bool ok = sp_r0 + 4 * i < ep.total_rows && ti < ep.T;
-            base[i] = ok ? ((long long)ci * ep.T + ti) * ep.nb : -1;
-#pragma unroll
-            for (int e2 = 0; e2 < 2; ++e2)
-              so[i][e2] = (ok && b0 + e2 < ep.nb) ? __ldg(aux2 + base[i] + b0 + e2) : make_float2(0.f, 0.f);
+            const bool ok = sp_base[i] >= 0;
+            so[i][0] = ok && v0 ? __ldg(aux2 + sp_base[i] + b0) : make_float2(0.f, 0.f);
+            so[i][1] = ok && v1 ? __ldg(aux2 + sp_base[i] + b0 + 1) : make_float2(0.f, 0.f);
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            if (base[i] < 0) continue;
+            if (sp_base[i] < 0) continue;
+            float* mrow = ep.mag + sp_base[i] + b0;
+            float2* qrow = ep.qph + sp_base[i] + b0;
 #pragma unroll
             for (int e2 = 0; e2 < 2; ++e2) {
-              const int b = b0 + e2;
-              if (b >= ep.nb) continue;
+              if (!(e2 == 0 ? v0 : v1)) continue;
               const float xr = w[i][2 * e2] + so[i][e2].x, xi = w[i][2 * e2 + 1] + so[i][e2].y;
               const float p2 = xr * xr + xi * xi;
               const float iv = p2 > 0.f ? rsqrtf(p2) : 0.f;
-              ep.mag[base[i] + b] = p2 * iv;
-              ep.qph[base[i] + b] = make_float2(xr * iv, xi * iv);
+              mrow[e2] = p2 * iv;
+              qrow[e2] = make_float2(xr * iv, xi * iv);
             }
           }
           continue;
@@ -628,7 +638,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       if (EPI == EPI_PEAK) {
 #pragma unroll
         for (int z = 0; z < 2; ++z) {
-          const unsigned long long pw = warp_max_u64(sp_pk[z]);
+          const unsigned long long mine = sp_bn[z] >= 0 ? gemm_pack_peak_s(sp_bv[z], (unsigned)sp_bn[z]) : 0ull;
+          const unsigned long long pw = warp_max_u64(mine);
           if (lane == 0 && pw) atomicMax(ep.peak + sp_clip0 + z, pw);
         }
       }
