@@ -436,11 +436,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       // epilogue warps are few -- two per scheduler -- so their instruction count is what bounds these
       // epilogues): GEMM row -> (clip, frame row), validity, the row's base pointer / offset
       const int sp_clip0 = EPI == EPI_PEAK ? (row_tile * 128) / ep.rpc : 0;   // a 128-row tile spans <= 2 clips
-      // (32-bit element offsets: y_oob and the band spectra of one wave stay far below 2^31 elements)
-      unsigned sp_yoff[8];           // PEAK: clip * L + 256 (hop - 2) into y_oob
-      int sp_n0[8], sp_kind[8];      // PEAK: sample index of the hop's first sample; kind: 0 interior, 1 hop 2, 2 hop T,
-                                     //       bit 4 clip slot, bit 8 = the row is a valid hop
-      int sp_base[8];                // SPEC: (clip * T + t) * nb, or -1
+      const float* sp_yrow[8];       // PEAK: y_oob + clip * L + 256 (hop - 2), or null when the row is not a valid hop
+      int sp_n0[8], sp_kind[8];      // PEAK: sample index of the hop's first sample; 0 interior, 1 hop 2, 2 hop T
+      long long sp_base[8];          // SPEC: (clip * T + t) * nb, or -1
       float sp_bv[2] = {0.f, 0.f};   // PEAK: signed value with the largest |.| per clip slot, and its sample index
       int sp_bn[2] = {-1, -1};
       if (EPI == EPI_PEAK || EPI == EPI_SPEC) {
@@ -454,10 +452,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           if (EPI == EPI_PEAK) {
             const bool ok = in && ti >= 2 && ti <= ep.T;
             sp_n0[i] = AW_HOP * (ti - 2);
-            sp_yoff[i] = ok ? (unsigned)ci * (unsigned)ep.L + (unsigned)sp_n0[i] : 0u;
-            sp_kind[i] = (ti == 2 ? 1 : (ti == ep.T ? 2 : 0)) | ((ci - sp_clip0) << 4) | (ok ? 256 : 0);
+            sp_yrow[i] = ok ? ep.aux + (long long)ci * ep.L + sp_n0[i] : nullptr;
+            sp_kind[i] = (ti == 2 ? 1 : (ti == ep.T ? 2 : 0)) | ((ci - sp_clip0) << 4);
           } else {
-            sp_base[i] = in && ti < ep.T ? (ci * ep.T + ti) * ep.nb : -1;
+            sp_base[i] = in && ti < ep.T ? ((long long)ci * ep.T + ti) * ep.nb : -1;
           }
         }
       }
@@ -469,29 +467,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
         for (int i = 0; i < 8; ++i) act_ld4g(abase + (long long)(4 * i) * ep.ldo, ga[i]);
       }
-      // EPI_PEAK / EPI_SPEC: the constant operand of chunk c + 1 is requested while chunk c is processed, and
-      // chunk 0's before the wait for the accumulator (read-only path: cannot alias the stores)
-      float4 pk_nxt[8];
-      float2 so_nxt[8][2];
-      auto peak_load = [&](int cc) {
-        const int j0 = half * (BN / 2) + cc * 32 + cg;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          pk_nxt[i] = (sp_kind[i] & 256) ? __ldg(reinterpret_cast<const float4*>(ep.aux + sp_yoff[i] + j0))
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-      };
-      auto spec_load = [&](int cc) {
-        const int b0 = (half * (BN / 2) + cc * 32 + cg) >> 1;
-        const float2* aux2 = reinterpret_cast<const float2*>(ep.aux);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const bool ok = sp_base[i] >= 0;
-          so_nxt[i][0] = ok && b0 < ep.nb ? __ldg(aux2 + sp_base[i] + b0) : make_float2(0.f, 0.f);
-          so_nxt[i][1] = ok && b0 + 1 < ep.nb ? __ldg(aux2 + sp_base[i] + b0 + 1) : make_float2(0.f, 0.f);
-        }
-      };
-      if (EPI == EPI_PEAK) peak_load(0);
-      if (EPI == EPI_SPEC) spec_load(0);
       mbar_wait(tfull + ab, (it >> 1) & 1);
       tc_fence_after();
       // the TMEM load of chunk c+1 is in flight while chunk c is processed
@@ -534,12 +509,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           const float4 fr = __ldg(reinterpret_cast<const float4*>(ep.fix + 512 + j0));
           float4 yo[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) yo[i] = pk_nxt[i];
-          if (c + 1 < CHUNKS) peak_load(c + 1);
+          for (int i = 0; i < 8; ++i)
+            yo[i] = sp_yrow[i] ? __ldg(reinterpret_cast<const float4*>(sp_yrow[i] + j0)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            if (!(sp_kind[i] & 256)) continue;
-            const int kind = sp_kind[i] & 3, slot = (sp_kind[i] >> 4) & 1;
+            if (!sp_yrow[i]) continue;
+            const int kind = sp_kind[i] & 3, slot = sp_kind[i] >> 4;
             const float4 sc = kind == 0 ? make_float4(f0, f0, f0, f0) : (kind == 1 ? fl : fr);
             const float v4[4] = {fmaf(w[i][0], sc.x, yo[i].x), fmaf(w[i][1], sc.y, yo[i].y),
                                  fmaf(w[i][2], sc.z, yo[i].z), fmaf(w[i][3], sc.w, yo[i].w)};
@@ -559,11 +534,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           // S = S_band (this GEMM) + S_oob; |S| and the phasor S/|S| of two bins per lane and row.
           // Loads of the whole chunk first, through the read-only path (no aliasing with the stores).
           const int b0 = (half * (BN / 2) + c * 32 + cg) >> 1;
+          const float2* aux2 = reinterpret_cast<const float2*>(ep.aux);
           const bool v0 = b0 < ep.nb, v1 = b0 + 1 < ep.nb;
           float2 so[8][2];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { so[i][0] = so_nxt[i][0]; so[i][1] = so_nxt[i][1]; }
-          if (c + 1 < CHUNKS) spec_load(c + 1);
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = sp_base[i] >= 0;
+            so[i][0] = ok && v0 ? __ldg(aux2 + sp_base[i] + b0) : make_float2(0.f, 0.f);
+            so[i][1] = ok && v1 ? __ldg(aux2 + sp_base[i] + b0 + 1) : make_float2(0.f, 0.f);
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (sp_base[i] < 0) continue;
