@@ -1387,7 +1387,7 @@ static EpiArgsT<float> tc_epi(const Dims& d) {
 static int tc_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, cudaStream_t st) {
   const int r128 = (int)tc_rows128(d);
   EpiArgsT<float> ep = tc_epi(d);
-  ep.aux = (const float*)ctx->yoob.p; ep.fix = ctx->tcm.fix; ep.peak = acc.peak_y;
+  ep.aux = (const float*)ctx->yoob.p; ep.fix = ctx->tcm.fix; ep.fix0 = 1.0f / 1024.0f; ep.peak = acc.peak_y;
   if (launch_tc<__half, float, 256, EPI_PEAK>(ctx, ctx->tm_tcX, ctx->tcm.tm_peakB, r128, 256, 4 * AW_TC_P, ep, st)) return 1;
   EpiArgsT<float> es = tc_epi(d);
   es.aux = (const float*)ctx->tc_soob.p; es.mag = (float*)ctx->mag.p; es.qph = (float2*)ctx->ph_q.p;

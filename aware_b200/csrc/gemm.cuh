@@ -284,7 +284,8 @@ struct EpiArgsT {
   int total_rows;        // n_clips * rpc
   int T, L, nb;
   const float* aux;      // PEAK: y_oob [clip][L]      SPEC: S_oob [clip][T][nb] (float2)
-  const float* fix;      // PEAK: [0] interior scale, [256..512) hop-2 scale, [512..768) hop-T scale
+  const float* fix;      // PEAK: [256..512) hop-2 scale, [512..768) hop-T scale per sample of the hop
+  float fix0;            // PEAK: interior scale
   unsigned long long* peak;  // PEAK: [clip] packed peak (pack_peak_s), atomicMax
   float* mag;            // SPEC: [clip][T][nb]
   float2* qph;           // SPEC: [clip][T][nb]
@@ -436,11 +437,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       // epilogue warps are few -- two per scheduler -- so their instruction count is what bounds these
       // epilogues): GEMM row -> (clip, frame row), validity, the row's base pointer / offset
       const int sp_clip0 = EPI == EPI_PEAK ? (row_tile * 128) / ep.rpc : 0;   // a 128-row tile spans <= 2 clips
-      const float* sp_yrow[8];       // PEAK: y_oob + clip * L + 256 (hop - 2), or null when the row is not a valid hop
-      int sp_n0[8], sp_kind[8];      // PEAK: sample index of the hop's first sample; 0 interior, 1 hop 2, 2 hop T
-      long long sp_base[8];          // SPEC: (clip * T + t) * nb, or -1
-      float sp_bv[2] = {0.f, 0.f};   // PEAK: signed value with the largest |.| per clip slot, and its sample index
-      int sp_bn[2] = {-1, -1};
+      // (32-bit element offsets: y_oob and the band spectra of one wave stay far below 2^31 elements)
+      unsigned sp_yoff[8];           // PEAK: clip * L + 256 (hop - 2) into y_oob
+      int sp_n0[8], sp_kind[8];      // PEAK: sample index of the hop's first sample; kind: 0 interior, 1 hop 2, 2 hop T,
+                                     //       bit 4 clip slot, bit 8 = the row is a valid hop
+      int sp_base[8];                // SPEC: (clip * T + t) * nb, or -1
+      // PEAK: per clip slot (a tile spans <= 2 clips) the largest |y| so far, its signed value and sample index
+      float sp_ba0 = -1.f, sp_ba1 = -1.f, sp_bv0 = 0.f, sp_bv1 = 0.f;
+      int sp_bn0 = 0x7fffffff, sp_bn1 = 0x7fffffff;
       if (EPI == EPI_PEAK || EPI == EPI_SPEC) {
         const int r0 = row_tile * 128 + q * 32 + sr;
         const int c0_ = r0 / ep.rpc, t0_ = r0 - c0_ * ep.rpc;
@@ -452,10 +456,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           if (EPI == EPI_PEAK) {
             const bool ok = in && ti >= 2 && ti <= ep.T;
             sp_n0[i] = AW_HOP * (ti - 2);
-            sp_yrow[i] = ok ? ep.aux + (long long)ci * ep.L + sp_n0[i] : nullptr;
-            sp_kind[i] = (ti == 2 ? 1 : (ti == ep.T ? 2 : 0)) | ((ci - sp_clip0) << 4);
+            sp_yoff[i] = ok ? (unsigned)ci * (unsigned)ep.L + (unsigned)sp_n0[i] : 0u;
+            sp_kind[i] = (ti == 2 ? 1 : (ti == ep.T ? 2 : 0)) | ((ci - sp_clip0) << 4) | (ok ? 256 : 0);
           } else {
-            sp_base[i] = in && ti < ep.T ? ((long long)ci * ep.T + ti) * ep.nb : -1;
+            sp_base[i] = in && ti < ep.T ? (ci * ep.T + ti) * ep.nb : -1;
           }
         }
       }
@@ -502,31 +506,36 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         __syncwarp();
         if (EPI == EPI_PEAK) {
           // y = y_band (this GEMM, scaled) + y_oob; only max |y| with its sample index and sign survives.
-          // The chunk's loads are issued first, through the read-only path.
+          // Straight-line code: the chunk's loads first (read-only path), then compare / select per row --
+          // the epilogue warps are two per scheduler, so instruction count and branches are what it costs.
           const int j0 = half * (BN / 2) + c * 32 + cg;          // sample inside the hop (N = 256: one column tile)
-          const float f0 = __ldg(ep.fix);
-          const float4 fl = __ldg(reinterpret_cast<const float4*>(ep.fix + 256 + j0));
-          const float4 fr = __ldg(reinterpret_cast<const float4*>(ep.fix + 512 + j0));
+          const float f0 = ep.fix0;
           float4 yo[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            yo[i] = sp_yrow[i] ? __ldg(reinterpret_cast<const float4*>(sp_yrow[i] + j0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            yo[i] = (sp_kind[i] & 256) ? __ldg(reinterpret_cast<const float4*>(ep.aux + sp_yoff[i] + j0))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            if (!sp_yrow[i]) continue;
-            const int kind = sp_kind[i] & 3, slot = sp_kind[i] >> 4;
-            const float4 sc = kind == 0 ? make_float4(f0, f0, f0, f0) : (kind == 1 ? fl : fr);
-            const float v4[4] = {fmaf(w[i][0], sc.x, yo[i].x), fmaf(w[i][1], sc.y, yo[i].y),
-                                 fmaf(w[i][2], sc.z, yo[i].z), fmaf(w[i][3], sc.w, yo[i].w)};
-            float bv = v4[0];                                   // largest |v| of the four, lowest index on ties
-            int bk = 0;
-#pragma unroll
-            for (int k = 1; k < 4; ++k)
-              if (fabsf(v4[k]) > fabsf(bv)) { bv = v4[k]; bk = k; }
-            const int n = sp_n0[i] + j0 + bk;
-            float& cv = slot == 0 ? sp_bv[0] : sp_bv[1];
-            int& cn = slot == 0 ? sp_bn[0] : sp_bn[1];
-            if (fabsf(bv) > fabsf(cv) || cn < 0 || (fabsf(bv) == fabsf(cv) && n < cn)) { cv = bv; cn = n; }
+            float4 sc = make_float4(f0, f0, f0, f0);
+            if (sp_kind[i] & 3)                                 // hop 2 / hop T of a clip: edge envelope (rare)
+              sc = __ldg(reinterpret_cast<const float4*>(ep.fix + ((sp_kind[i] & 3) << 8) + j0));
+            const float v0 = fmaf(w[i][0], sc.x, yo[i].x), v1 = fmaf(w[i][1], sc.y, yo[i].y);
+            const float v2 = fmaf(w[i][2], sc.z, yo[i].z), v3 = fmaf(w[i][3], sc.w, yo[i].w);
+            // largest |v| of the four, lowest index on ties
+            const bool p1 = fabsf(v1) > fabsf(v0);
+            const float a01 = p1 ? v1 : v0;
+            const bool p3 = fabsf(v3) > fabsf(v2);
+            const float a23 = p3 ? v3 : v2;
+            const bool ph = fabsf(a23) > fabsf(a01);
+            const float bv = ph ? a23 : a01;
+            const int n = sp_n0[i] + j0 + (ph ? (p3 ? 3 : 2) : (p1 ? 1 : 0));
+            const float ab = (sp_kind[i] & 256) ? fabsf(bv) : -2.f;
+            const bool s1 = (sp_kind[i] & 16) != 0;
+            const bool t0 = !s1 && (ab > sp_ba0 || (ab == sp_ba0 && n < sp_bn0));
+            const bool t1 = s1 && (ab > sp_ba1 || (ab == sp_ba1 && n < sp_bn1));
+            sp_ba0 = t0 ? ab : sp_ba0; sp_bv0 = t0 ? bv : sp_bv0; sp_bn0 = t0 ? n : sp_bn0;
+            sp_ba1 = t1 ? ab : sp_ba1; sp_bv1 = t1 ? bv : sp_bv1; sp_bn1 = t1 ? n : sp_bn1;
           }
           continue;
         }
@@ -636,12 +645,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         }
       }
       if (EPI == EPI_PEAK) {
-#pragma unroll
-        for (int z = 0; z < 2; ++z) {
-          const unsigned long long mine = sp_bn[z] >= 0 ? gemm_pack_peak_s(sp_bv[z], (unsigned)sp_bn[z]) : 0ull;
-          const unsigned long long pw = warp_max_u64(mine);
-          if (lane == 0 && pw) atomicMax(ep.peak + sp_clip0 + z, pw);
-        }
+        const unsigned long long m0 = sp_ba0 >= 0.f ? gemm_pack_peak_s(sp_bv0, (unsigned)sp_bn0) : 0ull;
+        const unsigned long long m1 = sp_ba1 >= 0.f ? gemm_pack_peak_s(sp_bv1, (unsigned)sp_bn1) : 0ull;
+        const unsigned long long w0 = warp_max_u64(m0), w1 = warp_max_u64(m1);
+        if (lane == 0 && w0) atomicMax(ep.peak + sp_clip0, w0);
+        if (lane == 0 && w1) atomicMax(ep.peak + sp_clip0 + 1, w1);
       }
       if (epi_has_stats(EPI)) {
         asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps
