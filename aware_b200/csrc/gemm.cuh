@@ -548,23 +548,25 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           float2 so[8][2];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const bool ok = sp_base[i] >= 0;
-            so[i][0] = ok && v0 ? __ldg(aux2 + sp_base[i] + b0) : make_float2(0.f, 0.f);
-            so[i][1] = ok && v1 ? __ldg(aux2 + sp_base[i] + b0 + 1) : make_float2(0.f, 0.f);
+            const float2* ap = aux2 + (sp_base[i] < 0 ? 0 : sp_base[i]) + b0;
+            so[i][0] = v0 ? __ldg(ap) : make_float2(0.f, 0.f);          // row / bin validity only gates the stores
+            so[i][1] = v1 ? __ldg(ap + 1) : make_float2(0.f, 0.f);
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            if (sp_base[i] < 0) continue;
-            float* mrow = ep.mag + sp_base[i] + b0;
-            float2* qrow = ep.qph + sp_base[i] + b0;
-#pragma unroll
-            for (int e2 = 0; e2 < 2; ++e2) {
-              if (!(e2 == 0 ? v0 : v1)) continue;
-              const float xr = w[i][2 * e2] + so[i][e2].x, xi = w[i][2 * e2 + 1] + so[i][e2].y;
-              const float p2 = xr * xr + xi * xi;
-              const float iv = p2 > 0.f ? rsqrtf(p2) : 0.f;
-              mrow[e2] = p2 * iv;
-              qrow[e2] = make_float2(xr * iv, xi * iv);
+            const float xr0 = w[i][0] + so[i][0].x, xi0 = w[i][1] + so[i][0].y;
+            const float xr1 = w[i][2] + so[i][1].x, xi1 = w[i][3] + so[i][1].y;
+            const float p0 = fmaf(xr0, xr0, xi0 * xi0), p1 = fmaf(xr1, xr1, xi1 * xi1);
+            float r0, r1;                                              // MUFU reciprocal square root (<= 2 ulp), 0 -> inf
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p0));
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p1));
+            r0 = p0 > 0.f ? r0 : 0.f;
+            r1 = p1 > 0.f ? r1 : 0.f;
+            if (sp_base[i] >= 0) {
+              float* mrow = ep.mag + sp_base[i] + b0;
+              float2* qrow = ep.qph + sp_base[i] + b0;
+              if (v0) { mrow[0] = p0 * r0; qrow[0] = make_float2(xr0 * r0, xi0 * r0); }
+              if (v1) { mrow[1] = p1 * r1; qrow[1] = make_float2(xr1 * r1, xi1 * r1); }
             }
           }
           continue;

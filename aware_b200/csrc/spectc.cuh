@@ -204,6 +204,25 @@ struct TcUpdateArgs {
   __half* X;                   // next iteration's frame rows
 };
 
+__device__ __forceinline__ void tc_nadam(float g, float& m1, float& v1, float& c1, float c0, const NadamStep& st,
+                                         float tol_ratio) {
+  // NAdam (torch/optim/nadam.py), clamp (:116-117): same arithmetic as k_spec<BWD>
+  m1 = __fadd_rn(m1, __fmul_rn(0.1f, __fsub_rn(g, m1)));
+  v1 = __fmul_rn(v1, 0.999f);
+  v1 = __fadd_rn(v1, __fmul_rn(__fmul_rn(0.001f, g), g));
+  float sq, rden;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(__fmul_rn(v1, st.inv_bc2)));
+  const float den = __fadd_rn(sq, 1e-8f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rden) : "f"(den));
+  c1 = __fadd_rn(c1, __fmul_rn(__fmul_rn(st.a_g, g), rden));
+  c1 = __fadd_rn(c1, __fmul_rn(__fmul_rn(st.a_m, m1), rden));
+  const float dl = __fmul_rn(c0, tol_ratio);
+  const float lo = fmaxf(0.f, __fsub_rn(c0, dl)), hi = __fadd_rn(c0, dl);
+  c1 = fminf(fmaxf(c1, lo), hi);
+}
+
+// One thread = one bin of one frame; a block = AW_TC_FR consecutive frames of a clip (contiguous in the
+// [T][nb] state arrays).  All loads of an element are issued before its first store.
 __global__ void __launch_bounds__(256) k_tc_update(TcUpdateArgs a) {
   const int clip = blockIdx.y, t0 = blockIdx.x * AW_TC_FR, T = a.T, nb = a.nb;
   const int nf = min(AW_TC_FR, T - t0);
@@ -213,51 +232,56 @@ __global__ void __launch_bounds__(256) k_tc_update(TcUpdateArgs a) {
   const float gs = cs.inv / tc_grad_scale(a.dmax[(size_t)(it & 1) * a.n_clips + clip]);
   const bool improved = a.improved[clip] != 0;
   const int mstar = cs.nstar + AW_HALF;
-  for (int e = threadIdx.x; e < nf * nb; e += blockDim.x) {
-    const int f = e / nb, b = e - f * nb, t = t0 + f;
-    const long long o = ((long long)clip * T + t0) * nb + e;
-    const float* dx = a.dX + ((long long)clip * a.rpc + t) * AW_TC_P;
-    __half2* xrow = reinterpret_cast<__half2*>(a.X + ((long long)clip * a.rpc + t + 3) * AW_TC_P);
-    // peak-normaliser sub-gradient (waveform.py:19 twice): dy[n*] -= corr reaches the (at most four) frames
-    // that cover sample n*; through the iSTFT adjoint it is one windowed complex exponential per frame
-    const int nn = mstar - AW_HOP * t;
-    const bool has_corr = cs.corr != 0.f && nn >= 0 && nn < AW_NFFT && cs.nstar >= 0;
-    float cw = 0.f;
-    if (has_corr) cw = (2.0f / AW_NFFT) * a.window[nn] * (-cs.corr * ola_inv_envelope(mstar, T, a.window, a.env256));
-    const int er = t < 6 ? t : (t >= T - 6 ? 6 + (t - (T - 6)) : -1);      // row of g_edge, or -1
-    const float2 uv = __ldg(a.u + o);
-    const float2 d2 = __ldg(reinterpret_cast<const float2*>(dx + 2 * b));
-    float g = gs * (d2.x * uv.x + d2.y * uv.y);
-    if (er >= 0) g += __ldg(a.g_edge + ((long long)clip * 12 + er) * nb + b);
-    if (has_corr) {
-      float sn, cn;
-      sincospif((float)(((a.bin0 + b) * nn) & (AW_NFFT - 1)) * (2.0f / AW_NFFT), &sn, &cn);
-      g += cw * (cn * uv.x - sn * uv.y);
+  const long long o0 = ((long long)clip * T + t0) * nb;
+  constexpr int U = 2;                                       // elements in flight per thread
+  for (int e0 = threadIdx.x; e0 < nf * nb; e0 += U * blockDim.x) {
+    float2 uv[U], d2[U];
+    float m1[U], v1[U], c1[U], c0[U], ge[U];
+    int tt[U], bb[U];
+    bool on[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int e = e0 + k * blockDim.x;
+      on[k] = e < nf * nb;
+      const int ec = on[k] ? e : e0;
+      const int f = ec / nb;
+      bb[k] = ec - f * nb;
+      tt[k] = t0 + f;
+      const long long o = o0 + ec;
+      uv[k] = __ldg(a.u + o);
+      d2[k] = __ldg(reinterpret_cast<const float2*>(a.dX + ((long long)clip * a.rpc + tt[k]) * AW_TC_P + 2 * bb[k]));
+      m1[k] = a.m[o]; v1[k] = a.v[o]; c1[k] = a.c[o];
+      c0[k] = __ldg(a.c0 + o);
+      const int t = tt[k];
+      const int er = t < 6 ? t : (t >= T - 6 ? 6 + (t - (T - 6)) : -1);      // row of g_edge, or -1
+      ge[k] = er >= 0 ? __ldg(a.g_edge + ((long long)clip * 12 + er) * nb + bb[k]) : 0.f;
     }
-    float m1 = a.m[o], v1 = a.v[o], c1 = a.c[o];
-    const float c0 = __ldg(a.c0 + o);
-    if ((__float_as_uint(g) & 0x7f800000u) == 0x7f800000u) {
-      if (a.nonfinite) a.nonfinite[clip] = 1;
-    } else {
-      // NAdam (torch/optim/nadam.py), clamp (:116-117), best (:120-122): same arithmetic as k_spec<BWD>
-      m1 = __fadd_rn(m1, __fmul_rn(0.1f, __fsub_rn(g, m1)));
-      v1 = __fmul_rn(v1, 0.999f);
-      v1 = __fadd_rn(v1, __fmul_rn(__fmul_rn(0.001f, g), g));
-      float sq, rden;
-      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(__fmul_rn(v1, st.inv_bc2)));
-      const float den = __fadd_rn(sq, 1e-8f);
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rden) : "f"(den));
-      c1 = __fadd_rn(c1, __fmul_rn(__fmul_rn(st.a_g, g), rden));
-      c1 = __fadd_rn(c1, __fmul_rn(__fmul_rn(st.a_m, m1), rden));
-      const float dl = __fmul_rn(c0, a.tol_ratio);
-      const float lo = fmaxf(0.f, __fsub_rn(c0, dl)), hi = __fadd_rn(c0, dl);
-      c1 = fminf(fmaxf(c1, lo), hi);
-      a.m[o] = m1;
-      a.v[o] = v1;
-      a.c[o] = c1;
-      if (improved) a.cbest[o] = c1;
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      if (!on[k]) continue;
+      const long long o = o0 + e0 + k * blockDim.x;
+      float g = gs * (d2[k].x * uv[k].x + d2[k].y * uv[k].y) + ge[k];
+      // peak-normaliser sub-gradient (waveform.py:19 twice): dy[n*] -= corr reaches the (at most four) frames
+      // that cover sample n*; through the iSTFT adjoint it is one windowed complex exponential per frame
+      const int nn = mstar - AW_HOP * tt[k];
+      if (cs.corr != 0.f && nn >= 0 && nn < AW_NFFT && cs.nstar >= 0) {
+        const float cw = (2.0f / AW_NFFT) * a.window[nn] * (-cs.corr * ola_inv_envelope(mstar, T, a.window, a.env256));
+        float sn, cn;
+        sincospif((float)(((a.bin0 + bb[k]) * nn) & (AW_NFFT - 1)) * (2.0f / AW_NFFT), &sn, &cn);
+        g += cw * (cn * uv[k].x - sn * uv[k].y);
+      }
+      if ((__float_as_uint(g) & 0x7f800000u) == 0x7f800000u) {
+        if (a.nonfinite) a.nonfinite[clip] = 1;
+      } else {
+        tc_nadam(g, m1[k], v1[k], c1[k], c0[k], st, a.tol_ratio);
+        a.m[o] = m1[k];
+        a.v[o] = v1[k];
+        a.c[o] = c1[k];
+        if (improved) a.cbest[o] = c1[k];                  // best (:120-122)
+      }
+      reinterpret_cast<__half2*>(a.X + ((long long)clip * a.rpc + tt[k] + 3) * AW_TC_P)[bb[k]] =
+          __floats2half2_rn(c1[k] * uv[k].x, c1[k] * uv[k].y);
     }
-    xrow[b] = __floats2half2_rn(c1 * uv.x, c1 * uv.y);
   }
 }
 
