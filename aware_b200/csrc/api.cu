@@ -2122,7 +2122,7 @@ extern "C" int aw_attack_lfilter(aw_ctx* ctx, const float* d_in, int n_clips, in
   ia.o32 = d_out; ia.so32 = out_stride;
   prof_mark(ctx, (cudaStream_t)stream, "attack_lfilter");
   if (warm <= 0)
-    k_iir_seq<IIR_SRC_F32, IIR_DST_F32><<<(n_clips + 31) / 32, 32, 0, (cudaStream_t)stream>>>(ia);
+    k_iir_seq8<IIR_SRC_F32, IIR_DST_F32><<<(n_clips + 3) / 4, 32, 0, (cudaStream_t)stream>>>(ia);
   else
     k_iir<IIR_SRC_F32, IIR_DST_F32><<<g, 128, 0, (cudaStream_t)stream>>>(ia);
   ctx->launches++;
@@ -2152,7 +2152,7 @@ extern "C" int aw_attack_filtfilt(aw_ctx* ctx, const float* d_in, int n_clips, i
   ia.o64 = (double*)ctx->ga.p; ia.so64 = next;
   prof_mark(ctx, (cudaStream_t)stream, "attack_filtfilt_fwd");
   if (warm <= 0)
-    k_iir_seq<IIR_SRC_ODDEXT, IIR_DST_F64><<<(n_clips + 31) / 32, 32, 0, st>>>(ia);
+    k_iir_seq8<IIR_SRC_ODDEXT, IIR_DST_F64><<<(n_clips + 3) / 4, 32, 0, st>>>(ia);
   else
     k_iir<IIR_SRC_ODDEXT, IIR_DST_F64><<<g, 128, 0, st>>>(ia);
   IirArgs ib = ia;
@@ -2160,7 +2160,7 @@ extern "C" int aw_attack_filtfilt(aw_ctx* ctx, const float* d_in, int n_clips, i
   ib.o32 = d_out; ib.so32 = out_stride;
   prof_mark(ctx, (cudaStream_t)stream, "attack_filtfilt_bwd");
   if (warm <= 0)
-    k_iir_seq<IIR_SRC_REV_F64, IIR_DST_REVTRIM_F32><<<(n_clips + 31) / 32, 32, 0, st>>>(ib);
+    k_iir_seq8<IIR_SRC_REV_F64, IIR_DST_REVTRIM_F32><<<(n_clips + 3) / 4, 32, 0, st>>>(ib);
   else
     k_iir<IIR_SRC_REV_F64, IIR_DST_REVTRIM_F32><<<g, 128, 0, st>>>(ib);
   ctx->launches += 2;
