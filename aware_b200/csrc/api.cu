@@ -91,6 +91,7 @@ struct aw_ctx {
   bool two_pass = true;            // small-K layers as statistics pass + apply pass (AW_B200_ONE_PASS=1: off)
   // tensor-core spectral path of the fp16 embed loop (spectc.cuh; AW_B200_FFT_SPEC=1: off)
   bool tc_spec = true;
+  int tc_min_frames = 24 * 1024;   // n_clips * frames from which the tensor-core path is used (AW_OPT_TC_SPECTRAL value > 1 sets it)
   struct TcMats {
     int bin0 = -1, nb = 0;
     __half *peakB = nullptr, *compB = nullptr, *compBT = nullptr;
@@ -515,7 +516,10 @@ extern "C" int aw_ctx_set_option(aw_ctx* ctx, int option, double value) {
       AW_REQUIRE(value >= 0.0, "aw_ctx_set_option: margin must be >= 0");
       ctx->exact_margin = value;
       return 0;
-    case AW_OPT_TC_SPECTRAL: ctx->tc_spec = value != 0.0; return 0;
+    case AW_OPT_TC_SPECTRAL:
+      ctx->tc_spec = value != 0.0;
+      if (value > 1.0) ctx->tc_min_frames = (int)value;      // 1 = on with the default batch threshold
+      return 0;
     case AW_OPT_TWO_PASS: ctx->two_pass = value != 0.0; return 0;
     default: return set_error("aw_ctx_set_option: unknown option %d", option);
   }
@@ -1313,8 +1317,12 @@ static void nadam_table(int iters, std::vector<NadamStep>& out) {
 // ---------------------------------------------------------------------------
 // tensor-core spectral path of the fp16 embed loop (spectc.cuh)
 // ---------------------------------------------------------------------------
+// Large batches only: the path adds five launches per iteration (peak, spectrum, adjoint, two edge passes, frame
+// rows, update instead of two fused kernels), which costs more than it saves while an iteration is launch-latency
+// bound -- a single clip (the service API's shape) stays on the fused FFT kernels.
 static bool tc_eligible(aw_ctx* ctx, const Dims& d) {
-  return ctx->tc_spec && ctx->prec == AW_PREC_FP16 && 2 * d.nb <= AW_TC_P && d.T >= 128 && !ctx->sh;
+  return ctx->tc_spec && ctx->prec == AW_PREC_FP16 && 2 * d.nb <= AW_TC_P && d.T >= 128 && !ctx->sh &&
+         (long long)d.n * d.T >= (long long)ctx->tc_min_frames;
 }
 static long long tc_rows128(const Dims& d) { return (((long long)d.n * (d.T + 6) + 127) / 128) * 128; }
 

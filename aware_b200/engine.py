@@ -96,10 +96,11 @@ class Engine:
         _lib.check(self.lib.aw_ctx_set_option(self._ctx, _lib.OPT_EXACT_MARGIN, float(margin)))
         self.exact_margin = float(margin)
 
-    def set_tc_spectral(self, on: bool):
-        """fp16 embed loop at 44.1 / 48 kHz: band-limited STFT / iSTFT as tcgen05 GEMMs (default) or the
-        fp32 FFT kernels."""
-        _lib.check(self.lib.aw_ctx_set_option(self._ctx, _lib.OPT_TC_SPECTRAL, 1.0 if on else 0.0))
+    def set_tc_spectral(self, on: bool, min_frames: int | None = None):
+        """fp16 embed loop at 44.1 / 48 kHz: band-limited STFT / iSTFT as tcgen05 GEMMs (default for batches
+        of at least `min_frames` = n_clips * frames, 24 576 unless given) or the fp32 FFT kernels."""
+        v = 0.0 if not on else (float(min_frames) if min_frames and min_frames > 1 else 1.0)
+        _lib.check(self.lib.aw_ctx_set_option(self._ctx, _lib.OPT_TC_SPECTRAL, v))
 
     def set_two_pass(self, on: bool):
         _lib.check(self.lib.aw_ctx_set_option(self._ctx, _lib.OPT_TWO_PASS, 1.0 if on else 0.0))

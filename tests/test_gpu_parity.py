@@ -800,3 +800,33 @@ def test_compression_approx_matches_its_numpy_definition(model):
     finally:
         emb.num_iterations = prev
         emb.enforce_16k = det.enforce_16k = True
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp16"])
+def test_two_pass_small_k_layers_match_the_one_pass_form(eng, precision):
+    """The K <= 128 layers run as a statistics pass + an apply pass (the raw H1 / dHhat3 never reach HBM).
+    Same GEMM, same column sums; the apply pass normalises the fp32 accumulator instead of the stored
+    (fp16 / TF32-rounded) value, so it can only be closer to the oracle: detector outputs and the first
+    losses agree with the one-pass form at storage-rounding level, and with the oracle as before."""
+    sr = 44100
+    x = _clips([0, 1, 2], 1.5, sr)
+    xd = torch.from_numpy(x).cuda()
+    pat = torch.from_numpy(np.stack([O.encode_bits(b) for b in O.synth_bits(3)]))
+    eng.set_precision(precision)
+    eng.set_exact_margin(0.0)
+    try:
+        out = {}
+        for two in (False, True):
+            eng.set_two_pass(two)
+            v = eng.detect(xd, sr).cpu().numpy()
+            _, _, losses = eng.embed(xd, sr, pat, iters=3, return_losses=True, precision=precision)
+            out[two] = (v, losses[:3].cpu().numpy())
+    finally:
+        eng.set_two_pass(True)
+        eng.set_precision("tf32")
+        eng.set_exact_margin(1e-3)
+    ref = np.stack([O.detect(x[i], sr) for i in range(3)])
+    tol = 1e-3
+    assert np.abs(out[True][0] - out[False][0]).max() <= tol
+    assert np.abs(out[True][0] - ref).max() <= tol
+    assert np.abs(out[True][1] - out[False][1]).max() <= 5e-3

@@ -22,11 +22,11 @@ def eng():
 
 
 def _run(eng, x, pat, iters, tc):
-    eng.set_tc_spectral(tc)
+    eng.set_tc_spectral(tc, min_frames=2)          # the default only switches the path on for large batches
     try:
         out, best, losses = eng.embed(x, SR, pat, iters=iters, precision="fp16", return_losses=True)
     finally:
-        eng.set_tc_spectral(True)
+        eng.set_tc_spectral(True, min_frames=24 * 1024)
     n, T = x.shape[0], 1 + x.shape[1] // 256
     _, nb = eng.band_bins(SR)
     st = {k: eng.embed_state(k, n, T, SR).cpu().numpy() for k in ("c", "m", "c0")}
