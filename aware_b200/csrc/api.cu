@@ -72,6 +72,9 @@ struct aw_ctx {
   std::vector<MelCfg> mels;
   PFN_encodeTiled encode = nullptr;
   CUtensorMap tm_w[4], tm_wt[4], tm_w16[4], tm_wt16[4], tm_w16h[4], tm_wt16h[4];
+  // the same weights with a 128-row box: every CTA of a CTA pair stages half of the 256-wide B tile
+  CUtensorMap tm_w_p[4], tm_wt_p[4], tm_w16_p[4], tm_wt16_p[4], tm_w16h_p[4], tm_wt16h_p[4];
+  bool pair_gemm = true;           // K >= 512 layers on CTA pairs (cta_group::2); AW_B200_NO_PAIR=1 / AW_OPT_PAIR_GEMM: off
   // workspace (grow-only)
   Buf scal, zoob, p0coef, p0scal, hpart, hcoef, red_a, red_b, red_c;
   // CUDA-graph replay of the optimisation iteration (AW_B200_NO_GRAPH=1 disables): the ~50 launches
@@ -323,6 +326,36 @@ static int launch_tc(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, 
   return 0;
 }
 
+// CTA-pair form (cta_group::2): 256 x 256 tiles, `mb_half` = the weight map with a 128-row box
+template <typename T, typename OT, int EPI>
+static int launch_tc_pair(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb_half, int rows, int n,
+                          int k, const EpiArgsT<OT>& ep, cudaStream_t st) {
+  constexpr int BN = 256;
+  if (raise_smem_limit(ctx, (const void*)k_gemm_tc_pair<T, OT, BN, EPI>, gemm_tc_smem_pair<BN>())) return 1;
+  const int n_row_tiles = rows / 128, n_col_tiles = n / BN;
+  const int pairs = n_row_tiles / 2 * n_col_tiles;
+  const int grid = 2 * std::min(pairs, ctx->num_sms / 2);
+  aw_ctx::ProfRec pr;
+  if (ctx->prof_on) {
+    pr.n = n; pr.k = k; pr.epi = EPI;
+    pr.a = prof_event(ctx); pr.b = prof_event(ctx);
+    cudaEventRecord(pr.a, st);
+  }
+  prof_mark(ctx, st, gemm_label(EPI, n, k));
+  k_gemm_tc_pair<T, OT, BN, EPI><<<grid, AW_GEMM_THREADS, gemm_tc_smem_pair<BN>(), st>>>(ma, mb_half, k, n_row_tiles,
+                                                                                        n_col_tiles, ep);
+  if (ctx->prof_on) {
+    cudaEventRecord(pr.b, st);
+    ctx->prof.push_back(pr);
+  }
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+static bool pair_ok(aw_ctx* ctx, int rows, int n, int k) {
+  return ctx->pair_gemm && (rows / 128) % 2 == 0 && n % 256 == 0 && k >= 512;
+}
+
 // tensor-core GEMM, operands of type T, output/activation type OT
 template <typename T, typename OT, int EPI>
 static int launch_tc_bn(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, int rows, int n,
@@ -385,6 +418,8 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
     ctx->two_pass = !(e2 && e2[0] == '1');
     const char* e3 = getenv("AW_B200_FFT_SPEC");
     ctx->tc_spec = !(e3 && e3[0] == '1');
+    const char* e4 = getenv("AW_B200_NO_PAIR");
+    ctx->pair_gemm = !(e4 && e4[0] == '1');
   }
 
   void* fn = nullptr;
@@ -428,6 +463,16 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
     AW_CUDA(cudaMemcpy(ctx->d_wt16h[l], wt16h.data(), wt16h.size() * 2, cudaMemcpyHostToDevice));
     if (make_map(ctx, &ctx->tm_w16h[l], ctx->d_w16h[l], cop, cip, bn_for(cop), true)) return 1;
     if (make_map(ctx, &ctx->tm_wt16h[l], ctx->d_wt16h[l], cip, cop, bn_for(cip), true)) return 1;
+    if (cop >= 256) {
+      if (make_map(ctx, &ctx->tm_w_p[l], ctx->d_w[l], cop, cip, 128, false)) return 1;
+      if (make_map(ctx, &ctx->tm_w16_p[l], ctx->d_w16[l], cop, cip, 128, true)) return 1;
+      if (make_map(ctx, &ctx->tm_w16h_p[l], ctx->d_w16h[l], cop, cip, 128, true)) return 1;
+    }
+    if (cip >= 256) {
+      if (make_map(ctx, &ctx->tm_wt_p[l], ctx->d_wt[l], cip, cop, 128, false)) return 1;
+      if (make_map(ctx, &ctx->tm_wt16_p[l], ctx->d_wt16[l], cip, cop, 128, true)) return 1;
+      if (make_map(ctx, &ctx->tm_wt16h_p[l], ctx->d_wt16h[l], cip, cop, 128, true)) return 1;
+    }
   }
   ctx->num_sms = prop.multiProcessorCount;
   AW_CUDA(cudaMalloc(&ctx->d_window, 1024 * 4));
@@ -521,6 +566,7 @@ extern "C" int aw_ctx_set_option(aw_ctx* ctx, int option, double value) {
       if (value > 1.0) ctx->tc_min_frames = (int)value;      // 1 = on with the default batch threshold
       return 0;
     case AW_OPT_TWO_PASS: ctx->two_pass = value != 0.0; return 0;
+    case AW_OPT_PAIR_GEMM: ctx->pair_gemm = value != 0.0; return 0;
     default: return set_error("aw_ctx_set_option: unknown option %d", option);
   }
 }
@@ -834,7 +880,9 @@ int gemm_layer<__half, EPI_BWD>(aw_ctx* ctx, const CUtensorMap& ma, const void*,
 template <typename AT> struct ModeOf {
   static constexpr int B = 0;
   static const CUtensorMap& w(aw_ctx* c, int l) { return c->tm_w[l]; }
+  static const CUtensorMap& wP(aw_ctx* c, int l) { return c->tm_w_p[l]; }
   static const CUtensorMap& wt(aw_ctx* c, int l) { return c->tm_wt[l]; }
+  static const CUtensorMap& wtP(aw_ctx* c, int l) { return c->tm_wt_p[l]; }
   static const void* wp(aw_ctx* c, int l) { return c->d_w[l]; }
   static const void* wtp(aw_ctx* c, int l) { return c->d_wt[l]; }
   static constexpr float GSCALE = 1.0f;
@@ -842,7 +890,9 @@ template <typename AT> struct ModeOf {
 template <> struct ModeOf<__nv_bfloat16> {
   static constexpr int B = 1;
   static const CUtensorMap& w(aw_ctx* c, int l) { return c->tm_w16[l]; }
+  static const CUtensorMap& wP(aw_ctx* c, int l) { return c->tm_w16_p[l]; }
   static const CUtensorMap& wt(aw_ctx* c, int l) { return c->tm_wt16[l]; }
+  static const CUtensorMap& wtP(aw_ctx* c, int l) { return c->tm_wt16_p[l]; }
   static const void* wp(aw_ctx* c, int l) { return c->d_w16[l]; }
   static const void* wtp(aw_ctx* c, int l) { return c->d_wt16[l]; }
   static constexpr float GSCALE = 1.0f;
@@ -850,7 +900,9 @@ template <> struct ModeOf<__nv_bfloat16> {
 template <> struct ModeOf<__half> {
   static constexpr int B = 1;
   static const CUtensorMap& w(aw_ctx* c, int l) { return c->tm_w16h[l]; }
+  static const CUtensorMap& wP(aw_ctx* c, int l) { return c->tm_w16h_p[l]; }
   static const CUtensorMap& wt(aw_ctx* c, int l) { return c->tm_wt16h[l]; }
+  static const CUtensorMap& wtP(aw_ctx* c, int l) { return c->tm_wt16h_p[l]; }
   static const void* wp(aw_ctx* c, int l) { return c->d_w16h[l]; }
   static const void* wtp(aw_ctx* c, int l) { return c->d_wt16h[l]; }
   // gradients are ~1e-4 .. 1e-8 at T' = 861, shrink like 1/T' (the head seeds dz / T') and shrink
@@ -924,6 +976,9 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
     const bool two_pass = l == 0 && ctx->prec != AW_PREC_FP32 && ctx->two_pass;
     if (two_pass) {
       if (launch_tc<AT, AT, 256, EPI_FWD_STATS>(ctx, ctx->tm_act[B][l], mw, d.rows, cout, cin, ep, st)) return 1;
+    } else if (ctx->prec != AW_PREC_FP32 && pair_ok(ctx, d.rows, cout, cin)) {
+      if (launch_tc_pair<AT, AT, EPI_FWD>(ctx, ctx->tm_act[B][l], ModeOf<AT>::wP(ctx, l), d.rows, cout, cin, ep, st))
+        return 1;
     } else if (gemm_layer<AT, EPI_FWD>(ctx, ctx->tm_act[B][l], ctx->act[l].p, mw, w, d.rows, cout, cin, ep, st))
       return 1;
     dim3 g((cout + 31) / 32, d.n);
@@ -977,6 +1032,8 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
     const bool two_pass = s == 0 && ctx->prec != AW_PREC_FP32 && ctx->two_pass;
     if (two_pass) {
       if (launch_tc<AT, AT, 256, EPI_BWD_STATS>(ctx, *steps[s].ma, mw, d.rows, n, k, ep, st)) return 1;
+    } else if (ctx->prec != AW_PREC_FP32 && pair_ok(ctx, d.rows, n, k)) {
+      if (launch_tc_pair<AT, AT, EPI_BWD>(ctx, *steps[s].ma, ModeOf<AT>::wtP(ctx, l), d.rows, n, k, ep, st)) return 1;
     } else if (gemm_layer<AT, EPI_BWD>(ctx, *steps[s].ma, steps[s].a, mw, w, d.rows, n, k, ep, st)) return 1;
     dim3 g((n + 31) / 32, d.n);
     prof_mark(ctx, st, "finalize_bwd");

@@ -97,6 +97,58 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers ----------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose transaction bytes are counted on a barrier of the LEADER CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// commit of the leader's MMAs, arriving on the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+template <int KIND_F16>
+__device__ __forceinline__ void tc_mma_pair(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (KIND_F16)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+        "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+        "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -302,6 +354,14 @@ template <int BN>
 __host__ __device__ constexpr int gemm_stages() { return BN == 256 ? 3 : AW_GEMM_STAGES; }
 template <int BN>
 __host__ __device__ constexpr int gemm_tmem_cols() { return BN == 192 ? 512 : 2 * BN; }   // power of two >= 2 BN
+// CTA pair: every CTA stages its own 128 rows of A and HALF of the B tile, so a stage is a third smaller
+template <int BN>
+__host__ __device__ constexpr int gemm_stages_pair() { return BN == 256 ? 5 : 6; }
+template <int BN>
+constexpr int gemm_tc_smem_pair() {
+  return gemm_stages_pair<BN>() * (128 * 128 + BN / 2 * 128) + 1024 + 256 + 2 * 2 * 4 * BN * 4 +
+         8 * AW_EPI_STAGE_WORDS * 4;
+}
 template <int BN>
 constexpr int gemm_tc_smem() {
   return gemm_stages<BN>() * (128 * 128 + BN * 128) + 1024 /*align*/ + 256 /*barriers*/ +
@@ -314,16 +374,22 @@ constexpr int gemm_tc_smem() {
 // concurrently share A row tiles in L2).  The fp32 accumulator is double-buffered in TMEM
 // (2 x BN columns): while the 8 epilogue warps drain tile i, the MMA warp already
 // accumulates tile i+1 and the TMA warp prefetches tile i+2's operands.
-template <typename T, typename OT, int BN, int EPI>
-__global__ void __launch_bounds__(AW_GEMM_THREADS, 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-          int K, int n_row_tiles, int n_col_tiles, EpiArgsT<OT> ep) {
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA PAIR (cluster of 2, cta_group::2) per 256 x BN tile --
+// each CTA stages its own 128 rows of A and half of the B tile (the weight tile is shared by the pair:
+// half the shared-memory and L2 operand traffic per CTA), the leader issues one M = 256 MMA for both,
+// each CTA's TMEM holds and each CTA's epilogue warps drain its own 128 rows.
+template <typename T, typename OT, int BN, int EPI, int CG>
+__device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_a, const CUtensorMap& map_b,
+                                             int K, int n_row_tiles, int n_col_tiles, const EpiArgsT<OT>& ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
   constexpr int BK = GemmElem<T>::BK;
-  constexpr int NSTAGE = gemm_stages<BN>();
-  constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE = A_BYTES + B_BYTES;
+  constexpr int NSTAGE = CG == 2 ? gemm_stages_pair<BN>() : gemm_stages<BN>();
+  constexpr int A_BYTES = 128 * 128, B_BYTES = BN / CG * 128, STAGE = A_BYTES + B_BYTES;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // tile walker: CTA or CTA pair
+  const int n_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   uint8_t* tiles = smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE);
   uint64_t* empty = full + NSTAGE;
@@ -335,7 +401,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = K / BK;
-  const int n_tiles = n_row_tiles * n_col_tiles;
+  const int n_tiles = n_row_tiles / CG * n_col_tiles;                            // CG = 2: tiles of 256 rows
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -346,31 +412,52 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull + b, 1);
-      mbar_init(tempty + b, 8);
+      mbar_init(tempty + b, 8 * CG);                 // the leader's: epilogue warps of both CTAs arrive
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "n"(gemm_tmem_cols<BN>())
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(tmem_slot)),
+                   "n"(gemm_tmem_cols<BN>())
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(tmem_slot)),
+                   "n"(gemm_tmem_cols<BN>())
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();                   // both CTAs' barriers exist before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t leader_full = CG == 2 ? mapa_u32(smem_u32(full), 0) : 0u;
+  const uint32_t leader_tempty = CG == 2 ? mapa_u32(smem_u32(tempty), 0) : 0u;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int row0 = (tile / n_col_tiles) * 128, n0 = (tile % n_col_tiles) * BN;
+      for (int tile = unit; tile < n_tiles; tile += n_units) {
+        const int row0 = ((tile / n_col_tiles) * CG + (int)rank) * 128, n0 = (tile % n_col_tiles) * BN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty + s, ph ^ 1);
+          if (CG == 2) {
+            // both CTAs' bytes are counted on the LEADER's barrier (it issues the MMA for the pair)
+            if (rank == 0) mbar_expect_tx(full + s, 2 * STAGE);
+            const int arow = ep.toep_P > 0 ? row0 + kb / (ep.toep_P / BK) : row0;
+            const int acol = ep.toep_P > 0 ? (kb % (ep.toep_P / BK)) * BK : kb * BK;
+            tma_load_2d_pair(tiles + s * STAGE, &map_a, leader_full + 8 * s, acol, arow);
+            tma_load_2d_pair(tiles + s * STAGE + A_BYTES, &map_b, leader_full + 8 * s, kb * BK, n0 + (int)rank * (BN / 2));
+            if (++s == NSTAGE) { s = 0; ph ^= 1; }
+            continue;
+          }
           mbar_expect_tx(full + s, STAGE);
           if (ep.toep_P > 0) {
             // Toeplitz operand: GEMM row r, k-block kb = the ordinary 2-D box of the frame-row array at
@@ -386,14 +473,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       // instruction descriptor: D=F32 [4,6)=1, A/B format [7,10),[10,13), K-major A/B,
-      // N>>3 at [17,23), M>>4 at [24,29)
+      // N>>3 at [17,23), M>>4 at [24,29)  (M = 256 for the CTA pair)
       const uint32_t idesc = (1u << 4) | (GemmElem<T>::FMT << 7) | (GemmElem<T>::FMT << 10) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
       int s = 0, it = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < n_tiles; tile += n_units, ++it) {
         const int ab = it & 1;
         mbar_wait(tempty + ab, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -404,12 +491,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           const uint64_t ad = make_sw128_desc(smem_u32(tiles + s * STAGE));
           const uint64_t bd = make_sw128_desc(smem_u32(tiles + s * STAGE + A_BYTES));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // 4 x 32 bytes per 128-byte swizzle row
-            GemmElem<T>::mma(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-          tc_commit(empty + s);
+          for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes per 128-byte swizzle row
+            if (CG == 2)
+              tc_mma_pair<(GemmElem<T>::BK == 64)>(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            else
+              GemmElem<T>::mma(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          if (CG == 2) tc_commit_pair(empty + s); else tc_commit(empty + s);
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
-        tc_commit(tfull + ab);
+        if (CG == 2) tc_commit_pair(tfull + ab); else tc_commit(tfull + ab);
       }
     }
   } else {
@@ -419,9 +510,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     const int half = e >> 2;                        // which half of the BN columns
     constexpr int CHUNKS = BN / 64;                 // 32-column chunks per warp
     int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < n_tiles; tile += n_units, ++it) {
       const int ab = it & 1;
-      const int row_tile = tile / n_col_tiles, n0 = (tile % n_col_tiles) * BN;
+      const int row_tile = (tile / n_col_tiles) * CG + (int)rank, n0 = (tile % n_col_tiles) * BN;
       // Global traffic goes through a per-warp 32 x 32 transpose tile: TMEM hands every lane
       // one ROW (32 columns in registers), but a warp-wide access is only coalesced when
       // adjacent lanes touch adjacent columns.  Staged, one 16-byte instruction covers 4 rows
@@ -487,7 +578,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           if (c == CHUNKS - 1) {                    // accumulator fully read: hand it back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tempty + ab)) : "memory");
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(leader_tempty + 8 * ab);
+              else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tempty + ab)) : "memory");
+            }
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -672,10 +766,30 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();                   // the peer may still be draining its half of the pair's TMEM
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(gemm_tmem_cols<BN>())
-                 : "memory");
+    if (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(gemm_tmem_cols<BN>())
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(gemm_tmem_cols<BN>())
+                   : "memory");
   }
+}
+
+template <typename T, typename OT, int BN, int EPI>
+__global__ void __launch_bounds__(AW_GEMM_THREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+          int K, int n_row_tiles, int n_col_tiles, EpiArgsT<OT> ep) {
+  gemm_tc_body<T, OT, BN, EPI, 1>(map_a, map_b, K, n_row_tiles, n_col_tiles, ep);
+}
+
+// CTA-pair form: map_b's box holds BN / 2 rows; n_row_tiles must be even; grid = 2 x #pairs
+template <typename T, typename OT, int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AW_GEMM_THREADS, 1)
+k_gemm_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               int K, int n_row_tiles, int n_col_tiles, EpiArgsT<OT> ep) {
+  gemm_tc_body<T, OT, BN, EPI, 2>(map_a, map_b, K, n_row_tiles, n_col_tiles, ep);
 }
 
 // ---------------------------------------------------------------------------

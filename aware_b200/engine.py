@@ -105,6 +105,10 @@ class Engine:
     def set_two_pass(self, on: bool):
         _lib.check(self.lib.aw_ctx_set_option(self._ctx, _lib.OPT_TWO_PASS, 1.0 if on else 0.0))
 
+    def set_pair_gemm(self, on: bool):
+        """K >= 512 layers on CTA pairs (cta_group::2); off = the one-CTA kernel (bit-identical results)."""
+        _lib.check(self.lib.aw_ctx_set_option(self._ctx, _lib.OPT_PAIR_GEMM, 1.0 if on else 0.0))
+
     def detect_stats(self):
         """(clips seen by detect, clips re-evaluated exactly) since the engine was created."""
         out = []

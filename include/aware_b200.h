@@ -69,8 +69,12 @@ int64_t aw_launch_count(aw_ctx* ctx);
  * AW_OPT_TC_SPECTRAL (default 1): with fp16 loop GEMMs and a band of <= 96 bins (44.1 / 48 kHz) the
  * embed loop's band-limited STFT / iSTFT run as tcgen05 GEMMs over Toeplitz views of the frame rows
  * (csrc/spectc.cuh); 0 keeps the fp32 FFT kernels.  AW_OPT_TWO_PASS (default 1): the K <= 128 layers run
- * as a statistics pass + an apply pass instead of materialising their raw output. */
-enum { AW_OPT_THRESHOLD = 0, AW_OPT_EXACT_MARGIN = 1, AW_OPT_TC_SPECTRAL = 2, AW_OPT_TWO_PASS = 3 };
+ * as a statistics pass + an apply pass instead of materialising their raw output.  AW_OPT_PAIR_GEMM
+ * (default 1): the K >= 512 layers run on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, each CTA
+ * staging half of the weight tile) when the batch has an even number of 128-row tiles; results are
+ * bit-identical to the one-CTA kernel. */
+enum { AW_OPT_THRESHOLD = 0, AW_OPT_EXACT_MARGIN = 1, AW_OPT_TC_SPECTRAL = 2, AW_OPT_TWO_PASS = 3,
+       AW_OPT_PAIR_GEMM = 4 };
 int aw_ctx_set_option(aw_ctx* ctx, int option, double value);
 /* counters since context creation: clips seen by aw_detect_batch / clips it re-evaluated exactly */
 enum { AW_STAT_DETECT_CLIPS = 0, AW_STAT_REEVAL_CLIPS = 1 };

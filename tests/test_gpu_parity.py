@@ -830,3 +830,35 @@ def test_two_pass_small_k_layers_match_the_one_pass_form(eng, precision):
     assert np.abs(out[True][0] - out[False][0]).max() <= tol
     assert np.abs(out[True][0] - ref).max() <= tol
     assert np.abs(out[True][1] - out[False][1]).max() <= 5e-3
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp16", "bf16"])
+def test_cta_pair_gemm_is_bit_identical_to_the_one_cta_kernel(eng, precision):
+    """The K >= 512 layers on CTA pairs (tcgen05 cta_group::2, M = 256, each CTA staging half of the weight
+    tile): the same products accumulated in the same k order per output element, so detector values, the
+    watermarked clips of a short embed and its losses are IDENTICAL to the one-CTA kernel's; with an odd number
+    of 128-row tiles the library falls back to the one-CTA kernel by itself."""
+    sr = 44100
+    x = _clips([0, 1, 2, 3], 1.5, sr)
+    xd = torch.from_numpy(x).cuda()
+    pat = torch.from_numpy(np.stack([O.encode_bits(b) for b in O.synth_bits(4)]))
+    eng.set_precision(precision)
+    eng.set_exact_margin(0.0)
+    try:
+        out = {}
+        for pair in (False, True):
+            eng.set_pair_gemm(pair)
+            n0 = eng.launch_count()
+            v = eng.detect(xd, sr).cpu().numpy()
+            y, _, losses = eng.embed(xd, sr, pat, iters=3, return_losses=True, precision=precision)
+            v3 = eng.detect(xd[:3], sr).cpu().numpy()       # 21 row tiles: odd -> one-CTA kernel either way
+            out[pair] = (v, y.cpu().numpy(), losses[:3].cpu().numpy(), v3, eng.launch_count() - n0)
+    finally:
+        eng.set_pair_gemm(True)
+        eng.set_precision("tf32")
+        eng.set_exact_margin(1e-3)
+    for a, b in zip(out[True][:4], out[False][:4]):
+        assert np.array_equal(a, b)
+    assert out[True][4] == out[False][4]
+    ref = np.stack([O.detect(x[i], sr) for i in range(4)])
+    assert np.abs(out[True][0] - ref).max() <= (1e-3 if precision == "tf32" else 3e-2)
