@@ -352,8 +352,11 @@ static int launch_tc_pair(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap&
   AW_LAUNCH_CHECK();
   return 0;
 }
-static bool pair_ok(aw_ctx* ctx, int rows, int n, int k) {
-  return ctx->pair_gemm && (rows / 128) % 2 == 0 && n % 256 == 0 && k >= 512;
+// Measured (256 clips x 10 s, profiles/r2_pair_gemm.txt): the pair wins where operand staging bounds the
+// tile -- K bytes per row >= 2 KB (TF32 K >= 512: -16 %, fp16 K = 1024: -5..10 %); at fp16 K = 512 the
+// tile is epilogue-bound and coupling the two CTAs' drains costs 15 %, so that layer stays on single CTAs.
+static bool pair_ok(aw_ctx* ctx, int rows, int n, int k, int elem_bytes) {
+  return ctx->pair_gemm && (rows / 128) % 2 == 0 && n % 256 == 0 && k * elem_bytes >= 2048;
 }
 
 // tensor-core GEMM, operands of type T, output/activation type OT
@@ -976,7 +979,7 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
     const bool two_pass = l == 0 && ctx->prec != AW_PREC_FP32 && ctx->two_pass;
     if (two_pass) {
       if (launch_tc<AT, AT, 256, EPI_FWD_STATS>(ctx, ctx->tm_act[B][l], mw, d.rows, cout, cin, ep, st)) return 1;
-    } else if (ctx->prec != AW_PREC_FP32 && pair_ok(ctx, d.rows, cout, cin)) {
+    } else if (ctx->prec != AW_PREC_FP32 && pair_ok(ctx, d.rows, cout, cin, (int)sizeof(AT))) {
       if (launch_tc_pair<AT, AT, EPI_FWD>(ctx, ctx->tm_act[B][l], ModeOf<AT>::wP(ctx, l), d.rows, cout, cin, ep, st))
         return 1;
     } else if (gemm_layer<AT, EPI_FWD>(ctx, ctx->tm_act[B][l], ctx->act[l].p, mw, w, d.rows, cout, cin, ep, st))
@@ -1032,7 +1035,7 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
     const bool two_pass = s == 0 && ctx->prec != AW_PREC_FP32 && ctx->two_pass;
     if (two_pass) {
       if (launch_tc<AT, AT, 256, EPI_BWD_STATS>(ctx, *steps[s].ma, mw, d.rows, n, k, ep, st)) return 1;
-    } else if (ctx->prec != AW_PREC_FP32 && pair_ok(ctx, d.rows, n, k)) {
+    } else if (ctx->prec != AW_PREC_FP32 && pair_ok(ctx, d.rows, n, k, (int)sizeof(AT))) {
       if (launch_tc_pair<AT, AT, EPI_BWD>(ctx, *steps[s].ma, ModeOf<AT>::wtP(ctx, l), d.rows, n, k, ep, st)) return 1;
     } else if (gemm_layer<AT, EPI_BWD>(ctx, *steps[s].ma, steps[s].a, mw, w, d.rows, n, k, ep, st)) return 1;
     dim3 g((n + 31) / 32, d.n);

@@ -79,3 +79,43 @@ def tcprof():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "tcprof":
     tcprof()
+
+
+def pair():
+    """K >= 512 layers on CTA pairs vs one CTA per tile: instrumented per-kernel times and the
+    un-instrumented (graph replay) time of 100 iterations, 256 clips x 10 s, fp16 and tf32 loops"""
+    from aware_b200.synth import synth_batch, synth_bits
+    from aware_b200.utils.models import load
+    emb, det = load(); emb.verbose = False
+    eng = emb.engine
+    sr = 44100
+    n = int(os.environ.get("CLIPS", "256"))
+    x = torch.from_numpy(synth_batch(n, 10.0, sr)).cuda()
+    pat = torch.from_numpy(2 * synth_bits(n) - 1)
+    for prec in ("fp16", "tf32"):
+        for on in (True, False, True, False):
+            eng.set_pair_gemm(on)
+            eng.embed(x, sr, pat, iters=4, precision=prec)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.embed(x, sr, pat, iters=100, precision=prec)
+            b.record()
+            torch.cuda.synchronize()
+            print("%s pair=%s: %.3f ms per iteration (graph replay)" % (prec, on, a.elapsed_time(b) / 100))
+        for on in (True, False):
+            eng.set_pair_gemm(on)
+            eng.profile(True)
+            eng.embed(x, sr, pat, iters=10, precision=prec)
+            torch.cuda.synchronize()
+            eng.profile(False)
+            eng.profile_read()
+            t = eng.profile_read_named()
+            tot = sum(v[1] for v in t.values())
+            print("%s pair=%s instrumented total %.2f ms per iteration" % (prec, on, tot / 10))
+            for k, v in sorted(t.items(), key=lambda kv: -kv[1][1])[:12]:
+                print("   %-28s %4d launches %8.3f ms/iter" % (k, v[0], v[1] / 10))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "pair":
+    pair()
