@@ -315,7 +315,7 @@ static int launch_tc(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, 
     cudaEventRecord(pr.a, st);
   }
   prof_mark(ctx, st, gemm_label(EPI, n, k));
-  k_gemm_tc<T, OT, BN, EPI><<<grid, AW_GEMM_THREADS, gemm_tc_smem<BN>(), st>>>(ma, mb, k, n_row_tiles,
+  k_gemm_tc<T, OT, BN, EPI><<<grid, gemm_threads(EPI), gemm_tc_smem<BN>(), st>>>(ma, mb, k, n_row_tiles,
                                                                               n_col_tiles, ep);
   if (ctx->prof_on) {
     cudaEventRecord(pr.b, st);
@@ -342,7 +342,7 @@ static int launch_tc_pair(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap&
     cudaEventRecord(pr.a, st);
   }
   prof_mark(ctx, st, gemm_label(EPI, n, k));
-  k_gemm_tc_pair<T, OT, BN, EPI><<<grid, AW_GEMM_THREADS, gemm_tc_smem_pair<BN>(), st>>>(ma, mb_half, k, n_row_tiles,
+  k_gemm_tc_pair<T, OT, BN, EPI><<<grid, gemm_threads(EPI), gemm_tc_smem_pair<BN>(), st>>>(ma, mb_half, k, n_row_tiles,
                                                                                         n_col_tiles, ep);
   if (ctx->prof_on) {
     cudaEventRecord(pr.b, st);

@@ -245,7 +245,20 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 #define AW_GEMM_STAGES 4                  // BN <= 128; the 256-wide tile runs 3 stages (see gemm_stages)
 #define AW_EPI_STRIDE 36                  // words per staged row: 16-byte accesses stay conflict-free
 #define AW_EPI_STAGE_WORDS (32 * AW_EPI_STRIDE)
-#define AW_GEMM_THREADS 320               // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+// Three warpgroups: 0 = TMA producer (warp 0), MMA issuer (warp 1) and two idle warps; 1 and 2 = the eight
+// epilogue warps.  Whole warpgroups so that `setmaxnreg` can move registers from the two single-thread roles
+// to the epilogue: with 12 warps ptxas caps a thread at 168 registers, which is what made every attempt to
+// keep more epilogue loads in flight spill (profiles/r2_ncu_summary.md); after the hand-over the epilogue
+// warps own 232 each and hold a ring of prefetched operand chunks.
+#define AW_GEMM_THREADS 384
+// Epilogues that hold an operand ring in registers run the three-warpgroup layout; the others keep the
+// compact one (warp 0 TMA, warp 1 MMA, warps 2..9 epilogue; 320 threads, no register hand-over).
+__host__ __device__ constexpr bool gemm_big_epi(int e) {
+  return e == EPI_PEAK || e == EPI_SPEC || e == EPI_BWD || e == EPI_BWD_STATS;
+}
+__host__ __device__ constexpr int gemm_threads(int e) { return gemm_big_epi(e) ? AW_GEMM_THREADS : 320; }
+#define AW_GEMM_REGS_LIGHT 56
+#define AW_GEMM_REGS_EPI 224
 
 // Operand element: float -> kind::tf32 (32 elements per 128-byte swizzle row, K=8 per MMA),
 // __nv_bfloat16 -> kind::f16 (64 elements per row, K=16 per MMA).  Either way one k-block is
@@ -312,6 +325,32 @@ __device__ __forceinline__ void act_st4g(__nv_bfloat16* p, const float (&v)[4]) 
   const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
   *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a),
                                             *reinterpret_cast<const uint32_t*>(&b));
+}
+
+// Four activations as loaded (converted when consumed): what the epilogue's prefetch ring holds, so that a
+// 2-byte activation chunk in flight costs 16 registers instead of 32.
+template <typename OT> struct ActRaw { uint2 v; };
+template <> struct ActRaw<float> { float4 v; };
+__device__ __forceinline__ void act_ldraw(const float* p, ActRaw<float>& r) {
+  r.v = __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void act_ldraw(const __half* p, ActRaw<__half>& r) {
+  r.v = __ldg(reinterpret_cast<const uint2*>(p));
+}
+__device__ __forceinline__ void act_ldraw(const __nv_bfloat16* p, ActRaw<__nv_bfloat16>& r) {
+  r.v = __ldg(reinterpret_cast<const uint2*>(p));
+}
+__device__ __forceinline__ void act_cvt(const ActRaw<float>& r, float (&v)[4]) {
+  v[0] = r.v.x; v[1] = r.v.y; v[2] = r.v.z; v[3] = r.v.w;
+}
+__device__ __forceinline__ void act_cvt(const ActRaw<__nv_bfloat16>& r, float (&v)[4]) {
+  v[0] = __uint_as_float(r.v.x << 16); v[1] = __uint_as_float(r.v.x & 0xffff0000u);
+  v[2] = __uint_as_float(r.v.y << 16); v[3] = __uint_as_float(r.v.y & 0xffff0000u);
+}
+__device__ __forceinline__ void act_cvt(const ActRaw<__half>& r, float (&v)[4]) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.v.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.v.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
 template <typename OT>
@@ -382,8 +421,15 @@ template <typename T, typename OT, int BN, int EPI, int CG>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_a, const CUtensorMap& map_b,
                                              int K, int n_row_tiles, int n_col_tiles, const EpiArgsT<OT>& ep) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~(uintptr_t)1023);
+  // 1024-byte alignment by POINTER arithmetic on the __shared__ array: a round trip through uintptr_t made
+  // the compiler forget the address space, every epilogue staging access became a generic LD.E / ST.E on the
+  // long scoreboard, and a chunk's math then waited for the global prefetches queued behind them (ncu source
+  // view, round 2)
+#ifdef AW_GENERIC_SMEM
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+#else
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+#endif
   constexpr int BK = GemmElem<T>::BK;
   constexpr int NSTAGE = CG == 2 ? gemm_stages_pair<BN>() : gemm_stages<BN>();
   constexpr int A_BYTES = 128 * 128, B_BYTES = BN / CG * 128, STAGE = A_BYTES + B_BYTES;
@@ -438,7 +484,12 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_a, const CUt
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t leader_full = CG == 2 ? mapa_u32(smem_u32(full), 0) : 0u;
   const uint32_t leader_tempty = CG == 2 ? mapa_u32(smem_u32(tempty), 0) : 0u;
-
+  // register hand-over between warpgroups (see AW_GEMM_THREADS); each setmaxnreg sits at the head of the
+  // branch it governs, which is how ptxas learns the register budget of that branch
+  constexpr bool BIG = gemm_big_epi(EPI);
+  constexpr int EW0 = BIG ? 4 : 2;                   // first epilogue warp
+  if (warp < EW0) {
+  if (BIG) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AW_GEMM_REGS_LIGHT));
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
@@ -503,16 +554,56 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_a, const CUt
         if (CG == 2) tc_commit_pair(tfull + ab); else tc_commit(tfull + ab);
       }
     }
+  }
   } else {
     // -------------------------------- epilogue --------------------------------
-    const int e = warp - 2;
+    if (BIG) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AW_GEMM_REGS_EPI));
+    const int e = warp - EW0;
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int half = e >> 2;                        // which half of the BN columns
     constexpr int CHUNKS = BN / 64;                 // 32-column chunks per warp
+    // Backward epilogues read the layer's activations P (LeakyReLU', IN-adjoint sums) and the *_APPLY ones
+    // the per-clip column statistics: both are loaded ONE chunk ahead -- across the tile boundary -- into a
+    // two-slot register ring, and the loads of chunk c + 1 are issued right after chunk c's registers have
+    // been consumed.  (Issuing further ahead does not help: the hardware scoreboards are few, the wait for
+    // chunk c's data then also waits for the younger loads queued on the same scoreboard -- ncu source view.)
+    constexpr bool PF = (EPI == EPI_BWD || EPI == EPI_BWD_STATS) && CHUNKS == 4;
+    constexpr bool SPF = EPI == EPI_FWD_APPLY && CHUNKS == 4;
+    constexpr int NB = 2;
+    ActRaw<OT> gr[PF ? NB : 1][8];
+    float4 stq[SPF ? NB : 1][4];                    // (mean, rstd) x 4 columns, (a1, a2) x 4 columns
+    const int sr_ = lane >> 3, cg_ = (lane & 7) * 4;
+    auto act_tile_base = [&](int tile_) -> const OT* {
+      const int rt = (tile_ / n_col_tiles) * CG + (int)rank, n0_ = (tile_ % n_col_tiles) * BN;
+      return ep.act + (long long)(rt * 128 + q * 32 + sr_) * ep.ldo + n0_ + half * (BN / 2) + cg_;
+    };
+    auto stat_tile_base = [&](int tile_) -> long long {
+      const int rt = (tile_ / n_col_tiles) * CG + (int)rank, n0_ = (tile_ % n_col_tiles) * BN;
+      return ((long long)(rt / ep.tiles_per_clip) * ep.ldo + n0_ + half * (BN / 2) + cg_) * 2;
+    };
+    auto stat_load = [&](long long sb, float4 (&dst)[4]) {
+      dst[0] = __ldg(reinterpret_cast<const float4*>(ep.stat + sb));
+      dst[1] = __ldg(reinterpret_cast<const float4*>(ep.stat + sb + 4));
+      if (EPI == EPI_BWD_APPLY) {
+        dst[2] = __ldg(reinterpret_cast<const float4*>(ep.bstat + sb));
+        dst[3] = __ldg(reinterpret_cast<const float4*>(ep.bstat + sb + 4));
+      }
+    };
+    if (unit < n_tiles) {
+      if (PF) {
+        const OT* ab0 = act_tile_base(unit);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) act_ldraw(ab0 + (long long)(4 * i) * ep.ldo, gr[0][i]);
+      }
+      if (SPF) stat_load(stat_tile_base(unit), stq[0]);
+    }
     int it = 0;
     for (int tile = unit; tile < n_tiles; tile += n_units, ++it) {
       const int ab = it & 1;
       const int row_tile = (tile / n_col_tiles) * CG + (int)rank, n0 = (tile % n_col_tiles) * BN;
+      const bool has_next = tile + n_units < n_tiles;
+      const OT* abase_next = PF && has_next ? act_tile_base(tile + n_units) : nullptr;
+      const long long sbase_next = SPF && has_next ? stat_tile_base(tile + n_units) : 0;
       // Global traffic goes through a per-warp 32 x 32 transpose tile: TMEM hands every lane
       // one ROW (32 columns in registers), but a warp-wide access is only coalesced when
       // adjacent lanes touch adjacent columns.  Staged, one 16-byte instruction covers 4 rows
@@ -558,10 +649,34 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_a, const CUt
       const int clip_ = epi_applies(EPI) ? row_tile / ep.tiles_per_clip : 0;
       const int jrow0 = epi_applies(EPI) ? (row_tile - clip_ * ep.tiles_per_clip) * 128 + q * 32 + sr : 0;
       const long long sbase = epi_applies(EPI) ? ((long long)clip_ * ep.ldo + n0 + half * (BN / 2) + cg) * 2 : 0;
-      if (epi_is_bwd(EPI)) {                          // overlaps the wait for the accumulator
+      if (epi_is_bwd(EPI) && !PF) {                   // overlaps the wait for the accumulator
 #pragma unroll
         for (int i = 0; i < 8; ++i) act_ld4g(abase + (long long)(4 * i) * ep.ldo, ga[i]);
       }
+      // EPI_PEAK / EPI_SPEC: the constant operand (y_oob / S_oob) of chunk c + 1 is loaded while chunk c is
+      // processed (two register buffers; chunk 0 overlaps the wait for the accumulator)
+      float4 yo[EPI == EPI_PEAK ? 2 : 1][8];
+      float2 so[EPI == EPI_SPEC ? 2 : 1][8][2];
+      auto peak_load = [&](int c_, float4 (&dst)[8]) {
+        const int j0_ = half * (BN / 2) + c_ * 32 + cg;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dst[i] = (sp_kind[i] & 256) ? __ldg(reinterpret_cast<const float4*>(ep.aux + sp_yoff[i] + j0_))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      auto spec_load = [&](int c_, float2 (&dst)[8][2]) {
+        const int b0_ = (half * (BN / 2) + c_ * 32 + cg) >> 1;
+        const float2* aux2 = reinterpret_cast<const float2*>(ep.aux);
+        const bool v0 = b0_ < ep.nb, v1 = b0_ + 1 < ep.nb;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2* ap = aux2 + (sp_base[i] < 0 ? 0 : sp_base[i]) + b0_;
+          dst[i][0] = v0 ? __ldg(ap) : make_float2(0.f, 0.f);          // row / bin validity only gates the stores
+          dst[i][1] = v1 ? __ldg(ap + 1) : make_float2(0.f, 0.f);
+        }
+      };
+      if (EPI == EPI_PEAK) peak_load(0, yo[0]);
+      if (EPI == EPI_SPEC) spec_load(0, so[0]);
       mbar_wait(tfull + ab, (it >> 1) & 1);
       tc_fence_after();
       // the TMEM load of chunk c+1 is in flight while chunk c is processed
@@ -570,6 +685,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_a, const CUt
 #pragma unroll
       for (int c = 0; c < CHUNKS; ++c) {
         const int c0 = half * (BN / 2) + c * 32;    // column inside the tile
+        if (EPI == EPI_PEAK && c + 1 < CHUNKS) peak_load(c + 1, yo[EPI == EPI_PEAK ? ((c + 1) & 1) : 0]);
+        if (EPI == EPI_SPEC && c + 1 < CHUNKS) spec_load(c + 1, so[EPI == EPI_SPEC ? ((c + 1) & 1) : 0]);
         {
           uint32_t (&v)[32] = vbuf[c & 1];
           tc_wait_ld(v);
@@ -604,18 +721,14 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_a, const CUt
           // the epilogue warps are two per scheduler, so instruction count and branches are what it costs.
           const int j0 = half * (BN / 2) + c * 32 + cg;          // sample inside the hop (N = 256: one column tile)
           const float f0 = ep.fix0;
-          float4 yo[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            yo[i] = (sp_kind[i] & 256) ? __ldg(reinterpret_cast<const float4*>(ep.aux + sp_yoff[i] + j0))
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 (&yc)[8] = yo[EPI == EPI_PEAK ? (c & 1) : 0];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4 sc = make_float4(f0, f0, f0, f0);
             if (sp_kind[i] & 3)                                 // hop 2 / hop T of a clip: edge envelope (rare)
               sc = __ldg(reinterpret_cast<const float4*>(ep.fix + ((sp_kind[i] & 3) << 8) + j0));
-            const float v0 = fmaf(w[i][0], sc.x, yo[i].x), v1 = fmaf(w[i][1], sc.y, yo[i].y);
-            const float v2 = fmaf(w[i][2], sc.z, yo[i].z), v3 = fmaf(w[i][3], sc.w, yo[i].w);
+            const float v0 = fmaf(w[i][0], sc.x, yc[i].x), v1 = fmaf(w[i][1], sc.y, yc[i].y);
+            const float v2 = fmaf(w[i][2], sc.z, yc[i].z), v3 = fmaf(w[i][3], sc.w, yc[i].w);
             // largest |v| of the four, lowest index on ties
             const bool p1 = fabsf(v1) > fabsf(v0);
             const float a01 = p1 ? v1 : v0;
@@ -637,19 +750,12 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_a, const CUt
           // S = S_band (this GEMM) + S_oob; |S| and the phasor S/|S| of two bins per lane and row.
           // Loads of the whole chunk first, through the read-only path (no aliasing with the stores).
           const int b0 = (half * (BN / 2) + c * 32 + cg) >> 1;
-          const float2* aux2 = reinterpret_cast<const float2*>(ep.aux);
           const bool v0 = b0 < ep.nb, v1 = b0 + 1 < ep.nb;
-          float2 so[8][2];
+          float2 (&sc2)[8][2] = so[EPI == EPI_SPEC ? (c & 1) : 0];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float2* ap = aux2 + (sp_base[i] < 0 ? 0 : sp_base[i]) + b0;
-            so[i][0] = v0 ? __ldg(ap) : make_float2(0.f, 0.f);          // row / bin validity only gates the stores
-            so[i][1] = v1 ? __ldg(ap + 1) : make_float2(0.f, 0.f);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float xr0 = w[i][0] + so[i][0].x, xi0 = w[i][1] + so[i][0].y;
-            const float xr1 = w[i][2] + so[i][1].x, xi1 = w[i][3] + so[i][1].y;
+            const float xr0 = w[i][0] + sc2[i][0].x, xi0 = w[i][1] + sc2[i][0].y;
+            const float xr1 = w[i][2] + sc2[i][1].x, xi1 = w[i][3] + sc2[i][1].y;
             const float p0 = fmaf(xr0, xr0, xi0 * xi0), p1 = fmaf(xr1, xr1, xi1 * xi1);
             float r0, r1;                                              // MUFU reciprocal square root (<= 2 ulp), 0 -> inf
             asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p0));
@@ -668,30 +774,58 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_a, const CUt
         float s1c[4] = {0.f, 0.f, 0.f, 0.f}, s2c[4] = {0.f, 0.f, 0.f, 0.f};
         float st_mu[4], st_rs[4], st_a1[4], st_a2[4];
         if (epi_applies(EPI)) {
-          const float4 s01 = *reinterpret_cast<const float4*>(ep.stat + sbase + c * 64);
-          const float4 s23 = *reinterpret_cast<const float4*>(ep.stat + sbase + c * 64 + 4);
+          float4 s01, s23, b01 = make_float4(0.f, 0.f, 0.f, 0.f), b23 = b01;
+          if (SPF) {
+            s01 = stq[SPF ? (c & 1) : 0][0]; s23 = stq[SPF ? (c & 1) : 0][1];
+            if (EPI == EPI_BWD_APPLY) { b01 = stq[SPF ? (c & 1) : 0][2]; b23 = stq[SPF ? (c & 1) : 0][3]; }
+          } else {
+            s01 = *reinterpret_cast<const float4*>(ep.stat + sbase + c * 64);
+            s23 = *reinterpret_cast<const float4*>(ep.stat + sbase + c * 64 + 4);
+            if (EPI == EPI_BWD_APPLY) {
+              b01 = *reinterpret_cast<const float4*>(ep.bstat + sbase + c * 64);
+              b23 = *reinterpret_cast<const float4*>(ep.bstat + sbase + c * 64 + 4);
+            }
+          }
           st_mu[0] = s01.x; st_rs[0] = s01.y; st_mu[1] = s01.z; st_rs[1] = s01.w;
           st_mu[2] = s23.x; st_rs[2] = s23.y; st_mu[3] = s23.z; st_rs[3] = s23.w;
           if (EPI == EPI_BWD_APPLY) {
-            const float4 b01 = *reinterpret_cast<const float4*>(ep.bstat + sbase + c * 64);
-            const float4 b23 = *reinterpret_cast<const float4*>(ep.bstat + sbase + c * 64 + 4);
             st_a1[0] = b01.x; st_a2[0] = b01.y; st_a1[1] = b01.z; st_a2[1] = b01.w;
             st_a1[2] = b23.x; st_a2[2] = b23.y; st_a1[3] = b23.z; st_a2[3] = b23.w;
           }
         }
+        float gaf[PF ? 8 : 1][4];
+        if (PF) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) act_cvt(gr[PF ? (c & 1) : 0][i], gaf[i]);
+        }
+        // chunk c's operands are in plain registers now: queue the loads of the next chunk
+        if (PF) {
+          const OT* src = c + 1 < CHUNKS ? abase + (c + 1) * 32 : abase_next;
+          if (src) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) act_ldraw(src + (long long)(4 * i) * ep.ldo, gr[PF ? ((c + 1) & 1) : 0][i]);
+          }
+        }
+        if (SPF) {
+          if (c + 1 < CHUNKS) stat_load(sbase + (c + 1) * 64, stq[SPF ? ((c + 1) & 1) : 0]);
+          else if (has_next) stat_load(sbase_next, stq[0]);
+        }
         if (epi_is_bwd(EPI)) {
           // d(IN out) = dP * LeakyReLU'(P);  IN out recovered from P
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+          for (int i = 0; i < 8; ++i) {
+            float gai[4];
+            if (PF) { gai[0] = gaf[PF ? i : 0][0]; gai[1] = gaf[PF ? i : 0][1]; gai[2] = gaf[PF ? i : 0][2]; gai[3] = gaf[PF ? i : 0][3]; }
+            else { gai[0] = ga[i][0]; gai[1] = ga[i][1]; gai[2] = ga[i][2]; gai[3] = ga[i][3]; }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float pv = ga[i][k];
+              const float pv = gai[k];
               const bool pos = pv > 0.f;
               const float g = pos ? w[i][k] : AW_LEAKY * w[i][k];
               const float hh = pos ? pv : pv * (1.0f / AW_LEAKY);
               if (EPI == EPI_BWD_APPLY) {               // dH = rstd (dHhat - a1 - Hhat a2), pad rows 0 (k_norm_rows<BWD>)
                 float o = st_rs[k] * (g - st_a1[k] - hh * st_a2[k]);
-                if (ep.round_tf32) o = to_tf32(o);
+                if (sizeof(OT) == 4 && ep.round_tf32) o = to_tf32(o);   // TF32 mode stores float activations
                 w[i][k] = jrow0 + 4 * i < ep.Tp ? o : 0.f;
               } else {
                 w[i][k] = g;
@@ -699,7 +833,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_a, const CUt
                 s2c[k] = fmaf(hh, g, s2c[k]);
               }
             }
-          if (c + 1 < CHUNKS) {                     // prefetch the next chunk's activations
+          }
+          if (!PF && c + 1 < CHUNKS) {              // prefetch the next chunk's activations
 #pragma unroll
             for (int i = 0; i < 8; ++i) act_ld4g(abase + (c + 1) * 32 + (long long)(4 * i) * ep.ldo, ga[i]);
           }
@@ -709,7 +844,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_a, const CUt
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               float o = leaky((w[i][k] - st_mu[k]) * st_rs[k]);
-              if (ep.round_tf32) o = to_tf32(o);
+              if (sizeof(OT) == 4 && ep.round_tf32) o = to_tf32(o);   // TF32 mode stores float activations
               w[i][k] = jrow0 + 4 * i < ep.Tp ? o : 0.f;
             }
         } else if (epi_is_fwd(EPI)) {
@@ -749,7 +884,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_a, const CUt
       }
       if (epi_has_stats(EPI)) {
         asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps
-        const int t = threadIdx.x - 64;                  // 0..255
+        const int t = threadIdx.x - 32 * EW0;            // 0..255
         for (int cc = t; cc < BN; cc += 256) {
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -778,7 +913,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_a, const CUt
 }
 
 template <typename T, typename OT, int BN, int EPI>
-__global__ void __launch_bounds__(AW_GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(EPI), 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           int K, int n_row_tiles, int n_col_tiles, EpiArgsT<OT> ep) {
   gemm_tc_body<T, OT, BN, EPI, 1>(map_a, map_b, K, n_row_tiles, n_col_tiles, ep);
@@ -786,7 +921,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
 // CTA-pair form: map_b's box holds BN / 2 rows; n_row_tiles must be even; grid = 2 x #pairs
 template <typename T, typename OT, int BN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AW_GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(EPI), 1)
 k_gemm_tc_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                int K, int n_row_tiles, int n_col_tiles, EpiArgsT<OT> ep) {
   gemm_tc_body<T, OT, BN, EPI, 2>(map_a, map_b, K, n_row_tiles, n_col_tiles, ep);

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(128) k_p0(const float* __restrict__ M, int T, 
         const float g0 = (a0[i] - fmu) * fr * inv;
         const float g1 = (a1[i] - fmu) * fr * inv;
         p = 0.5f * (g0 + g1);
-        if (round_tf32) p = to_tf32(p);
+        if (sizeof(AT) == 4 && round_tf32) p = to_tf32(p);
       }
       act_st(P0 + ((long long)clip * Tp_pad + j) * AW_NMEL + c, p);
     }
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(128) k_norm_rows(AT* __restrict__ X, const AT*
           const float hh = av > 0.f ? av : av * (1.0f / AW_LEAKY);
           o[k] = rs[k] * (h[i][k] - a1[k] - hh * a2[k]);
         }
-        if (round_tf32) o[k] = to_tf32(o[k]);
+        if (sizeof(AT) == 4 && round_tf32) o[k] = to_tf32(o[k]);
         if (j0 + r0 + i >= Tp) o[k] = 0.f;
       }
       st16(x + (long long)(r0 + i) * C, o);
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(256) k_head_seed(HeadArgs<AT> a) {
         const bool pos = p > 0.f;
         const float dh = pos ? dz : AW_LEAKY * dz;
         o = gscale * (rstd * (dh - a1 - (pos ? p : p * (1.0f / AW_LEAKY)) * a2));
-        if (a.round_tf32) o = to_tf32(o);
+        if (sizeof(AT) == 4 && a.round_tf32) o = to_tf32(o);
       }
       act_st(D + (long long)j * 64 + c, o);
     }

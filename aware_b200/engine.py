@@ -120,6 +120,7 @@ class Engine:
 
     def profile(self, on: bool):
         _lib.check(self.lib.aw_profile_enable(self._ctx, int(on)))
+        self.profiling = bool(on)      # the per-launch timeline is one ordered list: attacks.run_suite stays on one stream
 
     def profile_read(self):
         """[(n, k, epilogue, launches, total_ms)] of the tensor-core GEMMs since the last read."""

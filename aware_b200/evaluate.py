@@ -163,9 +163,9 @@ def evaluate_clips(clips, rates, embedder, detector, attack_list=None, seed: int
             decoded[i] = got[k].cpu().numpy()
             if keep_audio:
                 audio_out[i] = y[k].cpu().numpy()
-        for a_i, att in enumerate(attack_list):
-            z = att.apply_batch(y, TARGET_SR, rng=rng, engine=eng)
-            detect_watermark_batch(z, TARGET_SR, detector, bits, counters[a_i + 1])
+        A.run_suite(attack_list, y, TARGET_SR,
+                    lambda a_i, z: detect_watermark_batch(z, TARGET_SR, detector, bits, counters[a_i + 1]),
+                    rng=rng, engine=eng)
     allreduce_counters(counters, sums)
     c = counters.cpu().numpy()
     ber = {nm: (100.0 * c[k, 0] / c[k, 1] if c[k, 1] else float("nan")) for k, nm in enumerate(names)}

@@ -119,3 +119,39 @@ def pair():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "pair":
     pair()
+
+
+def quick():
+    """fp16 loop at 256 clips x 10 s: graph-replay ms per iteration (100 iterations, twice) and the
+    instrumented per-class times of 10 iterations"""
+    from aware_b200.synth import synth_batch, synth_bits
+    from aware_b200.utils.models import load
+    emb, det = load(); emb.verbose = False
+    eng = emb.engine
+    sr = 44100
+    n = int(os.environ.get("CLIPS", "256"))
+    x = torch.from_numpy(synth_batch(n, 10.0, sr)).cuda()
+    pat = torch.from_numpy(2 * synth_bits(n) - 1)
+    eng.embed(x, sr, pat, iters=4, precision="fp16")
+    torch.cuda.synchronize()
+    for _ in range(2):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.embed(x, sr, pat, iters=100, precision="fp16")
+        b.record()
+        torch.cuda.synchronize()
+        print("fp16: %.3f ms per iteration (graph replay, 100 iterations)" % (a.elapsed_time(b) / 100), flush=True)
+    eng.profile(True)
+    eng.embed(x, sr, pat, iters=10, precision="fp16")
+    torch.cuda.synchronize()
+    eng.profile(False)
+    eng.profile_read()
+    t = eng.profile_read_named()
+    tot = sum(v[1] for v in t.values())
+    print("instrumented total %.2f ms per iteration" % (tot / 10))
+    for k, v in sorted(t.items(), key=lambda kv: -kv[1][1])[:40]:
+        print("   %-28s %4d launches %8.3f ms/iter" % (k, v[0], v[1] / 10))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "quick":
+    quick()

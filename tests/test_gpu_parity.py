@@ -862,3 +862,39 @@ def test_cta_pair_gemm_is_bit_identical_to_the_one_cta_kernel(eng, precision):
     assert out[True][4] == out[False][4]
     ref = np.stack([O.detect(x[i], sr) for i in range(4)])
     assert np.abs(out[True][0] - ref).max() <= (1e-3 if precision == "tf32" else 3e-2)
+
+
+def test_run_suite_side_stream_equals_one_stream(model):
+    """attacks.run_suite launches the sequential (bit-exact) IIR attacks on a side stream and consumes them
+    last; every attacked batch must equal the one-stream result bit for bit, in the suite's own index order,
+    also when the next call reuses the scratch the filtfilt parks in the gradient buffers."""
+    from aware_b200 import attacks as A
+    emb, det = model
+    eng = emb.engine
+    sr = 16000
+    y = torch.from_numpy(_clips([0, 1, 2, 3, 4], 1.5, sr)).cuda()
+    suite = [A.PCMBitDepthConversion(16), A.RandomBandstop(f_low=1000.0, fast=False), A.SampleSupression(0.1, start=100),
+             A.LowPassFilter(fast=False), A.HighPassFilter(fast=True), A.RandomBandstop(f_low=333.0, fast=False)]
+    assert [getattr(a, "sequential", False) for a in suite] == [False, True, False, True, False, True]
+    want = [a.apply_batch(y, sr, engine=eng).clone() for a in suite]
+    for _ in range(2):
+        got, vals = {}, {}
+
+        def consume(i, z):
+            got[i] = z.clone()
+            vals[i] = eng.detect(z, sr)
+        A.run_suite(suite, y, sr, consume, engine=eng)
+        torch.cuda.synchronize()
+        assert sorted(got) == list(range(len(suite)))
+        for i in range(len(suite)):
+            assert torch.equal(got[i], want[i]), suite[i].name
+            assert torch.equal(vals[i], eng.detect(want[i], sr)), suite[i].name
+    eng.profile(True)                                      # profiling keeps everything on one stream
+    try:
+        order = []
+        A.run_suite(suite, y, sr, lambda i, z: order.append(i), engine=eng)
+    finally:
+        eng.profile(False)
+        eng.profile_read()
+        eng.profile_read_named()
+    assert order == list(range(len(suite)))
