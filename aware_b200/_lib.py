@@ -64,6 +64,7 @@ SIGNATURES = {
                               C.POINTER(_i64), _vp]),
     "aw_decide_and_count": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "aw_snr_batch": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "aw_stoi_batch": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _vp, _vp, C.c_double, _vp]),
     "aw_stft_band": (_i, [_vp, _vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp]),
     "aw_istft_band": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "aw_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

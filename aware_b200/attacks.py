@@ -157,10 +157,11 @@ class SampleSupression(Attack):
         return _eng(engine).attack_suppress(x, start, n_zero)
 
 
-def polyphase_plan(n_in: int, up: int, down: int, window=("kaiser", 5.0)):
+def polyphase_plan(n_in: int, up: int, down: int, window=("kaiser", 5.0), taps=None):
     """Host half of scipy.signal.resample_poly(x, up, down) for float32 input: the FIR
     (firwin, cast to float32, times `up`), its zero padding, the transposed+flipped tap
-    table scipy's upfirdn uses, and the output window.  Returns
+    table scipy's upfirdn uses, and the output window.  `taps` = an explicit FIR, as when
+    resample_poly is given an array for `window` (pystoi's resample_oct).  Returns
     (h_tf float32[up*taps_per_phase], taps_per_phase, first_out, n_out)."""
     from scipy.signal import firwin
     g = math.gcd(up, down)
@@ -168,9 +169,14 @@ def polyphase_plan(n_in: int, up: int, down: int, window=("kaiser", 5.0)):
     n_out = n_in * up
     n_out = n_out // down + bool(n_out % down)
     max_rate = max(up, down)
-    half_len = 10 * max_rate
-    h = firwin(2 * half_len + 1, 1.0 / max_rate, window=window).astype(np.float32)
-    h *= up
+    if taps is not None:
+        h = np.asarray(taps, dtype=np.float64).copy()
+        half_len = (len(h) - 1) // 2
+        h = (h * up).astype(np.float32)
+    else:
+        half_len = 10 * max_rate
+        h = firwin(2 * half_len + 1, 1.0 / max_rate, window=window).astype(np.float32)
+        h *= up
     n_pre_pad = down - half_len % down
     n_post_pad = 0
     n_pre_remove = (half_len + n_pre_pad) // down

@@ -21,6 +21,7 @@
 #include "net.cuh"
 #include "spec.cuh"
 #include "spectc.cuh"
+#include "stoi.cuh"
 
 namespace aw {
 thread_local char g_err[512] = "";
@@ -122,6 +123,8 @@ struct aw_ctx {
   // activation tensor maps, [0] = float32 view, [1] = bf16 view of the same buffers
   CUtensorMap tm_act[2][4], tm_dh4[2], tm_ga1024[2], tm_ga512[2], tm_gb1024[2];
   Buf cvt_a, cvt_b;    // aw_gemm bf16 test hook
+  Buf stoi_ws;         // aw_stoi_batch workspace
+  bool stoi_edges_set = false;
   // state of the last embed wave (for aw_embed_state)
   int last_n = 0, last_T = 0, last_nb = 0;
   // optional CUDA-event timing of the GEMM launches (aw_profile_*)
@@ -513,7 +516,7 @@ static std::vector<Buf*> all_bufs(aw_ctx* ctx) {
                  &ctx->values, &ctx->best, &ctx->improved, &ctx->pattern, &ctx->itc, &ctx->steps,
                  &ctx->scal, &ctx->zoob, &ctx->p0coef, &ctx->p0scal, &ctx->hpart, &ctx->hcoef, &ctx->red_a, &ctx->red_b, &ctx->red_c,
                  &ctx->gsc, &ctx->nonfinite, &ctx->smax, &ctx->lowm, &ctx->tc_X, &ctx->tc_dS, &ctx->tc_soob,
-                 &ctx->tc_dX, &ctx->tc_gedge, &ctx->tc_dmax, &ctx->tc_ones};
+                 &ctx->tc_dX, &ctx->tc_gedge, &ctx->tc_dmax, &ctx->tc_ones, &ctx->stoi_ws};
 }
 
 extern "C" int aw_ctx_destroy(aw_ctx* ctx) {
@@ -2007,6 +2010,64 @@ extern "C" int aw_snr_batch(aw_ctx* ctx, const float* d_out, int64_t out_stride,
   k_snr_partial<<<g, 256, 0, st>>>(d_out, out_stride, d_target, tgt_stride, n, (double*)ctx->bstat.p);
   k_snr_final<<<(n_clips + 127) / 128, 128, 0, st>>>((double*)ctx->bstat.p, n_clips, d_snr, d_snr_sum);
   ctx->launches += 2;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
+// STOI of n_clips (clean, processed) pairs at 10 kHz (metrics/audio.py:43-64 through pystoi; stoi.cuh)
+extern "C" int aw_stoi_batch(aw_ctx* ctx, const float* d_clean, int64_t clean_stride, const float* d_proc,
+                             int64_t proc_stride, int n_clips, int n, double* d_stoi, double* d_sum,
+                             double keep_above, void* stream) {
+  AW_REQUIRE(ctx && d_clean && d_proc && d_stoi, "null argument");
+  AW_REQUIRE(n_clips >= 1 && n >= 1, "bad argument");
+  if (ctx) cudaSetDevice(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  StoiArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = d_clean; a.y = d_proc; a.sx = clean_stride; a.sy = proc_stride; a.n = n;
+  a.F0 = n >= AW_STOI_FRAME ? (n - AW_STOI_FRAME) / AW_STOI_HOP + 1 : 0;
+  a.out = d_stoi; a.out_sum = d_sum; a.keep_above = keep_above;
+  const int F0 = std::max(a.F0, 1);
+  a.seg_blocks = (F0 + AW_STOI_SEGS_PER_BLOCK - 1) / AW_STOI_SEGS_PER_BLOCK;
+  // workspace: energy f64[F0] | part f64[seg_blocks] | emax u64 | tob f32[2][F0][16] | src i32[F0] | kept i32
+  const size_t per_clip = (size_t)F0 * 8 + (size_t)a.seg_blocks * 8 + 8 + (size_t)F0 * 2 * 16 * 4 + (size_t)F0 * 4 + 8;
+  if (ensure(ctx->stoi_ws, per_clip * n_clips)) return 1;
+  uint8_t* w = (uint8_t*)ctx->stoi_ws.p;
+  a.energy = (double*)w; w += (size_t)n_clips * F0 * 8;
+  a.part = (double*)w; w += (size_t)n_clips * a.seg_blocks * 8;
+  a.emax = (unsigned long long*)w; w += (size_t)n_clips * 8;
+  a.tob = (float*)w; w += (size_t)n_clips * F0 * 2 * 16 * 4;
+  a.src = (int*)w; w += (size_t)n_clips * F0 * 4;
+  a.kept = (int*)w;
+  if (!ctx->stoi_edges_set) {
+    // pystoi thirdoct(10000, 512, 15, 150): band i spans the bins nearest to 150 * 2^((2i -+ 1) / 6) Hz
+    int edge[AW_STOI_BANDS + 1];
+    for (int i = 0; i <= AW_STOI_BANDS; ++i) {
+      const double fr = 150.0 * pow(2.0, (2.0 * i - 1.0) / 6.0);
+      int best = 0;
+      double bd = 1e300;
+      for (int k = 0; k <= AW_STOI_NFFT / 2; ++k) {
+        const double f = 10000.0 * k / AW_STOI_NFFT, d = (f - fr) * (f - fr);
+        if (d < bd) { bd = d; best = k; }
+      }
+      edge[i] = best;
+    }
+    AW_REQUIRE(edge[0] == AW_STOI_BIN0 && edge[AW_STOI_BANDS] == AW_STOI_BIN0 + AW_STOI_NBIN, "STOI band table");
+    AW_CUDA(cudaMemcpyToSymbol(c_stoi_edge, edge, sizeof(edge)));
+    ctx->stoi_edges_set = true;
+  }
+  AW_CUDA(cudaMemsetAsync(a.emax, 0, (size_t)n_clips * 8, st));
+  AW_CUDA(cudaMemsetAsync(a.kept, 0, (size_t)n_clips * 4, st));
+  if (a.F0 > 0) {
+    prof_mark(ctx, st, "stoi");
+    k_stoi_energy<<<dim3((a.F0 + 7) / 8, n_clips), 256, 0, st>>>(a);
+    k_stoi_scan<<<n_clips, 256, 0, st>>>(a);
+    if (a.F0 > 1) k_stoi_tob<<<dim3(a.F0 - 1, n_clips), 256, 0, st>>>(a);
+    k_stoi_corr<<<dim3(a.seg_blocks, n_clips), 128, 0, st>>>(a);
+    ctx->launches += 4;
+  }
+  k_stoi_final<<<(n_clips + 127) / 128, 128, 0, st>>>(a, n_clips);
+  ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
 }

@@ -240,6 +240,24 @@ class Engine:
                                          n, m, _ptr(res), _ptr(snr_sum), _stream()))
         return res
 
+    def stoi(self, clean: torch.Tensor, processed: torch.Tensor, sample_rate: int,
+             stoi_sum: torch.Tensor | None = None, keep_above: float = 0.1):
+        """STOI per clip (float64 [n]) of processed against clean, both [n, N] float32 on the device at
+        `sample_rate` (metrics/audio.py:43-64 -> pystoi.stoi(clean, processed, sr)): resample to pystoi's
+        10 kHz with its Octave-style window through the polyphase kernel, then aw_stoi_batch.
+        stoi_sum: float64[2] += {sum of scores > keep_above, count} (scripts/test.py:86-88)."""
+        from . import metrics
+        x, y = self._audio(clean), self._audio(processed)
+        m = min(x.shape[1], y.shape[1])
+        x, y = x[:, :m], y[:, :m]
+        if int(sample_rate) != metrics.audio.STOI_FS:
+            x, y = (metrics.audio.resample_oct_batch(t, metrics.audio.STOI_FS, int(sample_rate), self) for t in (x, y))
+        n = x.shape[0]
+        res = torch.empty((n,), dtype=torch.float64, device=x.device)
+        _lib.check(self.lib.aw_stoi_batch(self._ctx, _ptr(x), x.stride(0), _ptr(y), y.stride(0), n, x.shape[1],
+                                          _ptr(res), _ptr(stoi_sum), float(keep_above), _stream()))
+        return res
+
     # ---------------------------------------------------------- stage hooks
     def stft_band(self, audio, sample_rate, normalize=True, phasor=False):
         x = self._audio(audio)

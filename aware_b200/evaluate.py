@@ -148,7 +148,15 @@ def evaluate_clips(clips, rates, embedder, detector, attack_list=None, seed: int
             at16[i] = y[k]
 
     counters = torch.zeros((len(names), 3), dtype=torch.int64, device=eng.device)
-    sums = torch.zeros(2, dtype=torch.float64, device=eng.device)        # sum of SNR, clips with finite SNR
+    # quality aggregates, all-reduced with the counters: [sum of SNR, clips with finite SNR,
+    # sum of STOI > 0.1, their count (scripts/test.py:86-88), sum of PESQ, clips PESQ could score (:79-84)]
+    sums = torch.zeros(6, dtype=torch.float64, device=eng.device)
+    try:
+        import pesq as _pesq_pkg  # noqa: F401
+        from .metrics.audio import PESQ
+        pesq_metric = PESQ()
+    except ImportError:
+        pesq_metric = None                                               # third-party host package, optional
     decoded, audio_out = {}, {}
     for n, idx_local in bucket_by_length([at16[i].shape[0] for i in mine]).items():
         idx = [mine[k] for k in idx_local]
@@ -158,7 +166,12 @@ def evaluate_clips(clips, rates, embedder, detector, attack_list=None, seed: int
         got, _ = detect_watermark_batch(y, TARGET_SR, detector, bits, counters[0])
         snr = eng.snr(y, x)
         ok = torch.isfinite(snr)
-        sums += torch.stack([snr[ok].sum(), ok.sum().double()])
+        sums[:2] += torch.stack([snr[ok].sum(), ok.sum().double()])
+        eng.stoi(x[:, :y.shape[1]], y, TARGET_SR, stoi_sum=sums[2:4])       # GPU STOI, scores > 0.1 accumulate
+        if pesq_metric is not None:
+            ps = np.asarray(pesq_metric.batch(list(y.cpu().numpy()), list(x.cpu().numpy()), TARGET_SR))
+            good = np.isfinite(ps)
+            sums[4:6] += torch.tensor([ps[good].sum(), good.sum()], dtype=torch.float64, device=eng.device)
         for k, i in enumerate(idx):
             decoded[i] = got[k].cpu().numpy()
             if keep_audio:
@@ -171,6 +184,8 @@ def evaluate_clips(clips, rates, embedder, detector, attack_list=None, seed: int
     ber = {nm: (100.0 * c[k, 0] / c[k, 1] if c[k, 1] else float("nan")) for k, nm in enumerate(names)}
     s = sums.cpu().numpy()
     return {"ber_percent": ber, "snr_db_mean": float(s[0] / s[1]) if s[1] else float("nan"),
+            "stoi_mean": float(s[2] / s[3]) if s[3] else float("nan"),
+            "pesq_mean": float(s[4] / s[5]) if s[5] else float("nan"),
             "n_clips": int(c[0, 2]), "n_silent_skipped": n_silent, "bits": bits_all, "decoded": decoded,
             "audio": audio_out}
 
@@ -194,6 +209,8 @@ def main(argv=None):
     for name, v in res["ber_percent"].items():
         logger.info(f"{name}: mean: {v:.4f}")
     logger.info(f"snr: mean: {res['snr_db_mean']:.2f} dB over {res['n_clips']} clips")
+    logger.info(f"stoi: mean: {res['stoi_mean']:.4f}")
+    logger.info(f"pesq: mean: {res['pesq_mean']:.4f}")
     return 0
 
 

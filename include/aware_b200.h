@@ -166,6 +166,15 @@ int aw_snr_batch(aw_ctx* ctx, const float* d_out, int64_t out_stride, const floa
                  int64_t tgt_stride, int n_clips, int n, double* d_snr, double* d_snr_sum,
                  void* stream);
 
+/* ---- STOI (metrics/audio.py:43-64 `STOI.__call__` -> pystoi.stoi(target, output, 16000), extended=False;
+ * scripts/test.py:86-88 keeps scores > 0.1).  Both signals already at pystoi's internal 10 kHz (the
+ * caller resamples with aw_attack_upfirdn and pystoi's Octave-style window), n samples per clip.
+ * d_stoi [n_clips] float64; d_sum (may be NULL) float64[2] += {sum of scores > keep_above, their count}.
+ * Clips with fewer than 30 analysis frames after silence removal score 1e-5, as pystoi does. */
+int aw_stoi_batch(aw_ctx* ctx, const float* d_clean, int64_t clean_stride, const float* d_proc,
+                  int64_t proc_stride, int n_clips, int n, double* d_stoi, double* d_sum,
+                  double keep_above, void* stream);
+
 /* ---- stage-level entry points (used by the parity tests and by callers that
  * want the STFT/iSTFT alone; reference utils/audio/stft.py:28,48,55,62) */
 int aw_stft_band(aw_ctx* ctx, const float* d_audio, int n_clips, int n_samples, int64_t stride,

@@ -550,6 +550,18 @@ def test_evaluation_driver_ragged_clips(model):
     assert {"pcm_8", "delete_0.1", "resample_16000", "low_pass", "high_pass"} <= set(res["ber_percent"])
     assert all(0.0 <= v <= 60.0 for v in res["ber_percent"].values())
     assert 15.0 < res["snr_db_mean"] < 45.0
+    # quality aggregates (scripts/test.py:76-88): GPU STOI of watermarked vs original audio, equal to the numpy
+    # restatement clip by clip; PESQ only where the third-party package exists
+    import stoi_oracle as S
+    from scipy.signal import resample_poly
+    st = []
+    for i in range(5):
+        x16 = clips[i] if rates[i] == 16000 else resample_poly(clips[i], 16000, rates[i])
+        w = res["audio"][i]
+        st.append(S.stoi(np.asarray(x16[:len(w)], dtype=np.float64), w.astype(np.float64), 16000))
+    st = np.array(st)
+    assert abs(res["stoi_mean"] - st[st > 0.1].mean()) <= 1e-4, (res["stoi_mean"], st)
+    assert np.isnan(res["pesq_mean"]) or 1.0 <= res["pesq_mean"] <= 4.7
     for i in range(5):
         np.testing.assert_array_equal(res["decoded"][i], res["bits"][i])
         np.testing.assert_array_equal(O.detect_watermark(res["audio"][i], 16000), res["bits"][i])
@@ -898,3 +910,44 @@ def test_run_suite_side_stream_equals_one_stream(model):
         eng.profile_read()
         eng.profile_read_named()
     assert order == list(range(len(suite)))
+
+
+def test_stoi_kernels_match_the_numpy_restatement(model):
+    """f4: GPU STOI (aw_stoi_batch) against oracle/stoi_oracle.py -- pystoi's algorithm restated
+    (the package is absent: parity unpinned to pystoi itself).  Tolerance 1e-4 absolute on the score (float32
+    resampling / DFT on the device, float64 in the restatement); covers a silence gap (frames removed by the
+    40 dB gate), noise levels from inaudible to destructive, the 10 kHz no-resample path, a clip that is too
+    short (1e-5 as pystoi answers), the reference metric's call signature, and the > 0.1 running sums of
+    scripts/test.py:86-88."""
+    import stoi_oracle as S
+    from aware_b200.metrics import STOI
+    emb, det = model
+    eng = emb.engine
+    sr = 16000
+    x = _clips([0, 1, 2, 3], 3.0, sr)
+    x[1, 8000:20000] *= 1e-4                                           # a gap the silence gate removes
+    rng = np.random.default_rng(5)
+    noise = rng.standard_normal(x.shape).astype(np.float32)
+    y = x + np.array([1e-3, 1e-2, 5e-2, 0.5], dtype=np.float32)[:, None] * noise
+    want = np.array([S.stoi(x[i].astype(np.float64), y[i].astype(np.float64), sr) for i in range(4)])
+    sums = torch.zeros(2, dtype=torch.float64, device="cuda")
+    got = eng.stoi(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), sr, stoi_sum=sums).cpu().numpy()
+    print("STOI gpu", got, "oracle", want)
+    assert np.abs(got - want).max() <= 1e-4
+    keep = want > 0.1
+    s = sums.cpu().numpy()
+    assert s[1] == keep.sum() and abs(s[0] - got[got > 0.1].sum()) < 1e-9
+    assert abs(eng.stoi(torch.from_numpy(x).cuda(), torch.from_numpy(x).cuda(), sr).cpu().numpy() - 1.0).max() < 1e-5
+    # already at pystoi's 10 kHz: no resampling
+    x10 = _clips([4, 5], 2.0, 10000)
+    y10 = x10 + 0.02 * rng.standard_normal(x10.shape).astype(np.float32)
+    w10 = np.array([S.stoi(x10[i].astype(np.float64), y10[i].astype(np.float64), 10000) for i in range(2)])
+    g10 = eng.stoi(torch.from_numpy(x10).cuda(), torch.from_numpy(y10).cuda(), 10000).cpu().numpy()
+    assert np.abs(g10 - w10).max() <= 1e-4
+    # too short for 30 frames
+    short = eng.stoi(torch.from_numpy(x[:, :4000].copy()).cuda(), torch.from_numpy(y[:, :4000].copy()).cuda(), sr)
+    assert np.all(short.cpu().numpy() == 1e-5)
+    # reference call signature: STOI()(output, target, sampling_rate) -> float, truncation to the shorter input
+    m = STOI(eng)
+    one = m(y[2], x[2][:-100], sr)
+    assert abs(one - S.stoi(x[2][:-100].astype(np.float64), y[2][:-100].astype(np.float64), sr)) <= 1e-4

@@ -157,3 +157,33 @@ def test_oracle_equals_live_reference():
         emb.num_iterations = 2
         wm = O.encode_bits(O.synth_bits(8)[3])
         np.testing.assert_allclose(emb.embed(x, sr, wm), O.embed(x, sr, wm, num_iters=2), atol=1e-6)
+
+
+def test_stoi_restatement_invariants():
+    """oracle/stoi_oracle.py restates pystoi 0.4.1 (absent here: parity unpinned).  What can be pinned without the
+    package: the published constants (15 one-third-octave bands from 150 Hz at 10 kHz / 512: bins 7..218), the
+    Octave-style resampling window pystoi builds for 16 kHz -> 10 kHz, STOI(x, x) = 1, monotone decrease with
+    additive noise, invariance to a common gain, the 1e-5 answer for clips with fewer than 30 frames, and the
+    vectorised overlap-add equal to a direct loop."""
+    import stoi_oracle as S
+    obm, edges = S.thirdoct()
+    assert obm.shape == (15, 257) and edges[0] == (7, 9) and edges[-1] == (174, 219)
+    assert all(edges[i][1] == edges[i + 1][0] for i in range(14))          # contiguous bands
+    h = S.resample_window_oct(10000, 16000)
+    assert len(h) == 581 and abs(h.sum() - 5.0) < 1e-3 and np.allclose(h, h[::-1])
+    x = O.synth_clip(0, 3.0, 16000).astype(np.float64)
+    rng = np.random.default_rng(0)
+    noise = rng.standard_normal(len(x))
+    assert abs(S.stoi(x, x, 16000) - 1.0) < 1e-12
+    d = [S.stoi(x, x + s * noise, 16000) for s in (1e-3, 1e-2, 5e-2, 2e-1)]
+    assert all(a > b for a, b in zip(d, d[1:])) and d[0] > 0.99 and d[-1] < 0.4
+    assert abs(S.stoi(3.0 * x, 3.0 * (x + 0.01 * noise), 16000) - d[1]) < 1e-9
+    assert S.stoi(x[:4000], x[:4000], 16000) == 1e-5                         # 0.25 s: fewer than 30 frames
+    with pytest.raises(Exception):
+        S.stoi(x, x[:-1], 16000)
+    # silence gate: frames 40 dB below the loudest frame are removed before the analysis
+    y = x.copy()
+    y[8000:20000] *= 1e-4
+    y10 = S.resample_oct(y, 10000, 16000)
+    xs, ys, mask = S.remove_silent_frames(y10, y10)
+    assert 0 < mask.sum() < len(mask) and len(xs) == (mask.sum() - 1) * 128 + 256
