@@ -541,8 +541,7 @@ def main():
 
             def sweep():
                 eng.decide(eng.detect(y1k, sr), b1k, c1k[0])
-                for i, a_ in enumerate(s1k):
-                    eng.decide(eng.detect(a_.apply_batch(y1k, sr, engine=eng), sr), b1k, c1k[i + 1])
+                A.run_suite(s1k, y1k, sr, lambda i, z: eng.decide(eng.detect(z, sr), b1k, c1k[i + 1]), engine=eng)
             sweep()
             ms_1k = timed(sweep)
             phases["config3_attack_sweep_1024_clips"] = {
