@@ -992,8 +992,12 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
     if (ctx->sh) {
       if (sh_finalize<false>(ctx, cout, d.tiles, (float*)ctx->stat[l + 1].p, st)) return 1;
     } else {
-      k_finalize<0><<<g, 256, 0, st>>>((float*)ctx->part.p, cout, d.tiles, cout, d.Tp,
-                                       (float*)ctx->stat[l + 1].p);
+      if (d.tiles <= 16)
+        k_finalize_small<0><<<dim3((cout + 255) / 256, d.n), 256, 0, st>>>((float*)ctx->part.p, cout, d.tiles, cout,
+                                                                           d.Tp, (float*)ctx->stat[l + 1].p);
+      else
+        k_finalize<0><<<g, 256, 0, st>>>((float*)ctx->part.p, cout, d.tiles, cout, d.Tp,
+                                         (float*)ctx->stat[l + 1].p);
       ctx->launches++;
       AW_LAUNCH_CHECK();
     }
@@ -1004,7 +1008,8 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
     }
     prof_mark(ctx, st, "norm_act");
     {
-      dim3 gn(d.Tp_pad / AW_NORM_ROWS, (cout / Vec16<AT>::N + 127) / 128, d.n);
+      const int rl = 128 / std::min(128, cout / Vec16<AT>::N);       // row lanes per block (narrow layers)
+      dim3 gn((d.Tp_pad + AW_NORM_ROWS * rl - 1) / (AW_NORM_ROWS * rl), (cout / Vec16<AT>::N + 127) / 128, d.n);
       k_norm_rows<AT, NORM_FWD><<<gn, 128, 0, st>>>((AT*)ctx->act[l + 1].p, nullptr, cout, d.Tp, d.Tp_pad,
                                                     (float*)ctx->stat[l + 1].p, nullptr, tf && l < 3);
     }
@@ -1046,8 +1051,12 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
     if (ctx->sh) {
       if (sh_finalize<true>(ctx, n, d.tiles, (float*)ctx->bstat.p, st)) return 1;
     } else {
-      k_finalize<1><<<g, 256, 0, st>>>((float*)ctx->part.p, n, d.tiles, n, d.Tp,
-                                       (float*)ctx->bstat.p);
+      if (d.tiles <= 16)
+        k_finalize_small<1><<<dim3((n + 255) / 256, d.n), 256, 0, st>>>((float*)ctx->part.p, n, d.tiles, n, d.Tp,
+                                                                        (float*)ctx->bstat.p);
+      else
+        k_finalize<1><<<g, 256, 0, st>>>((float*)ctx->part.p, n, d.tiles, n, d.Tp,
+                                         (float*)ctx->bstat.p);
       ctx->launches++;
       AW_LAUNCH_CHECK();
     }
@@ -1059,7 +1068,8 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
     }
     prof_mark(ctx, st, "in_bwd_apply");
     {
-      dim3 gn(d.Tp_pad / AW_NORM_ROWS, (n / Vec16<AT>::N + 127) / 128, d.n);
+      const int rl = 128 / std::min(128, n / Vec16<AT>::N);
+      dim3 gn((d.Tp_pad + AW_NORM_ROWS * rl - 1) / (AW_NORM_ROWS * rl), (n / Vec16<AT>::N + 127) / 128, d.n);
       k_norm_rows<AT, NORM_BWD><<<gn, 128, 0, st>>>(steps[s].out, (AT*)ctx->act[l].p, n, d.Tp, d.Tp_pad,
                                                     (float*)ctx->stat[l].p, (float*)ctx->bstat.p, tf);
     }

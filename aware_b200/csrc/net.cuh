@@ -243,6 +243,39 @@ __global__ void __launch_bounds__(256) k_finalize(const float* __restrict__ part
   }
 }
 
+// Short clips (a handful of tiles): one thread per channel, no shared memory, C / 256 blocks per clip instead
+// of C / 32 -- the slice kernel above spends its time being launched (8 192 blocks of 256 threads for 7 float2
+// each at 256 clips x 10 s).  Same float64 summation order (slice sums t = s, s + 8, ..., combined s = 0..7),
+// so the statistics are bit-identical to k_finalize's.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_finalize_small(const float* __restrict__ part, int ldp, int tiles,
+                                                        int C, int Tp, float* __restrict__ stat) {
+  const int clip = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  const float* p0 = part + (((long long)clip * tiles) * ldp + c) * 2;
+  double s1 = 0.0, s2 = 0.0;
+  for (int sl = 0; sl < 8; ++sl) {
+    double a1 = 0.0, a2 = 0.0;
+    for (int t = sl; t < tiles; t += 8) {
+      const float2 p = __ldg(reinterpret_cast<const float2*>(p0 + (long long)t * ldp * 2));
+      a1 += p.x;
+      a2 += p.y;
+    }
+    s1 = sl == 0 ? a1 : s1 + a1;
+    s2 = sl == 0 ? a2 : s2 + a2;
+  }
+  if (MODE == 1) {
+    stat[((long long)clip * C + c) * 2] = (float)(s1 / Tp);
+    stat[((long long)clip * C + c) * 2 + 1] = (float)(s2 / Tp);
+  } else {
+    const double mu = s1 / Tp;
+    double var = s2 / Tp - mu * mu;
+    if (var < 0.0) var = 0.0;
+    stat[((long long)clip * C + c) * 2] = (float)mu;
+    stat[((long long)clip * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + AW_IN_EPS));
+  }
+}
+
 // statistics from (all-reduced) raw sums; Tp = GLOBAL pooled frame count of the clip
 template <bool BWD>
 __global__ void __launch_bounds__(256) k_stat_from_sums(const double* __restrict__ raw, int C, int Tp,
@@ -268,7 +301,7 @@ __global__ void __launch_bounds__(256) k_stat_from_sums(const double* __restrict
 // pad rows (j >= Tp) are forced to 0.  One thread owns 4 adjacent channels of one clip for
 // AW_NORM_ROWS rows: the per-channel statistics are loaded once into registers and the
 // row loop is pure 16-byte streaming with 8 independent loads in flight.
-// grid = (Tp_pad / AW_NORM_ROWS, C / (4 * 128) rounded up, n_clips), block = 128.
+// grid = (Tp_pad / (AW_NORM_ROWS * RL) rounded up, C / (V * 128) rounded up, n_clips), block = 128.
 enum { NORM_FWD = 0, NORM_BWD = 1 };
 #define AW_NORM_ROWS 32
 // 16 bytes per access for every storage type: 4 floats or 8 half / bf16 values
@@ -318,9 +351,14 @@ __global__ void __launch_bounds__(128) k_norm_rows(AT* __restrict__ X, const AT*
                                                    const float* __restrict__ bstat, int round_tf32) {
   constexpr int V = Vec16<AT>::N;
   const int clip = blockIdx.z;
-  const int c = (blockIdx.y * 128 + threadIdx.x) * V;
+  // narrow layers (C / V < 128 column groups, e.g. the 64-channel last layer): the block's 128 threads are
+  // G column groups x RL row lanes and the block covers AW_NORM_ROWS * RL rows, so every thread still owns
+  // AW_NORM_ROWS rows (stride RL) and a warp's access stays contiguous; wide layers: G = 128, RL = 1
+  const int G = min(128, C / V), RL = 128 / G;
+  const int cgp = threadIdx.x % G, rl = threadIdx.x / G;
+  const int c = (blockIdx.y * 128 + cgp) * V;
   if (c >= C) return;
-  const int j0 = blockIdx.x * AW_NORM_ROWS;
+  const int j0 = blockIdx.x * AW_NORM_ROWS * RL + rl;
   float mu[V], rs[V], a1[V], a2[V];
 #pragma unroll
   for (int k = 0; k < V; k += 2) {
@@ -333,14 +371,16 @@ __global__ void __launch_bounds__(128) k_norm_rows(AT* __restrict__ X, const AT*
   }
   AT* x = X + ((long long)clip * Tp_pad + j0) * C + c;
   const AT* p = MODE == NORM_BWD ? P + ((long long)clip * Tp_pad + j0) * C + c : nullptr;
+  const long long rstride = (long long)RL * C;           // between two rows of this thread
   constexpr int NB = V == 4 ? 8 : 4;                     // 16-byte loads in flight per tensor
 #pragma unroll 1
   for (int r0 = 0; r0 < AW_NORM_ROWS; r0 += NB) {
+    if (j0 + r0 * RL >= Tp_pad) break;                   // Tp_pad is a multiple of 128 >= NB * RL rows
     float h[NB][V], a[MODE == NORM_BWD ? NB : 1][V];
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
-      ld16(x + (long long)(r0 + i) * C, h[i]);
-      if (MODE == NORM_BWD) ld16(p + (long long)(r0 + i) * C, a[i]);
+      ld16(x + (r0 + i) * rstride, h[i]);
+      if (MODE == NORM_BWD) ld16(p + (r0 + i) * rstride, a[i]);
     }
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
@@ -355,9 +395,9 @@ __global__ void __launch_bounds__(128) k_norm_rows(AT* __restrict__ X, const AT*
           o[k] = rs[k] * (h[i][k] - a1[k] - hh * a2[k]);
         }
         if (sizeof(AT) == 4 && round_tf32) o[k] = to_tf32(o[k]);
-        if (j0 + r0 + i >= Tp) o[k] = 0.f;
+        if (j0 + (r0 + i) * RL >= Tp) o[k] = 0.f;
       }
-      st16(x + (long long)(r0 + i) * C, o);
+      st16(x + (r0 + i) * rstride, o);
     }
   }
 }
