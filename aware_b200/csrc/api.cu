@@ -81,6 +81,8 @@ struct aw_ctx {
   // CUDA-graph replay of the optimisation iteration (AW_B200_NO_GRAPH=1 disables): the ~50 launches
   // of one iteration are captured once on a context-owned stream and replayed iters-1 times
   bool graphs = true;
+  bool pdl = false;                // set while the optimisation loop launches (aw_launch): programmatic dependent launch
+  bool pdl_ok = false;             // AW_B200_PDL=1: on (opt-in: measured neutral to negative)
   cudaStream_t gstream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   Buf accum, peakx, mag, ph_u, ph_q, c0, c, m, v, cbest, dA, yoob, y, M, cs, sigma;
@@ -178,6 +180,25 @@ static int raise_smem_limit(aw_ctx* ctx, const void* func, int bytes) {
   AW_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   ctx->smem_attr_done.push_back(func);
   return 0;
+}
+
+// Kernel launch on `st`.  Inside the optimisation loop (ctx->pdl) with programmatic stream serialisation: the
+// kernel may be scheduled while its predecessor drains and blocks in pdl_wait() until that one has completed
+// (every kernel launched through here starts with pdl_enter() / pdl_wait()); captured into the iteration's
+// CUDA graph as programmatic dependency edges.  Otherwise an ordinary launch.
+template <typename... KA, typename... A>
+static void aw_launch(aw_ctx* ctx, void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                      A&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at;
+  memset(&at, 0, sizeof(at));
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = ctx->pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, KA(args)...);
 }
 
 static int ensure(Buf& b, size_t bytes) {
@@ -318,7 +339,7 @@ static int launch_tc(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, 
     cudaEventRecord(pr.a, st);
   }
   prof_mark(ctx, st, gemm_label(EPI, n, k));
-  k_gemm_tc<T, OT, BN, EPI><<<grid, gemm_threads(EPI), gemm_tc_smem<BN>(), st>>>(ma, mb, k, n_row_tiles,
+  aw_launch(ctx, k_gemm_tc<T, OT, BN, EPI>, dim3(grid), dim3(gemm_threads(EPI)), gemm_tc_smem<BN>(), st, ma, mb, k, n_row_tiles,
                                                                               n_col_tiles, ep);
   if (ctx->prof_on) {
     cudaEventRecord(pr.b, st);
@@ -345,7 +366,7 @@ static int launch_tc_pair(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap&
     cudaEventRecord(pr.a, st);
   }
   prof_mark(ctx, st, gemm_label(EPI, n, k));
-  k_gemm_tc_pair<T, OT, BN, EPI><<<grid, gemm_threads(EPI), gemm_tc_smem_pair<BN>(), st>>>(ma, mb_half, k, n_row_tiles,
+  aw_launch(ctx, k_gemm_tc_pair<T, OT, BN, EPI>, dim3(grid), dim3(gemm_threads(EPI)), gemm_tc_smem_pair<BN>(), st, ma, mb_half, k, n_row_tiles,
                                                                                         n_col_tiles, ep);
   if (ctx->prof_on) {
     cudaEventRecord(pr.b, st);
@@ -420,6 +441,8 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
   {
     const char* e = getenv("AW_B200_NO_GRAPH");
     ctx->graphs = !(e && e[0] == '1');
+    const char* e0 = getenv("AW_B200_PDL");          // measured: no gain (experiments), hence opt-in
+    ctx->pdl_ok = e0 && e0[0] == '1';
     const char* e2 = getenv("AW_B200_ONE_PASS");
     ctx->two_pass = !(e2 && e2[0] == '1');
     const char* e3 = getenv("AW_B200_FFT_SPEC");
@@ -759,6 +782,7 @@ struct Acc {
 static Acc acc_view(aw_ctx* ctx, const struct Dims& d);
 
 __global__ void k_iter_begin(unsigned long long* peak, int n, int* it, unsigned* dmax = nullptr) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) peak[i] = 0ull;
   if (i < n && dmax) dmax[i] = 0u;
@@ -947,7 +971,7 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
   {
     dim3 g((d.T + AW_MEL_FRAMES - 1) / AW_MEL_FRAMES, d.n);
     prof_mark(ctx, st, "mel");
-    k_mel<<<g, 128, AW_MEL_FRAMES * d.nb * 4, st>>>(own_frames(ctx, (float*)ctx->mag.p, d.nb), d.T, d.nb, sm,
+    aw_launch(ctx, k_mel, dim3(g), dim3(128), AW_MEL_FRAMES * d.nb * 4, st, own_frames(ctx, (float*)ctx->mag.p, d.nb), d.T, d.nb, sm,
                                                     (float*)ctx->M.p, acc.chan_part, peak_scale);
     ctx->launches++;
     AW_LAUNCH_CHECK();
@@ -960,11 +984,11 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
       cb = 1;
     } else if (reduce_if_long(ctx, ctx->red_a, cp, cb, d.n, 2 * AW_NMEL, st)) return 1;
     prof_mark(ctx, st, "mel_stats");
-    k_mel_stats<<<d.n, 128, 0, st>>>(cp, cb, ctx->sh ? ctx->sh->T_glob : d.T, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p);
+    aw_launch(ctx, k_mel_stats, dim3(d.n), dim3(128), 0, st, cp, cb, ctx->sh ? ctx->sh->T_glob : d.T, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p);
     ctx->launches++;
     AW_LAUNCH_CHECK();
     prof_mark(ctx, st, "p0");
-    k_p0<AT><<<g2, 128, 0, st>>>((float*)ctx->M.p, d.T, d.Tp, d.Tp_pad, (ChanStats*)ctx->cs.p,
+    aw_launch(ctx, k_p0<AT>, dim3(g2), dim3(128), 0, st, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad, (ChanStats*)ctx->cs.p,
                                  (float*)ctx->sigma.p, (AT*)ctx->act[0].p, tf);
     ctx->launches++;
     AW_LAUNCH_CHECK();
@@ -993,11 +1017,11 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
       if (sh_finalize<false>(ctx, cout, d.tiles, (float*)ctx->stat[l + 1].p, st)) return 1;
     } else {
       if (d.tiles <= 16)
-        k_finalize_small<0><<<dim3((cout + 255) / 256, d.n), 256, 0, st>>>((float*)ctx->part.p, cout, d.tiles, cout,
+        aw_launch(ctx, k_finalize_small<0>, dim3((cout + 255) / 256, d.n), dim3(256), 0, st, (float*)ctx->part.p, cout, d.tiles, cout,
                                                                            d.Tp, (float*)ctx->stat[l + 1].p);
       else
-        k_finalize<0><<<g, 256, 0, st>>>((float*)ctx->part.p, cout, d.tiles, cout, d.Tp,
-                                         (float*)ctx->stat[l + 1].p);
+        aw_launch(ctx, k_finalize<0>, dim3(g), dim3(256), 0, st, (float*)ctx->part.p, cout, d.tiles, cout, d.Tp,
+                  (float*)ctx->stat[l + 1].p, nullptr);
       ctx->launches++;
       AW_LAUNCH_CHECK();
     }
@@ -1010,7 +1034,7 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
     {
       const int rl = 128 / std::min(128, cout / Vec16<AT>::N);       // row lanes per block (narrow layers)
       dim3 gn((d.Tp_pad + AW_NORM_ROWS * rl - 1) / (AW_NORM_ROWS * rl), (cout / Vec16<AT>::N + 127) / 128, d.n);
-      k_norm_rows<AT, NORM_FWD><<<gn, 128, 0, st>>>((AT*)ctx->act[l + 1].p, nullptr, cout, d.Tp, d.Tp_pad,
+      aw_launch(ctx, k_norm_rows<AT, NORM_FWD>, dim3(gn), dim3(128), 0, st, (AT*)ctx->act[l + 1].p, nullptr, cout, d.Tp, d.Tp_pad,
                                                     (float*)ctx->stat[l + 1].p, nullptr, tf && l < 3);
     }
     ctx->launches++;
@@ -1052,11 +1076,11 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
       if (sh_finalize<true>(ctx, n, d.tiles, (float*)ctx->bstat.p, st)) return 1;
     } else {
       if (d.tiles <= 16)
-        k_finalize_small<1><<<dim3((n + 255) / 256, d.n), 256, 0, st>>>((float*)ctx->part.p, n, d.tiles, n, d.Tp,
+        aw_launch(ctx, k_finalize_small<1>, dim3((n + 255) / 256, d.n), dim3(256), 0, st, (float*)ctx->part.p, n, d.tiles, n, d.Tp,
                                                                         (float*)ctx->bstat.p);
       else
-        k_finalize<1><<<g, 256, 0, st>>>((float*)ctx->part.p, n, d.tiles, n, d.Tp,
-                                         (float*)ctx->bstat.p);
+        aw_launch(ctx, k_finalize<1>, dim3(g), dim3(256), 0, st, (float*)ctx->part.p, n, d.tiles, n, d.Tp,
+                  (float*)ctx->bstat.p, nullptr);
       ctx->launches++;
       AW_LAUNCH_CHECK();
     }
@@ -1070,7 +1094,7 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
     {
       const int rl = 128 / std::min(128, n / Vec16<AT>::N);
       dim3 gn((d.Tp_pad + AW_NORM_ROWS * rl - 1) / (AW_NORM_ROWS * rl), (n / Vec16<AT>::N + 127) / 128, d.n);
-      k_norm_rows<AT, NORM_BWD><<<gn, 128, 0, st>>>(steps[s].out, (AT*)ctx->act[l].p, n, d.Tp, d.Tp_pad,
+      aw_launch(ctx, k_norm_rows<AT, NORM_BWD>, dim3(gn), dim3(128), 0, st, steps[s].out, (AT*)ctx->act[l].p, n, d.Tp, d.Tp_pad,
                                                     (float*)ctx->stat[l].p, (float*)ctx->bstat.p, tf);
     }
     ctx->launches++;
@@ -1094,7 +1118,7 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
   }
   dim3 g1((2 * d.Tp + AW_P0B_FRAMES - 1) / AW_P0B_FRAMES, d.n);
   prof_mark(ctx, st, "p0_bwd_reduce");
-  k_p0_bwd_reduce<<<g1, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
+  aw_launch(ctx, k_p0_bwd_reduce, dim3(g1), dim3(128), 0, st, (float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
                                       (ChanStats*)ctx->cs.p, acc.bpart, (const float*)ctx->gsc.p);
   ctx->launches++;
   AW_LAUNCH_CHECK();
@@ -1107,12 +1131,12 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
     bb = 1;
   } else if (reduce_if_long(ctx, ctx->red_b, bp, bb, d.n, 2 * AW_NMEL, st)) return 1;
   prof_mark(ctx, st, "p0_bwd_coef");
-  k_p0_bwd_coef<<<d.n, 128, 0, st>>>(bp, bb, ctx->sh ? ctx->sh->T_glob : d.T, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p,
+  aw_launch(ctx, k_p0_bwd_coef, dim3(d.n), dim3(128), 0, st, bp, bb, ctx->sh ? ctx->sh->T_glob : d.T, (ChanStats*)ctx->cs.p, (float*)ctx->sigma.p,
                                      (P0BwdCoef*)ctx->p0coef.p, (P0BwdScal*)ctx->p0scal.p);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   prof_mark(ctx, st, "p0_bwd_apply");
-  k_p0_bwd_apply<<<g2, 128, 0, st>>>((float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
+  aw_launch(ctx, k_p0_bwd_apply, dim3(g2), dim3(128), 0, st, (float*)ctx->dp0.p, (float*)ctx->M.p, d.T, d.Tp, d.Tp_pad,
                                      (ChanStats*)ctx->cs.p, (P0BwdCoef*)ctx->p0coef.p,
                                      (P0BwdScal*)ctx->p0scal.p, sm, d.nb, own_frames(ctx, (float*)ctx->dA.p, d.nb),
                                      euler_s2 ? (const float*)own_frames(ctx, (float*)ctx->mag.p, d.nb) : nullptr, acc.s2_part,
@@ -1139,18 +1163,18 @@ static int run_head(aw_ctx* ctx, const Dims& d, const float* pattern, float* val
   h.hpart = (double*)ctx->hpart.p;
   h.hcoef = (float*)ctx->hcoef.p;
   prof_mark(ctx, st, "head");
-  k_head_partial<AT><<<dim3(d.tiles, d.n), 256, 0, st>>>(h);
+  aw_launch(ctx, k_head_partial<AT>, dim3(d.tiles, d.n), dim3(256), 0, st, h);
   if (ctx->sh) {
     if (sh_reduce_sum(ctx, ctx->red_a, h.hpart, d.tiles, 64 * 3, st)) return 1;
     HeadArgs<AT> hf = h;
     hf.hpart = const_cast<double*>(sh_red(ctx));
-    k_head_final<AT><<<d.n, 64, 0, st>>>(hf, 1);
+    aw_launch(ctx, k_head_final<AT>, dim3(d.n), dim3(64), 0, st, hf, 1);
   } else {
-    k_head_final<AT><<<d.n, 64, 0, st>>>(h, d.tiles);
+    aw_launch(ctx, k_head_final<AT>, dim3(d.n), dim3(64), 0, st, h, d.tiles);
   }
   ctx->launches += 2;
   if (backward && pattern) {
-    k_head_seed<AT><<<dim3(d.tiles, d.n), 256, 0, st>>>(h);
+    aw_launch(ctx, k_head_seed<AT>, dim3(d.tiles, d.n), dim3(256), 0, st, h);
     ctx->launches++;
   }
   AW_LAUNCH_CHECK();
@@ -1217,7 +1241,7 @@ static int launch_spec_k(aw_ctx* ctx, const Dims& d, SpecArgs& a, cudaStream_t s
   const int items = a.edge_mode ? a.n_clips * 2 : a.n_clips * a.tiles;
   const int grid = std::min(items, 2 * ctx->num_sms);
   prof_mark(ctx, st, a.edge_mode ? (MODE == SPEC_FWD ? "spec_edge_fwd" : "spec_edge_bwd") : (MODE == SPEC_FWD ? "spec_fwd" : "spec_bwd"));
-  k_spec<MODE, K2LO, K2HI><<<grid, 32 * AW_SP_WARPS, AW_SP_SMEM, st>>>(a);
+  aw_launch(ctx, k_spec<MODE, K2LO, K2HI>, dim3(grid), dim3(32 * AW_SP_WARPS), AW_SP_SMEM, st, a);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
@@ -1250,7 +1274,7 @@ static int launch_peak(aw_ctx* ctx, const float* x, int64_t stride, int n, int n
 }
 static int begin_pass(aw_ctx* ctx, int n, int* it, cudaStream_t st, unsigned* dmax = nullptr) {
   prof_mark(ctx, st, "iter_begin");
-  k_iter_begin<<<(n + 255) / 256, 256, 0, st>>>((unsigned long long*)ctx->accum.p, n, it, dmax);
+  aw_launch(ctx, k_iter_begin, dim3((n + 255) / 256), dim3(256), 0, st, (unsigned long long*)ctx->accum.p, n, it, dmax);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
@@ -1491,7 +1515,7 @@ static int tc_backward(aw_ctx* ctx, const Dims& d, int* itc, cudaStream_t st, in
     ctx->launches++;
   }
   prof_mark(ctx, st, "tc_dsprep");
-  k_tc_dsprep<<<dim3((d.T + AW_TC_FR - 1) / AW_TC_FR, d.n), 256, 0, st>>>((const float*)ctx->dA.p, (const float2*)ctx->ph_q.p, d.T, d.nb,
+  aw_launch(ctx, k_tc_dsprep, dim3((d.T + AW_TC_FR - 1) / AW_TC_FR, d.n), dim3(256), 0, st, (const float*)ctx->dA.p, (const float2*)ctx->ph_q.p, d.T, d.nb,
                                                (unsigned*)ctx->tc_dmax.p, itc, d.n, (__half*)ctx->tc_dS.p);
   ctx->launches++;
   AW_LAUNCH_CHECK();
@@ -1521,7 +1545,7 @@ static int tc_backward(aw_ctx* ctx, const Dims& d, int* itc, cudaStream_t st, in
   u.X = (__half*)ctx->tc_X.p;
   u.nonfinite = nonfinite;
   prof_mark(ctx, st, "tc_update");
-  k_tc_update<<<dim3((d.T + AW_TC_FR - 1) / AW_TC_FR, d.n), 256, 0, st>>>(u);
+  aw_launch(ctx, k_tc_update, dim3((d.T + AW_TC_FR - 1) / AW_TC_FR, d.n), dim3(256), 0, st, u);
   ctx->launches++;
   AW_LAUNCH_CHECK();
   return 0;
@@ -1639,6 +1663,12 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
 
     // ---- optimisation loop (multibit_embedder.py:95-122)
     nvtxRangePushA("embed:nadam_loop");
+    // programmatic dependent launch inside the loop (opt-in, AW_B200_PDL=1): every kernel is scheduled while its
+    // predecessor drains and waits in pdl_wait() for its completion.  Measured: 256 clips 5.1-5.3 ms per
+    // iteration against 4.84-4.91 without (the early-resident successors take registers and issue slots from
+    // the running kernel), one clip 0.24-0.27 ms either way -- hence off by default
+    struct PdlScope { aw_ctx* c; ~PdlScope() { c->pdl = false; } } pdl_scope_{ctx};
+    ctx->pdl = ctx->pdl_ok && !ctx->prof_on;
     auto iteration = [&](bool first) -> int {
       // fused spectral passes (spec.cuh): y and dpad never leave shared memory
       if (begin_pass(ctx, dw.n, itc, st)) return 1;
@@ -1674,7 +1704,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       if (reduce_if_long(ctx, ctx->red_c, sp2, sb2, dw.n, 1, st)) return 1;
       if (sb2 > 512 && reduce_if_long(ctx, ctx->red_a, sp2, sb2, dw.n, 1, st)) return 1;   // 1 h: 38 760 -> 606 -> 10
       prof_mark(ctx, st, "clip_scalars");
-      k_clip_scalars<<<(dw.n + 127) / 128, 128, 0, st>>>(acc.peak_y, sp2, sb2, dw.n, (ClipScal*)ctx->scal.p, 0,
+      aw_launch(ctx, k_clip_scalars, dim3((dw.n + 127) / 128), dim3(128), 0, st, acc.peak_y, sp2, sb2, dw.n, (ClipScal*)ctx->scal.p, 0,
                                                          tc ? (unsigned*)ctx->tc_dmax.p : nullptr, itc);
       ctx->launches++;
       AW_LAUNCH_CHECK();
@@ -1725,6 +1755,7 @@ extern "C" int aw_embed_batch(aw_ctx* ctx, const float* d_audio, int n_clips, in
       for (int it = 0; it < iters; ++it)
         if (iteration(it == 0)) return 1;
     }
+    ctx->pdl = false;
     nvtxRangePop();
     // ---- final synthesis from the best coefficients (multibit_embedder.py:173-192)
     nvtxRangePushA("embed:final_synthesis");
@@ -1924,7 +1955,8 @@ extern "C" int aw_embed_sharded(aw_ctx* ctx, const float* d_segment, int seg_sam
     if (rc) return 1;
     if (sh_reduce_sum(ctx, ctx->red_c, acc.s2_part, p0a_blocks(dn), 1, st)) return 1;   // Euler sum over the clip
     prof_mark(ctx, st, "clip_scalars");
-    k_clip_scalars<<<1, 128, 0, st>>>(acc.peak_y, sh_red(ctx), 1, 1, (ClipScal*)ctx->scal.p, n_base);
+    aw_launch(ctx, k_clip_scalars, dim3(1), dim3(128), 0, st, acc.peak_y, sh_red(ctx), 1, 1, (ClipScal*)ctx->scal.p, n_base,
+              nullptr, nullptr);
     ctx->launches++;
     AW_LAUNCH_CHECK();
     if (sh_halo_exchange(ctx, (float*)ctx->dA.p, ds.nb, st)) return 1;   // spectral gradient of the halo frames

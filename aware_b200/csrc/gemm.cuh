@@ -420,6 +420,7 @@ constexpr int gemm_tc_smem() {
 template <typename T, typename OT, int BN, int EPI, int CG>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_a, const CUtensorMap& map_b,
                                              int K, int n_row_tiles, int n_col_tiles, const EpiArgsT<OT>& ep) {
+  pdl_trigger();                                     // the successor may be scheduled while this grid runs
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by POINTER arithmetic on the __shared__ array: a round trip through uintptr_t made
   // the compiler forget the address space, every epilogue staging access became a generic LD.E / ST.E on the
@@ -482,6 +483,9 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_a, const CUt
   if (CG == 2) cluster_sync_all();                   // both CTAs' barriers exist before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, TMEM and descriptors are set up: everything above overlapped the predecessor's tail (PDL);
+  // from here on its output is read
+  pdl_wait();
   const uint32_t leader_full = CG == 2 ? mapa_u32(smem_u32(full), 0) : 0u;
   const uint32_t leader_tempty = CG == 2 ? mapa_u32(smem_u32(tempty), 0) : 0u;
   // register hand-over between warpgroups (see AW_GEMM_THREADS); each setmaxnreg sits at the head of the
