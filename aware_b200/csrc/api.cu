@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "fft.cuh"
 #include "gemm.cuh"
+#include "gemm64.cuh"
 #include "net.cuh"
 #include "spec.cuh"
 #include "spectc.cuh"
@@ -95,6 +96,7 @@ struct aw_ctx {
   size_t h_lowm_cap = 0;
   double exact_margin = 1e-3;      // AW_OPT_EXACT_MARGIN
   bool two_pass = true;            // small-K layers as statistics pass + apply pass (AW_B200_ONE_PASS=1: off)
+  bool bwd64_stream = true;        // 16-bit loops: the backward K = 64 layer on k_gemm_bwd64 (TMA-streamed activations, AW_OPT_BWD64_STREAM)
   // tensor-core spectral path of the fp16 embed loop (spectc.cuh; AW_B200_FFT_SPEC=1: off)
   bool tc_spec = true;
   int tc_min_frames = 24 * 1024;   // n_clips * frames from which the tensor-core path is used (AW_OPT_TC_SPECTRAL value > 1 sets it)
@@ -383,6 +385,31 @@ static bool pair_ok(aw_ctx* ctx, int rows, int n, int k, int elem_bytes) {
   return ctx->pair_gemm && (rows / 128) % 2 == 0 && n % 256 == 0 && k * elem_bytes >= 2048;
 }
 
+// backward K = 64 layer as a streaming kernel (gemm64.cuh): activations in through a TMA ring, dH out through TMA
+template <typename T, int EPI>
+static int launch_bwd64(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb128, const CUtensorMap& mact,
+                        const CUtensorMap& mout, int rows, int n, int k, const Gemm64Args& ga, cudaStream_t st) {
+  if (raise_smem_limit(ctx, (const void*)k_gemm_bwd64<T, EPI>, gemm64_smem<EPI>())) return 1;
+  const int n_row_tiles = rows / 128, n_col_tiles = n / AW_G64_BN;
+  const int grid = std::min(n_row_tiles * n_col_tiles, ctx->num_sms);
+  aw_ctx::ProfRec pr;
+  if (ctx->prof_on) {
+    pr.n = n; pr.k = k; pr.epi = EPI;
+    pr.a = prof_event(ctx); pr.b = prof_event(ctx);
+    cudaEventRecord(pr.a, st);
+  }
+  prof_mark(ctx, st, gemm_label(EPI, n, k));
+  aw_launch(ctx, k_gemm_bwd64<T, EPI>, dim3(grid), dim3(320), gemm64_smem<EPI>(), st, ma, mb128, mact, mout, k,
+            n_row_tiles, n_col_tiles, ga);
+  if (ctx->prof_on) {
+    cudaEventRecord(pr.b, st);
+    ctx->prof.push_back(pr);
+  }
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+
 // tensor-core GEMM, operands of type T, output/activation type OT
 template <typename T, typename OT, int EPI>
 static int launch_tc_bn(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, int rows, int n,
@@ -596,6 +623,7 @@ extern "C" int aw_ctx_set_option(aw_ctx* ctx, int option, double value) {
       return 0;
     case AW_OPT_TWO_PASS: ctx->two_pass = value != 0.0; return 0;
     case AW_OPT_PAIR_GEMM: ctx->pair_gemm = value != 0.0; return 0;
+    case AW_OPT_BWD64_STREAM: ctx->bwd64_stream = value != 0.0; return 0;
     default: return set_error("aw_ctx_set_option: unknown option %d", option);
   }
 }
@@ -1065,7 +1093,19 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
     // dP3 = dH4 W3 has K = 64: recomputing it is cheaper than writing dHhat3 (470 MB at 256 clips) and
     // reading it back for the InstanceNorm adjoint -- statistics pass, then a pass that applies the adjoint
     const bool two_pass = s == 0 && ctx->prec != AW_PREC_FP32 && ctx->two_pass;
-    if (two_pass) {
+    // 16-bit loops: that layer on the streaming kernel (activations through a TMA ring, no epilogue loads)
+    const bool stream64 = two_pass && sizeof(AT) == 2 && ctx->bwd64_stream;
+    Gemm64Args g64;
+    memset(&g64, 0, sizeof(g64));
+    g64.part = (float*)ctx->part.p; g64.ldp = n; g64.ldo = n; g64.tiles_per_clip = d.tiles; g64.Tp = d.Tp;
+    g64.stat = (float*)ctx->stat[l].p; g64.bstat = (float*)ctx->bstat.p;
+    if (stream64) {
+      if constexpr (sizeof(AT) == 2) {
+        if (launch_bwd64<AT, EPI_BWD_STATS>(ctx, *steps[s].ma, ModeOf<AT>::wtP(ctx, l), ctx->tm_act[B][l], ctx->tm_ga1024[B],
+                                            d.rows, n, k, g64, st))
+          return 1;
+      }
+    } else if (two_pass) {
       if (launch_tc<AT, AT, 256, EPI_BWD_STATS>(ctx, *steps[s].ma, mw, d.rows, n, k, ep, st)) return 1;
     } else if (ctx->prec != AW_PREC_FP32 && pair_ok(ctx, d.rows, n, k, (int)sizeof(AT))) {
       if (launch_tc_pair<AT, AT, EPI_BWD>(ctx, *steps[s].ma, ModeOf<AT>::wtP(ctx, l), d.rows, n, k, ep, st)) return 1;
@@ -1083,6 +1123,14 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
                   (float*)ctx->bstat.p, nullptr);
       ctx->launches++;
       AW_LAUNCH_CHECK();
+    }
+    if (stream64) {
+      if constexpr (sizeof(AT) == 2) {
+        if (launch_bwd64<AT, EPI_BWD_APPLY>(ctx, *steps[s].ma, ModeOf<AT>::wtP(ctx, l), ctx->tm_act[B][l], ctx->tm_ga1024[B],
+                                            d.rows, n, k, g64, st))
+          return 1;
+      }
+      continue;
     }
     if (two_pass) {
       ep.stat = (float*)ctx->stat[l].p; ep.bstat = (float*)ctx->bstat.p;

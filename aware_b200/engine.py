@@ -109,6 +109,10 @@ class Engine:
         """K >= 512 layers on CTA pairs (cta_group::2); off = the one-CTA kernel (bit-identical results)."""
         _lib.check(self.lib.aw_ctx_set_option(self._ctx, _lib.OPT_PAIR_GEMM, 1.0 if on else 0.0))
 
+    def set_bwd64_stream(self, on: bool):
+        """16-bit loops: backward K = 64 layer on the TMA-streaming kernel (gemm64.cuh); off = generic GEMM epilogues."""
+        _lib.check(self.lib.aw_ctx_set_option(self._ctx, _lib.OPT_BWD64_STREAM, 1.0 if on else 0.0))
+
     def detect_stats(self):
         """(clips seen by detect, clips re-evaluated exactly) since the engine was created."""
         out = []

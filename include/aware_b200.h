@@ -72,9 +72,11 @@ int64_t aw_launch_count(aw_ctx* ctx);
  * as a statistics pass + an apply pass instead of materialising their raw output.  AW_OPT_PAIR_GEMM
  * (default 1): the K >= 512 layers run on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, each CTA
  * staging half of the weight tile) when the batch has an even number of 128-row tiles; results are
- * bit-identical to the one-CTA kernel. */
+ * bit-identical to the one-CTA kernel.  AW_OPT_BWD64_STREAM (default 1): in the 16-bit loops the backward
+ * K = 64 layer runs on k_gemm_bwd64 (csrc/gemm64.cuh: activation tiles streamed through a TMA ring, output
+ * through a TMA bulk store) instead of the generic GEMM's statistics / apply epilogues. */
 enum { AW_OPT_THRESHOLD = 0, AW_OPT_EXACT_MARGIN = 1, AW_OPT_TC_SPECTRAL = 2, AW_OPT_TWO_PASS = 3,
-       AW_OPT_PAIR_GEMM = 4 };
+       AW_OPT_PAIR_GEMM = 4, AW_OPT_BWD64_STREAM = 5 };
 int aw_ctx_set_option(aw_ctx* ctx, int option, double value);
 /* counters since context creation: clips seen by aw_detect_batch / clips it re-evaluated exactly */
 enum { AW_STAT_DETECT_CLIPS = 0, AW_STAT_REEVAL_CLIPS = 1 };

@@ -132,6 +132,8 @@ def quick():
     n = int(os.environ.get("CLIPS", "256"))
     x = torch.from_numpy(synth_batch(n, 10.0, sr)).cuda()
     pat = torch.from_numpy(2 * synth_bits(n) - 1)
+    if "BWD64" in os.environ:
+        eng.set_bwd64_stream(os.environ["BWD64"] == "1")
     eng.embed(x, sr, pat, iters=4, precision="fp16")
     torch.cuda.synchronize()
     for _ in range(2):

@@ -951,3 +951,38 @@ def test_stoi_kernels_match_the_numpy_restatement(model):
     m = STOI(eng)
     one = m(y[2], x[2][:-100], sr)
     assert abs(one - S.stoi(x[2][:-100].astype(np.float64), y[2][:-100].astype(np.float64), sr)) <= 1e-4
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_streaming_k64_backward_kernel_matches_the_generic_epilogues(eng, precision):
+    """csrc/gemm64.cuh: the backward K = 64 layer with its activation tiles streamed through a TMA ring and the
+    output written by a TMA bulk store, against the generic GEMM's statistics / apply epilogues: the same
+    products, statistics and adjoint formula -- only the order in which the 128 rows of a tile are summed into
+    the column sums differs (float32 rounding).  Compared on the first-moment estimate after ONE step (m = 0.1 g:
+    the gradient itself, before NAdam's sign-like normalisation amplifies rounding), on clips whose pooled length
+    is not a multiple of 128 (pad rows must come out zero), and on the losses of three iterations."""
+    sr = 44100
+    for secs in (1.5, 3.1):
+        x = _clips([0, 1, 2], secs, sr)
+        xd = torch.from_numpy(x).cuda()
+        pat = torch.from_numpy(np.stack([O.encode_bits(b) for b in O.synth_bits(3)]))
+        T = 1 + x.shape[1] // 256
+        out = {}
+        try:
+            for on in (False, True):
+                eng.set_bwd64_stream(on)
+                eng.embed(xd, sr, pat, iters=1, precision=precision)
+                m = eng.embed_state("m", 3, T, sr).cpu().numpy()
+                _, _, losses = eng.embed(xd, sr, pat, iters=3, return_losses=True, precision=precision)
+                out[on] = (m, losses[:3].cpu().numpy())
+        finally:
+            eng.set_bwd64_stream(True)
+        m0, m1 = out[False][0], out[True][0]
+        assert np.isfinite(m1).all() and np.abs(m1).max() > 0
+        scale = np.abs(m0).max(axis=(1, 2), keepdims=True)
+        err = np.abs(m1 - m0) / scale
+        print("k64 streaming vs generic (%s, %.1f s): max rel err %.2e, rms %.2e" %
+              (precision, secs, err.max(), np.sqrt((err ** 2).mean())))
+        assert err.max() <= (2e-3 if precision == "fp16" else 2e-2)
+        assert np.sqrt((err ** 2).mean()) <= (1e-4 if precision == "fp16" else 1e-3)
+        assert np.abs(out[True][1] - out[False][1]).max() <= 5e-3
