@@ -96,6 +96,14 @@ struct aw_ctx {
   size_t h_lowm_cap = 0;
   double exact_margin = 1e-3;      // AW_OPT_EXACT_MARGIN
   bool two_pass = true;            // small-K layers as statistics pass + apply pass (AW_B200_ONE_PASS=1: off)
+  // 16-bit loops, K >= 512 layers: InstanceNorm (+ LeakyReLU) / its adjoint inside the GEMM (EPI_*_FUSE); bit 0
+  // forward, bit 1 backward (AW_OPT_FUSE_NORM, AW_B200_FUSE_NORM=<mask>); fuse_pair: on CTA pairs where pair_ok
+  // DEFAULT OFF: measured a wash to a loss at 256 clips ("InstanceNorm inside the GEMM")
+  int fuse_norm = 0;
+  bool fuse_pair = false;
+  Buf fuse_cnt;
+  int fuse_cnt_tpc = 0;
+  bool fuse_cnt_fresh = true;
   bool bwd64_stream = true;        // 16-bit loops: the backward K = 64 layer on k_gemm_bwd64 (TMA-streamed activations, AW_OPT_BWD64_STREAM)
   // tensor-core spectral path of the fp16 embed loop (spectc.cuh; AW_B200_FFT_SPEC=1: off)
   bool tc_spec = true;
@@ -166,8 +174,9 @@ static const char* gemm_label(int epi, int n, int k) {
   static char table[32][32];
   static int used = 0;
   char buf[32];
-  static const char* kind[9] = {"plain", "fwd", "bwd", "fwd_stats", "fwd_apply", "bwd_stats", "bwd_apply", "peak", "spec"};
-  snprintf(buf, sizeof(buf), "gemm_%s_n%d_k%d", epi >= 0 && epi < 9 ? kind[epi] : "other", n, k);
+  static const char* kind[11] = {"plain", "fwd", "bwd", "fwd_stats", "fwd_apply", "bwd_stats", "bwd_apply", "peak", "spec",
+                                 "fwd_fuse", "bwd_fuse"};
+  snprintf(buf, sizeof(buf), "gemm_%s_n%d_k%d", epi >= 0 && epi < 11 ? kind[epi] : "other", n, k);
   for (int i = 0; i < used; ++i)
     if (strcmp(table[i], buf) == 0) return table[i];
   if (used == 32) return "gemm_other";
@@ -378,6 +387,60 @@ static int launch_tc_pair(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap&
   AW_LAUNCH_CHECK();
   return 0;
 }
+static bool pair_ok(aw_ctx* ctx, int rows, int n, int k, int elem_bytes);
+// EPI_FWD_FUSE / EPI_BWD_FUSE (gemm.cuh): InstanceNorm (+ LeakyReLU) / its adjoint inside the GEMM.  The grid is a
+// multiple of the group size (all row tiles of a clip -- of two clips for CTA pairs with an odd tile count -- for
+// one column panel), at most one CTA per SM: the CTAs of a group are co-resident and at the same tile when they
+// exchange their column sums.  `ep` must carry tiles_per_clip, Tp, part, stat / stat_out.
+template <typename T, typename OT, int EPI, int CG>
+static int launch_tc_fused(aw_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, int rows, int n, int k,
+                           EpiArgsT<OT> ep, int n_clips, cudaStream_t st) {
+  constexpr int BN = 256;
+  auto kern = CG == 2 ? k_gemm_tc_pair<T, OT, BN, EPI> : k_gemm_tc<T, OT, BN, EPI>;
+  const int smem = CG == 2 ? gemm_tc_smem_pair<BN, EPI>() : gemm_tc_smem<BN>();
+  if (raise_smem_limit(ctx, (const void*)kern, smem)) return 1;
+  const int n_row_tiles = rows / 128, n_col_tiles = n / BN, tpc = ep.tiles_per_clip;
+  const int gs = CG == 2 && tpc % 2 == 0 ? tpc / 2 : tpc;       // group size in tiles (CG = 2: pair-tiles)
+  const int tiles = n_row_tiles / CG * n_col_tiles;
+  AW_REQUIRE(tiles % gs == 0 && gs <= ctx->num_sms / CG, "fused InstanceNorm GEMM: bad tile grouping (%d tiles, groups of %d)", tiles, gs);
+  const int units = std::min(tiles, ctx->num_sms / CG / gs * gs);
+  {
+    const void* before = ctx->fuse_cnt.p;
+    if (ensure(ctx->fuse_cnt, (size_t)std::max(n_clips * n_col_tiles, 1) * sizeof(unsigned))) return 1;
+    if (ctx->fuse_cnt.p != before) ctx->fuse_cnt_fresh = true;
+  }
+  if (ctx->fuse_cnt_tpc != tpc || ctx->fuse_cnt_fresh) {
+    // counters only ever advance by tiles_per_clip per launch; a new clip length (or a grown buffer) restarts them
+    AW_CUDA(cudaMemsetAsync(ctx->fuse_cnt.p, 0, ctx->fuse_cnt.cap, st));
+    ctx->fuse_cnt_tpc = tpc;
+    ctx->fuse_cnt_fresh = false;
+  }
+  ep.fuse_cnt = (unsigned*)ctx->fuse_cnt.p;
+  ep.fuse_gs = gs;
+  aw_ctx::ProfRec pr;
+  if (ctx->prof_on) {
+    pr.n = n; pr.k = k; pr.epi = EPI;
+    pr.a = prof_event(ctx); pr.b = prof_event(ctx);
+    cudaEventRecord(pr.a, st);
+  }
+  prof_mark(ctx, st, gemm_label(EPI, n, k));
+  aw_launch(ctx, kern, dim3(units * CG), dim3(gemm_threads(EPI, CG)), (size_t)smem, st, ma, mb, k, n_row_tiles, n_col_tiles, ep);
+  if (ctx->prof_on) {
+    cudaEventRecord(pr.b, st);
+    ctx->prof.push_back(pr);
+  }
+  ctx->launches++;
+  AW_LAUNCH_CHECK();
+  return 0;
+}
+// which form (0 = none, 1 = single CTAs, 2 = CTA pairs) the fused layer takes: 16-bit loops only, not in the
+// frame-sharded mode (its statistics are all-reduced over ranks between the GEMM and the apply pass)
+static int fuse_form(aw_ctx* ctx, int mask, int n_clips, int tiles_per_clip, int rows, int n, int k, int elem_bytes) {
+  if (!(ctx->fuse_norm & mask) || ctx->sh || elem_bytes != 2 || n % 256 != 0 || tiles_per_clip > 32) return 0;
+  if (ctx->fuse_pair && pair_ok(ctx, rows, n, k, elem_bytes) && (tiles_per_clip % 2 == 0 || n_clips % 2 == 0)) return 2;
+  return 1;
+}
+
 // Measured (256 clips x 10 s, profiles/r2_pair_gemm.txt): the pair wins where operand staging bounds the
 // tile -- K bytes per row >= 2 KB (TF32 K >= 512: -16 %, fp16 K = 1024: -5..10 %); at fp16 K = 512 the
 // tile is epilogue-bound and coupling the two CTAs' drains costs 15 %, so that layer stays on single CTAs.
@@ -476,6 +539,10 @@ extern "C" int aw_ctx_create(aw_ctx** out, int device, const aw_model* model) {
     ctx->tc_spec = !(e3 && e3[0] == '1');
     const char* e4 = getenv("AW_B200_NO_PAIR");
     ctx->pair_gemm = !(e4 && e4[0] == '1');
+    const char* e5 = getenv("AW_B200_FUSE_NORM");
+    if (e5 && e5[0]) ctx->fuse_norm = atoi(e5) & 3;
+    const char* e6 = getenv("AW_B200_FUSE_PAIR");
+    if (e6 && e6[0]) ctx->fuse_pair = e6[0] == '1';
   }
 
   void* fn = nullptr;
@@ -624,6 +691,10 @@ extern "C" int aw_ctx_set_option(aw_ctx* ctx, int option, double value) {
     case AW_OPT_TWO_PASS: ctx->two_pass = value != 0.0; return 0;
     case AW_OPT_PAIR_GEMM: ctx->pair_gemm = value != 0.0; return 0;
     case AW_OPT_BWD64_STREAM: ctx->bwd64_stream = value != 0.0; return 0;
+    case AW_OPT_FUSE_NORM:
+      ctx->fuse_norm = (int)value & 3;
+      ctx->fuse_pair = ((int)value & 4) != 0;
+      return 0;
     default: return set_error("aw_ctx_set_option: unknown option %d", option);
   }
 }
@@ -827,7 +898,7 @@ static int p0b_blocks(const Dims& d) { return (2 * d.Tp + AW_P0B_FRAMES - 1) / A
 static int p0a_blocks(const Dims& d) { return (d.T + AW_P0A_FRAMES - 1) / AW_P0A_FRAMES; }
 static int s2_slots(const Dims& d) { return p0a_blocks(d); }
 static size_t acc_doubles(const Dims& d) {
-  return (size_t)d.n * (1 + s2_slots(d) + 256 * (size_t)mel_blocks(d) + 256 * (size_t)p0b_blocks(d));
+  return (size_t)d.n * (1 + s2_slots(d) + 256 * (size_t)mel_blocks(d) + 256 * (size_t)p0b_blocks(d)) + 1;   // + alignment pad
 }
 static Acc acc_view(aw_ctx* ctx, const Dims& d) {
   Acc a;
@@ -835,7 +906,8 @@ static Acc acc_view(aw_ctx* ctx, const Dims& d) {
   double* base = (double*)ctx->accum.p;
   a.peak_y = (unsigned long long*)base;
   a.s2_part = base + d.n;
-  a.chan_part = a.s2_part + (size_t)d.n * s2_slots(d);
+  // (sum, sum of squares) pairs are read as double2: 16-byte aligned
+  a.chan_part = base + (((size_t)d.n * (1 + s2_slots(d)) + 1) & ~(size_t)1);
   a.bpart = a.chan_part + (size_t)d.n * 256 * a.mel_blocks;
   return a;
 }
@@ -1032,6 +1104,17 @@ static int net_forward(aw_ctx* ctx, const Dims& d, const Acc& acc, const SparseM
     // output, so it runs twice -- column sums only, then again with InstanceNorm + LeakyReLU applied in
     // the epilogue -- and the raw H1 never exists (exact fp32 mode keeps the one-pass form)
     const bool two_pass = l == 0 && ctx->prec != AW_PREC_FP32 && ctx->two_pass;
+    const int fuse = two_pass || ctx->prec == AW_PREC_FP32 ? 0 : fuse_form(ctx, 1, d.n, d.tiles, d.rows, cout, cin, (int)sizeof(AT));
+    if (fuse) {
+      // InstanceNorm + LeakyReLU inside the GEMM: H never exists, no finalize / apply pass
+      if constexpr (sizeof(AT) == 2) {
+        ep.tiles_per_clip = d.tiles; ep.Tp = d.Tp; ep.stat_out = (float*)ctx->stat[l + 1].p;
+        if (fuse == 2 ? launch_tc_fused<AT, AT, EPI_FWD_FUSE, 2>(ctx, ctx->tm_act[B][l], ModeOf<AT>::wP(ctx, l), d.rows, cout, cin, ep, d.n, st)
+                      : launch_tc_fused<AT, AT, EPI_FWD_FUSE, 1>(ctx, ctx->tm_act[B][l], mw, d.rows, cout, cin, ep, d.n, st))
+          return 1;
+      }
+      continue;
+    }
     if (two_pass) {
       if (launch_tc<AT, AT, 256, EPI_FWD_STATS>(ctx, ctx->tm_act[B][l], mw, d.rows, cout, cin, ep, st)) return 1;
     } else if (ctx->prec != AW_PREC_FP32 && pair_ok(ctx, d.rows, cout, cin, (int)sizeof(AT))) {
@@ -1099,6 +1182,17 @@ static int net_backward(aw_ctx* ctx, const Dims& d, const Acc& acc, const Sparse
     memset(&g64, 0, sizeof(g64));
     g64.part = (float*)ctx->part.p; g64.ldp = n; g64.ldo = n; g64.tiles_per_clip = d.tiles; g64.Tp = d.Tp;
     g64.stat = (float*)ctx->stat[l].p; g64.bstat = (float*)ctx->bstat.p;
+    const int fuse = two_pass || ctx->prec == AW_PREC_FP32 ? 0 : fuse_form(ctx, 2, d.n, d.tiles, d.rows, n, k, (int)sizeof(AT));
+    if (fuse) {
+      // LeakyReLU' + InstanceNorm adjoint inside the GEMM: dHhat never exists, no finalize / apply pass
+      if constexpr (sizeof(AT) == 2) {
+        ep.tiles_per_clip = d.tiles; ep.Tp = d.Tp; ep.stat = (float*)ctx->stat[l].p;
+        if (fuse == 2 ? launch_tc_fused<AT, AT, EPI_BWD_FUSE, 2>(ctx, *steps[s].ma, ModeOf<AT>::wtP(ctx, l), d.rows, n, k, ep, d.n, st)
+                      : launch_tc_fused<AT, AT, EPI_BWD_FUSE, 1>(ctx, *steps[s].ma, mw, d.rows, n, k, ep, d.n, st))
+          return 1;
+      }
+      continue;
+    }
     if (stream64) {
       if constexpr (sizeof(AT) == 2) {
         if (launch_bwd64<AT, EPI_BWD_STATS>(ctx, *steps[s].ma, ModeOf<AT>::wtP(ctx, l), ctx->tm_act[B][l], ctx->tm_ga1024[B],

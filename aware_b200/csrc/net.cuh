@@ -130,7 +130,17 @@ __device__ __forceinline__ void sum_partials(const double* __restrict__ part, in
   s1 = 0.0;
   s2 = 0.0;
   const double* p = part + ((long long)clip * nblk * AW_NMEL + c) * 2;
-  for (int b = 0; b < nblk; ++b) {
+  // eight blocks' loads in flight at a time (one CTA per clip: the loop is pure L2 latency otherwise), added
+  // in block order
+  int b = 0;
+  for (; b + 8 <= nblk; b += 8) {
+    double2 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const double2*>(p + (long long)(b + i) * AW_NMEL * 2));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s1 += v[i].x; s2 += v[i].y; }
+  }
+  for (; b < nblk; ++b) {
     s1 += p[(long long)b * AW_NMEL * 2];
     s2 += p[(long long)b * AW_NMEL * 2 + 1];
   }
@@ -259,15 +269,30 @@ __global__ void __launch_bounds__(256) k_finalize_small(const float* __restrict_
   if (c >= C) return;
   const float* p0 = part + (((long long)clip * tiles) * ldp + c) * 2;
   double s1 = 0.0, s2 = 0.0;
-  for (int sl = 0; sl < 8; ++sl) {
-    double a1 = 0.0, a2 = 0.0;
-    for (int t = sl; t < tiles; t += 8) {
-      const float2 p = __ldg(reinterpret_cast<const float2*>(p0 + (long long)t * ldp * 2));
-      a1 += p.x;
-      a2 += p.y;
+  if (tiles <= 8) {
+    // one tile per slice: all loads in flight at once, then the same sums in the same (slice) order
+    float2 pv[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      pv[t] = t < tiles ? __ldg(reinterpret_cast<const float2*>(p0 + (long long)t * ldp * 2)) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (t < tiles) {
+        s1 = t == 0 ? (double)pv[t].x : s1 + (double)pv[t].x;
+        s2 = t == 0 ? (double)pv[t].y : s2 + (double)pv[t].y;
+      }
     }
-    s1 = sl == 0 ? a1 : s1 + a1;
-    s2 = sl == 0 ? a2 : s2 + a2;
+  } else {
+    for (int sl = 0; sl < 8; ++sl) {
+      double a1 = 0.0, a2 = 0.0;
+      for (int t = sl; t < tiles; t += 8) {
+        const float2 p = __ldg(reinterpret_cast<const float2*>(p0 + (long long)t * ldp * 2));
+        a1 += p.x;
+        a2 += p.y;
+      }
+      s1 = sl == 0 ? a1 : s1 + a1;
+      s2 = sl == 0 ? a2 : s2 + a2;
+    }
   }
   if (MODE == 1) {
     stat[((long long)clip * C + c) * 2] = (float)(s1 / Tp);
@@ -473,9 +498,16 @@ __global__ void __launch_bounds__(64) k_head_final(HeadArgs<AT> a, int tiles) {
   __shared__ float s_z[64], s_dz[64];
   const int clip = blockIdx.x, c = threadIdx.x;
   double sp = 0.0, sn = 0.0, np_ = 0.0;
-  for (int t = 0; t < tiles; ++t) {
-    const double* o = a.hpart + (((long long)clip * tiles + t) * 64 + c) * 3;
-    sp += o[0]; sn += o[1]; np_ += o[2];
+  for (int t0 = 0; t0 < tiles; t0 += 8) {                   // eight tiles' loads in flight, added in tile order
+    double o3[8][3];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double* o = a.hpart + (((long long)clip * tiles + min(t0 + i, tiles - 1)) * 64 + c) * 3;
+      o3[i][0] = o[0]; o3[i][1] = o[1]; o3[i][2] = o[2];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (t0 + i < tiles) { sp += o3[i][0]; sn += o3[i][1]; np_ += o3[i][2]; }
   }
   const float z = (float)((sp + (double)AW_LEAKY * sn) / a.Tp_glob);
   s_z[c] = z;

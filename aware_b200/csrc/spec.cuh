@@ -252,7 +252,19 @@ __global__ void __launch_bounds__(128) k_clip_scalars(const unsigned long long* 
   ClipScal cs;
   cs.inv = __fdiv_rn(__fdiv_rn(1.0f, d1), d2);
   double s2d = 0.0;
-  for (int i = 0; i < nblk; ++i) s2d += s2_part[(long long)clip * nblk + i];
+  {
+    // eight partials in flight at a time (one thread per clip: pure L2 latency otherwise), added in block order
+    const double* sp = s2_part + (long long)clip * nblk;
+    int i = 0;
+    for (; i + 8 <= nblk; i += 8) {
+      double v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldg(sp + i + k);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s2d += v[k];
+    }
+    for (; i < nblk; ++i) s2d += sp[i];
+  }
   const float s2 = (float)(s2d * (double)cs.inv);
   const float s1 = s2 * 1e-8f / d2;
   cs.corr = peak_s_sign(pk) * (s2 / d2 + s1) / d1;
