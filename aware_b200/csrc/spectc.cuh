@@ -161,15 +161,27 @@ __global__ void __launch_bounds__(256) k_tc_dsprep(const float* __restrict__ dA,
   const int slot = *it_ptr & 1;
   const float s = tc_grad_scale(dmax2[(size_t)slot * n_clips + clip]);
   float mx = 0.f;
-  for (int e = threadIdx.x; e < nf * nb; e += blockDim.x) {
+  // a block's AW_TC_FR x nb elements (nb <= 96) are at most U per thread: all loads first, then the stores
+  constexpr int U = (AW_TC_FR * 96 + 255) / 256;
+  float a0[U];
+  float2 qv[U];
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    const int e = threadIdx.x + k * 256;
+    const bool on = e < nf * nb;
+    a0[k] = on ? __ldg(dA + src + e) : 0.f;
+    qv[k] = on ? __ldg(q + src + e) : make_float2(0.f, 0.f);
+  }
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    const int e = threadIdx.x + k * 256;
+    if (e >= nf * nb) break;
     const int f = e / nb, b = e - f * nb, t = t0 + f;
+    mx = fmaxf(mx, fabsf(a0[k]));
     float2 v = make_float2(0.f, 0.f);
-    const float a0 = __ldg(dA + src + e);
-    mx = fmaxf(mx, fabsf(a0));
     if (t >= 3 && t < T - 3) {
-      const float g = a0 * s;
-      const float2 qv = __ldg(q + src + e);
-      v = make_float2(g * qv.x, g * qv.y);
+      const float g = a0[k] * s;
+      v = make_float2(g * qv[k].x, g * qv[k].y);
     }
     reinterpret_cast<__half2*>(dS + ((long long)clip * (T + 6) + t + 3) * AW_TC_P)[b] = __floats2half2_rn(v.x, v.y);
   }
