@@ -609,19 +609,29 @@ __global__ void __launch_bounds__(128) k_p0_bwd_reduce(const float* __restrict__
   const ChanStats st = cs[(long long)clip * AW_NMEL + c];
   double s1 = 0.0, s2 = 0.0;
   const int t1 = min(t0 + AW_P0B_FRAMES, 2 * Tp);
+  // ncu (profiles/r2_ncu_summary.md, front end): this kernel was ISSUE-bound (81 % issue-active, 37 instructions per
+  // element), not HBM-bound -- so: one base pointer per tensor and immediate offsets, each pooled row of dP0 loaded
+  // once for its two frames, predicates only in the clip's last block.  Same sums in the same order.
+  const float* dp = dP0 + ((long long)clip * Tp_pad + (t0 >> 1)) * AW_NMEL + c;      // t0 is even
+  const float* mp = M + ((long long)clip * T + t0) * AW_NMEL + c;
+  const float hg = 0.5f * ginv;
 #pragma unroll 1
-  for (int tb = t0; tb < t1; tb += 8) {
-    float d8[8], m8[8];
+  for (int tb = t0; tb < t1; tb += 8, dp += 4 * AW_NMEL, mp += 8 * AW_NMEL) {
+    float d4[4], m8[8];
+    if (tb + 8 <= t1) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int t = tb + i;
-      const bool ok = t < t1;
-      d8[i] = ok ? dP0[((long long)clip * Tp_pad + (t >> 1)) * AW_NMEL + c] : 0.f;
-      m8[i] = ok ? M[((long long)clip * T + t) * AW_NMEL + c] : st.mu;
+      for (int i = 0; i < 4; ++i) d4[i] = dp[i * AW_NMEL];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m8[i] = mp[i * AW_NMEL];
+    } else {                                                      // the clip's last block (2 Tp is even: whole pairs)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d4[i] = tb + 2 * i < t1 ? dp[i * AW_NMEL] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m8[i] = tb + i < t1 ? mp[i * AW_NMEL] : st.mu;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float dg = (0.5f * ginv) * d8[i];
+      const float dg = hg * d4[i >> 1];                           // masked rows: dg = 0 and mh = 0, as before
       const float mh = (m8[i] - st.mu) * st.rstd;
       s1 += dg;
       s2 += (double)dg * mh;
