@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(256) k_tc_dsprep(const float* __restrict__ dA,
   const int slot = *it_ptr & 1;
   const float s = tc_grad_scale(dmax2[(size_t)slot * n_clips + clip]);
   float mx = 0.f;
+  const unsigned long long nb_magic = 0xFFFFFFFFull / (unsigned)nb + 1ull;   // e / nb == (e * magic) >> 32 for e, nb < 2^16
   // a block's AW_TC_FR x nb elements (nb <= 96) are at most U per thread: all loads first, then the stores
   constexpr int U = (AW_TC_FR * 96 + 255) / 256;
   float a0[U];
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(256) k_tc_dsprep(const float* __restrict__ dA,
   for (int k = 0; k < U; ++k) {
     const int e = threadIdx.x + k * 256;
     if (e >= nf * nb) break;
-    const int f = e / nb, b = e - f * nb, t = t0 + f;
+    const int f = (int)(((unsigned long long)(unsigned)e * nb_magic) >> 32), b = e - f * nb, t = t0 + f;   // e / nb
     mx = fmaxf(mx, fabsf(a0[k]));
     float2 v = make_float2(0.f, 0.f);
     if (t >= 3 && t < T - 3) {
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(256) k_tc_update(TcUpdateArgs a) {
   const bool improved = a.improved[clip] != 0;
   const int mstar = cs.nstar + AW_HALF;
   const long long o0 = ((long long)clip * T + t0) * nb;
+  const unsigned long long nb_magic = 0xFFFFFFFFull / (unsigned)nb + 1ull;   // (e * magic) >> 32 == e / nb for e, nb < 2^16
   constexpr int U = 2;                                       // elements in flight per thread
   for (int e0 = threadIdx.x; e0 < nf * nb; e0 += U * blockDim.x) {
     float2 uv[U], d2[U];
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(256) k_tc_update(TcUpdateArgs a) {
       const int e = e0 + k * blockDim.x;
       on[k] = e < nf * nb;
       const int ec = on[k] ? e : e0;
-      const int f = ec / nb;
+      const int f = (int)(((unsigned long long)(unsigned)ec * nb_magic) >> 32);   // ec / nb without the division sequence
       bb[k] = ec - f * nb;
       tt[k] = t0 + f;
       const long long o = o0 + ec;
