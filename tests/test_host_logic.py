@@ -26,6 +26,22 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in handle.aw_version()
 
 
+def test_python_constants_equal_the_header_enums():
+    """Every AW_PREC_* / AW_OPT_* / AW_STAT_* / AW_COMM_* enumerator of include/aware_b200.h has the same value
+    on the ctypes side (aware_b200/_lib.py) -- a knob added to one and not the other would silently set another."""
+    from aware_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "aware_b200.h")).read()
+    enums = {m.group(1): int(m.group(2)) for m in re.finditer(r"\bAW_((?:PREC|OPT|STAT|COMM)_[A-Z0-9_]+)\s*=\s*(\d+)", header)}
+    assert len(enums) >= 17 and "OPT_FUSE_NORM" in enums
+    for name, value in enums.items():
+        assert getattr(_lib, name) == value, name
+    # multiply-shift division used by the frame-row kernels (csrc/spectc.cuh: e / nb == (e * magic) >> 32)
+    for nb in (1, 2, 40, 81, 96, 225, 256):
+        magic = 0xFFFFFFFF // nb + 1
+        e = np.arange(0, 1 << 16, dtype=np.uint64)
+        assert np.array_equal((e * np.uint64(magic)) >> np.uint64(32), e // np.uint64(nb))
+
+
 def test_context_creation_fails_loudly_without_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
