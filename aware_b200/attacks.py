@@ -340,7 +340,8 @@ class CompressionApprox(Attack):
     strongest band bin are dropped (masking) and the others are rounded to a `step_db` grid in
     log-magnitude (coarse quantisation); phases are kept; the change is resynthesised (overlap-add) and
     added to the input, so content outside the band passes through.  Output length 256 * (N // 256).
-    Pinned by `oracle_compression_approx` below (numpy restatement) in tests/test_gpu_parity.py."""
+    Pinned by its numpy restatement `oracle/aware_oracle.py::attack_compression_approx` in
+    tests/test_gpu_parity.py."""
 
     def __init__(self, step_db=1.5, floor_db=-60.0):
         self.step_db, self.floor_db = float(step_db), float(floor_db)
@@ -352,28 +353,6 @@ class CompressionApprox(Attack):
         mag, ph = eng.stft_band(x, sr, normalize=False, phasor=True)
         delta = eng.istft_band(eng.spectral_quantize(mag, self.step_db, self.floor_db), ph, sr)
         return eng.attack_affine(x[:, :L], 1.0, delta, 1.0)
-
-
-def oracle_compression_approx(x, sr, step_db=1.5, floor_db=-60.0, bands=(500.0, 4000.0)):
-    """numpy / torch-CPU restatement of CompressionApprox for ONE clip (test infrastructure)."""
-    x = np.asarray(x, dtype=np.float32)
-    win = torch.hann_window(1024)
-    S = torch.stft(torch.from_numpy(x), n_fft=1024, hop_length=256, win_length=1024, window=win, center=True,
-                   pad_mode="reflect", return_complex=True)
-    f = np.fft.rfftfreq(1024, 1.0 / sr)
-    band = torch.from_numpy((f >= bands[0]) & (f <= bands[1]))
-    mag = S.abs()[band].numpy()                                    # [nb, T]
-    k_log = np.float32(20.0 * np.log10(2.0) / step_db)
-    k_exp = np.float32(step_db / (20.0 * np.log10(2.0)))
-    floor = mag.max(axis=0, keepdims=True) * np.float32(10.0 ** (floor_db / 20.0))
-    with np.errstate(divide="ignore"):
-        q = np.exp2(np.rint(np.log2(mag) * k_log) * k_exp).astype(np.float32)
-    q = np.where((mag >= floor) & (mag > 0), q, np.float32(0.0))
-    D = torch.zeros_like(S)
-    ph = S[band] / torch.clamp(S[band].abs(), min=1e-30)
-    D[band] = torch.from_numpy(q - mag) * ph
-    delta = torch.istft(D, n_fft=1024, hop_length=256, win_length=1024, window=win, center=True).numpy()
-    return (x[:len(delta)] + delta).astype(np.float32), mag.T, q.T
 
 
 def reference_suite():

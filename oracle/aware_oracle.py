@@ -443,6 +443,30 @@ def attack_resample(audio: np.ndarray, sr: int, target_sr: int = 16000) -> np.nd
     return resample_poly(resample_poly(audio, 441, 160), 160, 441)
 
 
+def attack_compression_approx(x, sr, step_db=1.5, floor_db=-60.0, bands=(500.0, 4000.0)):
+    """numpy / torch-CPU restatement of aware_b200.attacks.CompressionApprox for ONE clip.  PARITY UNPINNED
+    to the reference: upstream's MP3Compression shells out to ffmpeg (scripts/attacks.py:73-148) and has
+    no arithmetic to follow; this pins the CUDA kernels to the attack's own definition."""
+    x = np.asarray(x, dtype=np.float32)
+    win = torch.hann_window(1024)
+    S = torch.stft(torch.from_numpy(x), n_fft=1024, hop_length=256, win_length=1024, window=win, center=True,
+                   pad_mode="reflect", return_complex=True)
+    f = np.fft.rfftfreq(1024, 1.0 / sr)
+    band = torch.from_numpy((f >= bands[0]) & (f <= bands[1]))
+    mag = S.abs()[band].numpy()                                    # [nb, T]
+    k_log = np.float32(20.0 * np.log10(2.0) / step_db)
+    k_exp = np.float32(step_db / (20.0 * np.log10(2.0)))
+    floor = mag.max(axis=0, keepdims=True) * np.float32(10.0 ** (floor_db / 20.0))
+    with np.errstate(divide="ignore"):
+        q = np.exp2(np.rint(np.log2(mag) * k_log) * k_exp).astype(np.float32)
+    q = np.where((mag >= floor) & (mag > 0), q, np.float32(0.0))
+    D = torch.zeros_like(S)
+    ph = S[band] / torch.clamp(S[band].abs(), min=1e-30)
+    D[band] = torch.from_numpy(q - mag) * ph
+    delta = torch.istft(D, n_fft=1024, hop_length=256, win_length=1024, window=win, center=True).numpy()
+    return (x[:len(delta)] + delta).astype(np.float32), mag.T, q.T
+
+
 def butter_coeffs(kind: str, sr: int, f_low: float | None = None):
     """Filter designs used by attacks.py:342-349, 413-416, 451-453 (host-side, scipy)."""
     from scipy.signal import butter

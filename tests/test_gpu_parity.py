@@ -774,7 +774,7 @@ def test_detector_threshold_reaches_the_batch_decision(model):
 
 def test_compression_approx_matches_its_numpy_definition(model):
     """X3 (parity unpinned to the reference -- upstream's MP3 attack is an ffmpeg call; pinned to the
-    definition restated in numpy, aware_b200.attacks.oracle_compression_approx).  The quantised
+    definition restated in numpy, oracle/aware_oracle.py::attack_compression_approx).  The quantised
     magnitudes agree except where log2 lands within rounding of a grid midpoint (device log2f vs numpy),
     the waveform to 1e-4 / 80 dB, and a watermark survives the attack."""
     from aware_b200 import attacks as A
@@ -788,7 +788,7 @@ def test_compression_approx_matches_its_numpy_definition(model):
     mag = eng.stft_band(xd, sr, normalize=False).cpu().numpy()
     dq = eng.spectral_quantize(torch.from_numpy(mag).cuda(), 1.5, -30.0).cpu().numpy()
     for i in range(2):
-        want, mag_ref, q_ref = A.oracle_compression_approx(x[i], sr, 1.5, -30.0)
+        want, mag_ref, q_ref = O.attack_compression_approx(x[i], sr, 1.5, -30.0)
         assert got[i].shape == want.shape == (256 * (x.shape[1] // 256),)
         assert np.abs(mag[i] - mag_ref).max() <= 1e-5 * mag_ref.max()
         q = dq[i] + mag[i]
