@@ -284,14 +284,22 @@ class RandomBandstop(Attack):
 
 # ---- extensions named by the build brief that have no reference arithmetic ("parity unpinned")
 class AdditiveNoise(Attack):
-    """y = x + sigma * buf, buf a host-seeded standard-normal buffer."""
+    """y = x + sigma * buf, buf a host-seeded standard-normal buffer.  `buffer` (float32 [n, >= N], host or
+    device) is the caller's own buffer -- a sweep draws it once and keeps it resident in HBM; without it the
+    buffer is drawn per call from `seed` on the host and copied over."""
 
-    def __init__(self, sigma=0.01, seed=99):
+    def __init__(self, sigma=0.01, seed=99, buffer=None):
         self.sigma, self.seed, self.name = sigma, seed, f"noise_{sigma}"
+        self.buffer = buffer
 
     def apply_batch(self, x, sr, rng=None, engine=None):
-        g = torch.Generator(device="cpu").manual_seed(self.seed)
-        buf = torch.randn(x.shape, generator=g, dtype=torch.float32).to(x.device)
+        if self.buffer is not None:
+            buf = torch.as_tensor(self.buffer, dtype=torch.float32).to(x.device)
+            if buf.dim() != 2 or buf.shape[0] != x.shape[0] or buf.shape[1] < x.shape[1] or buf.stride(1) != 1:
+                raise ValueError("noise buffer must be float32 [n_clips, >= n_samples] with unit sample stride")
+        else:
+            g = torch.Generator(device="cpu").manual_seed(self.seed)
+            buf = torch.randn(x.shape, generator=g, dtype=torch.float32).to(x.device)
         return _eng(engine).attack_affine(x, 1.0, buf, self.sigma)
 
 

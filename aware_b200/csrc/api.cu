@@ -2388,6 +2388,14 @@ extern "C" int aw_attack_upfirdn(aw_ctx* ctx, const float* d_in, int n_clips, in
   AW_REQUIRE(ctx && d_in && d_out && d_h_tf, "null argument");
   if (ctx) cudaSetDevice(ctx->device);
   prof_mark(ctx, (cudaStream_t)stream, "attack_upfirdn");
+  if (up == 1 && down == 1 && taps_per_phase >= 1 && taps_per_phase <= AW_FIR_MAXTAPS) {   // FIR filters: register-tiled
+    const int tiles = (n_out + AW_FIR_TILE - 1) / AW_FIR_TILE;
+    k_fir_tiled<<<dim3((unsigned)std::max(1, std::min(tiles, 65535)), n_clips), 256, 0, (cudaStream_t)stream>>>(
+        d_in, in_stride, n_in, d_h_tf, taps_per_phase, first_out, n_out, d_out, out_stride);
+    ctx->launches++;
+    AW_LAUNCH_CHECK();
+    return 0;
+  }
   k_upfirdn<<<ew_grid(n_out, n_clips), 256, 0, (cudaStream_t)stream>>>(
       d_in, in_stride, n_in, d_h_tf, taps_per_phase, up, down, first_out, n_out, d_out, out_stride);
   ctx->launches++;

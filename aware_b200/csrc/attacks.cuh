@@ -97,6 +97,63 @@ __global__ void __launch_bounds__(256) k_upfirdn(const float* __restrict__ x, lo
   }
 }
 
+// up = down = 1 (the FIR low / high / band-pass attacks): the same sums in the same order, register-tiled.
+// Every thread owns FIR_R consecutive outputs and keeps a sliding window of FIR_R inputs in registers, so a
+// tap costs one shared-memory load of x, one broadcast load of h and FIR_R multiply + add pairs (the products
+// are NOT fused: scipy's float32 loop rounds the product before the add).  Samples outside [0, n_in) are staged
+// as +0: acc + (+-0) == acc for every acc the loop can hold (acc is never -0), so that equals skipping them.
+// The input tile is stored with one pad word per eight (index i + i/8): thread t reads word 9t + c.
+#define AW_FIR_R 8
+#define AW_FIR_TILE (256 * AW_FIR_R)
+#define AW_FIR_MAXTAPS 1024
+__device__ __forceinline__ int fir_addr(int i) { return i + (i >> 3); }
+
+__global__ void __launch_bounds__(256) k_fir_tiled(const float* __restrict__ x, long long sx, int n_in,
+                                                   const float* __restrict__ h_tf, int hpp, int k_off,
+                                                   int n_out, float* __restrict__ out, long long so) {
+  __shared__ float xs[((AW_FIR_TILE + AW_FIR_MAXTAPS + 8) * 9) / 8 + 8];
+  __shared__ float hs[AW_FIR_MAXTAPS];
+  const int clip = blockIdx.y;
+  const float* p = x + (long long)clip * sx;
+  float* o = out + (long long)clip * so;
+  for (int j = threadIdx.x; j < hpp; j += 256) hs[j] = h_tf[j];
+  for (int tile0 = blockIdx.x * AW_FIR_TILE; tile0 < n_out; tile0 += gridDim.x * AW_FIR_TILE) {
+    const long long g0 = (long long)tile0 + k_off - hpp + 1;    // input index of staged word 0
+    const int n_stage = AW_FIR_TILE + hpp + 7;
+    __syncthreads();                                            // previous tile's output words are consumed
+    for (int i = threadIdx.x; i < n_stage; i += 256) {
+      const long long g = g0 + i;
+      xs[fir_addr(i)] = (g >= 0 && g < n_in) ? p[g] : 0.f;
+    }
+    __syncthreads();
+    const int base = threadIdx.x * AW_FIR_R;                    // output r sums xs[base + r + j] * hs[j], j ascending
+    float acc[AW_FIR_R], w[AW_FIR_R];
+#pragma unroll
+    for (int r = 0; r < AW_FIR_R; ++r) { acc[r] = 0.f; w[r] = xs[fir_addr(base + r)]; }
+    int j = 0;
+    for (; j + 8 <= hpp; j += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float h = hs[j + u];
+#pragma unroll
+        for (int r = 0; r < AW_FIR_R; ++r) acc[r] = __fadd_rn(acc[r], __fmul_rn(w[(u + r) & 7], h));
+        w[u] = xs[fir_addr(base + j + u + 8)];                  // x[base + j + u] is done; its slot takes x[.. + 8]
+      }
+    }
+    for (; j < hpp; ++j) {
+      const float h = hs[j];
+#pragma unroll
+      for (int r = 0; r < AW_FIR_R; ++r) acc[r] = __fadd_rn(acc[r], __fmul_rn(xs[fir_addr(base + j + r)], h));
+    }
+    __syncthreads();                                            // all reads of the input tile are done
+#pragma unroll
+    for (int r = 0; r < AW_FIR_R; ++r) xs[fir_addr(base + r)] = acc[r];
+    __syncthreads();
+    const int n_here = min(AW_FIR_TILE, n_out - tile0);
+    for (int i = threadIdx.x; i < n_here; i += 256) o[tile0 + i] = xs[fir_addr(i)];
+  }
+}
+
 // ---- A3/A4/A5 Butterworth IIR (attacks.py:342-349, 413-416, 451-453) ---------------
 // scipy lfilter = direct form II transposed in float64.  The recurrence is made
 // parallel by chunking: every thread owns one chunk and first runs `warm` samples
@@ -343,10 +400,31 @@ __global__ void __launch_bounds__(256) k_attack_affine(const float* __restrict__
                                                        long long sn, float sigma,
                                                        float* __restrict__ out, long long so) {
   const int clip = blockIdx.y;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float v = __fmul_rn(gain, x[(long long)clip * sx + i]);
-    if (noise) v = __fadd_rn(v, __fmul_rn(sigma, noise[(long long)clip * sn + i]));
-    out[(long long)clip * so + i] = v;
+  const float* xc = x + (long long)clip * sx;
+  const float* nc = noise ? noise + (long long)clip * sn : nullptr;
+  float* oc = out + (long long)clip * so;
+  int i0 = 0;
+  uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out);
+  long long st = sx | so;
+  if (noise) { al |= reinterpret_cast<uintptr_t>(noise); st |= sn; }
+  if ((st & 3) == 0 && (al & 15) == 0) {                      // 16-byte streaming: 4 samples per access
+    const int n4 = n >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+      const float4 t = __ldcs(reinterpret_cast<const float4*>(xc) + i);
+      float4 v = make_float4(__fmul_rn(gain, t.x), __fmul_rn(gain, t.y), __fmul_rn(gain, t.z), __fmul_rn(gain, t.w));
+      if (nc) {
+        const float4 q = __ldcs(reinterpret_cast<const float4*>(nc) + i);
+        v.x = __fadd_rn(v.x, __fmul_rn(sigma, q.x)); v.y = __fadd_rn(v.y, __fmul_rn(sigma, q.y));
+        v.z = __fadd_rn(v.z, __fmul_rn(sigma, q.z)); v.w = __fadd_rn(v.w, __fmul_rn(sigma, q.w));
+      }
+      reinterpret_cast<float4*>(oc)[i] = v;
+    }
+    i0 = n4 << 2;
+  }
+  for (int i = i0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float v = __fmul_rn(gain, xc[i]);
+    if (nc) v = __fadd_rn(v, __fmul_rn(sigma, nc[i]));
+    oc[i] = v;
   }
 }
 

@@ -612,6 +612,26 @@ def test_fir_attack_matches_scipy_upfirdn(model, kind, cutoff):
         np.testing.assert_array_equal(got[i], want)
 
 
+@pytest.mark.parametrize("numtaps", [1, 5, 8, 64, 101, 1023, 1024, 1500])
+def test_register_tiled_fir_equals_scipy_for_every_tap_count_and_window(eng, numtaps):
+    """k_fir_tiled (up = down = 1, <= 1024 taps; 1500 takes the generic polyphase kernel): tap counts below,
+    at and off the unroll width, clip lengths off the 2048-sample tile, output windows that start inside the
+    clip and run past its end (the convolution tail) -- bit-exact against scipy's float32 upfirdn."""
+    from scipy.signal import upfirdn
+    rng = np.random.default_rng(numtaps)
+    h = (rng.standard_normal(numtaps) / np.sqrt(numtaps)).astype(np.float32)
+    h_tf = torch.from_numpy(h[::-1].copy()).cuda()
+    for n in (1, 7, 2047, 2048, 6151):
+        x = rng.standard_normal((3, n)).astype(np.float32)
+        xd = torch.from_numpy(x).cuda()
+        full = np.stack([upfirdn(h, x[i], 1, 1) for i in range(3)])        # n + numtaps - 1 samples
+        assert full.dtype == np.float32
+        for first, n_out in ((0, n), (0, n + numtaps - 1), (min(3, n - 1), n + numtaps - 1 - min(3, n - 1)),
+                             (n // 2, n - n // 2)):
+            got = eng.attack_upfirdn(xd, h_tf, numtaps, 1, 1, first, n_out).cpu().numpy()
+            np.testing.assert_array_equal(got, full[:, first:first + n_out], err_msg=str((n, first, n_out)))
+
+
 def test_service_stereo_equals_two_mono_calls(model):
     """service/embed.py:37-59 and detect.py:23-43 semantics: a stereo clip is two independent mono
     embeds (each rescaled by its own signed max) and the decoder takes, per bit, the channel with
@@ -693,6 +713,13 @@ def test_noise_and_gain_attacks_match_their_definition(model):
         buf = torch.randn(xd.shape, generator=g, dtype=torch.float32).numpy()
         np.testing.assert_array_equal(got, np.float32(1.0) * x + np.float32(sigma) * buf)
         assert got.dtype == np.float32 and got.shape == x.shape
+        # the caller's own buffer, already resident in HBM (wider than the clips: row stride != n)
+        wide = torch.zeros((x.shape[0], x.shape[1] + 7), dtype=torch.float32)
+        wide[:, :x.shape[1]] = torch.from_numpy(buf)
+        got2 = A.AdditiveNoise(sigma, buffer=wide.cuda()).apply_batch(xd, sr).cpu().numpy()
+        np.testing.assert_array_equal(got2, got)
+    with pytest.raises(ValueError):
+        A.AdditiveNoise(0.01, buffer=torch.zeros((1, 8))).apply_batch(xd, sr)
     one = A.AdditiveNoise(0.01).apply(x[0], sr)                       # reference calling convention
     assert one.shape == x[0].shape and one.dtype == np.float32
 
