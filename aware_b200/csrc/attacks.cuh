@@ -66,8 +66,25 @@ __global__ void __launch_bounds__(256) k_attack_decim_interp(const float* __rest
   int i0 = 0;
   if ((so & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     const int n4 = n >> 2;                                  // 4 outputs per thread, one 16-byte store
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
-      reinterpret_cast<float4*>(oc)[i] = make_float4(one(4 * i), one(4 * i + 1), one(4 * i + 2), one(4 * i + 3));
+    // One division per four outputs: the knot index k0 and the offset r advance incrementally, and a knot
+    // value is loaded once (y1 of one interval is y0 of the next).  Same expression per output as `one`.
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+      int k0 = ((4 * i) / f) * f, r = 4 * i - k0;
+      float y0 = p[min(k0, last)], y1 = (k0 + f <= last) ? p[k0 + f] : 0.f;
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k0 >= last) v[u] = p[last];
+        else if (r == 0) v[u] = y0;
+        else {
+          const double d = __dsub_rn((double)y1, (double)y0);
+          const double slope = pow2 ? __dmul_rn(d, rf) : __ddiv_rn(d, (double)f);
+          v[u] = (float)__dadd_rn(__dmul_rn(slope, (double)r), (double)y0);
+        }
+        if (++r == f) { r = 0; k0 += f; y0 = y1; y1 = (k0 + f <= last) ? p[k0 + f] : 0.f; }
+      }
+      reinterpret_cast<float4*>(oc)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
     i0 = n4 << 2;
   }
   for (int i = i0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) oc[i] = one(i);
