@@ -182,3 +182,41 @@ class Model:
         dola[H:H + L] = dy / env[H:H + L]
         dX = analysis(dola, T, self.bins, "zero") * (2.0 / N_FFT)
         return np.real(dX * np.conj(self.u))
+
+
+# ---------------------------------------------------------------------------------------------
+# k_fir_tiled (aware_b200/csrc/attacks.cuh): the index arithmetic of the register-tiled FIR --
+# staged tile with one pad word per eight, a sliding window of R inputs per thread rotated in
+# place, non-fused float32 product and sum in scipy's tap order.  Vectorised over the threads of
+# one block; `threads` is a parameter so that the CPU test can use small tiles.
+# ---------------------------------------------------------------------------------------------
+def fir_tiled_model(x, h_tf, k_off, n_out, threads=256, R=8):
+    x = np.asarray(x, dtype=np.float32)
+    h_tf = np.asarray(h_tf, dtype=np.float32)
+    hpp, n_in, tile = len(h_tf), len(x), threads * R
+    addr = lambda i: i + (i >> 3)                                   # noqa: E731  (fir_addr)
+    out = np.zeros(n_out, dtype=np.float32)
+    base = np.arange(threads) * R
+    for tile0 in range(0, n_out, tile):
+        g0 = tile0 + k_off - hpp + 1
+        n_stage = tile + hpp + 7
+        xs = np.full(addr(n_stage) + 1, np.nan, dtype=np.float32)  # NaN = a word the kernel never staged
+        g = g0 + np.arange(n_stage)
+        ok = (g >= 0) & (g < n_in)
+        xs[addr(np.arange(n_stage))] = np.where(ok, x[np.clip(g, 0, n_in - 1)], np.float32(0))
+        acc = np.zeros((threads, R), dtype=np.float32)
+        w = np.stack([xs[addr(base + r)] for r in range(R)], axis=1)
+        j = 0
+        while j + 8 <= hpp:
+            for u in range(8):
+                for r in range(R):
+                    acc[:, r] = acc[:, r] + w[:, (u + r) & 7] * h_tf[j + u]     # float32 product, then float32 sum
+                w[:, u] = xs[addr(base + j + u + 8)]
+            j += 8
+        while j < hpp:
+            for r in range(R):
+                acc[:, r] = acc[:, r] + xs[addr(base + j + r)] * h_tf[j]
+            j += 1
+        n_here = min(tile, n_out - tile0)
+        out[tile0:tile0 + n_here] = acc.reshape(-1)[:n_here]
+    return out

@@ -57,3 +57,23 @@ def test_decomposition_matches_autograd(sr, secs):
     g = mdl.backward(pattern)
     scale = np.abs(g_ref).max()
     assert np.abs(g - g_ref.T).max() <= 1e-7 * scale
+
+
+@pytest.mark.parametrize("numtaps", [1, 5, 8, 21, 64, 101])
+def test_fir_tile_model_equals_scipy_upfirdn(numtaps):
+    """Index arithmetic of k_fir_tiled (padded staging, in-place window rotation, zero-staged samples
+    outside the clip, remainder taps) on the CPU: bit-exact against scipy's float32 upfirdn for output
+    windows at the start, inside and past the end of the clip.  The CUDA kernel itself is compared with
+    scipy in tests/test_gpu_parity.py::test_register_tiled_fir_equals_scipy_for_every_tap_count_and_window."""
+    from scipy.signal import upfirdn
+    from kernel_model import fir_tiled_model
+    rng = np.random.default_rng(numtaps)
+    h = (rng.standard_normal(numtaps) / np.sqrt(numtaps)).astype(np.float32)
+    for n in (1, 7, 255, 256, 700):
+        x = rng.standard_normal(n).astype(np.float32)
+        full = upfirdn(h, x, 1, 1)
+        assert full.dtype == np.float32 and len(full) == n + numtaps - 1
+        for first, n_out in ((0, n), (0, n + numtaps - 1), (n // 2, n - n // 2)):
+            got = fir_tiled_model(x, h[::-1].copy(), first, n_out, threads=32)
+            assert not np.isnan(got).any()
+            np.testing.assert_array_equal(got, full[first:first + n_out], err_msg=str((n, first, n_out)))
