@@ -77,3 +77,26 @@ def test_fir_tile_model_equals_scipy_upfirdn(numtaps):
             got = fir_tiled_model(x, h[::-1].copy(), first, n_out, threads=32)
             assert not np.isnan(got).any()
             np.testing.assert_array_equal(got, full[first:first + n_out], err_msg=str((n, first, n_out)))
+
+
+@pytest.mark.parametrize("f", [2, 3, 4])
+def test_decimate_interp_expression_equals_numpy_interp(f):
+    """k_attack_decim_interp's per-sample expression (attacks.cuh): knots are returned as they are, other
+    samples are fl64(fl64(slope * r) + y0) with slope = (y1 - y0) / f -- for f = 2 the kernel's 16-byte path
+    drops the exact `* 1.0`, for a power-of-two f the division is a multiplication by 1/f -- and the tail
+    holds the last knot.  Equal to the oracle's np.interp (scripts/attacks.py:276-287) bit for bit."""
+    rng = np.random.default_rng(f)
+    for n in (5, 64, 1001, 4410):
+        x = rng.standard_normal(n).astype(np.float32)
+        want = O.attack_resample(x, 16000 * f + 100).astype(np.float32)
+        last = ((n - 1) // f) * f
+        i = np.arange(n)
+        k0 = np.minimum((i // f) * f, last)
+        r = (i - k0).astype(np.float64)
+        y0 = x[k0].astype(np.float64)
+        y1 = x[np.minimum(k0 + f, last)].astype(np.float64)
+        d = y1 - y0
+        slope = d * (1.0 / f) if f & (f - 1) == 0 else d / f
+        got = np.where(f == 2, slope + y0, slope * r + y0)
+        got = np.where((i >= last) | (r == 0), x[np.minimum(k0, last)].astype(np.float64), got).astype(np.float32)
+        np.testing.assert_array_equal(got, want, err_msg=str((f, n)))
