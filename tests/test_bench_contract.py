@@ -46,3 +46,30 @@ def test_reference_arm_runs_on_the_cpu_and_follows_the_contract():
     assert d["impl"] == "reference"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
+
+
+def test_last_round2_record_carries_parity_phases_and_rooflines():
+    """The last full `python bench.py` record of round 2 (profiles/r2_bench_final_v6.json): the base contract,
+    the oracle parity block at the bench configuration for both loop precisions, SURVEY 8(d)'s phases (i)-(iv),
+    BASELINE configs[2] sweeps, and a roofline whose fraction follows from its own achieved / peak."""
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r2_bench_final_v6.json")).read().strip().splitlines()[-1])
+    _check_common(d)
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0
+    assert "profiling hooks off" in d["timed_region"]
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"]
+    assert all(abs(x["frac"] - x["achieved"] / x["peak"]) < 1e-9 for x in d["rooflines_all"])
+    p = d["parity"]
+    assert p["all_ok"] is True and p["clips"] >= 4
+    for loop in ("fp16_loop", "tf32_loop"):
+        assert p[loop]["gpu_bits_equal_oracle_bits_on_gpu_audio"] is True and p[loop]["flips_total"] == 0
+    assert p["cross_detect"]["ok"] is True
+    ph = d["phases"]
+    for k in ("detect_only", "attack_suite_to_detect", "embed", "full_step", "config3_attack_sweep_1024_clips",
+              "config3_extensions_1024_clips", "attack_kernels"):
+        assert k in ph, k
+    assert "error" not in ph["config3_extensions_1024_clips"]
+    assert abs(ph["full_step"]["value"] - d["value"]) < 1e-6
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["alt_precision"]["embed_precision"] == "tf32" and d["nonfinite_gradient_clips"] == 0
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
